@@ -1,0 +1,149 @@
+/*
+ * vdjgraph.h -- C ABI of libvdjgraph.so: B200-native de Bruijn graph build for V'DJer.
+ *
+ * This is the drop-in boundary for ONE stage of the reference: the scoped block in assemble(),
+ * /root/reference/src/main/c/assembler2_vdj.c:1381-1415, i.e. the calls
+ *
+ *     build_pre_graph(input, pre_nodes)            :1388   (definition :369-409)
+ *     build_pre_graph(unaligned_input, pre_nodes)  :1390
+ *     prune_pre_graph(pre_nodes)                   :1393   (definition :467-484)
+ *     build_graph2(input, nodes, pool, 1, pre_nodes)           :1402 (definition :412-452)
+ *     build_graph2(unaligned_input, nodes, pool, 0, pre_nodes) :1407
+ *
+ * The reference has no plugin/FFI interface for this stage; the functions above take C++
+ * sparsehash maps and read globals (read_length :97, kmer_size :98, p.min_node_freq,
+ * p.min_base_quality params.h:6-7).  The entry points below are what a cgo/ctypes/C++ caller
+ * binds instead: plain pointers and sizes in, plain arrays out.  INTEGRATION.md shows the
+ * reference-side call site and the host glue that rebuilds `nodes`/`pool` from the result.
+ *
+ * Conventions: every function returns VDJGRAPH_OK (0) or a negative vdjgraph_status; the library
+ * never calls exit(), never writes to stdout (the reference reserves stdout for SAM,
+ * quick_map3.c:168-180) and never throws across the ABI.  One build at a time per context.
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * VDJGRAPH_ERR_CUDA.
+ */
+#ifndef VDJGRAPH_H
+#define VDJGRAPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDJGRAPH_ABI_VERSION 1
+
+typedef enum vdjgraph_status {
+    VDJGRAPH_OK = 0,
+    VDJGRAPH_ERR_PARAM = -1,          /* k > 50 (MAX_KMER_LEN :70), k > read_length, read_length > 255 (bam_read.c:208), NULL pointers */
+    VDJGRAPH_ERR_STRAND = -2,         /* record does not start with '0' or '1'; the reference exit(-1)s, :383-391 */
+    VDJGRAPH_ERR_BASE = -3,           /* base outside ACGTN; the reference would hash it literally and exit(-1) in seq_to_int, seq_to_kmer.c:23-25 */
+    VDJGRAPH_ERR_TOO_MANY_NODES = -4, /* more than MAX_NODES = 900 M distinct gated k-mers (:73, :379) or > 2^32-2 records */
+    VDJGRAPH_ERR_CUDA = -5,           /* no device / CUDA runtime error; see vdjgraph_last_error() */
+    VDJGRAPH_ERR_NOMEM = -6,
+    VDJGRAPH_ERR_STATE = -7,          /* call sequence violated (e.g. run before stage) */
+    VDJGRAPH_ERR_INTERNAL = -8
+} vdjgraph_status;
+
+/* What the stage reads from the reference's globals, as one POD. */
+typedef struct vdjgraph_params {
+    int32_t read_length;      /* global read_length (:97); all records have exactly this many bases */
+    int32_t kmer_size;        /* global kmer_size (:98) = --k; 1..50 */
+    int32_t min_node_freq;    /* p.min_node_freq = --mf */
+    int32_t min_base_quality; /* p.min_base_quality = --mq; values > 254 are clamped like main() :1514-1516 */
+    int32_t device;           /* CUDA device ordinal; -1 = the calling thread's current device */
+    int32_t host_threads;     /* staging threads for text -> packed conversion; 0 = auto */
+    uint64_t table_capacity;  /* pass-1 table slots; 0 = auto (cardinality estimate on device) */
+    uint32_t flags;           /* VDJGRAPH_FLAG_* */
+    uint32_t reserved;
+} vdjgraph_params;
+
+#define VDJGRAPH_FLAG_EXPORT_KEYS 1u /* also export the packed k-mer of every node (kmer_lo/kmer_hi) */
+
+/*
+ * The graph the reference holds after build_graph2 (:1408), as structure-of-arrays indexed by
+ * node creation rank: node i is the node whose reference `id` is i+1 (new_node :190-204).
+ *
+ * Positions ("stamps"): records are numbered in processing order, primary buffer first, then
+ * secondary; w = read_length - kmer_size + 1; window o of record r has stamp r*w + o.
+ * node->kmer of the reference points at base o of record r (first_pos = r*w + o).
+ *
+ * Arrays are owned by the context and stay valid until the next vdjgraph_stage/build or
+ * vdjgraph_destroy on it.  They live in page-locked host memory.
+ */
+typedef struct vdjgraph_result {
+    uint64_t n_nodes;
+    const uint64_t *first_pos; /* [n] stamp of the first pass-2 occurrence -> node->kmer, node->kmer_seq[0] */
+    const uint16_t *frequency; /* [n] node->frequency: min(#N-free occurrences, 32765) (:199, :261-265) */
+    const uint8_t *out_deg;    /* [n] length of node->toNodes (0..4) */
+    const uint8_t *in_deg;     /* [n] length of node->fromNodes (0..4) */
+    const uint32_t *out_succ;  /* [n*4] toNodes in the reference's list order (head first = last first-seen, :223-229); node index, 0xFFFFFFFF = none */
+    const uint32_t *in_pred;   /* [n*4] fromNodes in the reference's list order (:231-236) */
+    const uint64_t *kmer_lo;   /* [n] packed k-mer, 2 bits/base, A=0 C=1 G=2 T=3, base j at bits 2j..2j+1; NULL unless VDJGRAPH_FLAG_EXPORT_KEYS */
+    const uint64_t *kmer_hi;   /* [n] bits 64.. of the same (bases 32..) */
+
+    /* counters the reference prints (:406-407, :449-450, :1394) and the roofline's h */
+    uint64_t n_records;        /* primary + secondary */
+    uint64_t n_windows;        /* n_records * w : the unit of "k-mers/s" */
+    uint64_t n_gated;          /* windows passing include_kmer (:240-259) */
+    uint64_t n_pre_total;      /* "Pre Num nodes": distinct gated k-mers */
+    uint64_t n_pre;            /* "pre nodes after pruning" (= n_nodes) */
+    uint64_t n_hits;           /* pass-2 windows whose k-mer survived (uncapped) */
+
+    /* timings of the last build, milliseconds */
+    float ms_stage;            /* host pack + H2D (wall clock) */
+    float ms_device;           /* all kernels, CUDA events on the build stream */
+    float ms_pass1, ms_prune, ms_pass2, ms_export; /* CUDA events */
+    float ms_fetch;            /* D2H of the result (wall clock) */
+    uint64_t table1_slots, table2_slots; /* capacities used */
+    uint64_t h2d_bytes, d2h_bytes;       /* bytes moved by stage / fetch */
+    uint64_t kernel_launches;            /* our kernels launched by run (incl. CUB sort passes) */
+} vdjgraph_result;
+
+/* Pruned pass-1 table (debug/parity export; unordered): what pre_nodes holds after :1393. */
+typedef struct vdjgraph_pre_table {
+    uint64_t n;
+    const uint64_t *kmer_lo, *kmer_hi; /* packed k-mer as above */
+    const uint16_t *frequency;         /* pre_node.frequency: min(#gated occurrences, 32765) */
+} vdjgraph_pre_table;
+
+typedef struct vdjgraph_ctx vdjgraph_ctx;
+
+int vdjgraph_version(void);
+/* Message of the last failure on the calling thread ("" if none). */
+const char *vdjgraph_last_error(void);
+
+/* Create a context (CUDA context, streams, staging threads' pinned buffers are created lazily
+ * and reused across builds).  Replaces nothing in the reference; it has no equivalent. */
+int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out);
+void vdjgraph_destroy(vdjgraph_ctx *ctx);
+/* Change --k/--mf/--mq/read_length between builds without recreating the context. */
+int vdjgraph_set_params(vdjgraph_ctx *ctx, const vdjgraph_params *params);
+
+/*
+ * One call = the whole block :1381-1415 on HOST buffers in the reference's record format
+ * (bam_read.c:206-244): record = strand char + read_length bases + read_length phred+33
+ * qualities, 2*read_length+1 bytes, no separators.  `primary` = assemble()'s `input`,
+ * `secondary` = `unaligned_input`; record counts replace the reference's strlen()/record_len
+ * (:370-374).  Buffers are borrowed for the call.  Equivalent to stage + run + fetch.
+ */
+int vdjgraph_build(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
+                   const char *secondary, size_t n_secondary_records, vdjgraph_result *out);
+
+/* The same in three steps, so that callers (and bench.py) can keep a read set resident in HBM. */
+/* 1. host staging: pack to 2-bit bases + gate/N masks + quality bytes, copy to the device */
+int vdjgraph_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
+                   const char *secondary, size_t n_secondary_records);
+/* 2. device only: estimate -> pass 1 -> prune -> pass 2 -> rank/edges/compaction; blocks until done */
+int vdjgraph_run(vdjgraph_ctx *ctx);
+/* 3. copy the compacted graph to host memory */
+int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
+
+/* Parity/debug: the pruned pass-1 table of the last run. */
+int vdjgraph_fetch_pre_table(vdjgraph_ctx *ctx, vdjgraph_pre_table *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,687 @@
+/*
+ * kernels.cuh -- sm_100a device code of the V'DJer de Bruijn graph build.
+ *
+ * Implements the order-free form of the reference's hot path; each kernel
+ * cites the reference lines (/root/reference/src/main/c/assembler2_vdj.c) whose result it must
+ * reproduce bit for bit.  Nothing here is a dense contraction: the work is HBM/L2-atomic bound
+ * integer and byte traffic, so the Blackwell features used are TMA bulk copies + mbarrier for
+ * the streaming input tiles, 256-bit global loads (one 32-B sector per table probe), 128-bit
+ * atomicCAS for the k > 31 keys, and persistent grids sized from the SM count.
+ *
+ * Packed layout in HBM (written by staging.cpp):
+ *   bases [R][nb] u64 : 2 bits/base, A=0 C=1 G=2 T=3 (N stored as 0), base j at bits 2j of the record
+ *   good  [R][nm] u64 : bit j = base j is ACGT and phred >= 20      (pass-1 gate, :240-259)
+ *   valid [R][nm] u64 : bit j = base j is ACGT                      (pass 2 has no quality gate, :272-274)
+ *   qual  [R][L]  u8  : (unsigned char)(ch - '!')                   (phred33 :150-152)
+ *   strand[R]     u8  : strand char - '0'                           (contributing_strand :336, :350)
+ * with nb = ceil(L/32), nm = ceil(L/64); R is padded to a multiple of the tile size with zeros.
+ */
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vdjg {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+constexpr u64 EMPTY64 = ~0ull;
+constexpr u64 INF64 = ~0ull;
+constexpr u32 NIL32 = 0xFFFFFFFFu;
+constexpr u32 CNT_CAP = 32765;   /* MAX_FREQUENCY-1, :66, :262, :345 */
+constexpr int GATE_Q = 20;       /* MIN_BASE_QUALITY, :76 */
+constexpr int QSUM_SAT = 214;    /* MAX_QUAL_SUM-41, :356 */
+constexpr int MAX_LOG_RANKS = 11;/* ceil(214/20) */
+constexpr u32 FLAG_MULTI = 1u;
+constexpr u32 FLAG_SURV = 2u;
+constexpr int THREADS = 256;
+constexpr u32 LOG_CHUNK = 128;   /* log entries a warp reserves per global atomic */
+constexpr u32 MAX_PROBE = 1u << 14;
+constexpr int HLL_BITS = 12;     /* 4096 registers, sigma ~ 1.6 % */
+
+/* pass-1 table slot: exactly one 32-byte sector */
+struct __align__(32) Slot1 {
+    u64 klo, khi;     /* packed k-mer; all ones = empty */
+    u32 count;        /* gated occurrences (stops counting a little above CNT_CAP) */
+    u32 first_rec;    /* record of the first ARRIVING gated occurrence: contributingRead :335 */
+    u32 head;         /* list of the first <= NB occurrences (log entry index) */
+    u32 flags;        /* FLAG_MULTI = hasMultipleUniqueReads :349-352, FLAG_SURV set by prune */
+};
+static_assert(sizeof(Slot1) == 32, "Slot1 must be one sector");
+
+/* pass-2 table slot (survivors only): two sectors, the hot one first */
+struct __align__(64) Slot2 {
+    u64 klo, khi;
+    u32 count;        /* N-free occurrences -> node->frequency */
+    u32 rank;         /* creation rank (node id - 1), filled by k_assign_rank */
+    u64 first_any;    /* min stamp over occurrences -> node->kmer, node id order */
+    u64 out_first[4]; /* min stamp of an occurrence followed by base c -> toNodes order */
+};
+static_assert(sizeof(Slot2) == 64, "Slot2 must be two sectors");
+
+struct __align__(16) LogEntry { u64 stamp; u32 next; u32 pad; };
+
+struct Geom {
+    int L, k, w, nb, nm;
+    u32 tile_rec;       /* records per tile (even) */
+    u32 tile_win;       /* tile_rec * w */
+    u32 div_magic;      /* ceil(2^32 / w) */
+    u64 R;              /* real records */
+    u64 n_tiles;
+    u64 kmask_lo, kmask_hi; /* 2k ones */
+    u64 kones;          /* k ones */
+};
+
+struct Counters {
+    u64 n_gated;
+    u64 n_distinct;
+    u64 n_surv;
+    u64 n_hits;
+    u64 n_nodes;
+    u32 log_used;
+    u32 overflow;     /* table full / probe bound hit */
+    u32 internal;     /* invariant violated */
+    u32 pad;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* PTX helpers                                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void ld_sector(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    /* one 256-bit load = one 32-B sector, cached in L2 only (table probes have no L1 reuse) */
+    asm volatile("ld.global.cg.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_sector(void *p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ u64 ld_cg_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+/* 128-bit compare-and-swap on a 16-byte aligned key (ATOMG.E.CAS.128 on sm_100a) */
+__device__ __forceinline__ void cas128(void *addr, u64 cmp_lo, u64 cmp_hi, u64 val_lo, u64 val_hi,
+                                       u64 &old_lo, u64 &old_hi) {
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\t"
+                 "mov.b128 c, {%2, %3};\n\t"
+                 "mov.b128 v, {%4, %5};\n\t"
+                 "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+                 "mov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old_lo), "=l"(old_hi)
+                 : "l"(cmp_lo), "l"(cmp_hi), "l"(val_lo), "l"(val_hi), "l"(addr) : "memory");
+}
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (UBLKCP in SASS) */
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* k-mer arithmetic                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ u64 hash_key(u64 lo, u64 hi) {
+    u64 h = lo ^ (hi * 0x9E3779B97F4A7C15ull);
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return h;
+}
+
+/* bits [2i, 2i+2k) of a record's base words */
+__device__ __forceinline__ void extract_kmer(const u64 *b, int nb, int i, u64 mlo, u64 mhi, u64 &lo, u64 &hi) {
+    int bit = 2 * i, wi = bit >> 6, sh = bit & 63;
+    u64 w0 = b[wi];
+    u64 w1 = wi + 1 < nb ? b[wi + 1] : 0ull;
+    u64 w2 = wi + 2 < nb ? b[wi + 2] : 0ull;
+    if (sh) { lo = (w0 >> sh) | (w1 << (64 - sh)); hi = (w1 >> sh) | (w2 << (64 - sh)); }
+    else { lo = w0; hi = w1; }
+    lo &= mlo; hi &= mhi;
+}
+/* k mask bits starting at bit i (k <= 50 < 64) */
+__device__ __forceinline__ u64 extract_mask(const u64 *m, int nm, int i) {
+    int wi = i >> 6, sh = i & 63;
+    u64 m0 = m[wi];
+    u64 m1 = wi + 1 < nm ? m[wi + 1] : 0ull;
+    return sh ? (m0 >> sh) | (m1 << (64 - sh)) : m0;
+}
+__device__ __forceinline__ u32 base_at(const u64 *b, int j) { return (u32)(b[j >> 5] >> ((j & 31) * 2)) & 3u; }
+__device__ __forceinline__ bool bit_at(const u64 *m, int j) { return (m[j >> 6] >> (j & 63)) & 1ull; }
+
+/* successor K[1:]+c and predecessor c+K[:-1] of a packed k-mer */
+__device__ __forceinline__ void kmer_succ(u64 lo, u64 hi, u32 c, int k, u64 &slo, u64 &shi) {
+    slo = (lo >> 2) | (hi << 62);
+    shi = hi >> 2;
+    int bit = 2 * (k - 1);
+    if (bit < 64) slo |= (u64)c << bit; else shi |= (u64)c << (bit - 64);
+}
+__device__ __forceinline__ void kmer_pred(u64 lo, u64 hi, u32 c, u64 mlo, u64 mhi, u64 &plo, u64 &phi) {
+    phi = ((hi << 2) | (lo >> 62)) & mhi;
+    plo = ((lo << 2) | (u64)c) & mlo;
+}
+__device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
+    int bit = 2 * (k - 1);
+    return (u32)(bit < 64 ? lo >> bit : hi >> (bit - 64)) & 3u;
+}
+
+/* two-stage TMA tile loader shared by the streaming kernels: arrays a (na words/record) and
+ * b (nbw words/record) of one tile land in buffer `buf`; one elected thread issues */
+struct TileBufs {
+    u64 *a[2];
+    u64 *b[2];
+    u64 *bar;   /* [2] */
+};
+__device__ __forceinline__ void tile_issue(const TileBufs &t, int buf, const u64 *ga, const u64 *gb,
+                                           u64 tile, u32 tile_rec, int na, int nbw) {
+    u32 bytes_a = tile_rec * (u32)na * 8u, bytes_b = tile_rec * (u32)nbw * 8u;
+    mbar_expect_tx(&t.bar[buf], bytes_a + bytes_b);
+    tma_load_1d(t.a[buf], ga + tile * tile_rec * (u64)na, bytes_a, &t.bar[buf]);
+    tma_load_1d(t.b[buf], gb + tile * tile_rec * (u64)nbw, bytes_b, &t.bar[buf]);
+}
+__device__ __forceinline__ TileBufs tile_setup(unsigned char *smem, u32 tile_rec, int na, int nbw) {
+    TileBufs t;
+    u64 *p = reinterpret_cast<u64 *>(smem);
+    t.a[0] = p; p += (size_t)tile_rec * na;
+    t.a[1] = p; p += (size_t)tile_rec * na;
+    t.b[0] = p; p += (size_t)tile_rec * nbw;
+    t.b[1] = p; p += (size_t)tile_rec * nbw;
+    t.bar = p;
+    if (threadIdx.x == 0) {
+        mbar_init(&t.bar[0], 1);
+        mbar_init(&t.bar[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    return t;
+}
+static inline size_t tile_smem_bytes(u32 tile_rec, int na, int nbw) {
+    return (size_t)2 * tile_rec * (size_t)(na + nbw) * 8 + 16;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K0: cardinality estimate (HyperLogLog over gated k-mers) + exact gated-window count.        */
+/* Sizes the pass-1 table so that it is neither rehashed (the reference's dense_hash_map grows */
+/* by doubling, internal/densehashtable.h:631-653) nor grossly over-allocated.                  */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(THREADS)
+k_estimate(const u64 *__restrict__ bases, const u64 *__restrict__ good, Geom g, u32 *hll, Counters *ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int M = 1 << HLL_BITS;
+    u32 *reg = reinterpret_cast<u32 *>(smem);
+    TileBufs t = tile_setup(smem + M * sizeof(u32), g.tile_rec, g.nb, g.nm);
+    for (int i = threadIdx.x; i < M; i += THREADS) reg[i] = 0;
+    __syncthreads();
+    u32 n_gated = 0;
+    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tile_issue(t, 0, bases, good, blockIdx.x, g.tile_rec, g.nb, g.nm);
+    u32 it = 0;
+    for (u64 tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+        int buf = it & 1;
+        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles)
+            tile_issue(t, buf ^ 1, bases, good, tile + gridDim.x, g.tile_rec, g.nb, g.nm);
+        mbar_wait(&t.bar[buf], (it >> 1) & 1);
+        const u64 *sb = t.a[buf], *sg = t.b[buf];
+        for (u32 win = threadIdx.x; win < g.tile_win; win += THREADS) {
+            u32 rec = __umulhi(win, g.div_magic);
+            int i = (int)(win - rec * (u32)g.w);
+            u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
+            if ((m & g.kones) != g.kones) continue;
+            n_gated++;
+            u64 lo, hi;
+            extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+            u64 h = hash_key(lo, hi);
+            u32 idx = (u32)(h >> (64 - HLL_BITS));
+            u32 rho = (u32)__clzll((long long)((h << HLL_BITS) | (1ull << (HLL_BITS - 1)))) + 1;
+            if (reg[idx] < rho) atomicMax(&reg[idx], rho);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < M; i += THREADS)
+        if (reg[i]) atomicMax(&hll[i], reg[i]);
+    /* block-reduce the gated count */
+    for (int o = 16; o; o >>= 1) n_gated += __shfl_xor_sync(0xFFFFFFFFu, n_gated, o);
+    __shared__ u32 wsum[THREADS / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n_gated;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 s = 0;
+        for (int i = 0; i < THREADS / 32; i++) s += wsum[i];
+        if (s) atomicAdd(&ctr->n_gated, s);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* table initialisation                                                                         */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void k_init_table1(Slot1 *t, u64 cap) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < cap; i += stride)
+        st_sector(&t[i], EMPTY64, EMPTY64, (u64)0 | ((u64)NIL32 << 32), (u64)NIL32 | ((u64)0 << 32));
+}
+__global__ void k_init_table2(Slot2 *t, u64 cap) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < cap; i += stride) {
+        st_sector(&t[i], EMPTY64, EMPTY64, (u64)0 | ((u64)NIL32 << 32), INF64);
+        st_sector(reinterpret_cast<char *>(&t[i]) + 32, INF64, INF64, INF64, INF64);
+    }
+}
+
+/* do records r1 and r2 hold the same L-character sequence and strand?
+ * compare_read :142-144 (strncmp over read_length) and the strand test :350 */
+__device__ __noinline__ bool same_read(const u64 *__restrict__ bases, const u64 *__restrict__ valid,
+                                       const u8 *__restrict__ strand, u64 r1, u64 r2, int nb, int nm) {
+    const u64 *b1 = bases + r1 * nb, *b2 = bases + r2 * nb;
+    for (int i = 0; i < nb; i++) if (b1[i] != b2[i]) return false;
+    const u64 *v1 = valid + r1 * nm, *v2 = valid + r2 * nm;
+    for (int i = 0; i < nm; i++) if (v1[i] != v2[i]) return false;
+    if (strand && strand[r1] != strand[r2]) return false;
+    return true;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1: pass 1 = build_pre_graph / add_to_table (:322-409) as commutative reductions.           */
+/*   count        -> pre_node.frequency (:334, :345-347)                                        */
+/*   FLAG_MULTI   -> hasMultipleUniqueReads (:349-352): some occurrence's record differs from   */
+/*                   the first ARRIVING one's; equivalent to ">= 2 distinct record sequences"   */
+/*   occurrence log: the first NB arrivals of every k-mer append their stamp, so that k-mers    */
+/*                   whose final count is <= NB have ALL their occurrences listed; only those   */
+/*                   can fail the quality-sum test (every gated quality is >= 20), see k_prune. */
+/* One 32-B sector read + one L2 atomic per gated window in the steady state.                   */
+/* ------------------------------------------------------------------------------------------ */
+struct Pass1Args {
+    const u64 *bases, *good, *valid;
+    const u8 *strand;
+    Slot1 *table;
+    u64 cap;
+    LogEntry *log;
+    u32 log_cap;
+    u32 nb_ranks;   /* NB: arrivals with rank < NB are logged */
+    Counters *ctr;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_pass1(Pass1Args a, Geom g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    TileBufs t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
+    const u32 lane = threadIdx.x & 31;
+    u32 chunk_base = 0, chunk_used = LOG_CHUNK; /* warp-uniform */
+    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tile_issue(t, 0, a.bases, a.good, blockIdx.x, g.tile_rec, g.nb, g.nm);
+    const u32 iters = (g.tile_win + THREADS - 1) / THREADS;
+    u32 it = 0;
+    for (u64 tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+        int buf = it & 1;
+        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles)
+            tile_issue(t, buf ^ 1, a.bases, a.good, tile + gridDim.x, g.tile_rec, g.nb, g.nm);
+        mbar_wait(&t.bar[buf], (it >> 1) & 1);
+        const u64 *sb = t.a[buf], *sg = t.b[buf];
+        const u64 rec0 = tile * g.tile_rec;
+        for (u32 j = 0; j < iters; j++) {
+            u32 win = j * THREADS + threadIdx.x;
+            bool need_log = false;
+            u64 stamp = 0;
+            Slot1 *slot = nullptr;
+            if (win < g.tile_win) {
+                u32 rec = __umulhi(win, g.div_magic);
+                int i = (int)(win - rec * (u32)g.w);
+                u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
+                if ((m & g.kones) == g.kones) {
+                    u64 lo, hi;
+                    extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+                    const u64 r = rec0 + rec;
+                    stamp = r * (u64)g.w + (u64)i;
+                    u64 idx = __umul64hi(hash_key(lo, hi), a.cap);
+                    u64 q0, q1, q2, q3;
+                    bool found = false;
+                    for (u32 probe = 0; probe < MAX_PROBE; probe++) {
+                        slot = a.table + idx;
+                        ld_sector(slot, q0, q1, q2, q3);
+                        if (q0 == EMPTY64 && q1 == EMPTY64) {
+                            cas128(slot, EMPTY64, EMPTY64, lo, hi, q0, q1);
+                            if (q0 == EMPTY64 && q1 == EMPTY64) { /* claimed: fields hold their initial values */
+                                q0 = lo; q1 = hi; q2 = (u64)NIL32 << 32; q3 = (u64)NIL32;
+                            }
+                        }
+                        if (q0 == lo && q1 == hi) { found = true; break; }
+                        if (++idx == a.cap) idx = 0;
+                    }
+                    if (!found) {
+                        atomicExch(&a.ctr->overflow, 1u);
+                    } else {
+                        u32 cnt = (u32)q2, first_rec = (u32)(q2 >> 32), flags = (u32)(q3 >> 32);
+                        u32 rank = NIL32;
+                        if (cnt < CNT_CAP) rank = atomicAdd(&slot->count, 1u);
+                        if (!(flags & FLAG_MULTI)) {
+                            if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
+                            if (first_rec != NIL32 && first_rec != (u32)r &&
+                                !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
+                                atomicOr(&slot->flags, FLAG_MULTI);
+                        }
+                        need_log = rank < a.nb_ranks;
+                    }
+                }
+            }
+            /* warp-converged log allocation out of per-warp chunks */
+            u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
+            if (ballot) {
+                u32 n = __popc(ballot);
+                if (chunk_used + n > LOG_CHUNK) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
+                    chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    chunk_used = 0;
+                }
+                u32 e = chunk_base + chunk_used + __popc(ballot & ((1u << lane) - 1));
+                chunk_used += n;
+                if (need_log) {
+                    if (e < a.log_cap) {
+                        u32 prev = atomicExch(&slot->head, e);
+                        LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
+                        a.log[e] = le;
+                    } else {
+                        atomicExch(&a.ctr->overflow, 2u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K2: prune = prune_pre_graph (:467-484) + is_base_quality_good (:454-465).                    */
+/* keep K iff frequency >= mf && hasMultipleUniqueReads && for all j qual_sums[j] >= mq.        */
+/* qual_sums[j] = S_j < 214 ? S_j : 255 with S_j = q_r0[j] + sum over the other gated           */
+/* occurrences of q_r[i+j] ((r0,i0) = first gated occurrence; seeding from the RECORD's first   */
+/* k qualities is the reference's behaviour, :337-339).  With mq <= 254 the test is             */
+/* S_j >= T, T = min(mq, 214).  Every gated quality is >= 20, so S_j >= 20*(count-1): k-mers    */
+/* with 20*(count-1) >= T pass without looking at qualities; the others have count <= NB and    */
+/* their complete occurrence list is in the log.                                                */
+/* ------------------------------------------------------------------------------------------ */
+struct PruneArgs {
+    Slot1 *table;
+    u64 cap;
+    const LogEntry *log;
+    const u8 *qual;
+    int mf, T;
+    Counters *ctr;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_prune(PruneArgs a, Geom g) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    u32 n_distinct = 0, n_surv = 0;
+    for (; i < a.cap; i += stride) {
+        u64 q0, q1, q2, q3;
+        ld_sector(&a.table[i], q0, q1, q2, q3);
+        if (q0 == EMPTY64 && q1 == EMPTY64) continue;
+        n_distinct++;
+        u32 cnt = (u32)q2, head = (u32)q3, flags = (u32)(q3 >> 32);
+        if (cnt > CNT_CAP) cnt = CNT_CAP;
+        if ((int)cnt < a.mf || !(flags & FLAG_MULTI)) continue;
+        bool pass = true;
+        if (GATE_Q * ((int)cnt - 1) < a.T) {
+            u64 st[MAX_LOG_RANKS];
+            int n = 0;
+            for (u32 e = head; e != NIL32 && n < MAX_LOG_RANKS; e = a.log[e].next) st[n++] = a.log[e].stamp;
+            if (n != (int)cnt) { atomicExch(&a.ctr->internal, 1u); continue; }
+            int first = 0;
+            for (int e = 1; e < n; e++) if (st[e] < st[first]) first = e;
+            /* byte offsets of each occurrence's quality window; the first one reads q_r0[j] */
+            u64 off[MAX_LOG_RANKS];
+            for (int e = 0; e < n; e++) {
+                u64 r = st[e] / (u64)g.w;
+                u64 o = st[e] - r * (u64)g.w;
+                off[e] = r * (u64)g.L + (e == first ? 0 : o);
+            }
+            for (int j = 0; j < g.k && pass; j++) {
+                int s = 0;
+                for (int e = 0; e < n; e++) s += a.qual[off[e] + j];
+                if (s < a.T) pass = false;
+            }
+        }
+        if (pass) {
+            a.table[i].flags = flags | FLAG_SURV;
+            n_surv++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        n_distinct += __shfl_xor_sync(0xFFFFFFFFu, n_distinct, o);
+        n_surv += __shfl_xor_sync(0xFFFFFFFFu, n_surv, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_distinct) atomicAdd(&a.ctr->n_distinct, (u64)n_distinct);
+        if (n_surv) atomicAdd(&a.ctr->n_surv, (u64)n_surv);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* survivor table (pass-2 membership + per-node reductions)                                     */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ u64 t2_insert(Slot2 *t, u64 cap, u64 lo, u64 hi) {
+    u64 idx = __umul64hi(hash_key(lo, hi), cap);
+    for (u32 probe = 0; probe < MAX_PROBE; probe++) {
+        u64 o0, o1;
+        cas128(&t[idx], EMPTY64, EMPTY64, lo, hi, o0, o1);
+        if ((o0 == EMPTY64 && o1 == EMPTY64) || (o0 == lo && o1 == hi)) return idx;
+        if (++idx == cap) idx = 0;
+    }
+    return INF64;
+}
+/* returns slot index or INF64; fills the hot sector of the slot */
+__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, u64 lo, u64 hi, u64 &q2, u64 &q3) {
+    u64 idx = __umul64hi(hash_key(lo, hi), cap);
+    for (u32 probe = 0; probe < MAX_PROBE; probe++) {
+        u64 q0, q1;
+        ld_sector(&t[idx], q0, q1, q2, q3);
+        if (q0 == lo && q1 == hi) return idx;
+        if (q0 == EMPTY64 && q1 == EMPTY64) return INF64;
+        if (++idx == cap) idx = 0;
+    }
+    return INF64;
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Counters *ctr) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < cap1; i += stride) {
+        u64 q0, q1, q2, q3;
+        ld_sector(&t1[i], q0, q1, q2, q3);
+        if (q0 == EMPTY64 && q1 == EMPTY64) continue;
+        if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
+        if (t2_insert(t2, cap2, q0, q1) == INF64) atomicExch(&ctr->overflow, 3u);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K3: pass 2 = build_graph2 / add_to_graph (:267-320, :412-452) as commutative reductions      */
+/* over every N-free window whose k-mer survived (no quality gate, :272-274):                   */
+/*   count        -> node->frequency (:199, :261-265, :308)                                     */
+/*   first_any    -> node->kmer and creation order / node id (:197-201)                         */
+/*   out_first[c] -> first time the edge K -> K[1:]+c can have been linked (:311-313); ordering */
+/*                   these reproduces the head-insertion order of toNodes (:223-229) and, read  */
+/*                   from the predecessor's side, of fromNodes (:231-236).                      */
+/* atomics are skipped when the loaded value already dominates, so hot k-mers cost reads only.  */
+/* ------------------------------------------------------------------------------------------ */
+struct Pass2Args {
+    const u64 *bases, *valid;
+    Slot2 *table;
+    u64 cap;
+    Counters *ctr;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_pass2(Pass2Args a, Geom g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    TileBufs t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
+    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tile_issue(t, 0, a.bases, a.valid, blockIdx.x, g.tile_rec, g.nb, g.nm);
+    u32 n_hits = 0;
+    u32 it = 0;
+    for (u64 tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+        int buf = it & 1;
+        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles)
+            tile_issue(t, buf ^ 1, a.bases, a.valid, tile + gridDim.x, g.tile_rec, g.nb, g.nm);
+        mbar_wait(&t.bar[buf], (it >> 1) & 1);
+        const u64 *sb = t.a[buf], *sv = t.b[buf];
+        const u64 rec0 = tile * g.tile_rec;
+        for (u32 win = threadIdx.x; win < g.tile_win; win += THREADS) {
+            u32 rec = __umulhi(win, g.div_magic);
+            int i = (int)(win - rec * (u32)g.w);
+            const u64 *vb = sv + (size_t)rec * g.nm;
+            u64 m = extract_mask(vb, g.nm, i);
+            if ((m & g.kones) != g.kones) continue;
+            const u64 *bb = sb + (size_t)rec * g.nb;
+            u64 lo, hi, q2, q3;
+            extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+            u64 idx = t2_find(a.table, a.cap, lo, hi, q2, q3);
+            if (idx == INF64) continue;
+            n_hits++;
+            Slot2 *slot = a.table + idx;
+            const u64 stamp = (rec0 + rec) * (u64)g.w + (u64)i;
+            if ((u32)q2 < CNT_CAP) atomicAdd(&slot->count, 1u);
+            if (stamp < q3) atomicMin(&slot->first_any, stamp);
+            if (i + 1 < g.w && bit_at(vb, i + g.k)) {
+                u32 c = base_at(bb, i + g.k);
+                if (stamp < ld_cg_u64(&slot->out_first[c])) atomicMin(&slot->out_first[c], stamp);
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
+    if ((threadIdx.x & 31) == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K4: export.  collect (first_any, slot) -> radix sort by first_any (host calls CUB) ->        */
+/* assign ranks -> emit nodes in creation order with ordered edge lists.                        */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(THREADS)
+k_collect(const Slot2 *t, u64 cap, u64 *keys, u32 *vals, Counters *ctr) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    const u32 lane = threadIdx.x & 31;
+    u64 n_iter = (cap + stride - 1) / stride;
+    for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
+        bool occ = false;
+        u64 q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (i < cap) {
+            ld_sector(&t[i], q0, q1, q2, q3);
+            occ = !(q0 == EMPTY64 && q1 == EMPTY64);
+        }
+        u32 ballot = __ballot_sync(0xFFFFFFFFu, occ);
+        if (!ballot) continue;
+        u64 base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->n_nodes, (u64)__popc(ballot));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (occ) {
+            u64 o = base + __popc(ballot & ((1u << lane) - 1));
+            keys[o] = q3;            /* first_any */
+            vals[o] = (u32)i;
+            if (q3 == INF64) atomicExch(&ctr->internal, 2u);
+        }
+    }
+}
+
+__global__ void k_assign_rank(Slot2 *t, const u32 *vals, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[vals[i]].rank = (u32)i;
+}
+
+struct ExportArgs {
+    const Slot2 *table;
+    u64 cap;
+    const u64 *keys;   /* sorted first_any */
+    const u32 *vals;   /* slot of rank i */
+    u64 n;
+    u64 *first_pos;
+    u16 *frequency;
+    u8 *out_deg, *in_deg;
+    u32 *out_succ, *in_pred;
+    u64 *kmer_lo, *kmer_hi; /* may be null */
+};
+
+__device__ __forceinline__ void sort_desc4(u64 (&t)[4], u32 (&v)[4], int n) {
+    for (int a = 1; a < n; a++)
+        for (int b = a; b > 0 && t[b] > t[b - 1]; b--) {
+            u64 x = t[b]; t[b] = t[b - 1]; t[b - 1] = x;
+            u32 y = v[b]; v[b] = v[b - 1]; v[b - 1] = y;
+        }
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_export(ExportArgs a, Geom g) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Slot2 *s = a.table + a.vals[i];
+    const u64 lo = s->klo, hi = s->khi;
+    u32 cnt = s->count;
+    a.first_pos[i] = a.keys[i];
+    a.frequency[i] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);
+    if (a.kmer_lo) { a.kmer_lo[i] = lo; a.kmer_hi[i] = hi; }
+    u64 tt[4]; u32 vv[4];
+    /* toNodes: successors K[1:]+c that survived, newest first-seen at the head (:223-229) */
+    int n = 0;
+    for (u32 c = 0; c < 4; c++) {
+        u64 tf = s->out_first[c];
+        if (tf == INF64) continue;
+        u64 slo, shi, q2, q3;
+        kmer_succ(lo, hi, c, g.k, slo, shi);
+        u64 idx = t2_find(a.table, a.cap, slo, shi, q2, q3);
+        if (idx == INF64) continue;
+        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+    }
+    sort_desc4(tt, vv, n);
+    a.out_deg[i] = (u8)n;
+    for (int e = 0; e < 4; e++) a.out_succ[i * 4 + e] = e < n ? vv[e] : NIL32;
+    /* fromNodes: predecessors c+K[:-1] that survived and were seen followed by K's last base;
+     * the edge P->K was first linked at P.out_first[last(K)] + 1 (:231-236) */
+    n = 0;
+    const u32 last = kmer_last(lo, hi, g.k);
+    for (u32 c = 0; c < 4; c++) {
+        u64 plo, phi, q2, q3;
+        kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
+        u64 idx = t2_find(a.table, a.cap, plo, phi, q2, q3);
+        if (idx == INF64) continue;
+        u64 tf = a.table[idx].out_first[last];
+        if (tf == INF64) continue;
+        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+    }
+    sort_desc4(tt, vv, n);
+    a.in_deg[i] = (u8)n;
+    for (int e = 0; e < 4; e++) a.in_pred[i * 4 + e] = e < n ? vv[e] : NIL32;
+}
+
+/* pruned pass-1 table for parity checks */
+__global__ void __launch_bounds__(THREADS)
+k_export_pre(const Slot1 *t, u64 cap, u64 *klo, u64 *khi, u16 *freq, u64 *n_out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < cap; i += stride) {
+        u64 q0, q1, q2, q3;
+        ld_sector(&t[i], q0, q1, q2, q3);
+        if (q0 == EMPTY64 && q1 == EMPTY64) continue;
+        if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
+        u64 o = atomicAdd(n_out, 1ull);
+        u32 cnt = (u32)q2;
+        klo[o] = q0; khi[o] = q1; freq[o] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);
+    }
+}
+
+} // namespace vdjg

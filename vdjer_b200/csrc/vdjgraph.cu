@@ -1,0 +1,703 @@
+/*
+ * vdjgraph.cu -- host side of libvdjgraph.so: C ABI (include/vdjgraph.h), read staging,
+ * kernel orchestration and result export.  Device code is in kernels.cuh.
+ *
+ * Replaces the scoped block assembler2_vdj.c:1381-1415 of the reference
+ * (build_pre_graph x2 -> prune_pre_graph -> build_graph2 x2).  There is no CPU fallback: every
+ * entry point fails with VDJGRAPH_ERR_CUDA when no sm_100a device is usable.
+ */
+#include "kernels.cuh"
+#include "../../include/vdjgraph.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace vdjg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(VDJGRAPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+double wall_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VDJGRAPH_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VDJGRAPH_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+/* one staging worker: a stream and two page-locked chunk buffers (double buffering) */
+struct StageWorker {
+    cudaStream_t stream = nullptr;
+    PinBuf buf[2];
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+    bool busy[2] = { false, false };
+};
+
+constexpr uint32_t STAGE_CHUNK = 32768; /* records per staging chunk */
+constexpr uint64_t REF_MAX_NODES = 900000000ull; /* MAX_NODES, assembler2_vdj.c:73 */
+
+} // namespace
+
+struct vdjgraph_ctx {
+    vdjgraph_params prm;
+    int device = 0;
+    int sm_count = 0;
+    Geom g;
+    uint64_t R_pad = 0;
+    bool any_strand1 = false;
+    bool staged = false, ran = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    std::vector<StageWorker> workers;
+
+    DevBuf d_bases, d_good, d_valid, d_qual, d_strand;
+    DevBuf d_t1, d_log, d_t2, d_hll, d_ctr;
+    DevBuf d_keys[2], d_vals[2], d_cub;
+    DevBuf d_first_pos, d_freq, d_odeg, d_ideg, d_osucc, d_ipred, d_klo, d_khi;
+    DevBuf d_pre_klo, d_pre_khi, d_pre_freq, d_pre_n;
+    PinBuf h_ctr, h_hll;
+    PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
+    PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
+
+    uint64_t cap1 = 0, cap2 = 0;
+    uint32_t log_cap = 0;
+    Counters ctr;
+    vdjgraph_result res;
+};
+
+namespace {
+
+int check_params(const vdjgraph_params *p) {
+    if (!p) return fail(VDJGRAPH_ERR_PARAM, "params is NULL");
+    if (p->read_length < 1 || p->read_length > 255)
+        return fail(VDJGRAPH_ERR_PARAM, "read_length %d outside 1..255 (bam_read.c:208 stores reads in char[256])", p->read_length);
+    if (p->kmer_size < 1 || p->kmer_size > 50)
+        return fail(VDJGRAPH_ERR_PARAM, "kmer_size %d outside 1..50 (MAX_KMER_LEN, assembler2_vdj.c:70)", p->kmer_size);
+    if (p->kmer_size > p->read_length)
+        return fail(VDJGRAPH_ERR_PARAM, "kmer_size %d > read_length %d", p->kmer_size, p->read_length);
+    return 0;
+}
+
+void make_geom(vdjgraph_ctx *c, uint64_t R) {
+    Geom &g = c->g;
+    g.L = c->prm.read_length;
+    g.k = c->prm.kmer_size;
+    g.w = g.L - g.k + 1;
+    g.nb = (g.L + 31) / 32;
+    g.nm = (g.L + 63) / 64;
+    uint32_t tr = 8192u / (uint32_t)g.w;
+    tr &= ~1u;
+    tr = std::max(32u, std::min(1024u, tr));
+    g.tile_rec = tr;
+    g.tile_win = tr * (uint32_t)g.w;
+    g.div_magic = (uint32_t)(((1ull << 32) + (uint64_t)g.w - 1) / (uint64_t)g.w);
+    g.R = R;
+    g.n_tiles = (R + tr - 1) / tr;
+    int bits = 2 * g.k;
+    g.kmask_lo = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
+    g.kmask_hi = bits > 64 ? ((1ull << (bits - 64)) - 1) : 0ull;
+    g.kones = (1ull << g.k) - 1;
+    c->R_pad = g.n_tiles * tr;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* staging: text records (bam_read.c:206-244) -> packed arrays, chunked through pinned memory */
+/* ---------------------------------------------------------------------------------------- */
+struct PackLut {
+    uint8_t v[256];
+    PackLut() {
+        memset(v, 0xFF, sizeof(v));
+        v[(unsigned char)'A'] = 0; v[(unsigned char)'C'] = 1; v[(unsigned char)'G'] = 2; v[(unsigned char)'T'] = 3;
+        v[(unsigned char)'N'] = 4;
+    }
+};
+const PackLut g_lut;
+
+struct ChunkPtrs {
+    uint64_t *bases, *good, *valid;
+    uint8_t *qual, *strand;
+};
+
+ChunkPtrs carve(void *base, const Geom &g, uint32_t n) {
+    ChunkPtrs c;
+    char *p = (char *)base;
+    c.bases = (uint64_t *)p; p += (size_t)n * g.nb * 8;
+    c.good = (uint64_t *)p;  p += (size_t)n * g.nm * 8;
+    c.valid = (uint64_t *)p; p += (size_t)n * g.nm * 8;
+    c.qual = (uint8_t *)p;   p += (size_t)n * g.L;
+    c.strand = (uint8_t *)p;
+    return c;
+}
+size_t chunk_bytes(const Geom &g, uint32_t n) { return (size_t)n * ((size_t)g.nb * 8 + (size_t)g.nm * 16 + g.L + 1); }
+
+/* returns 0 or a vdjgraph_status; *bad_rec receives the offending record */
+int pack_records(const char *primary, uint64_t np, const char *secondary, const Geom &g,
+                 uint64_t r_lo, uint64_t r_hi, const ChunkPtrs &out, bool *any_strand1, uint64_t *bad_rec) {
+    const int L = g.L;
+    const size_t rec_len = (size_t)2 * L + 1;
+    for (uint64_t r = r_lo; r < r_hi; r++) {
+        const char *rec = r < np ? primary + r * rec_len : secondary + (r - np) * rec_len;
+        const uint64_t o = r - r_lo;
+        unsigned sc = (unsigned char)rec[0];
+        if (sc != '0' && sc != '1') { *bad_rec = r; return VDJGRAPH_ERR_STRAND; }
+        out.strand[o] = (uint8_t)(sc - '0');
+        if (sc == '1') *any_strand1 = true;
+        const unsigned char *seq = (const unsigned char *)rec + 1;
+        const unsigned char *ql = seq + L;
+        uint64_t *bw = out.bases + o * g.nb, *gw = out.good + o * g.nm, *vw = out.valid + o * g.nm;
+        uint8_t *qo = out.qual + o * (size_t)L;
+        unsigned err = 0;
+        for (int j0 = 0; j0 < L; j0 += 64) {
+            uint64_t good = 0, valid = 0, b0 = 0, b1 = 0;
+            int jn = std::min(64, L - j0);
+            for (int j = 0; j < jn; j++) {
+                unsigned code = g_lut.v[seq[j0 + j]];
+                err |= code;
+                uint8_t q = (uint8_t)(ql[j0 + j] - '!');
+                qo[j0 + j] = q;
+                uint64_t isv = code < 4;
+                valid |= isv << j;
+                good |= (isv & (uint64_t)(q >= GATE_Q)) << j;
+                uint64_t two = (uint64_t)(code & 3u);
+                if (j < 32) b0 |= two << (2 * j); else b1 |= two << (2 * (j - 32));
+            }
+            gw[j0 >> 6] = good;
+            vw[j0 >> 6] = valid;
+            bw[j0 >> 5] = b0;
+            if ((j0 >> 5) + 1 < g.nb) bw[(j0 >> 5) + 1] = b1;
+        }
+        if (err & 0x80) { *bad_rec = r; return VDJGRAPH_ERR_BASE; }
+    }
+    return 0;
+}
+
+int ensure_workers(vdjgraph_ctx *c, int n) {
+    if ((int)c->workers.size() >= n) return 0;
+    size_t old = c->workers.size();
+    c->workers.resize(n);
+    for (size_t i = old; i < c->workers.size(); i++) {
+        CK(cudaStreamCreateWithFlags(&c->workers[i].stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->workers[i].ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->workers[i].ev[1], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+struct StageShared {
+    vdjgraph_ctx *c;
+    const char *primary, *secondary;
+    uint64_t np, R;
+    std::atomic<uint64_t> next_chunk{0};
+    std::atomic<int> status{0};
+    std::atomic<uint64_t> bad_rec{0};
+    std::atomic<bool> any_strand1{false};
+    std::string err;
+};
+
+void stage_worker(StageShared *s, int wi) {
+    vdjgraph_ctx *c = s->c;
+    StageWorker &w = c->workers[wi];
+    const Geom &g = c->g;
+    if (cudaSetDevice(c->device) != cudaSuccess) { s->status = VDJGRAPH_ERR_CUDA; return; }
+    const uint64_t n_chunks = (s->R + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    int b = 0;
+    bool any1 = false;
+    for (;;) {
+        uint64_t ch = s->next_chunk.fetch_add(1);
+        if (ch >= n_chunks || s->status.load() != 0) break;
+        uint64_t r_lo = ch * STAGE_CHUNK, r_hi = std::min<uint64_t>(s->R, r_lo + STAGE_CHUNK);
+        uint32_t n = (uint32_t)(r_hi - r_lo);
+        if (w.busy[b]) { cudaEventSynchronize(w.ev[b]); w.busy[b] = false; }
+        ChunkPtrs cp = carve(w.buf[b].p, g, n);
+        uint64_t bad = 0;
+        int rc = pack_records(s->primary, s->np, s->secondary, g, r_lo, r_hi, cp, &any1, &bad);
+        if (rc) { s->bad_rec = bad; s->status = rc; break; }
+        cudaError_t e = cudaSuccess;
+        auto cpy = [&](void *dst, const void *src, size_t bytes) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, w.stream);
+        };
+        cpy(c->d_bases.as<uint64_t>() + r_lo * g.nb, cp.bases, (size_t)n * g.nb * 8);
+        cpy(c->d_good.as<uint64_t>() + r_lo * g.nm, cp.good, (size_t)n * g.nm * 8);
+        cpy(c->d_valid.as<uint64_t>() + r_lo * g.nm, cp.valid, (size_t)n * g.nm * 8);
+        cpy(c->d_qual.as<uint8_t>() + r_lo * (size_t)g.L, cp.qual, (size_t)n * g.L);
+        cpy(c->d_strand.as<uint8_t>() + r_lo, cp.strand, (size_t)n);
+        if (e == cudaSuccess) e = cudaEventRecord(w.ev[b], w.stream);
+        if (e != cudaSuccess) { s->status = VDJGRAPH_ERR_CUDA; break; }
+        w.busy[b] = true;
+        b ^= 1;
+    }
+    if (cudaStreamSynchronize(w.stream) != cudaSuccess) s->status = VDJGRAPH_ERR_CUDA;
+    w.busy[0] = w.busy[1] = false;
+    if (any1) s->any_strand1 = true;
+}
+
+int blocks_per_sm(const void *kernel, size_t smem) {
+    int n = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, THREADS, smem);
+    return std::max(1, n);
+}
+
+double hll_estimate(const uint32_t *reg) {
+    const int M = 1 << HLL_BITS;
+    double sum = 0;
+    int zeros = 0;
+    for (int i = 0; i < M; i++) { sum += std::ldexp(1.0, -(int)reg[i]); zeros += reg[i] == 0; }
+    double alpha = 0.7213 / (1.0 + 1.079 / M);
+    double e = alpha * M * (double)M / sum;
+    if (e <= 2.5 * M && zeros) e = M * std::log((double)M / zeros);
+    return e;
+}
+
+int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }
+
+} // namespace
+
+/* ========================================================================================== */
+/* C ABI                                                                                       */
+/* ========================================================================================== */
+extern "C" int vdjgraph_version(void) { return VDJGRAPH_ABI_VERSION; }
+extern "C" const char *vdjgraph_last_error(void) { return g_err.c_str(); }
+
+extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out) {
+    if (!out) return fail(VDJGRAPH_ERR_PARAM, "out is NULL");
+    *out = nullptr;
+    int rc = check_params(params);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VDJGRAPH_ERR_CUDA, "no CUDA device (%s); libvdjgraph has no CPU path", cudaGetErrorString(e));
+    }
+    int dev = params->device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(VDJGRAPH_ERR_PARAM, "device %d out of range (have %d)", dev, ndev);
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(VDJGRAPH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    vdjgraph_ctx *c = new (std::nothrow) vdjgraph_ctx();
+    if (!c) return fail(VDJGRAPH_ERR_NOMEM, "out of host memory");
+    c->prm = *params;
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    memset(&c->res, 0, sizeof(c->res));
+    memset(&c->ctr, 0, sizeof(c->ctr));
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess) { delete c; return fail(VDJGRAPH_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return 0;
+}
+
+extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &w : c->workers) {
+        w.buf[0].release(); w.buf[1].release();
+        if (w.ev[0]) cudaEventDestroy(w.ev[0]);
+        if (w.ev[1]) cudaEventDestroy(w.ev[1]);
+        if (w.stream) cudaStreamDestroy(w.stream);
+    }
+    DevBuf *db[] = { &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+                     &c->d_hll, &c->d_ctr, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
+                     &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
+                     &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
+    for (DevBuf *b : db) b->release();
+    PinBuf *pb[] = { &c->h_ctr, &c->h_hll, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+                     &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
+    for (PinBuf *b : pb) b->release();
+    for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int vdjgraph_set_params(vdjgraph_ctx *c, const vdjgraph_params *params) {
+    if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
+    int rc = check_params(params);
+    if (rc) return rc;
+    bool regeom = params->read_length != c->prm.read_length || params->kmer_size != c->prm.kmer_size;
+    int dev = c->prm.device;
+    c->prm = *params;
+    c->prm.device = dev;
+    if (regeom) { c->staged = false; }
+    c->ran = false;
+    return 0;
+}
+
+extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns) {
+    if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
+    if ((np && !primary) || (ns && !secondary)) return fail(VDJGRAPH_ERR_PARAM, "NULL record buffer");
+    CK(cudaSetDevice(c->device));
+    c->staged = false; c->ran = false;
+    const uint64_t R = (uint64_t)np + (uint64_t)ns;
+    if (R > 0xFFFFFFFEull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu records exceed the 2^32-2 record limit", (unsigned long long)R);
+    double t0 = wall_ms();
+    make_geom(c, R);
+    const Geom &g = c->g;
+    int rc;
+    if ((rc = c->d_bases.ensure(std::max<size_t>(16, c->R_pad * g.nb * 8)))) return rc;
+    if ((rc = c->d_good.ensure(std::max<size_t>(16, c->R_pad * g.nm * 8)))) return rc;
+    if ((rc = c->d_valid.ensure(std::max<size_t>(16, c->R_pad * g.nm * 8)))) return rc;
+    if ((rc = c->d_qual.ensure(std::max<size_t>(16, c->R_pad * (size_t)g.L)))) return rc;
+    if ((rc = c->d_strand.ensure(std::max<size_t>(16, c->R_pad)))) return rc;
+    /* zero the padding records of the last tile: no window of theirs is gated or N-free */
+    if (c->R_pad > R) {
+        CK(cudaMemsetAsync(c->d_bases.as<uint64_t>() + R * g.nb, 0, (c->R_pad - R) * g.nb * 8, c->stream));
+        CK(cudaMemsetAsync(c->d_good.as<uint64_t>() + R * g.nm, 0, (c->R_pad - R) * g.nm * 8, c->stream));
+        CK(cudaMemsetAsync(c->d_valid.as<uint64_t>() + R * g.nm, 0, (c->R_pad - R) * g.nm * 8, c->stream));
+    }
+    uint64_t h2d = 0;
+    c->any_strand1 = false;
+    if (R) {
+        const uint64_t n_chunks = (R + STAGE_CHUNK - 1) / STAGE_CHUNK;
+        int nt = c->prm.host_threads > 0 ? c->prm.host_threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min<int>(nt, 64));
+        nt = (int)std::min<uint64_t>((uint64_t)nt, n_chunks);
+        if ((rc = ensure_workers(c, nt))) return rc;
+        for (int i = 0; i < nt; i++)
+            for (int b = 0; b < 2; b++)
+                if ((rc = c->workers[i].buf[b].ensure(chunk_bytes(g, STAGE_CHUNK)))) return rc;
+        StageShared sh;
+        sh.c = c; sh.primary = primary; sh.secondary = secondary; sh.np = np; sh.R = R;
+        std::vector<std::thread> th;
+        for (int i = 1; i < nt; i++) th.emplace_back(stage_worker, &sh, i);
+        stage_worker(&sh, 0);
+        for (auto &t : th) t.join();
+        if (int st = sh.status.load()) {
+            if (st == VDJGRAPH_ERR_STRAND)
+                return fail(st, "record %llu does not start with '0' or '1' (assembler2_vdj.c:383-391)", (unsigned long long)sh.bad_rec.load());
+            if (st == VDJGRAPH_ERR_BASE)
+                return fail(st, "record %llu holds a base outside ACGTN", (unsigned long long)sh.bad_rec.load());
+            cudaError_t e = cudaGetLastError();
+            return fail(st, "staging failed: %s", cudaGetErrorString(e));
+        }
+        c->any_strand1 = sh.any_strand1.load();
+        h2d = R * ((uint64_t)g.nb * 8 + (uint64_t)g.nm * 16 + (uint64_t)g.L + 1);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    memset(&c->res, 0, sizeof(c->res));
+    c->res.ms_stage = (float)(wall_ms() - t0);
+    c->res.h2d_bytes = h2d;
+    c->res.n_records = R;
+    c->res.n_windows = R * (uint64_t)g.w;
+    c->staged = true;
+    return 0;
+}
+
+extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
+    if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
+    if (!c->staged) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_run before vdjgraph_stage");
+    CK(cudaSetDevice(c->device));
+    c->ran = false;
+    make_geom(c, c->g.R);
+    const Geom g = c->g;
+    cudaStream_t s = c->stream;
+    int rc;
+    uint64_t launches = 0;
+    memset(&c->ctr, 0, sizeof(c->ctr));
+    vdjgraph_result &res = c->res;
+    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = 0;
+    res.ms_device = res.ms_pass1 = res.ms_prune = res.ms_pass2 = res.ms_export = 0;
+    res.table1_slots = res.table2_slots = 0;
+    res.kernel_launches = 0;
+    if (g.R == 0) { c->ran = true; return 0; }
+
+    /* pruning constants: T = min(mq, 214) after the <=254 clamp (:1514-1516, :356-360);
+     * NB = ceil(T/20) = largest count whose quality sums can still fail */
+    int mq = std::min(c->prm.min_base_quality, 254);
+    int T = std::min(mq, QSUM_SAT);
+    int NB = T > 0 ? (T + GATE_Q - 1) / GATE_Q : 0;
+
+    if ((rc = c->d_ctr.ensure(sizeof(Counters)))) return rc;
+    if ((rc = c->d_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
+    if ((rc = c->h_ctr.ensure(sizeof(Counters)))) return rc;
+    if ((rc = c->h_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
+    Counters *d_ctr = c->d_ctr.as<Counters>();
+    Counters *h_ctr = c->h_ctr.as<Counters>();
+
+    const size_t smem_tile = tile_smem_bytes(g.tile_rec, g.nb, g.nm);
+    const size_t smem_est = smem_tile + (sizeof(uint32_t) << HLL_BITS);
+    const int grid_est = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_estimate, smem_est));
+    const int grid_p1 = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass1, smem_tile));
+    const int grid_p2 = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass2, smem_tile));
+    const int grid_flat = c->sm_count * 8;
+
+    CK(cudaEventRecord(c->ev[0], s));
+    CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+    CK(cudaMemsetAsync(c->d_hll.p, 0, sizeof(uint32_t) << HLL_BITS, s));
+    k_estimate<<<grid_est, THREADS, smem_est, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), g, c->d_hll.as<u32>(), d_ctr);
+    launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, sizeof(uint32_t) << HLL_BITS, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t n_gated = h_ctr->n_gated;
+    double est = std::min<double>(hll_estimate(c->h_hll.as<uint32_t>()), (double)n_gated);
+    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity
+                                          : (uint64_t)(est * 1.06 / 0.5) + 1024;
+    cap1 = std::max<uint64_t>(cap1, 1024);
+
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 6) return fail(VDJGRAPH_ERR_INTERNAL, "pass-1 table kept overflowing (capacity %llu)", (unsigned long long)cap1);
+        /* log: at most NB entries per distinct k-mer and never more than the gated windows,
+         * plus one partially used chunk per warp */
+        uint64_t warps = (uint64_t)grid_p1 * (THREADS / 32);
+        uint64_t log_cap = std::min<uint64_t>(n_gated, (uint64_t)NB * (uint64_t)(0.75 * (double)cap1)) + warps * LOG_CHUNK + LOG_CHUNK;
+        if (NB == 0) log_cap = LOG_CHUNK;
+        if (log_cap > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "occurrence log would need %llu entries", (unsigned long long)log_cap);
+        if ((rc = c->d_t1.ensure(cap1 * sizeof(Slot1)))) return rc;
+        if ((rc = c->d_log.ensure(log_cap * sizeof(LogEntry)))) return rc;
+        c->cap1 = cap1; c->log_cap = (uint32_t)log_cap;
+
+        CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+        CK(cudaEventRecord(c->ev[1], s));
+        k_init_table1<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1);
+        Pass1Args a1;
+        a1.bases = c->d_bases.as<u64>(); a1.good = c->d_good.as<u64>(); a1.valid = c->d_valid.as<u64>();
+        a1.strand = c->any_strand1 ? c->d_strand.as<u8>() : nullptr;
+        a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
+        a1.log = c->d_log.as<LogEntry>(); a1.log_cap = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
+        a1.ctr = d_ctr;
+        k_pass1<<<grid_p1, THREADS, smem_tile, s>>>(a1, g);
+        CK(cudaEventRecord(c->ev[2], s));
+        PruneArgs ap;
+        ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<LogEntry>();
+        ap.qual = c->d_qual.as<u8>(); ap.mf = c->prm.min_node_freq; ap.T = T; ap.ctr = d_ctr;
+        k_prune<<<grid_flat, THREADS, 0, s>>>(ap, g);
+        launches += 3;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_ctr->overflow) { cap1 *= 2; continue; }
+        if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "occurrence log inconsistent (code %u)", h_ctr->internal);
+        break;
+    }
+    if (h_ctr->n_distinct > REF_MAX_NODES)
+        return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu distinct gated k-mers exceed MAX_NODES (assembler2_vdj.c:73)", (unsigned long long)h_ctr->n_distinct);
+    const uint64_t n_surv = h_ctr->n_surv;
+    const uint64_t n_distinct = h_ctr->n_distinct;
+
+    /* survivor table + pass 2 */
+    uint64_t cap2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
+    if (cap2 > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
+    if ((rc = c->d_t2.ensure(cap2 * sizeof(Slot2)))) return rc;
+    c->cap2 = cap2;
+    const size_t na = std::max<uint64_t>(n_surv, 1);
+    if ((rc = c->d_keys[0].ensure(na * 8)) || (rc = c->d_keys[1].ensure(na * 8)) ||
+        (rc = c->d_vals[0].ensure(na * 4)) || (rc = c->d_vals[1].ensure(na * 4)) ||
+        (rc = c->d_first_pos.ensure(na * 8)) || (rc = c->d_freq.ensure(na * 2)) ||
+        (rc = c->d_odeg.ensure(na)) || (rc = c->d_ideg.ensure(na)) ||
+        (rc = c->d_osucc.ensure(na * 16)) || (rc = c->d_ipred.ensure(na * 16)))
+        return rc;
+    const bool want_keys = c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS;
+    if (want_keys && ((rc = c->d_klo.ensure(na * 8)) || (rc = c->d_khi.ensure(na * 8)))) return rc;
+    const int end_bit = bits_for(g.R * (uint64_t)g.w);
+    size_t cub_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[1].as<u64>(),
+                                       c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_surv, 0, end_bit, s));
+    if ((rc = c->d_cub.ensure(std::max<size_t>(cub_bytes, 16)))) return rc;
+
+    k_init_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2);
+    k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, d_ctr);
+    CK(cudaEventRecord(c->ev[3], s));
+    Pass2Args a2;
+    a2.bases = c->d_bases.as<u64>(); a2.valid = c->d_valid.as<u64>();
+    a2.table = c->d_t2.as<Slot2>(); a2.cap = cap2; a2.ctr = d_ctr;
+    k_pass2<<<grid_p2, THREADS, smem_tile, s>>>(a2, g);
+    CK(cudaEventRecord(c->ev[4], s));
+    launches += 3;
+
+    /* export */
+    if (n_surv) {
+        k_collect<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2, c->d_keys[0].as<u64>(), c->d_vals[0].as<u32>(), d_ctr);
+        CK(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[1].as<u64>(),
+                                           c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_surv, 0, end_bit, s));
+        const int gb = (int)((n_surv + THREADS - 1) / THREADS);
+        k_assign_rank<<<gb, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), c->d_vals[1].as<u32>(), n_surv);
+        ExportArgs ae;
+        ae.table = c->d_t2.as<Slot2>(); ae.cap = cap2; ae.keys = c->d_keys[1].as<u64>(); ae.vals = c->d_vals[1].as<u32>();
+        ae.n = n_surv; ae.first_pos = c->d_first_pos.as<u64>(); ae.frequency = c->d_freq.as<u16>();
+        ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
+        ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
+        ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
+        k_export<<<gb, THREADS, 0, s>>>(ae, g);
+        launches += 3;
+    }
+    CK(cudaEventRecord(c->ev[5], s));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_ctr->overflow) return fail(VDJGRAPH_ERR_INTERNAL, "survivor table overflow (code %u)", h_ctr->overflow);
+    if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "export invariant violated (code %u)", h_ctr->internal);
+    if (n_surv && h_ctr->n_nodes != n_surv)
+        return fail(VDJGRAPH_ERR_INTERNAL, "collected %llu nodes, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
+    c->ctr = *h_ctr;
+
+    res.n_nodes = n_surv;
+    res.n_gated = n_gated;
+    res.n_pre_total = n_distinct;
+    res.n_pre = n_surv;
+    res.n_hits = h_ctr->n_hits;
+    res.table1_slots = cap1; res.table2_slots = cap2;
+    res.kernel_launches = launches;
+    cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[5]);
+    cudaEventElapsedTime(&res.ms_pass1, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&res.ms_prune, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res.ms_pass2, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&res.ms_export, c->ev[4], c->ev[5]);
+    c->ran = true;
+    return 0;
+}
+
+extern "C" int vdjgraph_fetch(vdjgraph_ctx *c, vdjgraph_result *out) {
+    if (!c || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if (!c->ran) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_fetch before vdjgraph_run");
+    CK(cudaSetDevice(c->device));
+    double t0 = wall_ms();
+    const uint64_t n = c->res.n_nodes;
+    const size_t na = std::max<uint64_t>(n, 1);
+    const bool want_keys = c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS;
+    int rc;
+    if ((rc = c->h_first_pos.ensure(na * 8)) || (rc = c->h_freq.ensure(na * 2)) || (rc = c->h_odeg.ensure(na)) ||
+        (rc = c->h_ideg.ensure(na)) || (rc = c->h_osucc.ensure(na * 16)) || (rc = c->h_ipred.ensure(na * 16)))
+        return rc;
+    if (want_keys && ((rc = c->h_klo.ensure(na * 8)) || (rc = c->h_khi.ensure(na * 8)))) return rc;
+    uint64_t bytes = 0;
+    if (n) {
+        cudaStream_t s = c->stream;
+        CK(cudaMemcpyAsync(c->h_first_pos.p, c->d_first_pos.p, n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_freq.p, c->d_freq.p, n * 2, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_odeg.p, c->d_odeg.p, n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_ideg.p, c->d_ideg.p, n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_osucc.p, c->d_osucc.p, n * 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_ipred.p, c->d_ipred.p, n * 16, cudaMemcpyDeviceToHost, s));
+        bytes = n * (8 + 2 + 1 + 1 + 16 + 16);
+        if (want_keys) {
+            CK(cudaMemcpyAsync(c->h_klo.p, c->d_klo.p, n * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(c->h_khi.p, c->d_khi.p, n * 8, cudaMemcpyDeviceToHost, s));
+            bytes += n * 16;
+        }
+        CK(cudaStreamSynchronize(s));
+    }
+    vdjgraph_result &r = c->res;
+    r.first_pos = c->h_first_pos.as<uint64_t>();
+    r.frequency = c->h_freq.as<uint16_t>();
+    r.out_deg = c->h_odeg.as<uint8_t>();
+    r.in_deg = c->h_ideg.as<uint8_t>();
+    r.out_succ = c->h_osucc.as<uint32_t>();
+    r.in_pred = c->h_ipred.as<uint32_t>();
+    r.kmer_lo = want_keys ? c->h_klo.as<uint64_t>() : nullptr;
+    r.kmer_hi = want_keys ? c->h_khi.as<uint64_t>() : nullptr;
+    r.d2h_bytes = bytes;
+    r.ms_fetch = (float)(wall_ms() - t0);
+    *out = r;
+    return 0;
+}
+
+extern "C" int vdjgraph_build(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns,
+                              vdjgraph_result *out) {
+    int rc = vdjgraph_stage(c, primary, np, secondary, ns);
+    if (rc) return rc;
+    if ((rc = vdjgraph_run(c))) return rc;
+    return vdjgraph_fetch(c, out);
+}
+
+extern "C" int vdjgraph_fetch_pre_table(vdjgraph_ctx *c, vdjgraph_pre_table *out) {
+    if (!c || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if (!c->ran) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_fetch_pre_table before vdjgraph_run");
+    CK(cudaSetDevice(c->device));
+    const uint64_t n = c->res.n_pre;
+    const size_t na = std::max<uint64_t>(n, 1);
+    int rc;
+    if ((rc = c->d_pre_klo.ensure(na * 8)) || (rc = c->d_pre_khi.ensure(na * 8)) || (rc = c->d_pre_freq.ensure(na * 2)) ||
+        (rc = c->d_pre_n.ensure(8)) || (rc = c->h_pre_klo.ensure(na * 8)) || (rc = c->h_pre_khi.ensure(na * 8)) ||
+        (rc = c->h_pre_freq.ensure(na * 2)) || (rc = c->h_pre_n.ensure(8)))
+        return rc;
+    cudaStream_t s = c->stream;
+    if (n) {
+        CK(cudaMemsetAsync(c->d_pre_n.p, 0, 8, s));
+        k_export_pre<<<c->sm_count * 8, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), c->cap1, c->d_pre_klo.as<u64>(),
+                                                          c->d_pre_khi.as<u64>(), c->d_pre_freq.as<u16>(), c->d_pre_n.as<u64>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_pre_klo.p, c->d_pre_klo.p, n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_pre_khi.p, c->d_pre_khi.p, n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_pre_freq.p, c->d_pre_freq.p, n * 2, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_pre_n.p, c->d_pre_n.p, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (*c->h_pre_n.as<uint64_t>() != n) return fail(VDJGRAPH_ERR_INTERNAL, "pre-table export count mismatch");
+    }
+    out->n = n;
+    out->kmer_lo = c->h_pre_klo.as<uint64_t>();
+    out->kmer_hi = c->h_pre_khi.as<uint64_t>();
+    out->frequency = c->h_pre_freq.as<uint16_t>();
+    return 0;
+}

@@ -1,0 +1,221 @@
+"""ctypes binding of include/vdjgraph.h.
+
+Names follow the reference's stage (assembler2_vdj.c): `primary` is assemble()'s `input`,
+`secondary` its `unaligned_input`; k / mf / mq are --k / --mf / --mq (params.c:53-73 defaults:
+35 / 3 / 90).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libvdjgraph.so")
+
+
+class VdjGraphError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vdjgraph error {code}: {msg}")
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("read_length", C.c_int32), ("kmer_size", C.c_int32), ("min_node_freq", C.c_int32),
+        ("min_base_quality", C.c_int32), ("device", C.c_int32), ("host_threads", C.c_int32),
+        ("table_capacity", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class _Result(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint64),
+        ("first_pos", C.POINTER(C.c_uint64)), ("frequency", C.POINTER(C.c_uint16)),
+        ("out_deg", C.POINTER(C.c_uint8)), ("in_deg", C.POINTER(C.c_uint8)),
+        ("out_succ", C.POINTER(C.c_uint32)), ("in_pred", C.POINTER(C.c_uint32)),
+        ("kmer_lo", C.POINTER(C.c_uint64)), ("kmer_hi", C.POINTER(C.c_uint64)),
+        ("n_records", C.c_uint64), ("n_windows", C.c_uint64), ("n_gated", C.c_uint64),
+        ("n_pre_total", C.c_uint64), ("n_pre", C.c_uint64), ("n_hits", C.c_uint64),
+        ("ms_stage", C.c_float), ("ms_device", C.c_float), ("ms_pass1", C.c_float),
+        ("ms_prune", C.c_float), ("ms_pass2", C.c_float), ("ms_export", C.c_float),
+        ("ms_fetch", C.c_float),
+        ("table1_slots", C.c_uint64), ("table2_slots", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+    ]
+
+
+class _PreTable(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("kmer_lo", C.POINTER(C.c_uint64)),
+                ("kmer_hi", C.POINTER(C.c_uint64)), ("frequency", C.POINTER(C.c_uint16))]
+
+
+FLAG_EXPORT_KEYS = 1
+
+EXPORTS = [
+    "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
+    "vdjgraph_set_params", "vdjgraph_build", "vdjgraph_stage", "vdjgraph_run", "vdjgraph_fetch",
+    "vdjgraph_fetch_pre_table",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libvdjgraph.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise VdjGraphError(-5, f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(make -C vdjer_b200/csrc); there is no CPU fallback")
+    lib = C.CDLL(path)
+    lib.vdjgraph_version.restype = C.c_int
+    lib.vdjgraph_last_error.restype = C.c_char_p
+    lib.vdjgraph_create.argtypes = [C.POINTER(_Params), C.POINTER(C.c_void_p)]
+    lib.vdjgraph_destroy.argtypes = [C.c_void_p]
+    lib.vdjgraph_destroy.restype = None
+    lib.vdjgraph_set_params.argtypes = [C.c_void_p, C.POINTER(_Params)]
+    lib.vdjgraph_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_Result)]
+    lib.vdjgraph_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    lib.vdjgraph_run.argtypes = [C.c_void_p]
+    lib.vdjgraph_fetch.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    lib.vdjgraph_fetch_pre_table.argtypes = [C.c_void_p, C.POINTER(_PreTable)]
+    _lib = lib
+    return lib
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, np.ndarray):
+        a = buf
+        if a.dtype != np.uint8:
+            a = a.view(np.uint8)
+        return np.ascontiguousarray(a)
+    return np.frombuffer(buf, dtype=np.uint8)
+
+
+@dataclass
+class Graph:
+    """The graph after build_graph2 (:1408): node i is the node with reference id i+1."""
+    n_nodes: int
+    first_pos: np.ndarray   # u64 [n]  r*w + o of node->kmer
+    frequency: np.ndarray   # u16 [n]
+    out_deg: np.ndarray     # u8  [n]
+    in_deg: np.ndarray      # u8  [n]
+    out_succ: np.ndarray    # u32 [n,4] toNodes, list order
+    in_pred: np.ndarray     # u32 [n,4] fromNodes, list order
+    kmer_lo: np.ndarray | None
+    kmer_hi: np.ndarray | None
+    stats: dict = field(default_factory=dict)
+
+
+@dataclass
+class PreTable:
+    """pre_nodes after prune_pre_graph (:1393), unordered."""
+    kmer_lo: np.ndarray
+    kmer_hi: np.ndarray
+    frequency: np.ndarray
+
+
+def _np_from(ptr, n, dtype, cols=1):
+    if n == 0 or not ptr:
+        shape = (0, cols) if cols > 1 else (0,)
+        return np.zeros(shape, dtype=dtype)
+    a = np.ctypeslib.as_array(ptr, shape=(n * cols,)).copy()
+    return a.reshape(n, cols) if cols > 1 else a
+
+
+class GraphBuilder:
+    """One libvdjgraph context (CUDA context, streams, staging buffers) reused across builds."""
+
+    def __init__(self, read_length: int, k: int = 35, mf: int = 3, mq: int = 90, device: int = -1,
+                 host_threads: int = 0, table_capacity: int = 0, export_keys: bool = False):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        self._p = _Params(read_length, k, mf, mq, device, host_threads, table_capacity,
+                          FLAG_EXPORT_KEYS if export_keys else 0, 0)
+        self._check(self._lib.vdjgraph_create(C.byref(self._p), C.byref(self._ctx)))
+        self._keep = None
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise VdjGraphError(rc, (self._lib.vdjgraph_last_error() or b"").decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.vdjgraph_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, read_length=None, k=None, mf=None, mq=None):
+        if read_length is not None:
+            self._p.read_length = read_length
+        if k is not None:
+            self._p.kmer_size = k
+        if mf is not None:
+            self._p.min_node_freq = mf
+        if mq is not None:
+            self._p.min_base_quality = mq
+        self._check(self._lib.vdjgraph_set_params(self._ctx, C.byref(self._p)))
+
+    def _counts(self, primary, secondary):
+        rec = 2 * self._p.read_length + 1
+        p, s = _as_u8(primary), _as_u8(secondary)
+        # a trailing NUL (the reference's buffers are C strings) is not a record
+        return p, s, p.size // rec, s.size // rec
+
+    def stage(self, primary, secondary=b""):
+        p, s, n_p, n_s = self._counts(primary, secondary)
+        self._keep = (p, s)
+        self._check(self._lib.vdjgraph_stage(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s))
+
+    def run(self):
+        self._check(self._lib.vdjgraph_run(self._ctx))
+
+    def fetch(self) -> Graph:
+        r = _Result()
+        self._check(self._lib.vdjgraph_fetch(self._ctx, C.byref(r)))
+        return self._graph(r)
+
+    def build(self, primary, secondary=b"") -> Graph:
+        """vdjgraph_build: HOST buffers in, graph out (stage + run + fetch)."""
+        p, s, n_p, n_s = self._counts(primary, secondary)
+        r = _Result()
+        self._check(self._lib.vdjgraph_build(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
+        return self._graph(r)
+
+    def pre_table(self) -> PreTable:
+        t = _PreTable()
+        self._check(self._lib.vdjgraph_fetch_pre_table(self._ctx, C.byref(t)))
+        n = int(t.n)
+        return PreTable(_np_from(t.kmer_lo, n, np.uint64), _np_from(t.kmer_hi, n, np.uint64),
+                        _np_from(t.frequency, n, np.uint16))
+
+    def _graph(self, r: _Result) -> Graph:
+        n = int(r.n_nodes)
+        stats = {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
+                 for k, _ in _Result._fields_
+                 if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel"))}
+        return Graph(
+            n, _np_from(r.first_pos, n, np.uint64), _np_from(r.frequency, n, np.uint16),
+            _np_from(r.out_deg, n, np.uint8), _np_from(r.in_deg, n, np.uint8),
+            _np_from(r.out_succ, n, np.uint32, 4), _np_from(r.in_pred, n, np.uint32, 4),
+            _np_from(r.kmer_lo, n, np.uint64) if r.kmer_lo else None,
+            _np_from(r.kmer_hi, n, np.uint64) if r.kmer_hi else None, stats)
