@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- V'DJer de Bruijn graph build+prune throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A step = one graph build (estimate -> pass 1 -> prune -> pass 2 -> export) over the whole
+synthetic read set.  Unit: windows (k-mer positions) per second, W = records * (L-k+1).
+
+  value     device-resident: reads already packed in HBM, K x vdjgraph_run, CUDA events on the
+            library's stream (inside the library), max over ranks
+  e2e       K x vdjgraph_build on HOST text buffers (the reference's record format): host
+            packing + H2D + kernels + D2H of the graph, wall clock, max over ranks
+  roofline  dominant kernel's algorithmic bytes / its CUDA-event time vs the measured
+            HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own functions (oracle/_ref, compiled from /root/reference) or the
+            oracle port, on a bounded subsample, one core (the stage is single-threaded in the
+            reference: assembler2_vdj.c:1381-1415; --t only sizes the traversal pool :1287-1299)
+
+--impl reference times that CPU path alone with the same metric/config.
+N > 1 (torchrun): every rank builds the graph of its own equal share of the read set (weak
+scaling, per-GPU work fixed = the N=1 workload with a rank-specific seed); no cross-GPU merge
+yet (see DESIGN.md "Multi-GPU").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "graph_build_prune_windows_per_sec"
+UNIT = "windows/s"
+DEFAULT_WORKLOAD = "igh_2x50_5M"  # BASELINE.json configs[1]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(L, k, h):
+    """bytes per window of each pass and of the whole path."""
+    w = L - k + 1
+    b_in = 1.25 * L / (2 * w)
+    p1 = b_in + 64.0          # packed read bytes + one slot sector read-modify-write
+    p2 = b_in + 32.0 + 64.0 * h  # packed read bytes + membership probe + hit RMW
+    return p1, p2, p1 + p2
+
+
+def cpu_baseline(wl: dict, sample_pairs: int):
+    """The reference's graph build on one host core, on the first `sample_pairs` pairs' worth of
+    the same generator.  Only place bench.py touches oracle/."""
+    from oracle import loader
+    from vdjer_b200 import synth
+    gen = {k: v for k, v in wl.items() if k not in ("k", "mf", "mq", "n_pairs")}
+    primary, secondary = synth.generate(n_pairs=sample_pairs, **gen)
+    kind = "reference" if loader.have_reference() else "port"
+    import contextlib
+    with open(os.devnull, "w") as dn, contextlib.redirect_stderr(dn):
+        fd = os.dup(2); os.dup2(dn.fileno(), 2)   # the reference logs progress to stderr
+        try:
+            t0 = time.perf_counter()
+            r = loader.build(primary, secondary, wl["read_length"], wl["k"], wl["mf"], wl["mq"], kind=kind)
+            dt = time.perf_counter() - t0
+        finally:
+            os.dup2(fd, 2); os.close(fd)
+    t_graph = r["t_pass1"] + r["t_prune"] + r["t_pass2"]
+    return {"value": r["n_windows"] / t_graph, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"first {sample_pairs} pairs of the same generator ({r['n_windows']} windows, "
+                      f"{t_graph:.1f} s: pass1 {r['t_pass1']:.1f} prune {r['t_prune']:.1f} pass2 {r['t_pass2']:.1f}; "
+                      f"{'compiled reference -O2' if kind == 'reference' else 'oracle port'}; the stage is single-threaded in the reference)",
+            "_windows": r["n_windows"], "_seconds": t_graph, "_wall": dt}
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    per_step = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(wl, args.cpu_sample_pairs)
+        if i >= args.warmup:
+            per_step.append(cb["_seconds"])
+    t = float(np.mean(per_step))
+    value = cb["_windows"] / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic",
+            "config": {"workload": args.workload, "read_length": wl["read_length"], "k": wl["k"], "mf": wl["mf"],
+                       "mq": wl["mq"], "pairs_per_step": args.cpu_sample_pairs,
+                       "note": "bounded subsample of the workload; CPU stage is single-threaded in the reference"},
+            "cpu_baseline": {k: v for k, v in cb.items() if not k.startswith("_")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["cpu_baseline"]["value"] = value
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--pairs", type=int, default=0, help="override the workload's pair count (debug)")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=150_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from vdjer_b200 import synth
+    wl = dict(synth.CONFIGS[args.workload])
+    if args.pairs:
+        wl["n_pairs"] = args.pairs
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vdjer_b200 import GraphBuilder
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L, k, mf, mq = wl["read_length"], wl["k"], wl["mf"], wl["mq"]
+    gen = {kk: v for kk, v in wl.items() if kk not in ("k", "mf", "mq")}
+    t0 = time.perf_counter()
+    primary, secondary = synth.generate(seed=12345 + rank, **gen)
+    t_gen = time.perf_counter() - t0
+
+    gb = GraphBuilder(L, k, mf, mq, device=local_rank)
+    # ---- device-resident metric ------------------------------------------------------------
+    gb.stage(primary, secondary)
+    for _ in range(args.warmup):
+        gb.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, per_kernel = [], []
+    for _ in range(args.steps):
+        gb.run()
+        g = gb.fetch_stats()
+        dev_ms.append(g["ms_device"])
+        per_kernel.append(g)
+    barrier()
+    wall_dev = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    stats = per_kernel[-1]
+    W = stats["n_windows"]
+    ms_dev = float(np.mean(dev_ms))
+
+    # ---- end to end through the C ABI on host buffers ------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        gb.build(primary, secondary)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        graph = gb.build(primary, secondary)
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+    e2e_stats = graph.stats
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e, float(W)], device="cuda", dtype=torch.float64)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_dev, ms_e2e, W_total = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        W_total = float(W)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        h = stats["n_hits"] / W
+        a1, a2, a_all = algorithmic_bytes(L, k, h)
+        kern = {n: float(np.mean([s[n] for s in per_kernel])) for n in
+                ["ms_estimate", "ms_init1", "ms_pass1", "ms_prune", "ms_table2", "ms_pass2", "ms_export"]}
+        dom = "k_pass1" if kern["ms_pass1"] >= kern["ms_pass2"] else "k_pass2"
+        dom_ms = max(kern["ms_pass1"], kern["ms_pass2"])
+        dom_bytes = W * (a1 if dom == "k_pass1" else a2)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": W_total / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic",
+            "config": {"workload": args.workload, "read_length": L, "k": k, "mf": mf, "mq": mq,
+                       "pairs_per_gpu": wl["n_pairs"], "records_per_gpu": stats["n_records"], "windows_per_gpu": W,
+                       "l2_policy": "inputs_larger_than_L2 (packed reads + tables >> 126 MB, tables re-initialised every step)",
+                       "parallelism": f"independent shard per GPU x{world}" if world > 1 else "1 GPU",
+                       "distinct_gated_kmers": stats["n_pre_total"], "nodes": stats["n_nodes"],
+                       "gated_fraction": stats["n_gated"] / W, "pass2_hit_fraction_h": h,
+                       "table1_slots": stats["table1_slots"], "table2_slots": stats["table2_slots"],
+                       "generator_s": round(t_gen, 2)},
+            "e2e": {"value": W_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": e2e_stats["h2d_bytes"], "d2h_bytes_per_step": e2e_stats["d2h_bytes"],
+                    "ms_stage": e2e_stats["ms_stage"], "ms_device": e2e_stats["ms_device"], "ms_fetch": e2e_stats["ms_fetch"],
+                    "host_text_bytes": int(primary.size + secondary.size)},
+            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
+            "kernel_ms": kern, "wall_ms_per_step_device_loop": wall_dev * 1e3,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_window": a1 if dom == "k_pass1" else a2,
+                         "windows_per_launch": W},
+            "roofline_path": {"algorithmic_bytes_per_window": a_all, "achieved": W * a_all / (ms_dev * 1e-3) / 1e9,
+                              "frac": W * a_all / (ms_dev * 1e-3) / 1e9 / peak},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            cb = cpu_baseline(wl, args.cpu_sample_pairs)
+            line["cpu_baseline"] = {k2: v for k2, v in cb.items() if not k2.startswith("_")}
+        print(json.dumps(line), flush=True)
+    gb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,12 +93,15 @@ typedef struct vdjgraph_result {
 
     /* timings of the last build, milliseconds */
     float ms_stage;            /* host pack + H2D (wall clock) */
-    float ms_device;           /* all kernels, CUDA events on the build stream */
-    float ms_pass1, ms_prune, ms_pass2, ms_export; /* CUDA events */
+    float ms_device;           /* whole vdjgraph_run, CUDA events on the build stream (includes the
+                                  two small counter read-backs that size the tables) */
+    /* per-kernel CUDA-event times: cardinality estimate, pass-1 table init, k_pass1, k_prune,
+     * survivor-table init+insert, k_pass2, export (collect + sort + rank + edges) */
+    float ms_estimate, ms_init1, ms_pass1, ms_prune, ms_table2, ms_pass2, ms_export;
     float ms_fetch;            /* D2H of the result (wall clock) */
     uint64_t table1_slots, table2_slots; /* capacities used */
     uint64_t h2d_bytes, d2h_bytes;       /* bytes moved by stage / fetch */
-    uint64_t kernel_launches;            /* our kernels launched by run (incl. CUB sort passes) */
+    uint64_t kernel_launches;            /* our kernels launched by the last run (CUB's sort passes not counted) */
 } vdjgraph_result;
 
 /* Pruned pass-1 table (debug/parity export; unordered): what pre_nodes holds after :1393. */
@@ -139,6 +142,9 @@ int vdjgraph_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_reco
 int vdjgraph_run(vdjgraph_ctx *ctx);
 /* 3. copy the compacted graph to host memory */
 int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
+
+/* Counters and timings of the last run without copying the graph (array pointers are NULL). */
+int vdjgraph_stats(vdjgraph_ctx *ctx, vdjgraph_result *out);
 
 /* Parity/debug: the pruned pass-1 table of the last run. */
 int vdjgraph_fetch_pre_table(vdjgraph_ctx *ctx, vdjgraph_pre_table *out);

@@ -1,0 +1,39 @@
+"""CPU: workload generator and record-format helpers."""
+import numpy as np
+
+from tests.util import kmer_codes_at, pack_codes
+from vdjer_b200 import synth
+
+
+def test_generator_is_deterministic_and_thread_independent(built):
+    a = synth.generate(n_pairs=500, read_length=50, seed=5, n_clones=20, threads=1)
+    b = synth.generate(n_pairs=500, read_length=50, seed=5, n_clones=20, threads=4)
+    c = synth.generate(n_pairs=500, read_length=50, seed=6, n_clones=20, threads=4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert not np.array_equal(a[0], c[0])
+
+
+def test_record_format(built):
+    L = 75
+    p, s = synth.generate(n_pairs=200, read_length=L, seed=1, n_clones=5, frac_secondary=0.25, threads=2)
+    rec = 2 * L + 1
+    assert p[-1] == 0 and s[-1] == 0
+    assert (p.size - 1) % rec == 0 and (p.size - 1) // rec == 600 and (s.size - 1) // rec == 200
+    r = p[:-1].reshape(-1, rec)
+    assert np.all(r[:, 0] == ord("0"))
+    assert set(np.unique(r[:, 1:1 + L])) <= set(b"ACGTN")
+    assert r[:, 1 + L:].min() >= 33
+    # record 2i+1 is the reverse complement of record 2i with reversed qualities (bam_read.c:206-244)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    assert np.array_equal(comp[r[0::2, 1:1 + L]][:, ::-1], r[1::2, 1:1 + L])
+    assert np.array_equal(r[0::2, 1 + L:][:, ::-1], r[1::2, 1 + L:])
+
+
+def test_pack_helpers():
+    buf = synth.records_from_reads(["ACGTACGTACGTACGTACGTACGTACGTACGTACGTA"], both_strands=False)
+    codes = kmer_codes_at(buf, np.zeros(1, np.uint8), 37, 35, [0, 2])
+    lo, hi = pack_codes(codes)
+    assert codes.shape == (2, 35) and list(codes[0][:4]) == [0, 1, 2, 3] and list(codes[1][:2]) == [2, 3]
+    assert int(lo[0]) & 0xFF == 0b11100100 and int(hi[0]) == (0 | (1 << 2) | (2 << 4))

@@ -1,0 +1,129 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the committed reference outputs.
+Bit-exact: integer/byte/index work only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import loader
+from tests.cases import CASES, make_inputs
+from tests.util import GOLDEN_DIR, assert_graph_equal, assert_pre_table_equal, graph_invariants
+from vdjer_b200 import GraphBuilder, VdjGraphError, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_reference_golden(built, name):
+    """CUDA result == what the compiled reference produced (tests/golden), every field."""
+    case = CASES[name]
+    gold = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    gold["n_nodes"] = len(gold["first_pos"])
+    gold["n_pre"] = len(gold["pre_first_pos"])
+    primary, secondary = make_inputs(case)
+    with GraphBuilder(case["L"], case["k"], case["mf"], case["mq"], export_keys=True) as gb:
+        got = gb.build(primary, secondary)
+        pre = gb.pre_table()
+    assert got.stats["n_pre_total"] == int(gold["n_pre_total"])
+    assert_pre_table_equal(pre, gold, primary, secondary, case["L"], case["k"], name)
+    assert_graph_equal(got, gold, name)
+
+
+@pytest.mark.parametrize("seed,L,k,mf,mq,pairs,clones", [
+    (31, 50, 35, 3, 90, 60000, 2000),     # configs[1] shape
+    (32, 50, 25, 2, 60, 60000, 20000),    # configs[2] shape, flat repertoire
+    (33, 75, 35, 3, 90, 40000, 1500),     # configs[3] shape
+    (34, 100, 35, 3, 90, 30000, 1500),    # configs[4] shape
+    (35, 100, 50, 2, 120, 20000, 500),
+    (36, 50, 25, 1, 20, 40000, 200),      # heavy branching
+    (37, 150, 41, 3, 90, 10000, 300),
+    (38, 255, 50, 3, 90, 4000, 100),      # longest read the reference stores
+])
+def test_matches_oracle_seeded(built, seed, L, k, mf, mq, pairs, clones):
+    primary, secondary = synth.generate(n_pairs=pairs, read_length=L, seed=seed, n_clones=clones, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    with GraphBuilder(L, k, mf, mq) as gb:
+        got = gb.build(primary, secondary)
+        pre = gb.pre_table()
+    assert got.stats["n_records"] == want["n_records"] and got.stats["n_windows"] == want["n_windows"]
+    assert got.stats["n_gated"] == want["n_gated"]
+    assert got.stats["n_pre_total"] == want["n_pre_total"]
+    assert got.stats["n_hits"] == want["n_hits"]
+    assert_pre_table_equal(pre, want, primary, secondary, L, k, f"seed{seed}")
+    assert_graph_equal(got, want, f"seed{seed}")
+
+
+def test_context_reuse_and_param_changes(built):
+    """One context, several builds with different --k/--mf/--mq and inputs: no state leaks."""
+    primary, secondary = synth.generate(n_pairs=8000, read_length=50, seed=41, n_clones=100, threads=4)
+    p2, s2 = synth.generate(n_pairs=3000, read_length=50, seed=42, n_clones=30, threads=4)
+    with GraphBuilder(50, 35, 3, 90) as gb:
+        for (pp, ss, k, mf, mq) in [(primary, secondary, 35, 3, 90), (p2, s2, 25, 2, 60), (primary, secondary, 35, 3, 90),
+                                     (primary, secondary, 35, 1, 214), (p2, s2, 35, 3, 90)]:
+            gb.set_params(k=k, mf=mf, mq=mq)
+            got = gb.build(pp, ss)
+            want = loader.build(pp, ss, 50, k, mf, mq, kind="port")
+            assert_graph_equal(got, want, f"k{k} mf{mf} mq{mq}")
+        # stage once, run with different pruning flags without re-staging
+        gb.set_params(k=35, mf=3, mq=90)
+        gb.stage(primary, secondary)
+        for mf, mq in [(3, 90), (2, 60), (5, 150)]:
+            gb.set_params(mf=mf, mq=mq)
+            gb.run()
+            assert_graph_equal(gb.fetch(), loader.build(primary, secondary, 50, 35, mf, mq, kind="port"), f"rerun mf{mf}")
+
+
+def test_tiny_table_capacity_grows(built):
+    """An undersized table_capacity hint must be recovered from (the reference's dense_hash_map
+    grows by rehashing, internal/densehashtable.h:631-653)."""
+    primary, secondary = synth.generate(n_pairs=5000, read_length=50, seed=43, n_clones=100, threads=4)
+    want = loader.build(primary, secondary, 50, 35, 3, 90, kind="port")
+    with GraphBuilder(50, 35, 3, 90, table_capacity=1024) as gb:
+        got = gb.build(primary, secondary)
+    assert got.stats["table1_slots"] > want["n_pre_total"]
+    assert_graph_equal(got, want, "grown")
+
+
+def test_empty_and_degenerate_inputs(built):
+    with GraphBuilder(50, 35, 3, 90) as gb:
+        g = gb.build(b"", b"")
+        assert g.n_nodes == 0 and g.stats["n_windows"] == 0
+        g = gb.build(np.zeros(1, np.uint8), np.zeros(1, np.uint8))
+        assert g.n_nodes == 0
+        one = synth.records_from_reads(["ACGTTGCAAC" * 5], both_strands=False)
+        g = gb.build(one, b"")
+        assert g.n_nodes == 0 and g.stats["n_pre_total"] == 16 and g.stats["n_gated"] == 16
+        alln = synth.records_from_reads(["N" * 50] * 7)
+        g = gb.build(alln, alln)
+        assert g.n_nodes == 0 and g.stats["n_gated"] == 0 and g.stats["n_pre_total"] == 0
+
+
+def test_input_errors_are_reported_not_fatal(built):
+    good = synth.records_from_reads(["ACGTTGCAAC" * 5] * 4)
+    with GraphBuilder(50, 35, 3, 90) as gb:
+        bad = good.copy(); bad[101 * 3] = ord("2")           # strand byte (reference: exit(-1), :383-391)
+        with pytest.raises(VdjGraphError) as e:
+            gb.build(bad, b"")
+        assert e.value.code == -2 and "record 3" in str(e.value)
+        bad = good.copy(); bad[101 * 5 + 7] = ord("M")        # IUPAC base
+        with pytest.raises(VdjGraphError) as e:
+            gb.build(b"", bad)
+        assert e.value.code == -3 and "record 5" in str(e.value)
+        with pytest.raises(VdjGraphError) as e:
+            gb.fetch()
+        assert e.value.code == -7
+        # the context stays usable
+        assert gb.build(good, b"").stats["n_windows"] == 8 * 16
+
+
+def test_large_invariants_and_cross_check(built):
+    """A mid-size run (1.3 M records): size-independent properties, plus agreement with the
+    oracle on the counters and the whole graph."""
+    L, k = 50, 35
+    primary, secondary = synth.generate(n_pairs=320000, read_length=L, seed=51, n_clones=20000, threads=8)
+    with GraphBuilder(L, k, 3, 90) as gb:
+        got = gb.build(primary, secondary)
+    graph_invariants(got, L, k, primary, secondary)
+    want = loader.build(primary, secondary, L, k, 3, 90, kind="port")
+    assert_graph_equal(got, want, "mid-size")
+    assert got.stats["n_hits"] == want["n_hits"]

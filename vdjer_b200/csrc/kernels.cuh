@@ -184,6 +184,9 @@ __device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
     return (u32)(bit < 64 ? lo >> bit : hi >> (bit - 64)) & 3u;
 }
 
+/* window index within a tile -> record within the tile (w == 1 has no 32-bit magic) */
+__device__ __forceinline__ u32 div_w(u32 win, const Geom &g) { return g.div_magic ? __umulhi(win, g.div_magic) : win; }
+
 /* two-stage TMA tile loader shared by the streaming kernels: arrays a (na words/record) and
  * b (nbw words/record) of one tile land in buffer `buf`; one elected thread issues */
 struct TileBufs {
@@ -242,7 +245,7 @@ k_estimate(const u64 *__restrict__ bases, const u64 *__restrict__ good, Geom g, 
         mbar_wait(&t.bar[buf], (it >> 1) & 1);
         const u64 *sb = t.a[buf], *sg = t.b[buf];
         for (u32 win = threadIdx.x; win < g.tile_win; win += THREADS) {
-            u32 rec = __umulhi(win, g.div_magic);
+            u32 rec = div_w(win, g);
             int i = (int)(win - rec * (u32)g.w);
             u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
             if ((m & g.kones) != g.kones) continue;
@@ -341,7 +344,7 @@ k_pass1(Pass1Args a, Geom g) {
             u64 stamp = 0;
             Slot1 *slot = nullptr;
             if (win < g.tile_win) {
-                u32 rec = __umulhi(win, g.div_magic);
+                u32 rec = div_w(win, g);
                 int i = (int)(win - rec * (u32)g.w);
                 u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
                 if ((m & g.kones) == g.kones) {
@@ -544,7 +547,7 @@ k_pass2(Pass2Args a, Geom g) {
         const u64 *sb = t.a[buf], *sv = t.b[buf];
         const u64 rec0 = tile * g.tile_rec;
         for (u32 win = threadIdx.x; win < g.tile_win; win += THREADS) {
-            u32 rec = __umulhi(win, g.div_magic);
+            u32 rec = div_w(win, g);
             int i = (int)(win - rec * (u32)g.w);
             const u64 *vb = sv + (size_t)rec * g.nm;
             u64 m = extract_mask(vb, g.nm, i);

@@ -112,7 +112,7 @@ struct vdjgraph_ctx {
     bool any_strand1 = false;
     bool staged = false, ran = false;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[10] = {};
     std::vector<StageWorker> workers;
 
     DevBuf d_bases, d_good, d_valid, d_qual, d_strand;
@@ -155,7 +155,7 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     tr = std::max(32u, std::min(1024u, tr));
     g.tile_rec = tr;
     g.tile_win = tr * (uint32_t)g.w;
-    g.div_magic = (uint32_t)(((1ull << 32) + (uint64_t)g.w - 1) / (uint64_t)g.w);
+    g.div_magic = g.w == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)g.w - 1) / (uint64_t)g.w);
     g.R = R;
     g.n_tiles = (R + tr - 1) / tr;
     int bits = 2 * g.k;
@@ -351,7 +351,7 @@ extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out
     memset(&c->res, 0, sizeof(c->res));
     memset(&c->ctr, 0, sizeof(c->ctr));
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 10 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) { delete c; return fail(VDJGRAPH_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return 0;
@@ -375,7 +375,7 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
     PinBuf *pb[] = { &c->h_ctr, &c->h_hll, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
-    for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 10; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -466,7 +466,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     memset(&c->ctr, 0, sizeof(c->ctr));
     vdjgraph_result &res = c->res;
     res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = 0;
-    res.ms_device = res.ms_pass1 = res.ms_prune = res.ms_pass2 = res.ms_export = 0;
+    res.ms_device = res.ms_estimate = res.ms_init1 = res.ms_pass1 = res.ms_prune = res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
     res.table1_slots = res.table2_slots = 0;
     res.kernel_launches = 0;
     if (g.R == 0) { c->ran = true; return 0; }
@@ -497,6 +497,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     k_estimate<<<grid_est, THREADS, smem_est, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), g, c->d_hll.as<u32>(), d_ctr);
     launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[1], s));
     CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, sizeof(uint32_t) << HLL_BITS, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -519,8 +520,9 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         c->cap1 = cap1; c->log_cap = (uint32_t)log_cap;
 
         CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
-        CK(cudaEventRecord(c->ev[1], s));
+        CK(cudaEventRecord(c->ev[9], s));
         k_init_table1<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1);
+        CK(cudaEventRecord(c->ev[2], s));
         Pass1Args a1;
         a1.bases = c->d_bases.as<u64>(); a1.good = c->d_good.as<u64>(); a1.valid = c->d_valid.as<u64>();
         a1.strand = c->any_strand1 ? c->d_strand.as<u8>() : nullptr;
@@ -528,11 +530,12 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         a1.log = c->d_log.as<LogEntry>(); a1.log_cap = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
         a1.ctr = d_ctr;
         k_pass1<<<grid_p1, THREADS, smem_tile, s>>>(a1, g);
-        CK(cudaEventRecord(c->ev[2], s));
+        CK(cudaEventRecord(c->ev[3], s));
         PruneArgs ap;
         ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<LogEntry>();
         ap.qual = c->d_qual.as<u8>(); ap.mf = c->prm.min_node_freq; ap.T = T; ap.ctr = d_ctr;
         k_prune<<<grid_flat, THREADS, 0, s>>>(ap, g);
+        CK(cudaEventRecord(c->ev[4], s));
         launches += 3;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -566,14 +569,15 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
                                        c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_surv, 0, end_bit, s));
     if ((rc = c->d_cub.ensure(std::max<size_t>(cub_bytes, 16)))) return rc;
 
+    CK(cudaEventRecord(c->ev[5], s));
     k_init_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2);
     k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, d_ctr);
-    CK(cudaEventRecord(c->ev[3], s));
+    CK(cudaEventRecord(c->ev[6], s));
     Pass2Args a2;
     a2.bases = c->d_bases.as<u64>(); a2.valid = c->d_valid.as<u64>();
     a2.table = c->d_t2.as<Slot2>(); a2.cap = cap2; a2.ctr = d_ctr;
     k_pass2<<<grid_p2, THREADS, smem_tile, s>>>(a2, g);
-    CK(cudaEventRecord(c->ev[4], s));
+    CK(cudaEventRecord(c->ev[7], s));
     launches += 3;
 
     /* export */
@@ -592,7 +596,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         k_export<<<gb, THREADS, 0, s>>>(ae, g);
         launches += 3;
     }
-    CK(cudaEventRecord(c->ev[5], s));
+    CK(cudaEventRecord(c->ev[8], s));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -609,11 +613,14 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     res.n_hits = h_ctr->n_hits;
     res.table1_slots = cap1; res.table2_slots = cap2;
     res.kernel_launches = launches;
-    cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[5]);
-    cudaEventElapsedTime(&res.ms_pass1, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&res.ms_prune, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&res.ms_pass2, c->ev[3], c->ev[4]);
-    cudaEventElapsedTime(&res.ms_export, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
+    cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
+    cudaEventElapsedTime(&res.ms_pass1, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&res.ms_table2, c->ev[5], c->ev[6]);
+    cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
+    cudaEventElapsedTime(&res.ms_export, c->ev[7], c->ev[8]);
     c->ran = true;
     return 0;
 }
@@ -660,6 +667,15 @@ extern "C" int vdjgraph_fetch(vdjgraph_ctx *c, vdjgraph_result *out) {
     r.d2h_bytes = bytes;
     r.ms_fetch = (float)(wall_ms() - t0);
     *out = r;
+    return 0;
+}
+
+extern "C" int vdjgraph_stats(vdjgraph_ctx *c, vdjgraph_result *out) {
+    if (!c || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if (!c->ran) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_stats before vdjgraph_run");
+    *out = c->res;
+    out->first_pos = nullptr; out->frequency = nullptr; out->out_deg = out->in_deg = nullptr;
+    out->out_succ = out->in_pred = nullptr; out->kmer_lo = out->kmer_hi = nullptr;
     return 0;
 }
 

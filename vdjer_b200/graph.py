@@ -42,9 +42,9 @@ class _Result(C.Structure):
         ("kmer_lo", C.POINTER(C.c_uint64)), ("kmer_hi", C.POINTER(C.c_uint64)),
         ("n_records", C.c_uint64), ("n_windows", C.c_uint64), ("n_gated", C.c_uint64),
         ("n_pre_total", C.c_uint64), ("n_pre", C.c_uint64), ("n_hits", C.c_uint64),
-        ("ms_stage", C.c_float), ("ms_device", C.c_float), ("ms_pass1", C.c_float),
-        ("ms_prune", C.c_float), ("ms_pass2", C.c_float), ("ms_export", C.c_float),
-        ("ms_fetch", C.c_float),
+        ("ms_stage", C.c_float), ("ms_device", C.c_float), ("ms_estimate", C.c_float),
+        ("ms_init1", C.c_float), ("ms_pass1", C.c_float), ("ms_prune", C.c_float), ("ms_table2", C.c_float),
+        ("ms_pass2", C.c_float), ("ms_export", C.c_float), ("ms_fetch", C.c_float),
         ("table1_slots", C.c_uint64), ("table2_slots", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
     ]
@@ -60,7 +60,7 @@ FLAG_EXPORT_KEYS = 1
 EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
     "vdjgraph_set_params", "vdjgraph_build", "vdjgraph_stage", "vdjgraph_run", "vdjgraph_fetch",
-    "vdjgraph_fetch_pre_table",
+    "vdjgraph_fetch_pre_table", "vdjgraph_stats",
 ]
 
 _lib = None
@@ -86,6 +86,7 @@ def load_library():
     lib.vdjgraph_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     lib.vdjgraph_run.argtypes = [C.c_void_p]
     lib.vdjgraph_fetch.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    lib.vdjgraph_stats.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.vdjgraph_fetch_pre_table.argtypes = [C.c_void_p, C.POINTER(_PreTable)]
     _lib = lib
     return lib
@@ -194,6 +195,12 @@ class GraphBuilder:
         self._check(self._lib.vdjgraph_fetch(self._ctx, C.byref(r)))
         return self._graph(r)
 
+    def fetch_stats(self) -> dict:
+        """Counters and timings of the last run() without the device-to-host copy of the graph."""
+        r = _Result()
+        self._check(self._lib.vdjgraph_stats(self._ctx, C.byref(r)))
+        return self._stats(r)
+
     def build(self, primary, secondary=b"") -> Graph:
         """vdjgraph_build: HOST buffers in, graph out (stage + run + fetch)."""
         p, s, n_p, n_s = self._counts(primary, secondary)
@@ -208,11 +215,15 @@ class GraphBuilder:
         return PreTable(_np_from(t.kmer_lo, n, np.uint64), _np_from(t.kmer_hi, n, np.uint64),
                         _np_from(t.frequency, n, np.uint16))
 
+    @staticmethod
+    def _stats(r: _Result) -> dict:
+        return {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
+                for k, _ in _Result._fields_
+                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel"))}
+
     def _graph(self, r: _Result) -> Graph:
         n = int(r.n_nodes)
-        stats = {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
-                 for k, _ in _Result._fields_
-                 if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel"))}
+        stats = self._stats(r)
         return Graph(
             n, _np_from(r.first_pos, n, np.uint64), _np_from(r.frequency, n, np.uint16),
             _np_from(r.out_deg, n, np.uint8), _np_from(r.in_deg, n, np.uint8),
