@@ -1,0 +1,19 @@
+"""Prints the interesting numbers of a bench.py JSON line (stdin)."""
+import json
+import sys
+
+for line in sys.stdin:
+    line = line.strip()
+    if not line.startswith("{"):
+        continue
+    d = json.loads(line)
+    if d.get("impl") == "reference":
+        print("reference:", d["value"] / 1e6, "M windows/s", d["cpu_baseline"]["sample"])
+        continue
+    print(f"value {d['value'] / 1e9:.2f} G windows/s  ms/step {d['ms_per_step']:.2f}  e2e {d['e2e']['value'] / 1e9:.2f} G/s "
+          f"({d['e2e']['ms_per_step']:.1f} ms: stage {d['e2e']['ms_stage']:.1f} dev {d['e2e']['ms_device']:.1f} fetch {d['e2e']['ms_fetch']:.1f})")
+    print("kernel_ms", {k: round(v, 3) for k, v in d["kernel_ms"].items()})
+    print("roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), "path", round(d["roofline_path"]["frac"], 3),
+          "clocks", d["clocks"])
+    if "cpu_baseline" in d:
+        print("cpu", d["cpu_baseline"]["value"] / 1e6, "M windows/s")

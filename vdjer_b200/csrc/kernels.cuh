@@ -34,20 +34,24 @@ constexpr u32 CNT_CAP = 32765;   /* MAX_FREQUENCY-1, :66, :262, :345 */
 constexpr int GATE_Q = 20;       /* MIN_BASE_QUALITY, :76 */
 constexpr int QSUM_SAT = 214;    /* MAX_QUAL_SUM-41, :356 */
 constexpr int MAX_LOG_RANKS = 11;/* ceil(214/20) */
-constexpr u32 FLAG_MULTI = 1u;
+constexpr u32 CNT_MULTI = 0x80000000u; /* top bit of Slot1::count = hasMultipleUniqueReads */
+constexpr u32 CNT_MASK = 0x7FFFFFFFu;
 constexpr u32 FLAG_SURV = 2u;
 constexpr int THREADS = 256;
 constexpr u32 LOG_CHUNK = 128;   /* log entries a warp reserves per global atomic */
 constexpr u32 MAX_PROBE = 1u << 14;
 constexpr int HLL_BITS = 12;     /* 4096 registers, sigma ~ 1.6 % */
+constexpr int BATCH = 4;         /* table probes a thread keeps in flight (independent loads issued back to back) */
+constexpr int WARPS = THREADS / 32;
 
 /* pass-1 table slot: exactly one 32-byte sector */
 struct __align__(32) Slot1 {
     u64 klo, khi;     /* packed k-mer; all ones = empty */
-    u32 count;        /* gated occurrences (stops counting a little above CNT_CAP) */
+    u32 count;        /* bits 0..30: gated occurrences (stops counting a little above CNT_CAP);
+                         bit 31 (CNT_MULTI): hasMultipleUniqueReads :349-352 */
     u32 first_rec;    /* record of the first ARRIVING gated occurrence: contributingRead :335 */
     u32 head;         /* list of the first <= NB occurrences (log entry index) */
-    u32 flags;        /* FLAG_MULTI = hasMultipleUniqueReads :349-352, FLAG_SURV set by prune */
+    u32 flags;        /* FLAG_SURV set by prune */
 };
 static_assert(sizeof(Slot1) == 32, "Slot1 must be one sector");
 
@@ -65,7 +69,7 @@ struct __align__(16) LogEntry { u64 stamp; u32 next; u32 pad; };
 
 struct Geom {
     int L, k, w, nb, nm;
-    u32 tile_rec;       /* records per tile (even) */
+    u32 tile_rec;       /* records per warp tile (even) */
     u32 tile_win;       /* tile_rec * w */
     u32 div_magic;      /* ceil(2^32 / w) */
     u64 R;              /* real records */
@@ -96,6 +100,9 @@ __device__ __forceinline__ void ld_sector(const void *p, u64 &a, u64 &b, u64 &c,
 }
 __device__ __forceinline__ void st_sector(void *p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void ld_cg_v2(const void *p, u64 &a, u64 &b) {
+    asm volatile("ld.global.cg.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ u64 ld_cg_u64(const u64 *p) {
     u64 v;
@@ -187,29 +194,37 @@ __device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
 /* window index within a tile -> record within the tile (w == 1 has no 32-bit magic) */
 __device__ __forceinline__ u32 div_w(u32 win, const Geom &g) { return g.div_magic ? __umulhi(win, g.div_magic) : win; }
 
-/* two-stage TMA tile loader shared by the streaming kernels: arrays a (na words/record) and
- * b (nbw words/record) of one tile land in buffer `buf`; one elected thread issues */
-struct TileBufs {
-    u64 *a[2];
-    u64 *b[2];
+/* Warp-private two-stage TMA tile loader shared by the streaming kernels.  Every warp owns two
+ * shared-memory buffers and two mbarriers and walks the tiles warp-stride, so there is no
+ * block-wide barrier anywhere in the streaming loops: arrays a (na words/record) and b (nbw
+ * words/record) of one tile land in buffer `buf`; lane 0 issues, all lanes wait on the mbarrier */
+struct WarpTiles {
+    u64 *a0, *a1, *b0, *b1;
     u64 *bar;   /* [2] */
+    __device__ __forceinline__ const u64 *a(int buf) const { return buf ? a1 : a0; }
+    __device__ __forceinline__ const u64 *b(int buf) const { return buf ? b1 : b0; }
 };
-__device__ __forceinline__ void tile_issue(const TileBufs &t, int buf, const u64 *ga, const u64 *gb,
+__host__ __device__ inline size_t warp_tile_bytes(u32 tile_rec, int na, int nbw) {
+    return (size_t)2 * tile_rec * (size_t)(na + nbw) * 8 + 16;
+}
+__device__ __forceinline__ void tile_issue(const WarpTiles &t, int buf, const u64 *ga, const u64 *gb,
                                            u64 tile, u32 tile_rec, int na, int nbw) {
     u32 bytes_a = tile_rec * (u32)na * 8u, bytes_b = tile_rec * (u32)nbw * 8u;
-    mbar_expect_tx(&t.bar[buf], bytes_a + bytes_b);
-    tma_load_1d(t.a[buf], ga + tile * tile_rec * (u64)na, bytes_a, &t.bar[buf]);
-    tma_load_1d(t.b[buf], gb + tile * tile_rec * (u64)nbw, bytes_b, &t.bar[buf]);
+    u64 *bar = t.bar + buf;
+    mbar_expect_tx(bar, bytes_a + bytes_b);
+    tma_load_1d(buf ? t.a1 : t.a0, ga + tile * tile_rec * (u64)na, bytes_a, bar);
+    tma_load_1d(buf ? t.b1 : t.b0, gb + tile * tile_rec * (u64)nbw, bytes_b, bar);
 }
-__device__ __forceinline__ TileBufs tile_setup(unsigned char *smem, u32 tile_rec, int na, int nbw) {
-    TileBufs t;
-    u64 *p = reinterpret_cast<u64 *>(smem);
-    t.a[0] = p; p += (size_t)tile_rec * na;
-    t.a[1] = p; p += (size_t)tile_rec * na;
-    t.b[0] = p; p += (size_t)tile_rec * nbw;
-    t.b[1] = p; p += (size_t)tile_rec * nbw;
+__device__ __forceinline__ WarpTiles tile_setup(unsigned char *smem, u32 tile_rec, int na, int nbw) {
+    WarpTiles t;
+    const u32 wid = threadIdx.x >> 5;
+    u64 *p = reinterpret_cast<u64 *>(smem + wid * warp_tile_bytes(tile_rec, na, nbw));
+    t.a0 = p; p += (size_t)tile_rec * na;
+    t.a1 = p; p += (size_t)tile_rec * na;
+    t.b0 = p; p += (size_t)tile_rec * nbw;
+    t.b1 = p; p += (size_t)tile_rec * nbw;
     t.bar = p;
-    if (threadIdx.x == 0) {
+    if ((threadIdx.x & 31) == 0) {
         mbar_init(&t.bar[0], 1);
         mbar_init(&t.bar[1], 1);
         fence_mbar_init();
@@ -219,7 +234,7 @@ __device__ __forceinline__ TileBufs tile_setup(unsigned char *smem, u32 tile_rec
     return t;
 }
 static inline size_t tile_smem_bytes(u32 tile_rec, int na, int nbw) {
-    return (size_t)2 * tile_rec * (size_t)(na + nbw) * 8 + 16;
+    return (size_t)WARPS * warp_tile_bytes(tile_rec, na, nbw);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -232,19 +247,20 @@ k_estimate(const u64 *__restrict__ bases, const u64 *__restrict__ good, Geom g, 
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int M = 1 << HLL_BITS;
     u32 *reg = reinterpret_cast<u32 *>(smem);
-    TileBufs t = tile_setup(smem + M * sizeof(u32), g.tile_rec, g.nb, g.nm);
     for (int i = threadIdx.x; i < M; i += THREADS) reg[i] = 0;
-    __syncthreads();
+    WarpTiles t = tile_setup(smem + M * sizeof(u32), g.tile_rec, g.nb, g.nm);
+    const u32 lane = threadIdx.x & 31;
+    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
     u32 n_gated = 0;
-    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tile_issue(t, 0, bases, good, blockIdx.x, g.tile_rec, g.nb, g.nm);
+    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, bases, good, gw, g.tile_rec, g.nb, g.nm);
     u32 it = 0;
-    for (u64 tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+    for (u64 tile = gw; tile < g.n_tiles; tile += gstride, it++) {
         int buf = it & 1;
-        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles)
-            tile_issue(t, buf ^ 1, bases, good, tile + gridDim.x, g.tile_rec, g.nb, g.nm);
+        if (lane == 0 && tile + gstride < g.n_tiles)
+            tile_issue(t, buf ^ 1, bases, good, tile + gstride, g.tile_rec, g.nb, g.nm);
         mbar_wait(&t.bar[buf], (it >> 1) & 1);
-        const u64 *sb = t.a[buf], *sg = t.b[buf];
-        for (u32 win = threadIdx.x; win < g.tile_win; win += THREADS) {
+        const u64 *sb = t.a(buf), *sg = t.b(buf);
+        for (u32 win = lane; win < g.tile_win; win += 32) {
             u32 rec = div_w(win, g);
             int i = (int)(win - rec * (u32)g.w);
             u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
@@ -257,20 +273,13 @@ k_estimate(const u64 *__restrict__ bases, const u64 *__restrict__ good, Geom g, 
             u32 rho = (u32)__clzll((long long)((h << HLL_BITS) | (1ull << (HLL_BITS - 1)))) + 1;
             if (reg[idx] < rho) atomicMax(&reg[idx], rho);
         }
-        __syncthreads();
+        __syncwarp();
     }
+    __syncthreads();
     for (int i = threadIdx.x; i < M; i += THREADS)
         if (reg[i]) atomicMax(&hll[i], reg[i]);
-    /* block-reduce the gated count */
     for (int o = 16; o; o >>= 1) n_gated += __shfl_xor_sync(0xFFFFFFFFu, n_gated, o);
-    __shared__ u32 wsum[THREADS / 32];
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n_gated;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 s = 0;
-        for (int i = 0; i < THREADS / 32; i++) s += wsum[i];
-        if (s) atomicAdd(&ctr->n_gated, s);
-    }
+    if (lane == 0 && n_gated) atomicAdd(&ctr->n_gated, (u64)n_gated);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -304,7 +313,7 @@ __device__ __noinline__ bool same_read(const u64 *__restrict__ bases, const u64 
 /* ------------------------------------------------------------------------------------------ */
 /* K1: pass 1 = build_pre_graph / add_to_table (:322-409) as commutative reductions.           */
 /*   count        -> pre_node.frequency (:334, :345-347)                                        */
-/*   FLAG_MULTI   -> hasMultipleUniqueReads (:349-352): some occurrence's record differs from   */
+/*   CNT_MULTI    -> hasMultipleUniqueReads (:349-352): some occurrence's record differs from   */
 /*                   the first ARRIVING one's; equivalent to ">= 2 distinct record sequences"   */
 /*   occurrence log: the first NB arrivals of every k-mer append their stamp, so that k-mers    */
 /*                   whose final count is <= NB have ALL their occurrences listed; only those   */
@@ -322,91 +331,121 @@ struct Pass1Args {
     Counters *ctr;
 };
 
-__global__ void __launch_bounds__(THREADS)
+/* slow path of pass 1: the home slot did not hold this k-mer -> linear probing with insertion.
+ * On return slot/q2 describe the slot that now holds (lo,hi); false = table full. */
+__device__ __noinline__ bool pass1_probe(const Pass1Args &a, u64 lo, u64 hi, u64 idx, Slot1 *&slot, u64 &q2) {
+    for (u32 probe = 0; probe < MAX_PROBE; probe++) {
+        slot = a.table + idx;
+        u64 q0, q1, q3;
+        ld_sector(slot, q0, q1, q2, q3);
+        if (q0 == EMPTY64 && q1 == EMPTY64) {
+            cas128(slot, EMPTY64, EMPTY64, lo, hi, q0, q1);
+            if (q0 == EMPTY64 && q1 == EMPTY64) { q2 = (u64)NIL32 << 32; return true; } /* claimed: initial fields */
+        }
+        if (q0 == lo && q1 == hi) return true;
+        if (++idx == a.cap) idx = 0;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(THREADS, 4)
 k_pass1(Pass1Args a, Geom g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    TileBufs t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
+    WarpTiles t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
     const u32 lane = threadIdx.x & 31;
+    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
     u32 chunk_base = 0, chunk_used = LOG_CHUNK; /* warp-uniform */
-    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tile_issue(t, 0, a.bases, a.good, blockIdx.x, g.tile_rec, g.nb, g.nm);
-    const u32 iters = (g.tile_win + THREADS - 1) / THREADS;
+    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, a.bases, a.good, gw, g.tile_rec, g.nb, g.nm);
+    const u32 n_batch = (g.tile_win + 32 * BATCH - 1) / (32 * BATCH);
     u32 it = 0;
-    for (u64 tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+    for (u64 tile = gw; tile < g.n_tiles; tile += gstride, it++) {
         int buf = it & 1;
-        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles)
-            tile_issue(t, buf ^ 1, a.bases, a.good, tile + gridDim.x, g.tile_rec, g.nb, g.nm);
+        if (lane == 0 && tile + gstride < g.n_tiles)
+            tile_issue(t, buf ^ 1, a.bases, a.good, tile + gstride, g.tile_rec, g.nb, g.nm);
         mbar_wait(&t.bar[buf], (it >> 1) & 1);
-        const u64 *sb = t.a[buf], *sg = t.b[buf];
+        const u64 *sb = t.a(buf), *sg = t.b(buf);
         const u64 rec0 = tile * g.tile_rec;
-        for (u32 j = 0; j < iters; j++) {
-            u32 win = j * THREADS + threadIdx.x;
-            bool need_log = false;
-            u64 stamp = 0;
-            Slot1 *slot = nullptr;
-            if (win < g.tile_win) {
-                u32 rec = div_w(win, g);
-                int i = (int)(win - rec * (u32)g.w);
-                u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
-                if ((m & g.kones) == g.kones) {
+        for (u32 b = 0; b < n_batch; b++) {
+            /* phase A: BATCH independent home-slot reads per lane, issued back to back */
+            u64 idx[BATCH], k0[BATCH], k1[BATCH], m2[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const u32 win = (b * BATCH + u) * 32 + lane;
+                idx[u] = INF64;
+                if (win < g.tile_win) {
+                    u32 rec = div_w(win, g);
+                    int i = (int)(win - rec * (u32)g.w);
+                    u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
+                    if ((m & g.kones) == g.kones) {
+                        u64 lo, hi;
+                        extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+                        idx[u] = __umul64hi(hash_key(lo, hi), a.cap);
+                        const Slot1 *s = a.table + idx[u];
+                        ld_cg_v2(s, k0[u], k1[u]);
+                        m2[u] = ld_cg_u64(reinterpret_cast<const u64 *>(s) + 2);
+                    }
+                }
+            }
+            /* phase B: consume */
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const u32 win = (b * BATCH + u) * 32 + lane;
+                bool need_log = false;
+                u64 stamp = 0;
+                Slot1 *slot = nullptr;
+                if (idx[u] != INF64) {
+                    u32 rec = div_w(win, g);
+                    int i = (int)(win - rec * (u32)g.w);
                     u64 lo, hi;
                     extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
                     const u64 r = rec0 + rec;
                     stamp = r * (u64)g.w + (u64)i;
-                    u64 idx = __umul64hi(hash_key(lo, hi), a.cap);
-                    u64 q0, q1, q2, q3;
-                    bool found = false;
-                    for (u32 probe = 0; probe < MAX_PROBE; probe++) {
-                        slot = a.table + idx;
-                        ld_sector(slot, q0, q1, q2, q3);
-                        if (q0 == EMPTY64 && q1 == EMPTY64) {
-                            cas128(slot, EMPTY64, EMPTY64, lo, hi, q0, q1);
-                            if (q0 == EMPTY64 && q1 == EMPTY64) { /* claimed: fields hold their initial values */
-                                q0 = lo; q1 = hi; q2 = (u64)NIL32 << 32; q3 = (u64)NIL32;
-                            }
-                        }
-                        if (q0 == lo && q1 == hi) { found = true; break; }
-                        if (++idx == a.cap) idx = 0;
-                    }
+                    slot = a.table + idx[u];
+                    u64 q2 = m2[u];
+                    bool found = (k0[u] == lo && k1[u] == hi);
+                    if (!found) found = pass1_probe(a, lo, hi, idx[u], slot, q2);
                     if (!found) {
                         atomicExch(&a.ctr->overflow, 1u);
                     } else {
-                        u32 cnt = (u32)q2, first_rec = (u32)(q2 >> 32), flags = (u32)(q3 >> 32);
+                        const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
+                        u32 first_rec = (u32)(q2 >> 32);
                         u32 rank = NIL32;
-                        if (cnt < CNT_CAP) rank = atomicAdd(&slot->count, 1u);
-                        if (!(flags & FLAG_MULTI)) {
+                        if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u) & CNT_MASK; /* arrival rank decides logging */
+                        else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                 /* result unused: RED, no stall */
+                        if (!(cw & CNT_MULTI)) {
                             if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
                             if (first_rec != NIL32 && first_rec != (u32)r &&
                                 !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
-                                atomicOr(&slot->flags, FLAG_MULTI);
+                                atomicOr(&slot->count, CNT_MULTI);
                         }
                         need_log = rank < a.nb_ranks;
                     }
                 }
-            }
-            /* warp-converged log allocation out of per-warp chunks */
-            u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
-            if (ballot) {
-                u32 n = __popc(ballot);
-                if (chunk_used + n > LOG_CHUNK) {
-                    u32 base = 0;
-                    if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
-                    chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    chunk_used = 0;
-                }
-                u32 e = chunk_base + chunk_used + __popc(ballot & ((1u << lane) - 1));
-                chunk_used += n;
-                if (need_log) {
-                    if (e < a.log_cap) {
-                        u32 prev = atomicExch(&slot->head, e);
-                        LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
-                        a.log[e] = le;
-                    } else {
-                        atomicExch(&a.ctr->overflow, 2u);
+                /* warp-converged log allocation out of per-warp chunks */
+                u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
+                if (ballot) {
+                    u32 n = __popc(ballot);
+                    if (chunk_used + n > LOG_CHUNK) {
+                        u32 base = 0;
+                        if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
+                        chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        chunk_used = 0;
+                    }
+                    u32 e = chunk_base + chunk_used + __popc(ballot & ((1u << lane) - 1));
+                    chunk_used += n;
+                    if (need_log) {
+                        if (e < a.log_cap) {
+                            u32 prev = atomicExch(&slot->head, e);
+                            LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
+                            a.log[e] = le;
+                        } else {
+                            atomicExch(&a.ctr->overflow, 2u);
+                        }
                     }
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -431,36 +470,58 @@ struct PruneArgs {
 
 __global__ void __launch_bounds__(THREADS)
 k_prune(PruneArgs a, Geom g) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    /* lane = one slot; slots whose quality sums must be evaluated are then handled by the whole
+     * warp: lane j owns k-mer positions j and j+32, so each occurrence's k quality bytes are one
+     * coalesced read */
+    __shared__ u64 s_st[THREADS / 32][32][MAX_LOG_RANKS];
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 n_iter = (a.cap + stride - 1) / stride;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 n_distinct = 0, n_surv = 0;
-    for (; i < a.cap; i += stride) {
-        u64 q0, q1, q2, q3;
-        ld_sector(&a.table[i], q0, q1, q2, q3);
-        if (q0 == EMPTY64 && q1 == EMPTY64) continue;
-        n_distinct++;
-        u32 cnt = (u32)q2, head = (u32)q3, flags = (u32)(q3 >> 32);
-        if (cnt > CNT_CAP) cnt = CNT_CAP;
-        if ((int)cnt < a.mf || !(flags & FLAG_MULTI)) continue;
-        bool pass = true;
-        if (GATE_Q * ((int)cnt - 1) < a.T) {
-            u64 st[MAX_LOG_RANKS];
-            int n = 0;
-            for (u32 e = head; e != NIL32 && n < MAX_LOG_RANKS; e = a.log[e].next) st[n++] = a.log[e].stamp;
-            if (n != (int)cnt) { atomicExch(&a.ctr->internal, 1u); continue; }
-            int first = 0;
-            for (int e = 1; e < n; e++) if (st[e] < st[first]) first = e;
-            /* byte offsets of each occurrence's quality window; the first one reads q_r0[j] */
-            u64 off[MAX_LOG_RANKS];
+    for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
+        u32 cnt = 0, flags = 0;
+        bool pass = false, border = false;
+        if (i < a.cap) {
+            u64 q0, q1, q2, q3;
+            ld_sector(&a.table[i], q0, q1, q2, q3);
+            if (!(q0 == EMPTY64 && q1 == EMPTY64)) {
+                n_distinct++;
+                const bool multi = ((u32)q2 & CNT_MULTI) != 0;
+                cnt = (u32)q2 & CNT_MASK; flags = (u32)(q3 >> 32);
+                u32 head = (u32)q3;
+                if (cnt > CNT_CAP) cnt = CNT_CAP;
+                if ((int)cnt >= a.mf && multi) {
+                    pass = true;
+                    if (GATE_Q * ((int)cnt - 1) < a.T) {
+                        border = true;
+                        int n = 0;
+                        for (u32 e = head; e != NIL32 && n < MAX_LOG_RANKS; e = a.log[e].next) s_st[wid][lane][n++] = a.log[e].stamp;
+                        if (n != (int)cnt) { atomicExch(&a.ctr->internal, 1u); border = false; pass = false; }
+                    }
+                }
+            }
+        }
+        u32 todo = __ballot_sync(0xFFFFFFFFu, border);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int n = (int)__shfl_sync(0xFFFFFFFFu, cnt, b);
+            __syncwarp();
+            u64 first = INF64;
+            for (int e = 0; e < n; e++) first = min(first, s_st[wid][b][e]);
+            int s0 = 0, s1 = 0;
             for (int e = 0; e < n; e++) {
-                u64 r = st[e] / (u64)g.w;
-                u64 o = st[e] - r * (u64)g.w;
-                off[e] = r * (u64)g.L + (e == first ? 0 : o);
+                u64 st = s_st[wid][b][e];
+                u64 r = st / (u64)g.w;
+                u64 o = st == first ? 0 : st - r * (u64)g.w;   /* first occurrence reads q_r0[j], :337-339 */
+                const u8 *q = a.qual + r * (u64)g.L + o;
+                if ((int)lane < g.k) s0 += q[lane];
+                if ((int)lane + 32 < g.k) s1 += q[lane + 32];
             }
-            for (int j = 0; j < g.k && pass; j++) {
-                int s = 0;
-                for (int e = 0; e < n; e++) s += a.qual[off[e] + j];
-                if (s < a.T) pass = false;
-            }
+            bool bad = ((int)lane < g.k && s0 < a.T) || ((int)lane + 32 < g.k && s1 < a.T);
+            u32 any_bad = __ballot_sync(0xFFFFFFFFu, bad);
+            if ((int)lane == b && any_bad) pass = false;
         }
         if (pass) {
             a.table[i].flags = flags | FLAG_SURV;
@@ -471,7 +532,7 @@ k_prune(PruneArgs a, Geom g) {
         n_distinct += __shfl_xor_sync(0xFFFFFFFFu, n_distinct, o);
         n_surv += __shfl_xor_sync(0xFFFFFFFFu, n_surv, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (n_distinct) atomicAdd(&a.ctr->n_distinct, (u64)n_distinct);
         if (n_surv) atomicAdd(&a.ctr->n_surv, (u64)n_surv);
     }
@@ -490,9 +551,8 @@ __device__ __forceinline__ u64 t2_insert(Slot2 *t, u64 cap, u64 lo, u64 hi) {
     }
     return INF64;
 }
-/* returns slot index or INF64; fills the hot sector of the slot */
-__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, u64 lo, u64 hi, u64 &q2, u64 &q3) {
-    u64 idx = __umul64hi(hash_key(lo, hi), cap);
+/* linear probe from idx; returns slot index or INF64; fills words 2,3 of the hot sector */
+__device__ __forceinline__ u64 t2_probe_from(const Slot2 *t, u64 cap, u64 idx, u64 lo, u64 hi, u64 &q2, u64 &q3) {
     for (u32 probe = 0; probe < MAX_PROBE; probe++) {
         u64 q0, q1;
         ld_sector(&t[idx], q0, q1, q2, q3);
@@ -501,6 +561,9 @@ __device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, u64 lo, u64 hi, 
         if (++idx == cap) idx = 0;
     }
     return INF64;
+}
+__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, u64 lo, u64 hi, u64 &q2, u64 &q3) {
+    return t2_probe_from(t, cap, __umul64hi(hash_key(lo, hi), cap), lo, hi, q2, q3);
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -532,45 +595,81 @@ struct Pass2Args {
     Counters *ctr;
 };
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 k_pass2(Pass2Args a, Geom g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    TileBufs t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
-    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tile_issue(t, 0, a.bases, a.valid, blockIdx.x, g.tile_rec, g.nb, g.nm);
+    WarpTiles t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
+    const u32 lane = threadIdx.x & 31;
+    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
+    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, a.bases, a.valid, gw, g.tile_rec, g.nb, g.nm);
+    const u32 n_batch = (g.tile_win + 32 * BATCH - 1) / (32 * BATCH);
     u32 n_hits = 0;
     u32 it = 0;
-    for (u64 tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+    for (u64 tile = gw; tile < g.n_tiles; tile += gstride, it++) {
         int buf = it & 1;
-        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles)
-            tile_issue(t, buf ^ 1, a.bases, a.valid, tile + gridDim.x, g.tile_rec, g.nb, g.nm);
+        if (lane == 0 && tile + gstride < g.n_tiles)
+            tile_issue(t, buf ^ 1, a.bases, a.valid, tile + gstride, g.tile_rec, g.nb, g.nm);
         mbar_wait(&t.bar[buf], (it >> 1) & 1);
-        const u64 *sb = t.a[buf], *sv = t.b[buf];
+        const u64 *sb = t.a(buf), *sv = t.b(buf);
         const u64 rec0 = tile * g.tile_rec;
-        for (u32 win = threadIdx.x; win < g.tile_win; win += THREADS) {
-            u32 rec = div_w(win, g);
-            int i = (int)(win - rec * (u32)g.w);
-            const u64 *vb = sv + (size_t)rec * g.nm;
-            u64 m = extract_mask(vb, g.nm, i);
-            if ((m & g.kones) != g.kones) continue;
-            const u64 *bb = sb + (size_t)rec * g.nb;
-            u64 lo, hi, q2, q3;
-            extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-            u64 idx = t2_find(a.table, a.cap, lo, hi, q2, q3);
-            if (idx == INF64) continue;
-            n_hits++;
-            Slot2 *slot = a.table + idx;
-            const u64 stamp = (rec0 + rec) * (u64)g.w + (u64)i;
-            if ((u32)q2 < CNT_CAP) atomicAdd(&slot->count, 1u);
-            if (stamp < q3) atomicMin(&slot->first_any, stamp);
-            if (i + 1 < g.w && bit_at(vb, i + g.k)) {
-                u32 c = base_at(bb, i + g.k);
-                if (stamp < ld_cg_u64(&slot->out_first[c])) atomicMin(&slot->out_first[c], stamp);
+        for (u32 b = 0; b < n_batch; b++) {
+            /* phase A: per lane BATCH independent probes: the hot sector of the home slot and,
+             * speculatively, the out_first word this window would update */
+            u64 idx[BATCH], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const u32 win = (b * BATCH + u) * 32 + lane;
+                idx[u] = INF64;
+                of[u] = 0;
+                if (win < g.tile_win) {
+                    u32 rec = div_w(win, g);
+                    int i = (int)(win - rec * (u32)g.w);
+                    const u64 *vb = sv + (size_t)rec * g.nm;
+                    u64 m = extract_mask(vb, g.nm, i);
+                    if ((m & g.kones) == g.kones) {
+                        const u64 *bb = sb + (size_t)rec * g.nb;
+                        u64 lo, hi;
+                        extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+                        idx[u] = __umul64hi(hash_key(lo, hi), a.cap);
+                        const Slot2 *s = a.table + idx[u];
+                        ld_sector(s, q0[u], q1[u], q2[u], q3[u]);
+                        if (i + 1 < g.w && bit_at(vb, i + g.k)) of[u] = ld_cg_u64(&s->out_first[base_at(bb, i + g.k)]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                if (idx[u] == INF64) continue;
+                const u32 win = (b * BATCH + u) * 32 + lane;
+                u32 rec = div_w(win, g);
+                int i = (int)(win - rec * (u32)g.w);
+                const u64 *vb = sv + (size_t)rec * g.nm;
+                const u64 *bb = sb + (size_t)rec * g.nb;
+                u64 lo, hi;
+                extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+                const bool has_next = i + 1 < g.w && bit_at(vb, i + g.k);
+                const u32 c = has_next ? base_at(bb, i + g.k) : 0;
+                u64 id = idx[u], c2 = q2[u], c3 = q3[u], o = of[u];
+                if (!(q0[u] == lo && q1[u] == hi)) {
+                    if (q0[u] == EMPTY64 && q1[u] == EMPTY64) continue;
+                    /* collision at the home slot: probe on (rare at load <= 0.5) */
+                    if (++id == a.cap) id = 0;
+                    id = t2_probe_from(a.table, a.cap, id, lo, hi, c2, c3);
+                    if (id == INF64) continue;
+                    if (has_next) o = ld_cg_u64(&a.table[id].out_first[c]);
+                }
+                n_hits++;
+                Slot2 *slot = a.table + id;
+                const u64 stamp = (rec0 + rec) * (u64)g.w + (u64)i;
+                if ((u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
+                if (stamp < c3) atomicMin(&slot->first_any, stamp);
+                if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
-    if ((threadIdx.x & 31) == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
+    if (lane == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -682,7 +781,7 @@ k_export_pre(const Slot1 *t, u64 cap, u64 *klo, u64 *khi, u16 *freq, u64 *n_out)
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
         if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
         u64 o = atomicAdd(n_out, 1ull);
-        u32 cnt = (u32)q2;
+        u32 cnt = (u32)q2 & CNT_MASK;
         klo[o] = q0; khi[o] = q1; freq[o] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);
     }
 }

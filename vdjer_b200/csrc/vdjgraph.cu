@@ -150,9 +150,10 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     g.w = g.L - g.k + 1;
     g.nb = (g.L + 31) / 32;
     g.nm = (g.L + 63) / 64;
-    uint32_t tr = 8192u / (uint32_t)g.w;
+    /* warp tile: about 32 lanes x BATCH probes x 8 batches of windows, an even record count */
+    uint32_t tr = (32u * BATCH * 8u) / (uint32_t)g.w;
     tr &= ~1u;
-    tr = std::max(32u, std::min(1024u, tr));
+    tr = std::max(2u, std::min(128u, tr));
     g.tile_rec = tr;
     g.tile_win = tr * (uint32_t)g.w;
     g.div_magic = g.w == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)g.w - 1) / (uint64_t)g.w);
@@ -486,9 +487,10 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
 
     const size_t smem_tile = tile_smem_bytes(g.tile_rec, g.nb, g.nm);
     const size_t smem_est = smem_tile + (sizeof(uint32_t) << HLL_BITS);
-    const int grid_est = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_estimate, smem_est));
-    const int grid_p1 = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass1, smem_tile));
-    const int grid_p2 = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass2, smem_tile));
+    const uint64_t tile_blocks = (g.n_tiles + WARPS - 1) / WARPS;
+    const int grid_est = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_estimate, smem_est));
+    const int grid_p1 = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass1, smem_tile));
+    const int grid_p2 = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass2, smem_tile));
     const int grid_flat = c->sm_count * 8;
 
     CK(cudaEventRecord(c->ev[0], s));
