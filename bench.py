@@ -239,7 +239,7 @@ def main():
         h = stats["n_hits"] / W
         a1, a2, a_all = algorithmic_bytes(L, k, h)
         kern = {n: float(np.mean([s[n] for s in per_kernel])) for n in
-                ["ms_estimate", "ms_init1", "ms_pass1", "ms_prune", "ms_table2", "ms_pass2", "ms_export"]}
+                ["ms_estimate", "ms_scatter", "ms_init1", "ms_pass1", "ms_prune", "ms_table2", "ms_pass2", "ms_export"]}
         dom = "k_pass1" if kern["ms_pass1"] >= kern["ms_pass2"] else "k_pass2"
         dom_ms = max(kern["ms_pass1"], kern["ms_pass2"])
         dom_bytes = W * (a1 if dom == "k_pass1" else a2)
@@ -255,6 +255,7 @@ def main():
                        "distinct_gated_kmers": stats["n_pre_total"], "nodes": stats["n_nodes"],
                        "gated_fraction": stats["n_gated"] / W, "pass2_hit_fraction_h": h,
                        "table1_slots": stats["table1_slots"], "table2_slots": stats["table2_slots"],
+                       "hash_partitions": stats["partitions"], "tuple_bytes": stats["tuple_bytes"],
                        "generator_s": round(t_gen, 2)},
             "e2e": {"value": W_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": e2e_stats["h2d_bytes"], "d2h_bytes_per_step": e2e_stats["d2h_bytes"],

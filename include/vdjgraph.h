@@ -56,10 +56,11 @@ typedef struct vdjgraph_params {
     int32_t host_threads;     /* staging threads for text -> packed conversion; 0 = auto */
     uint64_t table_capacity;  /* pass-1 table slots; 0 = auto (cardinality estimate on device) */
     uint32_t flags;           /* VDJGRAPH_FLAG_* */
-    uint32_t reserved;
+    uint32_t partitions;      /* hash partitions (power of two <= 256); 0 = auto (table slice ~24 MB, L2-resident) */
 } vdjgraph_params;
 
 #define VDJGRAPH_FLAG_EXPORT_KEYS 1u /* also export the packed k-mer of every node (kmer_lo/kmer_hi) */
+#define VDJGRAPH_FLAG_WIDE_TUPLES 2u /* force the 24-byte tuple format (normally chosen when k and the input size need it) */
 
 /*
  * The graph the reference holds after build_graph2 (:1408), as structure-of-arrays indexed by
@@ -95,11 +96,13 @@ typedef struct vdjgraph_result {
     float ms_stage;            /* host pack + H2D (wall clock) */
     float ms_device;           /* whole vdjgraph_run, CUDA events on the build stream (includes the
                                   two small counter read-backs that size the tables) */
-    /* per-kernel CUDA-event times: cardinality estimate, pass-1 table init, k_pass1, k_prune,
-     * survivor-table init+insert, k_pass2, export (collect + sort + rank + edges) */
-    float ms_estimate, ms_init1, ms_pass1, ms_prune, ms_table2, ms_pass2, ms_export;
+    /* per-kernel CUDA-event times: k_count (window histogram + cardinality estimate), k_scatter,
+     * pass-1 table init, k_pass1, k_prune, survivor-table init+insert, k_pass2,
+     * export (collect + sort + rank + edges) */
+    float ms_estimate, ms_scatter, ms_init1, ms_pass1, ms_prune, ms_table2, ms_pass2, ms_export;
     float ms_fetch;            /* D2H of the result (wall clock) */
     uint64_t table1_slots, table2_slots; /* capacities used */
+    uint32_t partitions, tuple_bytes;    /* hash partitions and tuple size used */
     uint64_t h2d_bytes, d2h_bytes;       /* bytes moved by stage / fetch */
     uint64_t kernel_launches;            /* our kernels launched by the last run (CUB's sort passes not counted) */
 } vdjgraph_result;

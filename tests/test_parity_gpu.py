@@ -53,6 +53,21 @@ def test_matches_oracle_seeded(built, seed, L, k, mf, mq, pairs, clones):
     assert_graph_equal(got, want, f"seed{seed}")
 
 
+@pytest.mark.parametrize("partitions,wide", [(1, False), (2, False), (16, True), (256, False), (64, True)])
+@pytest.mark.parametrize("L,k,mf,mq", [(50, 35, 3, 90), (100, 50, 2, 120), (50, 25, 1, 20)])
+def test_partition_count_and_tuple_format_do_not_change_the_result(built, partitions, wide, L, k, mf, mq):
+    """The hash-partition count and the 16/24-byte tuple format are performance knobs only."""
+    primary, secondary = synth.generate(n_pairs=15000, read_length=L, seed=61 + L + k, n_clones=300, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    with GraphBuilder(L, k, mf, mq, partitions=partitions, wide_tuples=wide) as gb:
+        got = gb.build(primary, secondary)
+        pre = gb.pre_table()
+    assert got.stats["partitions"] == partitions and got.stats["tuple_bytes"] == (24 if wide else 16)
+    assert_pre_table_equal(pre, want, primary, secondary, L, k, f"P{partitions}")
+    assert_graph_equal(got, want, f"P{partitions} wide{wide}")
+    assert got.stats["n_hits"] == want["n_hits"] and got.stats["n_gated"] == want["n_gated"]
+
+
 def test_context_reuse_and_param_changes(built):
     """One context, several builds with different --k/--mf/--mq and inputs: no state leaks."""
     primary, secondary = synth.generate(n_pairs=8000, read_length=50, seed=41, n_clones=100, threads=4)

@@ -3,12 +3,18 @@
  *
  * Implements the order-free form of the reference's hot path; each kernel
  * cites the reference lines (/root/reference/src/main/c/assembler2_vdj.c) whose result it must
- * reproduce bit for bit.  Nothing here is a dense contraction: the work is HBM/L2-atomic bound
- * integer and byte traffic, so the Blackwell features used are TMA bulk copies + mbarrier for
- * the streaming input tiles, 256-bit global loads (one 32-B sector per table probe), 128-bit
- * atomicCAS for the k > 31 keys, and persistent grids sized from the SM count.
+ * reproduce bit for bit.  Nothing here is a dense contraction: the work is integer/byte traffic
+ * bounded by HBM and by L2 atomics, so tensor cores are not used.
  *
- * Packed layout in HBM (written by staging.cpp):
+ * Design: a hash table probed at random from 3e8 windows misses L2 on almost
+ * every probe, and this B200 sustains only ~20 G random read-modify-writes/s out of HBM
+ * (profiles/microbench_r1.json) against ~190 G/s inside its 126 MB L2.  So the windows are
+ * first SCATTERED, as 16-byte (key, stamp) tuples, into P hash partitions (one streaming write),
+ * and both table passes then walk the tuples partition by partition: the slice of the table a
+ * partition addresses is a few MB and stays L2-resident, every probe and atomic is an L2 hit,
+ * and HBM only sees streaming traffic.
+ *
+ * Packed read layout in HBM (written by the host staging code in vdjgraph.cu):
  *   bases [R][nb] u64 : 2 bits/base, A=0 C=1 G=2 T=3 (N stored as 0), base j at bits 2j of the record
  *   good  [R][nm] u64 : bit j = base j is ACGT and phred >= 20      (pass-1 gate, :240-259)
  *   valid [R][nm] u64 : bit j = base j is ACGT                      (pass 2 has no quality gate, :272-274)
@@ -38,11 +44,12 @@ constexpr u32 CNT_MULTI = 0x80000000u; /* top bit of Slot1::count = hasMultipleU
 constexpr u32 CNT_MASK = 0x7FFFFFFFu;
 constexpr u32 FLAG_SURV = 2u;
 constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
 constexpr u32 LOG_CHUNK = 128;   /* log entries a warp reserves per global atomic */
 constexpr u32 MAX_PROBE = 1u << 14;
 constexpr int HLL_BITS = 12;     /* 4096 registers, sigma ~ 1.6 % */
-constexpr int BATCH = 4;         /* table probes a thread keeps in flight (independent loads issued back to back) */
-constexpr int WARPS = THREADS / 32;
+constexpr int HIST_BITS = 8;     /* k_count histograms the top 8 hash bits; P <= 256 partitions */
+constexpr int BATCH = 4;         /* independent table probes a thread keeps in flight */
 
 /* pass-1 table slot: exactly one 32-byte sector */
 struct __align__(32) Slot1 {
@@ -71,11 +78,21 @@ struct Geom {
     int L, k, w, nb, nm;
     u32 tile_rec;       /* records per warp tile (even) */
     u32 tile_win;       /* tile_rec * w */
-    u32 div_magic;      /* ceil(2^32 / w) */
+    u32 div_magic;      /* ceil(2^32 / w), 0 when w == 1 */
     u64 R;              /* real records */
     u64 n_tiles;
     u64 kmask_lo, kmask_hi; /* 2k ones */
     u64 kones;          /* k ones */
+};
+
+/* hash partitioning + tuple format */
+struct Part {
+    int pbits;          /* P = 1 << pbits partitions by the top hash bits */
+    int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
+    int wide;           /* 1: 24-byte tuples (stamp in a third word) */
+    int pad;
+    u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
+    u64 n_gated, n_valid; /* tuples in the gated region / in both regions */
 };
 
 struct Counters {
@@ -85,7 +102,7 @@ struct Counters {
     u64 n_hits;
     u64 n_nodes;
     u32 log_used;
-    u32 overflow;     /* table full / probe bound hit */
+    u32 overflow;     /* table full / probe bound hit / region overrun */
     u32 internal;     /* invariant violated */
     u32 pad;
 };
@@ -108,6 +125,22 @@ __device__ __forceinline__ u64 ld_cg_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+/* streaming (touched-once) tuple traffic: evict-first so it does not push the L2-resident
+ * table slice out */
+__device__ __forceinline__ void ld_stream_v2(const void *p, u64 &a, u64 &b) {
+    asm volatile("ld.global.cs.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ u64 ld_stream_u64(const void *p) {
+    u64 v;
+    asm volatile("ld.global.cs.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_stream_v2(void *p, u64 a, u64 b) {
+    asm volatile("st.global.cs.v2.b64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream_u64(void *p, u64 a) {
+    asm volatile("st.global.cs.b64 [%0], %1;" :: "l"(p), "l"(a) : "memory");
 }
 /* 128-bit compare-and-swap on a 16-byte aligned key (ATOMG.E.CAS.128 on sm_100a) */
 __device__ __forceinline__ void cas128(void *addr, u64 cmp_lo, u64 cmp_hi, u64 val_lo, u64 val_hi,
@@ -154,6 +187,12 @@ __device__ __forceinline__ u64 hash_key(u64 lo, u64 hi) {
     h ^= h >> 32;
     return h;
 }
+/* home slot: the top pbits of the hash select the partition (= a contiguous slice of the
+ * table), the remaining bits a slot inside it */
+__device__ __forceinline__ u64 home_slot(u64 h, int pbits, u64 slice) {
+    if (pbits == 0) return __umul64hi(h, slice);
+    return (h >> (64 - pbits)) * slice + __umul64hi(h << pbits, slice);
+}
 
 /* bits [2i, 2i+2k) of a record's base words */
 __device__ __forceinline__ void extract_kmer(const u64 *b, int nb, int i, u64 mlo, u64 mhi, u64 &lo, u64 &hi) {
@@ -194,36 +233,73 @@ __device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
 /* window index within a tile -> record within the tile (w == 1 has no 32-bit magic) */
 __device__ __forceinline__ u32 div_w(u32 win, const Geom &g) { return g.div_magic ? __umulhi(win, g.div_magic) : win; }
 
-/* Warp-private two-stage TMA tile loader shared by the streaming kernels.  Every warp owns two
- * shared-memory buffers and two mbarriers and walks the tiles warp-stride, so there is no
- * block-wide barrier anywhere in the streaming loops: arrays a (na words/record) and b (nbw
- * words/record) of one tile land in buffer `buf`; lane 0 issues, all lanes wait on the mbarrier */
+/* ------------------------------------------------------------------------------------------ */
+/* tuples: one per N-free window.  word0 = k-mer bits 0..63; word1 = k-mer bits 64.. (hb bits)  */
+/* | has_next << hb | next_base << (hb+1) | stamp << (hb+4)   (narrow, 16 B), or the stamp in a  */
+/* third word (wide, 24 B) when it does not fit.  The gate bit is implied by the region.        */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void tuple_store(u64 *base, u64 t, const Part &pt, u64 lo, u64 hi, u32 fl, u64 stamp) {
+    u64 w1 = hi | ((u64)fl << pt.hb);
+    if (pt.wide) {
+        u64 *p = base + t * 3;
+        st_stream_u64(p, lo); st_stream_u64(p + 1, w1); st_stream_u64(p + 2, stamp);
+    } else {
+        st_stream_v2(base + t * 2, lo, w1 | (stamp << (pt.hb + 4)));
+    }
+}
+template <bool WIDE>
+__device__ __forceinline__ void tuple_load(const u64 *base, u64 t, u64 &lo, u64 &w1, u64 &w2) {
+    if (WIDE) {
+        const u64 *p = base + t * 3;
+        lo = ld_stream_u64(p); w1 = ld_stream_u64(p + 1); w2 = ld_stream_u64(p + 2);
+    } else {
+        ld_stream_v2(base + t * 2, lo, w1);
+        w2 = 0;
+    }
+}
+template <bool WIDE>
+__device__ __forceinline__ void tuple_decode(const Part &pt, u64 w1, u64 w2, u64 &hi, u32 &fl, u64 &stamp) {
+    hi = pt.hb ? (w1 & ((1ull << pt.hb) - 1)) : 0ull;
+    fl = (u32)(w1 >> pt.hb) & 15u;
+    stamp = WIDE ? w2 : (w1 >> (pt.hb + 4));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Warp-private two-stage TMA tile loader for the kernels that stream the packed reads.        */
+/* Every warp owns two shared-memory buffers and two mbarriers and walks the tiles warp-stride: */
+/* arrays a (nb words/record), b and c (nm words/record) of one tile land in buffer `buf`;     */
+/* lane 0 issues, all lanes wait on the mbarrier.                                               */
+/* ------------------------------------------------------------------------------------------ */
 struct WarpTiles {
-    u64 *a0, *a1, *b0, *b1;
+    u64 *base;  /* warp's region: [buf][a | b | c] */
     u64 *bar;   /* [2] */
-    __device__ __forceinline__ const u64 *a(int buf) const { return buf ? a1 : a0; }
-    __device__ __forceinline__ const u64 *b(int buf) const { return buf ? b1 : b0; }
+    u32 words;  /* per buffer */
+    u32 off_b, off_c;
+    __device__ __forceinline__ const u64 *a(int buf) const { return base + buf * words; }
+    __device__ __forceinline__ const u64 *b(int buf) const { return base + buf * words + off_b; }
+    __device__ __forceinline__ const u64 *c(int buf) const { return base + buf * words + off_c; }
 };
-__host__ __device__ inline size_t warp_tile_bytes(u32 tile_rec, int na, int nbw) {
-    return (size_t)2 * tile_rec * (size_t)(na + nbw) * 8 + 16;
+__host__ __device__ inline size_t warp_tile_bytes(u32 tile_rec, int nb, int nm, int n_masks) {
+    return (size_t)2 * tile_rec * (size_t)(nb + n_masks * nm) * 8 + 16;
 }
-__device__ __forceinline__ void tile_issue(const WarpTiles &t, int buf, const u64 *ga, const u64 *gb,
-                                           u64 tile, u32 tile_rec, int na, int nbw) {
-    u32 bytes_a = tile_rec * (u32)na * 8u, bytes_b = tile_rec * (u32)nbw * 8u;
+__device__ __forceinline__ void tile_issue(const WarpTiles &t, int buf, const Geom &g, u64 tile,
+                                           const u64 *ga, const u64 *gb, const u64 *gc) {
+    const u32 bytes_a = g.tile_rec * (u32)g.nb * 8u, bytes_m = g.tile_rec * (u32)g.nm * 8u;
     u64 *bar = t.bar + buf;
-    mbar_expect_tx(bar, bytes_a + bytes_b);
-    tma_load_1d(buf ? t.a1 : t.a0, ga + tile * tile_rec * (u64)na, bytes_a, bar);
-    tma_load_1d(buf ? t.b1 : t.b0, gb + tile * tile_rec * (u64)nbw, bytes_b, bar);
+    u64 *dst = t.base + buf * t.words;
+    mbar_expect_tx(bar, bytes_a + bytes_m + (gc ? bytes_m : 0u));
+    tma_load_1d(dst, ga + tile * g.tile_rec * (u64)g.nb, bytes_a, bar);
+    tma_load_1d(dst + t.off_b, gb + tile * g.tile_rec * (u64)g.nm, bytes_m, bar);
+    if (gc) tma_load_1d(dst + t.off_c, gc + tile * g.tile_rec * (u64)g.nm, bytes_m, bar);
 }
-__device__ __forceinline__ WarpTiles tile_setup(unsigned char *smem, u32 tile_rec, int na, int nbw) {
+__device__ __forceinline__ WarpTiles tile_setup(unsigned char *smem, const Geom &g, int n_masks) {
     WarpTiles t;
     const u32 wid = threadIdx.x >> 5;
-    u64 *p = reinterpret_cast<u64 *>(smem + wid * warp_tile_bytes(tile_rec, na, nbw));
-    t.a0 = p; p += (size_t)tile_rec * na;
-    t.a1 = p; p += (size_t)tile_rec * na;
-    t.b0 = p; p += (size_t)tile_rec * nbw;
-    t.b1 = p; p += (size_t)tile_rec * nbw;
-    t.bar = p;
+    t.words = g.tile_rec * (u32)(g.nb + n_masks * g.nm);
+    t.off_b = g.tile_rec * (u32)g.nb;
+    t.off_c = t.off_b + g.tile_rec * (u32)g.nm;
+    t.base = reinterpret_cast<u64 *>(smem + wid * warp_tile_bytes(g.tile_rec, g.nb, g.nm, n_masks));
+    t.bar = t.base + 2 * t.words;
     if ((threadIdx.x & 31) == 0) {
         mbar_init(&t.bar[0], 1);
         mbar_init(&t.bar[1], 1);
@@ -233,53 +309,166 @@ __device__ __forceinline__ WarpTiles tile_setup(unsigned char *smem, u32 tile_re
     __syncthreads();
     return t;
 }
-static inline size_t tile_smem_bytes(u32 tile_rec, int na, int nbw) {
-    return (size_t)WARPS * warp_tile_bytes(tile_rec, na, nbw);
+static inline size_t tile_smem_bytes(const Geom &g, int n_masks) {
+    return (size_t)WARPS * warp_tile_bytes(g.tile_rec, g.nb, g.nm, n_masks);
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K0: cardinality estimate (HyperLogLog over gated k-mers) + exact gated-window count.        */
-/* Sizes the pass-1 table so that it is neither rehashed (the reference's dense_hash_map grows */
-/* by doubling, internal/densehashtable.h:631-653) nor grossly over-allocated.                  */
+/* K0 k_count: one streaming pass over the packed reads that sizes everything else:            */
+/*   - exact number of gated / N-free-but-ungated windows per top-8-bit hash bucket (tuple      */
+/*     region sizes for any P <= 256),                                                           */
+/*   - HyperLogLog over the gated k-mers -> pass-1 table capacity, so that the table is neither */
+/*     rehashed (the reference's dense_hash_map doubles, internal/densehashtable.h:631-653) nor */
+/*     grossly over-allocated.                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(THREADS)
-k_estimate(const u64 *__restrict__ bases, const u64 *__restrict__ good, Geom g, u32 *hll, Counters *ctr) {
+k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *__restrict__ valid,
+        Geom g, u32 *hll, u64 *hist /* [2][256] */) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int M = 1 << HLL_BITS;
+    constexpr int M = 1 << HLL_BITS, HB = 1 << HIST_BITS;
     u32 *reg = reinterpret_cast<u32 *>(smem);
-    for (int i = threadIdx.x; i < M; i += THREADS) reg[i] = 0;
-    WarpTiles t = tile_setup(smem + M * sizeof(u32), g.tile_rec, g.nb, g.nm);
+    u32 *sh = reg + M;  /* [2][HB] */
+    for (int i = threadIdx.x; i < M + 2 * HB; i += THREADS) reg[i] = 0;
+    WarpTiles t = tile_setup(smem + (M + 2 * HB) * sizeof(u32), g, 2);
     const u32 lane = threadIdx.x & 31;
     const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
-    u32 n_gated = 0;
-    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, bases, good, gw, g.tile_rec, g.nb, g.nm);
-    u32 it = 0;
-    for (u64 tile = gw; tile < g.n_tiles; tile += gstride, it++) {
-        int buf = it & 1;
-        if (lane == 0 && tile + gstride < g.n_tiles)
-            tile_issue(t, buf ^ 1, bases, good, tile + gstride, g.tile_rec, g.nb, g.nm);
-        mbar_wait(&t.bar[buf], (it >> 1) & 1);
-        const u64 *sb = t.a(buf), *sg = t.b(buf);
-        for (u32 win = lane; win < g.tile_win; win += 32) {
-            u32 rec = div_w(win, g);
-            int i = (int)(win - rec * (u32)g.w);
-            u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
-            if ((m & g.kones) != g.kones) continue;
-            n_gated++;
-            u64 lo, hi;
-            extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-            u64 h = hash_key(lo, hi);
-            u32 idx = (u32)(h >> (64 - HLL_BITS));
-            u32 rho = (u32)__clzll((long long)((h << HLL_BITS) | (1ull << (HLL_BITS - 1)))) + 1;
-            if (reg[idx] < rho) atomicMax(&reg[idx], rho);
+    const u64 n_iter = (g.n_tiles + gstride - 1) / gstride;
+    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, g, gw, bases, good, valid);
+    u64 tile = gw;
+    for (u64 it = 0; it < n_iter; it++, tile += gstride) {
+        const int buf = (int)(it & 1);
+        if (tile < g.n_tiles) {
+            if (lane == 0 && tile + gstride < g.n_tiles) tile_issue(t, buf ^ 1, g, tile + gstride, bases, good, valid);
+            mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
+            const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf);
+            for (u32 win = lane; win < g.tile_win; win += 32) {
+                u32 rec = div_w(win, g);
+                int i = (int)(win - rec * (u32)g.w);
+                u64 mv = extract_mask(sv + (size_t)rec * g.nm, g.nm, i);
+                if ((mv & g.kones) != g.kones) continue;
+                u64 mg = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
+                const bool gated = (mg & g.kones) == g.kones;
+                u64 lo, hi;
+                extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+                u64 h = hash_key(lo, hi);
+                atomicAdd(&sh[(gated ? 0 : HB) + (u32)(h >> (64 - HIST_BITS))], 1u);
+                if (gated) {
+                    /* HLL uses the low hash bits so that it is independent of the partition bits */
+                    u32 idx = (u32)h & (M - 1);
+                    u32 rho = (u32)__clzll((long long)((h << 8) | (1ull << 20))) + 1;
+                    if (reg[idx] < rho) atomicMax(&reg[idx], rho);
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        /* u32 block counters: flush long before they can overflow (uniform trip count) */
+        if ((it & 1023) == 1023) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 2 * HB; i += THREADS) { u32 v = sh[i]; if (v) { atomicAdd(&hist[i], (u64)v); sh[i] = 0; } }
+            __syncthreads();
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < M; i += THREADS)
         if (reg[i]) atomicMax(&hll[i], reg[i]);
-    for (int o = 16; o; o >>= 1) n_gated += __shfl_xor_sync(0xFFFFFFFFu, n_gated, o);
-    if (lane == 0 && n_gated) atomicAdd(&ctr->n_gated, (u64)n_gated);
+    for (int i = threadIdx.x; i < 2 * HB; i += THREADS)
+        if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1 k_scatter: every N-free window becomes a tuple in its hash partition's region:           */
+/* regions [gated p=0..P-1][ungated p=0..P-1]; cursor[] starts at the region offsets (exclusive */
+/* scan of k_count's histogram).  A block processes WARPS warp tiles per iteration: windows are */
+/* counted per bucket in shared memory (the returned value is the tuple's rank inside the       */
+/* block's run), one global atomic per non-empty bucket reserves the run, then tuples are       */
+/* written with streaming stores.                                                                */
+/* ------------------------------------------------------------------------------------------ */
+__host__ __device__ inline size_t scatter_head_bytes(const Geom &g) {
+    size_t b = 512 * sizeof(u32) + 512 * sizeof(u64) + (size_t)((g.tile_win + 31) / 32) * THREADS * sizeof(u32);
+    return (b + 127) & ~(size_t)127;
+}
+struct ScatterArgs {
+    const u64 *bases, *good, *valid;
+    u64 *tuples;
+    u64 *cursor;      /* [2 << pbits] */
+    const u64 *limit; /* [2 << pbits] end of each region (overrun check) */
+    Counters *ctr;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_scatter(ScatterArgs a, Geom g, Part pt) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int NBK = 2 << pt.pbits;
+    const u32 per_lane = (g.tile_win + 31) / 32;
+    u32 *cnt = reinterpret_cast<u32 *>(smem);          /* [512] */
+    u64 *gbase = reinterpret_cast<u64 *>(cnt + 512);   /* [512] */
+    u32 *meta = reinterpret_cast<u32 *>(gbase + 512);  /* [per_lane][THREADS] */
+    WarpTiles t = tile_setup(smem + scatter_head_bytes(g), g, 2);
+    const u32 lane = threadIdx.x & 31;
+    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
+    const u64 n_iter = (g.n_tiles + gstride - 1) / gstride;
+    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, g, gw, a.bases, a.good, a.valid);
+    for (int i = threadIdx.x; i < NBK; i += THREADS) cnt[i] = 0;
+    __syncthreads();
+    u64 tile = gw;
+    for (u64 it = 0; it < n_iter; it++, tile += gstride) {
+        const int buf = (int)(it & 1);
+        const bool have = tile < g.n_tiles;
+        if (have) {
+            if (lane == 0 && tile + gstride < g.n_tiles) tile_issue(t, buf ^ 1, g, tile + gstride, a.bases, a.good, a.valid);
+            mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
+        }
+        const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf);
+        /* phase A: bucket and rank of every window this lane owns (packed bucket<<20 | rank) */
+        for (u32 j = 0; j < per_lane; j++) {
+            u32 m = NIL32;
+            const u32 win = j * 32 + lane;
+            if (have && win < g.tile_win) {
+                u32 rec = div_w(win, g);
+                int i = (int)(win - rec * (u32)g.w);
+                u64 mv = extract_mask(sv + (size_t)rec * g.nm, g.nm, i);
+                if ((mv & g.kones) == g.kones) {
+                    u64 mg = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
+                    const bool gated = (mg & g.kones) == g.kones;
+                    u64 lo, hi;
+                    extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+                    u64 h = hash_key(lo, hi);
+                    u32 bk = (pt.pbits ? (u32)(h >> (64 - pt.pbits)) : 0u) + (gated ? 0u : (1u << pt.pbits));
+                    m = (bk << 20) | atomicAdd(&cnt[bk], 1u);
+                }
+            }
+            meta[j * THREADS + threadIdx.x] = m;
+        }
+        __syncthreads();
+        /* phase B: reserve one run per non-empty bucket */
+        for (int i = threadIdx.x; i < NBK; i += THREADS) {
+            u32 n = cnt[i];
+            if (n) {
+                u64 b = atomicAdd(&a.cursor[i], (u64)n);
+                if (b + n > a.limit[i]) { atomicExch(&a.ctr->overflow, 4u); b = INF64; }
+                gbase[i] = b;
+                cnt[i] = 0;
+            }
+        }
+        __syncthreads();
+        /* phase C: write the tuples */
+        for (u32 j = 0; j < per_lane; j++) {
+            const u32 m = meta[j * THREADS + threadIdx.x];
+            if (m == NIL32) continue;
+            const u32 win = j * 32 + lane;
+            u32 rec = div_w(win, g);
+            int i = (int)(win - rec * (u32)g.w);
+            const u64 *bb = sb + (size_t)rec * g.nb;
+            u64 lo, hi;
+            extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
+            u32 fl = 0;
+            if (i + 1 < g.w && bit_at(sv + (size_t)rec * g.nm, i + g.k)) fl = 1u | (base_at(bb, i + g.k) << 1);
+            const u64 stamp = (tile * g.tile_rec + rec) * (u64)g.w + (u64)i;
+            const u64 b = gbase[m >> 20];
+            if (b != INF64) tuple_store(a.tuples, b + (m & 0xFFFFFu), pt, lo, hi, fl, stamp);
+        }
+        __syncthreads();
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -311,17 +500,19 @@ __device__ __noinline__ bool same_read(const u64 *__restrict__ bases, const u64 
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K1: pass 1 = build_pre_graph / add_to_table (:322-409) as commutative reductions.           */
+/* K2 k_pass1: pass 1 = build_pre_graph / add_to_table (:322-409) as commutative reductions    */
+/* over the GATED tuples, walked in partition order so that the table slice being updated is    */
+/* L2-resident:                                                                                  */
 /*   count        -> pre_node.frequency (:334, :345-347)                                        */
 /*   CNT_MULTI    -> hasMultipleUniqueReads (:349-352): some occurrence's record differs from   */
 /*                   the first ARRIVING one's; equivalent to ">= 2 distinct record sequences"   */
 /*   occurrence log: the first NB arrivals of every k-mer append their stamp, so that k-mers    */
 /*                   whose final count is <= NB have ALL their occurrences listed; only those   */
 /*                   can fail the quality-sum test (every gated quality is >= 20), see k_prune. */
-/* One 32-B sector read + one L2 atomic per gated window in the steady state.                   */
 /* ------------------------------------------------------------------------------------------ */
 struct Pass1Args {
-    const u64 *bases, *good, *valid;
+    const u64 *tuples;
+    const u64 *bases, *valid;
     const u8 *strand;
     Slot1 *table;
     u64 cap;
@@ -348,109 +539,90 @@ __device__ __noinline__ bool pass1_probe(const Pass1Args &a, u64 lo, u64 hi, u64
     return false;
 }
 
-__global__ void __launch_bounds__(THREADS, 4)
-k_pass1(Pass1Args a, Geom g) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    WarpTiles t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
+template <bool WIDE>
+__global__ void __launch_bounds__(THREADS, 3)
+k_pass1(Pass1Args a, Geom g, Part pt) {
     const u32 lane = threadIdx.x & 31;
-    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
     u32 chunk_base = 0, chunk_used = LOG_CHUNK; /* warp-uniform */
-    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, a.bases, a.good, gw, g.tile_rec, g.nb, g.nm);
-    const u32 n_batch = (g.tile_win + 32 * BATCH - 1) / (32 * BATCH);
-    u32 it = 0;
-    for (u64 tile = gw; tile < g.n_tiles; tile += gstride, it++) {
-        int buf = it & 1;
-        if (lane == 0 && tile + gstride < g.n_tiles)
-            tile_issue(t, buf ^ 1, a.bases, a.good, tile + gstride, g.tile_rec, g.nb, g.nm);
-        mbar_wait(&t.bar[buf], (it >> 1) & 1);
-        const u64 *sb = t.a(buf), *sg = t.b(buf);
-        const u64 rec0 = tile * g.tile_rec;
-        for (u32 b = 0; b < n_batch; b++) {
-            /* phase A: BATCH independent home-slot reads per lane, issued back to back */
-            u64 idx[BATCH], k0[BATCH], k1[BATCH], m2[BATCH];
+    const u64 span = (u64)THREADS * BATCH;
+    const u64 n_blk = (pt.n_gated + span - 1) / span;
+    for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const u64 t0 = blk * span + threadIdx.x;
+        /* phase A: BATCH tuples per thread (coalesced), their home-slot reads issued back to back */
+        u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], k0[BATCH], k1[BATCH], m2[BATCH];
+        u32 idx[BATCH];   /* table capacities stay below 2^32 slots (checked on the host) */
 #pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                const u32 win = (b * BATCH + u) * 32 + lane;
-                idx[u] = INF64;
-                if (win < g.tile_win) {
-                    u32 rec = div_w(win, g);
-                    int i = (int)(win - rec * (u32)g.w);
-                    u64 m = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
-                    if ((m & g.kones) == g.kones) {
-                        u64 lo, hi;
-                        extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-                        idx[u] = __umul64hi(hash_key(lo, hi), a.cap);
-                        const Slot1 *s = a.table + idx[u];
-                        ld_cg_v2(s, k0[u], k1[u]);
-                        m2[u] = ld_cg_u64(reinterpret_cast<const u64 *>(s) + 2);
+        for (int u = 0; u < BATCH; u++) {
+            const u64 t = t0 + (u64)u * THREADS;
+            idx[u] = NIL32;
+            if (t < pt.n_gated) {
+                tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
+                u64 hi = pt.hb ? (w1[u] & ((1ull << pt.hb) - 1)) : 0ull;
+                idx[u] = (u32)home_slot(hash_key(lo[u], hi), pt.pbits, pt.slice1);
+                const Slot1 *s = a.table + idx[u];
+                ld_cg_v2(s, k0[u], k1[u]);
+                m2[u] = ld_cg_u64(reinterpret_cast<const u64 *>(s) + 2);
+            }
+        }
+        /* phase B: consume */
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            bool need_log = false;
+            u64 stamp = 0;
+            Slot1 *slot = nullptr;
+            if (idx[u] != NIL32) {
+                u64 hi; u32 fl;
+                tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, stamp);
+                const u64 r = stamp / (u64)g.w;
+                slot = a.table + idx[u];
+                u64 q2 = m2[u];
+                bool found = (k0[u] == lo[u] && k1[u] == hi);
+                if (!found) found = pass1_probe(a, lo[u], hi, idx[u], slot, q2);
+                if (!found) {
+                    atomicExch(&a.ctr->overflow, 1u);
+                } else {
+                    const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
+                    u32 first_rec = (u32)(q2 >> 32);
+                    u32 rank = NIL32;
+                    if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u) & CNT_MASK; /* arrival rank decides logging */
+                    else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                 /* result unused: RED, no stall */
+                    if (!(cw & CNT_MULTI)) {
+                        if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
+                        if (first_rec != NIL32 && first_rec != (u32)r &&
+                            !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
+                            atomicOr(&slot->count, CNT_MULTI);
                     }
+                    need_log = rank < a.nb_ranks;
                 }
             }
-            /* phase B: consume */
-#pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                const u32 win = (b * BATCH + u) * 32 + lane;
-                bool need_log = false;
-                u64 stamp = 0;
-                Slot1 *slot = nullptr;
-                if (idx[u] != INF64) {
-                    u32 rec = div_w(win, g);
-                    int i = (int)(win - rec * (u32)g.w);
-                    u64 lo, hi;
-                    extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-                    const u64 r = rec0 + rec;
-                    stamp = r * (u64)g.w + (u64)i;
-                    slot = a.table + idx[u];
-                    u64 q2 = m2[u];
-                    bool found = (k0[u] == lo && k1[u] == hi);
-                    if (!found) found = pass1_probe(a, lo, hi, idx[u], slot, q2);
-                    if (!found) {
-                        atomicExch(&a.ctr->overflow, 1u);
-                    } else {
-                        const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
-                        u32 first_rec = (u32)(q2 >> 32);
-                        u32 rank = NIL32;
-                        if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u) & CNT_MASK; /* arrival rank decides logging */
-                        else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                 /* result unused: RED, no stall */
-                        if (!(cw & CNT_MULTI)) {
-                            if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
-                            if (first_rec != NIL32 && first_rec != (u32)r &&
-                                !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
-                                atomicOr(&slot->count, CNT_MULTI);
-                        }
-                        need_log = rank < a.nb_ranks;
-                    }
+            /* warp-converged log allocation out of per-warp chunks */
+            u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
+            if (ballot) {
+                u32 n = __popc(ballot);
+                if (chunk_used + n > LOG_CHUNK) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
+                    chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    chunk_used = 0;
                 }
-                /* warp-converged log allocation out of per-warp chunks */
-                u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
-                if (ballot) {
-                    u32 n = __popc(ballot);
-                    if (chunk_used + n > LOG_CHUNK) {
-                        u32 base = 0;
-                        if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
-                        chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                        chunk_used = 0;
-                    }
-                    u32 e = chunk_base + chunk_used + __popc(ballot & ((1u << lane) - 1));
-                    chunk_used += n;
-                    if (need_log) {
-                        if (e < a.log_cap) {
-                            u32 prev = atomicExch(&slot->head, e);
-                            LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
-                            a.log[e] = le;
-                        } else {
-                            atomicExch(&a.ctr->overflow, 2u);
-                        }
+                u32 e = chunk_base + chunk_used + __popc(ballot & ((1u << lane) - 1));
+                chunk_used += n;
+                if (need_log) {
+                    if (e < a.log_cap) {
+                        u32 prev = atomicExch(&slot->head, e);
+                        LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
+                        a.log[e] = le;
+                    } else {
+                        atomicExch(&a.ctr->overflow, 2u);
                     }
                 }
             }
         }
-        __syncwarp();
     }
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K2: prune = prune_pre_graph (:467-484) + is_base_quality_good (:454-465).                    */
+/* K3 k_prune = prune_pre_graph (:467-484) + is_base_quality_good (:454-465).                   */
 /* keep K iff frequency >= mf && hasMultipleUniqueReads && for all j qual_sums[j] >= mq.        */
 /* qual_sums[j] = S_j < 214 ? S_j : 255 with S_j = q_r0[j] + sum over the other gated           */
 /* occurrences of q_r[i+j] ((r0,i0) = first gated occurrence; seeding from the RECORD's first   */
@@ -539,10 +711,9 @@ k_prune(PruneArgs a, Geom g) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* survivor table (pass-2 membership + per-node reductions)                                     */
+/* survivor table (pass-2 membership + per-node reductions), partitioned like table 1           */
 /* ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ u64 t2_insert(Slot2 *t, u64 cap, u64 lo, u64 hi) {
-    u64 idx = __umul64hi(hash_key(lo, hi), cap);
+__device__ __forceinline__ u64 t2_insert(Slot2 *t, u64 cap, u64 idx, u64 lo, u64 hi) {
     for (u32 probe = 0; probe < MAX_PROBE; probe++) {
         u64 o0, o1;
         cas128(&t[idx], EMPTY64, EMPTY64, lo, hi, o0, o1);
@@ -562,118 +733,98 @@ __device__ __forceinline__ u64 t2_probe_from(const Slot2 *t, u64 cap, u64 idx, u
     }
     return INF64;
 }
-__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, u64 lo, u64 hi, u64 &q2, u64 &q3) {
-    return t2_probe_from(t, cap, __umul64hi(hash_key(lo, hi), cap), lo, hi, q2, q3);
+__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, const Part &pt, u64 lo, u64 hi, u64 &q2, u64 &q3) {
+    return t2_probe_from(t, cap, home_slot(hash_key(lo, hi), pt.pbits, pt.slice2), lo, hi, q2, q3);
 }
 
 __global__ void __launch_bounds__(THREADS)
-k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Counters *ctr) {
+k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters *ctr) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
     for (; i < cap1; i += stride) {
         u64 q0, q1, q2, q3;
         ld_sector(&t1[i], q0, q1, q2, q3);
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
         if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
-        if (t2_insert(t2, cap2, q0, q1) == INF64) atomicExch(&ctr->overflow, 3u);
+        if (t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.slice2), q0, q1) == INF64)
+            atomicExch(&ctr->overflow, 3u);
     }
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K3: pass 2 = build_graph2 / add_to_graph (:267-320, :412-452) as commutative reductions      */
-/* over every N-free window whose k-mer survived (no quality gate, :272-274):                   */
+/* K4 k_pass2: pass 2 = build_graph2 / add_to_graph (:267-320, :412-452) as commutative         */
+/* reductions over every N-free window whose k-mer survived (no quality gate, :272-274):        */
 /*   count        -> node->frequency (:199, :261-265, :308)                                     */
 /*   first_any    -> node->kmer and creation order / node id (:197-201)                         */
 /*   out_first[c] -> first time the edge K -> K[1:]+c can have been linked (:311-313); ordering */
 /*                   these reproduces the head-insertion order of toNodes (:223-229) and, read  */
 /*                   from the predecessor's side, of fromNodes (:231-236).                      */
-/* atomics are skipped when the loaded value already dominates, so hot k-mers cost reads only.  */
+/* All tuples (gated region, then ungated region) in partition order; atomics are skipped when  */
+/* the loaded value already dominates, so hot k-mers cost reads only.                           */
 /* ------------------------------------------------------------------------------------------ */
 struct Pass2Args {
-    const u64 *bases, *valid;
+    const u64 *tuples;
     Slot2 *table;
     u64 cap;
     Counters *ctr;
 };
 
+template <bool WIDE>
 __global__ void __launch_bounds__(THREADS, 3)
-k_pass2(Pass2Args a, Geom g) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    WarpTiles t = tile_setup(smem, g.tile_rec, g.nb, g.nm);
+k_pass2(Pass2Args a, Geom g, Part pt) {
     const u32 lane = threadIdx.x & 31;
-    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
-    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, a.bases, a.valid, gw, g.tile_rec, g.nb, g.nm);
-    const u32 n_batch = (g.tile_win + 32 * BATCH - 1) / (32 * BATCH);
+    const u64 span = (u64)THREADS * BATCH;
+    const u64 n_blk = (pt.n_valid + span - 1) / span;
     u32 n_hits = 0;
-    u32 it = 0;
-    for (u64 tile = gw; tile < g.n_tiles; tile += gstride, it++) {
-        int buf = it & 1;
-        if (lane == 0 && tile + gstride < g.n_tiles)
-            tile_issue(t, buf ^ 1, a.bases, a.valid, tile + gstride, g.tile_rec, g.nb, g.nm);
-        mbar_wait(&t.bar[buf], (it >> 1) & 1);
-        const u64 *sb = t.a(buf), *sv = t.b(buf);
-        const u64 rec0 = tile * g.tile_rec;
-        for (u32 b = 0; b < n_batch; b++) {
-            /* phase A: per lane BATCH independent probes: the hot sector of the home slot and,
-             * speculatively, the out_first word this window would update */
-            u64 idx[BATCH], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
+    for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const u64 t0 = blk * span + threadIdx.x;
+        /* phase A: BATCH independent probes per thread: the hot sector of the home slot and,
+         * speculatively, the out_first word this window would update */
+        u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
+        u32 idx[BATCH];
 #pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                const u32 win = (b * BATCH + u) * 32 + lane;
-                idx[u] = INF64;
-                of[u] = 0;
-                if (win < g.tile_win) {
-                    u32 rec = div_w(win, g);
-                    int i = (int)(win - rec * (u32)g.w);
-                    const u64 *vb = sv + (size_t)rec * g.nm;
-                    u64 m = extract_mask(vb, g.nm, i);
-                    if ((m & g.kones) == g.kones) {
-                        const u64 *bb = sb + (size_t)rec * g.nb;
-                        u64 lo, hi;
-                        extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-                        idx[u] = __umul64hi(hash_key(lo, hi), a.cap);
-                        const Slot2 *s = a.table + idx[u];
-                        ld_sector(s, q0[u], q1[u], q2[u], q3[u]);
-                        if (i + 1 < g.w && bit_at(vb, i + g.k)) of[u] = ld_cg_u64(&s->out_first[base_at(bb, i + g.k)]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                if (idx[u] == INF64) continue;
-                const u32 win = (b * BATCH + u) * 32 + lane;
-                u32 rec = div_w(win, g);
-                int i = (int)(win - rec * (u32)g.w);
-                const u64 *vb = sv + (size_t)rec * g.nm;
-                const u64 *bb = sb + (size_t)rec * g.nb;
-                u64 lo, hi;
-                extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-                const bool has_next = i + 1 < g.w && bit_at(vb, i + g.k);
-                const u32 c = has_next ? base_at(bb, i + g.k) : 0;
-                u64 id = idx[u], c2 = q2[u], c3 = q3[u], o = of[u];
-                if (!(q0[u] == lo && q1[u] == hi)) {
-                    if (q0[u] == EMPTY64 && q1[u] == EMPTY64) continue;
-                    /* collision at the home slot: probe on (rare at load <= 0.5) */
-                    if (++id == a.cap) id = 0;
-                    id = t2_probe_from(a.table, a.cap, id, lo, hi, c2, c3);
-                    if (id == INF64) continue;
-                    if (has_next) o = ld_cg_u64(&a.table[id].out_first[c]);
-                }
-                n_hits++;
-                Slot2 *slot = a.table + id;
-                const u64 stamp = (rec0 + rec) * (u64)g.w + (u64)i;
-                if ((u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
-                if (stamp < c3) atomicMin(&slot->first_any, stamp);
-                if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
+        for (int u = 0; u < BATCH; u++) {
+            const u64 t = t0 + (u64)u * THREADS;
+            idx[u] = NIL32;
+            of[u] = 0;
+            if (t < pt.n_valid) {
+                tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
+                u64 hi = pt.hb ? (w1[u] & ((1ull << pt.hb) - 1)) : 0ull;
+                u32 fl = (u32)(w1[u] >> pt.hb) & 15u;
+                idx[u] = (u32)home_slot(hash_key(lo[u], hi), pt.pbits, pt.slice2);
+                const Slot2 *s = a.table + idx[u];
+                ld_sector(s, q0[u], q1[u], q2[u], q3[u]);
+                if (fl & 1u) of[u] = ld_cg_u64(&s->out_first[fl >> 1]);
             }
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            if (idx[u] == NIL32) continue;
+            u64 hi, stamp; u32 fl;
+            tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, stamp);
+            const bool has_next = fl & 1u;
+            const u32 c = fl >> 1;
+            u64 id = idx[u], c2 = q2[u], c3 = q3[u], o = of[u];
+            if (!(q0[u] == lo[u] && q1[u] == hi)) {
+                if (q0[u] == EMPTY64 && q1[u] == EMPTY64) continue;
+                /* collision at the home slot: probe on (rare at load <= 0.5) */
+                if (++id == a.cap) id = 0;
+                id = t2_probe_from(a.table, a.cap, id, lo[u], hi, c2, c3);
+                if (id == INF64) continue;
+                if (has_next) o = ld_cg_u64(&a.table[id].out_first[c]);
+            }
+            n_hits++;
+            Slot2 *slot = a.table + id;
+            if ((u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
+            if (stamp < c3) atomicMin(&slot->first_any, stamp);
+            if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
+        }
     }
     for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
     if (lane == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K4: export.  collect (first_any, slot) -> radix sort by first_any (host calls CUB) ->        */
+/* K5 export.  collect (first_any, slot) -> radix sort by first_any (host calls CUB) ->        */
 /* assign ranks -> emit nodes in creation order with ordered edge lists.                        */
 /* ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(THREADS)
@@ -729,7 +880,7 @@ __device__ __forceinline__ void sort_desc4(u64 (&t)[4], u32 (&v)[4], int n) {
 }
 
 __global__ void __launch_bounds__(THREADS)
-k_export(ExportArgs a, Geom g) {
+k_export(ExportArgs a, Geom g, Part pt) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const Slot2 *s = a.table + a.vals[i];
@@ -746,7 +897,7 @@ k_export(ExportArgs a, Geom g) {
         if (tf == INF64) continue;
         u64 slo, shi, q2, q3;
         kmer_succ(lo, hi, c, g.k, slo, shi);
-        u64 idx = t2_find(a.table, a.cap, slo, shi, q2, q3);
+        u64 idx = t2_find(a.table, a.cap, pt, slo, shi, q2, q3);
         if (idx == INF64) continue;
         tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
     }
@@ -760,7 +911,7 @@ k_export(ExportArgs a, Geom g) {
     for (u32 c = 0; c < 4; c++) {
         u64 plo, phi, q2, q3;
         kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
-        u64 idx = t2_find(a.table, a.cap, plo, phi, q2, q3);
+        u64 idx = t2_find(a.table, a.cap, pt, plo, phi, q2, q3);
         if (idx == INF64) continue;
         u64 tf = a.table[idx].out_first[last];
         if (tf == INF64) continue;

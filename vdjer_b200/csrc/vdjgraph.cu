@@ -100,6 +100,7 @@ struct StageWorker {
 
 constexpr uint32_t STAGE_CHUNK = 32768; /* records per staging chunk */
 constexpr uint64_t REF_MAX_NODES = 900000000ull; /* MAX_NODES, assembler2_vdj.c:73 */
+constexpr uint64_t SLICE_BYTES = 24ull << 20;   /* table-1 bytes one hash partition addresses: L2-resident */
 
 } // namespace
 
@@ -112,15 +113,16 @@ struct vdjgraph_ctx {
     bool any_strand1 = false;
     bool staged = false, ran = false;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[12] = {};
     std::vector<StageWorker> workers;
 
     DevBuf d_bases, d_good, d_valid, d_qual, d_strand;
-    DevBuf d_t1, d_log, d_t2, d_hll, d_ctr;
+    DevBuf d_t1, d_log, d_t2, d_hll, d_ctr, d_hist, d_cursor, d_tuples;
     DevBuf d_keys[2], d_vals[2], d_cub;
     DevBuf d_first_pos, d_freq, d_odeg, d_ideg, d_osucc, d_ipred, d_klo, d_khi;
     DevBuf d_pre_klo, d_pre_khi, d_pre_freq, d_pre_n;
-    PinBuf h_ctr, h_hll;
+    PinBuf h_ctr, h_hll, h_hist, h_cursor;
+    Part part;
     PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
 
@@ -352,7 +354,7 @@ extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out
     memset(&c->res, 0, sizeof(c->res));
     memset(&c->ctr, 0, sizeof(c->ctr));
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 10 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 12 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) { delete c; return fail(VDJGRAPH_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return 0;
@@ -369,14 +371,14 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.stream) cudaStreamDestroy(w.stream);
     }
     DevBuf *db[] = { &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
-                     &c->d_hll, &c->d_ctr, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
+                     &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
     for (DevBuf *b : db) b->release();
-    PinBuf *pb[] = { &c->h_ctr, &c->h_hll, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+    PinBuf *pb[] = { &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
-    for (int i = 0; i < 10; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 12; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -467,8 +469,10 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     memset(&c->ctr, 0, sizeof(c->ctr));
     vdjgraph_result &res = c->res;
     res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = 0;
-    res.ms_device = res.ms_estimate = res.ms_init1 = res.ms_pass1 = res.ms_prune = res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
+    res.ms_device = res.ms_estimate = res.ms_scatter = res.ms_init1 = res.ms_pass1 = res.ms_prune = 0;
+    res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
     res.table1_slots = res.table2_slots = 0;
+    res.partitions = 0; res.tuple_bytes = 0;
     res.kernel_launches = 0;
     if (g.R == 0) { c->ran = true; return 0; }
 
@@ -478,45 +482,114 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     int T = std::min(mq, QSUM_SAT);
     int NB = T > 0 ? (T + GATE_Q - 1) / GATE_Q : 0;
 
+    constexpr int HB = 1 << HIST_BITS;
     if ((rc = c->d_ctr.ensure(sizeof(Counters)))) return rc;
     if ((rc = c->d_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
+    if ((rc = c->d_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
+    if ((rc = c->d_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
     if ((rc = c->h_ctr.ensure(sizeof(Counters)))) return rc;
     if ((rc = c->h_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
+    if ((rc = c->h_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
+    if ((rc = c->h_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
     Counters *d_ctr = c->d_ctr.as<Counters>();
     Counters *h_ctr = c->h_ctr.as<Counters>();
 
-    const size_t smem_tile = tile_smem_bytes(g.tile_rec, g.nb, g.nm);
-    const size_t smem_est = smem_tile + (sizeof(uint32_t) << HLL_BITS);
+    const size_t smem_count = tile_smem_bytes(g, 2) + ((sizeof(uint32_t) << HLL_BITS) + 2 * HB * sizeof(uint32_t));
+    const size_t smem_scatter = tile_smem_bytes(g, 2) + scatter_head_bytes(g);
     const uint64_t tile_blocks = (g.n_tiles + WARPS - 1) / WARPS;
-    const int grid_est = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_estimate, smem_est));
-    const int grid_p1 = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass1, smem_tile));
-    const int grid_p2 = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_pass2, smem_tile));
+    const int grid_count = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
+    const int grid_scatter = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
     const int grid_flat = c->sm_count * 8;
 
+    /* ---- K0: window counts per hash bucket + cardinality estimate ---- */
     CK(cudaEventRecord(c->ev[0], s));
     CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
     CK(cudaMemsetAsync(c->d_hll.p, 0, sizeof(uint32_t) << HLL_BITS, s));
-    k_estimate<<<grid_est, THREADS, smem_est, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), g, c->d_hll.as<u32>(), d_ctr);
+    CK(cudaMemsetAsync(c->d_hist.p, 0, 2 * HB * sizeof(uint64_t), s));
+    k_count<<<grid_count, THREADS, smem_count, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g,
+                                                     c->d_hll.as<u32>(), c->d_hist.as<u64>());
     launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev[1], s));
-    CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, 2 * HB * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, sizeof(uint32_t) << HLL_BITS, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const uint64_t n_gated = h_ctr->n_gated;
+    const uint64_t *hist = c->h_hist.as<uint64_t>();
+    uint64_t n_gated = 0, n_ungated = 0;
+    for (int i = 0; i < HB; i++) { n_gated += hist[i]; n_ungated += hist[HB + i]; }
+    const uint64_t n_valid = n_gated + n_ungated;
     double est = std::min<double>(hll_estimate(c->h_hll.as<uint32_t>()), (double)n_gated);
-    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity
-                                          : (uint64_t)(est * 1.06 / 0.5) + 1024;
+    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(est * 1.06 / 0.5) + 1024;
     cap1 = std::max<uint64_t>(cap1, 1024);
 
+    /* ---- partitioning: table-1 slices of at most SLICE_BYTES so that a slice is L2-resident ---- */
+    Part pt;
+    memset(&pt, 0, sizeof(pt));
+    {
+        int pbits = 0;
+        if (c->prm.partitions) {
+            while ((1u << pbits) < c->prm.partitions && pbits < HIST_BITS) pbits++;
+        } else {
+            while (pbits < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits) > SLICE_BYTES) pbits++;
+        }
+        pt.pbits = pbits;
+        pt.hb = std::max(0, 2 * g.k - 64);
+        const int sbits = bits_for(g.R * (uint64_t)g.w);
+        pt.wide = (pt.hb + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
+        pt.n_gated = n_gated;
+        pt.n_valid = n_valid;
+    }
+    const int P = 1 << pt.pbits;
+    const size_t tuple_bytes = pt.wide ? 24 : 16;
+    if ((rc = c->d_tuples.ensure(std::max<size_t>(16, n_valid * tuple_bytes)))) return rc;
+    {
+        /* region offsets: [gated p=0..P-1][ungated p=0..P-1] */
+        uint64_t *cur = c->h_cursor.as<uint64_t>(), *lim = cur + 2 * HB;
+        const int fold = HB / P;
+        uint64_t off = 0;
+        for (int cls = 0; cls < 2; cls++)
+            for (int p = 0; p < P; p++) {
+                uint64_t n = 0;
+                for (int j = 0; j < fold; j++) n += hist[cls * HB + p * fold + j];
+                cur[cls * P + p] = off;
+                off += n;
+                lim[cls * P + p] = off;
+            }
+        CK(cudaMemcpyAsync(c->d_cursor.p, cur, 4 * HB * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    }
+
+    /* ---- K1: scatter the windows into their partitions ---- */
+    CK(cudaEventRecord(c->ev[10], s));
+    {
+        ScatterArgs as;
+        as.bases = c->d_bases.as<u64>(); as.good = c->d_good.as<u64>(); as.valid = c->d_valid.as<u64>();
+        as.tuples = c->d_tuples.as<u64>();
+        as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + 2 * HB;
+        as.ctr = d_ctr;
+        k_scatter<<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
+        launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev[11], s));
+
+    const uint64_t span = (uint64_t)THREADS * BATCH;
+    const int grid_p1 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_gated + span - 1) / span,
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, 0)));
+    const int grid_p2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_valid + span - 1) / span,
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, 0)));
+
+    /* ---- K2 + K3: pass 1 and prune (retried with a larger table if it overflows) ---- */
     for (int attempt = 0;; attempt++) {
         if (attempt > 6) return fail(VDJGRAPH_ERR_INTERNAL, "pass-1 table kept overflowing (capacity %llu)", (unsigned long long)cap1);
+        pt.slice1 = (cap1 + P - 1) / P;
+        cap1 = pt.slice1 * (uint64_t)P;
         /* log: at most NB entries per distinct k-mer and never more than the gated windows,
          * plus one partially used chunk per warp */
-        uint64_t warps = (uint64_t)grid_p1 * (THREADS / 32);
+        uint64_t warps = (uint64_t)grid_p1 * WARPS;
         uint64_t log_cap = std::min<uint64_t>(n_gated, (uint64_t)NB * (uint64_t)(0.75 * (double)cap1)) + warps * LOG_CHUNK + LOG_CHUNK;
         if (NB == 0) log_cap = LOG_CHUNK;
         if (log_cap > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "occurrence log would need %llu entries", (unsigned long long)log_cap);
+        if (cap1 > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "pass-1 table would need %llu slots", (unsigned long long)cap1);
         if ((rc = c->d_t1.ensure(cap1 * sizeof(Slot1)))) return rc;
         if ((rc = c->d_log.ensure(log_cap * sizeof(LogEntry)))) return rc;
         c->cap1 = cap1; c->log_cap = (uint32_t)log_cap;
@@ -526,12 +599,14 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         k_init_table1<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1);
         CK(cudaEventRecord(c->ev[2], s));
         Pass1Args a1;
-        a1.bases = c->d_bases.as<u64>(); a1.good = c->d_good.as<u64>(); a1.valid = c->d_valid.as<u64>();
+        a1.tuples = c->d_tuples.as<u64>();
+        a1.bases = c->d_bases.as<u64>(); a1.valid = c->d_valid.as<u64>();
         a1.strand = c->any_strand1 ? c->d_strand.as<u8>() : nullptr;
         a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
         a1.log = c->d_log.as<LogEntry>(); a1.log_cap = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
         a1.ctr = d_ctr;
-        k_pass1<<<grid_p1, THREADS, smem_tile, s>>>(a1, g);
+        if (pt.wide) k_pass1<true><<<grid_p1, THREADS, 0, s>>>(a1, g, pt);
+        else k_pass1<false><<<grid_p1, THREADS, 0, s>>>(a1, g, pt);
         CK(cudaEventRecord(c->ev[3], s));
         PruneArgs ap;
         ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<LogEntry>();
@@ -542,6 +617,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        if (h_ctr->overflow == 4) return fail(VDJGRAPH_ERR_INTERNAL, "tuple region overrun in k_scatter");
         if (h_ctr->overflow) { cap1 *= 2; continue; }
         if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "occurrence log inconsistent (code %u)", h_ctr->internal);
         break;
@@ -551,11 +627,13 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     const uint64_t n_surv = h_ctr->n_surv;
     const uint64_t n_distinct = h_ctr->n_distinct;
 
-    /* survivor table + pass 2 */
-    uint64_t cap2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
+    /* ---- survivor table + pass 2 ---- */
+    pt.slice2 = (std::max<uint64_t>(1024, n_surv * 2 + 64) + P - 1) / P;
+    const uint64_t cap2 = pt.slice2 * (uint64_t)P;
     if (cap2 > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
     if ((rc = c->d_t2.ensure(cap2 * sizeof(Slot2)))) return rc;
     c->cap2 = cap2;
+    c->part = pt;
     const size_t na = std::max<uint64_t>(n_surv, 1);
     if ((rc = c->d_keys[0].ensure(na * 8)) || (rc = c->d_keys[1].ensure(na * 8)) ||
         (rc = c->d_vals[0].ensure(na * 4)) || (rc = c->d_vals[1].ensure(na * 4)) ||
@@ -573,16 +651,17 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
 
     CK(cudaEventRecord(c->ev[5], s));
     k_init_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2);
-    k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, d_ctr);
+    k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, pt, d_ctr);
     CK(cudaEventRecord(c->ev[6], s));
     Pass2Args a2;
-    a2.bases = c->d_bases.as<u64>(); a2.valid = c->d_valid.as<u64>();
+    a2.tuples = c->d_tuples.as<u64>();
     a2.table = c->d_t2.as<Slot2>(); a2.cap = cap2; a2.ctr = d_ctr;
-    k_pass2<<<grid_p2, THREADS, smem_tile, s>>>(a2, g);
+    if (pt.wide) k_pass2<true><<<grid_p2, THREADS, 0, s>>>(a2, g, pt);
+    else k_pass2<false><<<grid_p2, THREADS, 0, s>>>(a2, g, pt);
     CK(cudaEventRecord(c->ev[7], s));
     launches += 3;
 
-    /* export */
+    /* ---- export ---- */
     if (n_surv) {
         k_collect<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2, c->d_keys[0].as<u64>(), c->d_vals[0].as<u32>(), d_ctr);
         CK(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[1].as<u64>(),
@@ -595,7 +674,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
         ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
         ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
-        k_export<<<gb, THREADS, 0, s>>>(ae, g);
+        k_export<<<gb, THREADS, 0, s>>>(ae, g, pt);
         launches += 3;
     }
     CK(cudaEventRecord(c->ev[8], s));
@@ -614,9 +693,11 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     res.n_pre = n_surv;
     res.n_hits = h_ctr->n_hits;
     res.table1_slots = cap1; res.table2_slots = cap2;
+    res.partitions = (uint32_t)P; res.tuple_bytes = (uint32_t)tuple_bytes;
     res.kernel_launches = launches;
     cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
     cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&res.ms_scatter, c->ev[10], c->ev[11]);
     cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
     cudaEventElapsedTime(&res.ms_pass1, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);

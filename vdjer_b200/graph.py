@@ -29,7 +29,7 @@ class _Params(C.Structure):
     _fields_ = [
         ("read_length", C.c_int32), ("kmer_size", C.c_int32), ("min_node_freq", C.c_int32),
         ("min_base_quality", C.c_int32), ("device", C.c_int32), ("host_threads", C.c_int32),
-        ("table_capacity", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("table_capacity", C.c_uint64), ("flags", C.c_uint32), ("partitions", C.c_uint32),
     ]
 
 
@@ -43,9 +43,10 @@ class _Result(C.Structure):
         ("n_records", C.c_uint64), ("n_windows", C.c_uint64), ("n_gated", C.c_uint64),
         ("n_pre_total", C.c_uint64), ("n_pre", C.c_uint64), ("n_hits", C.c_uint64),
         ("ms_stage", C.c_float), ("ms_device", C.c_float), ("ms_estimate", C.c_float),
-        ("ms_init1", C.c_float), ("ms_pass1", C.c_float), ("ms_prune", C.c_float), ("ms_table2", C.c_float),
+        ("ms_scatter", C.c_float), ("ms_init1", C.c_float), ("ms_pass1", C.c_float), ("ms_prune", C.c_float), ("ms_table2", C.c_float),
         ("ms_pass2", C.c_float), ("ms_export", C.c_float), ("ms_fetch", C.c_float),
         ("table1_slots", C.c_uint64), ("table2_slots", C.c_uint64),
+        ("partitions", C.c_uint32), ("tuple_bytes", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
     ]
 
@@ -56,6 +57,7 @@ class _PreTable(C.Structure):
 
 
 FLAG_EXPORT_KEYS = 1
+FLAG_WIDE_TUPLES = 2
 
 EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
@@ -136,11 +138,13 @@ class GraphBuilder:
     """One libvdjgraph context (CUDA context, streams, staging buffers) reused across builds."""
 
     def __init__(self, read_length: int, k: int = 35, mf: int = 3, mq: int = 90, device: int = -1,
-                 host_threads: int = 0, table_capacity: int = 0, export_keys: bool = False):
+                 host_threads: int = 0, table_capacity: int = 0, export_keys: bool = False,
+                 partitions: int = 0, wide_tuples: bool = False):
         self._lib = load_library()
         self._ctx = C.c_void_p()
         self._p = _Params(read_length, k, mf, mq, device, host_threads, table_capacity,
-                          FLAG_EXPORT_KEYS if export_keys else 0, 0)
+                          (FLAG_EXPORT_KEYS if export_keys else 0) | (FLAG_WIDE_TUPLES if wide_tuples else 0),
+                          partitions)
         self._check(self._lib.vdjgraph_create(C.byref(self._p), C.byref(self._ctx)))
         self._keep = None
 
@@ -219,7 +223,7 @@ class GraphBuilder:
     def _stats(r: _Result) -> dict:
         return {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
                 for k, _ in _Result._fields_
-                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel"))}
+                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple"))}
 
     def _graph(self, r: _Result) -> Graph:
         n = int(r.n_nodes)
