@@ -796,27 +796,37 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
                 if (fl & 1u) of[u] = ld_cg_u64(&s->out_first[fl >> 1]);
             }
         }
+        /* phase B: consume.  No `continue`/early exits: with independent thread scheduling a
+         * lane that leaves the unrolled body early is not guaranteed to rejoin its warp, and a
+         * fragmented warp issues every later instruction once per fragment. */
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
-            if (idx[u] == NIL32) continue;
             u64 hi, stamp; u32 fl;
             tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, stamp);
             const bool has_next = fl & 1u;
             const u32 c = fl >> 1;
             u64 id = idx[u], c2 = q2[u], c3 = q3[u], o = of[u];
-            if (!(q0[u] == lo[u] && q1[u] == hi)) {
-                if (q0[u] == EMPTY64 && q1[u] == EMPTY64) continue;
-                /* collision at the home slot: probe on (rare at load <= 0.5) */
-                if (++id == a.cap) id = 0;
-                id = t2_probe_from(a.table, a.cap, id, lo[u], hi, c2, c3);
-                if (id == INF64) continue;
-                if (has_next) o = ld_cg_u64(&a.table[id].out_first[c]);
+            bool hit = idx[u] != NIL32;
+            if (hit && !(q0[u] == lo[u] && q1[u] == hi)) {
+                hit = false;
+                if (!(q0[u] == EMPTY64 && q1[u] == EMPTY64)) {
+                    /* collision at the home slot: probe on (rare at load <= 0.5) */
+                    if (++id == a.cap) id = 0;
+                    id = t2_probe_from(a.table, a.cap, id, lo[u], hi, c2, c3);
+                    if (id != INF64) {
+                        hit = true;
+                        if (has_next) o = ld_cg_u64(&a.table[id].out_first[c]);
+                    }
+                }
             }
-            n_hits++;
-            Slot2 *slot = a.table + id;
-            if ((u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
-            if (stamp < c3) atomicMin(&slot->first_any, stamp);
-            if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
+            if (hit) {
+                n_hits++;
+                Slot2 *slot = a.table + id;
+                if ((u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
+                if (stamp < c3) atomicMin(&slot->first_any, stamp);
+                if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
+            }
+            __syncwarp();
         }
     }
     for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
