@@ -522,103 +522,179 @@ struct Pass1Args {
     Counters *ctr;
 };
 
-/* slow path of pass 1: the home slot did not hold this k-mer -> linear probing with insertion.
- * On return slot/q2 describe the slot that now holds (lo,hi); false = table full. */
-__device__ __noinline__ bool pass1_probe(const Pass1Args &a, u64 lo, u64 hi, u64 idx, Slot1 *&slot, u64 &q2) {
-    for (u32 probe = 0; probe < MAX_PROBE; probe++) {
-        slot = a.table + idx;
-        u64 q0, q1, q3;
-        ld_sector(slot, q0, q1, q2, q3);
-        if (q0 == EMPTY64 && q1 == EMPTY64) {
-            cas128(slot, EMPTY64, EMPTY64, lo, hi, q0, q1);
-            if (q0 == EMPTY64 && q1 == EMPTY64) { q2 = (u64)NIL32 << 32; return true; } /* claimed: initial fields */
-        }
-        if (q0 == lo && q1 == hi) return true;
-        if (++idx == a.cap) idx = 0;
+/* Per-warp queue of deferred tuples in shared memory.  Both table passes split their work in
+ * two: a branch-free FAST path for tuples whose home slot resolves them with plain loads and at
+ * most a fire-and-forget RED, and a SLOW path (insertion, probing past the home slot, arrival
+ * ranks, read comparison, logging) for the rest.  Slow tuples are queued and drained by a lane
+ * state machine in which every lane always holds a tuple: a lane that finishes takes the next
+ * queue entry, so probe chains of different length do not idle the warp. */
+constexpr u32 QFLUSH = 64;                       /* drain when at least this many are queued */
+constexpr u32 QCAP = 32 * BATCH + QFLUSH;        /* a batch can add 32*BATCH entries */
+template <bool WIDE>
+struct WarpQueue {
+    u64 *lo, *w1, *w2;
+    u32 *idx;
+    __device__ __forceinline__ void setup(unsigned char *smem) {
+        unsigned char *p = smem + (threadIdx.x >> 5) * bytes();
+        lo = reinterpret_cast<u64 *>(p);
+        w1 = lo + QCAP;
+        w2 = w1 + QCAP;
+        idx = reinterpret_cast<u32 *>(w1 + (WIDE ? 2 : 1) * QCAP);
     }
-    return false;
+    __host__ __device__ static constexpr size_t bytes() { return (size_t)QCAP * (WIDE ? 28 : 20); }
+    /* warp-converged push of the lanes with `defer` set; returns the new count */
+    __device__ __forceinline__ u32 push(u32 qn, bool defer, u64 l, u64 a, u64 b, u32 i) {
+        const u32 lane = threadIdx.x & 31;
+        const u32 ballot = __ballot_sync(0xFFFFFFFFu, defer);
+        if (defer) {
+            const u32 pos = qn + __popc(ballot & ((1u << lane) - 1));
+            lo[pos] = l; w1[pos] = a; idx[pos] = i;
+            if (WIDE) w2[pos] = b;
+        }
+        return qn + __popc(ballot);
+    }
+};
+
+struct LogCursor { u32 base, used; };   /* warp-uniform: the warp's current log chunk */
+
+/* slow path of pass 1 for `qn` queued tuples */
+template <bool WIDE>
+__device__ __forceinline__ void pass1_drain(const Pass1Args &a, const Geom &g, const Part &pt, const WarpQueue<WIDE> &q,
+                                         u32 qn, LogCursor &lc) {
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    u32 next = 0;
+    bool have = false;
+    u64 lo = 0, hi = 0, stamp = 0;
+    u32 idx = 0, probe = 0;
+    __syncwarp();
+    for (;;) {
+        /* refill idle lanes */
+        const u32 need = __ballot_sync(0xFFFFFFFFu, !have);
+        const u32 avail = qn - next;
+        if (need == 0xFFFFFFFFu && avail == 0) break;
+        if (need && avail) {
+            const u32 my = __popc(need & lt);
+            if (!have && my < avail) {
+                const u32 e = next + my;
+                u32 fl;
+                lo = q.lo[e];
+                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, stamp);
+                idx = q.idx[e];
+                probe = 0;
+                have = true;
+            }
+            next += min((u32)__popc(need), avail);
+        }
+        /* one probe step: find or claim the slot of (lo,hi) */
+        bool found = false;
+        u64 q2 = 0;
+        Slot1 *slot = a.table + idx;
+        if (have) {
+            u64 q0, q1, q3;
+            ld_sector(slot, q0, q1, q2, q3);
+            if (q0 == EMPTY64 && q1 == EMPTY64) {
+                cas128(slot, EMPTY64, EMPTY64, lo, hi, q0, q1);
+                if (q0 == EMPTY64 && q1 == EMPTY64) { found = true; q2 = (u64)NIL32 << 32; }   /* claimed: initial fields */
+                else if (q0 == lo && q1 == hi) { found = true; q2 = ld_cg_u64(reinterpret_cast<const u64 *>(slot) + 2); }
+            } else if (q0 == lo && q1 == hi) {
+                found = true;
+            }
+            if (!found) {
+                if (++idx == (u32)a.cap) idx = 0;
+                if (++probe >= MAX_PROBE) { atomicExch(&a.ctr->overflow, 1u); have = false; }
+            }
+        }
+        /* update the slot (:334-352) */
+        bool need_log = false;
+        if (found) {
+            const u64 r = stamp / (u64)g.w;
+            const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
+            u32 first_rec = (u32)(q2 >> 32);
+            u32 rank = NIL32;
+            if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u) & CNT_MASK; /* arrival rank decides logging */
+            else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                 /* result unused: RED */
+            if (!(cw & CNT_MULTI)) {
+                if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
+                if (first_rec != NIL32 && first_rec != (u32)r &&
+                    !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
+                    atomicOr(&slot->count, CNT_MULTI);
+            }
+            need_log = rank < a.nb_ranks;
+            have = false;
+        }
+        /* warp-converged log allocation out of per-warp chunks */
+        const u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
+        if (ballot) {
+            const u32 n = __popc(ballot);
+            if (lc.used + n > LOG_CHUNK) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
+                lc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                lc.used = 0;
+            }
+            const u32 e = lc.base + lc.used + __popc(ballot & lt);
+            lc.used += n;
+            if (need_log) {
+                if (e < a.log_cap) {
+                    u32 prev = atomicExch(&slot->head, e);
+                    LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
+                    a.log[e] = le;
+                } else {
+                    atomicExch(&a.ctr->overflow, 2u);
+                }
+            }
+        }
+    }
+    __syncwarp();
 }
 
 template <bool WIDE>
 __global__ void __launch_bounds__(THREADS, 3)
 k_pass1(Pass1Args a, Geom g, Part pt) {
-    const u32 lane = threadIdx.x & 31;
-    u32 chunk_base = 0, chunk_used = LOG_CHUNK; /* warp-uniform */
+    extern __shared__ __align__(128) unsigned char smem[];
+    WarpQueue<WIDE> q;
+    q.setup(smem);
+    LogCursor lc; lc.base = 0; lc.used = LOG_CHUNK;
+    u32 qn = 0;
     const u64 span = (u64)THREADS * BATCH;
     const u64 n_blk = (pt.n_gated + span - 1) / span;
+    const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
     for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
         const u64 t0 = blk * span + threadIdx.x;
-        /* phase A: BATCH tuples per thread (coalesced), their home-slot reads issued back to back */
         u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], k0[BATCH], k1[BATCH], m2[BATCH];
         u32 idx[BATCH];   /* table capacities stay below 2^32 slots (checked on the host) */
+        /* A1: the batch's tuples (coalesced, streaming), all loads in flight together */
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const u64 t = t0 + (u64)u * THREADS;
-            idx[u] = NIL32;
-            if (t < pt.n_gated) {
-                tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
-                u64 hi = pt.hb ? (w1[u] & ((1ull << pt.hb) - 1)) : 0ull;
-                idx[u] = (u32)home_slot(hash_key(lo[u], hi), pt.pbits, pt.slice1);
+            lo[u] = w1[u] = 0; if (WIDE) w2[u] = 0;
+            idx[u] = t < pt.n_gated ? 0u : NIL32;
+            if (t < pt.n_gated) tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
+        }
+        /* A2: their home slots */
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            k0[u] = k1[u] = m2[u] = 0;
+            if (idx[u] != NIL32) {
+                idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice1);
                 const Slot1 *s = a.table + idx[u];
                 ld_cg_v2(s, k0[u], k1[u]);
                 m2[u] = ld_cg_u64(reinterpret_cast<const u64 *>(s) + 2);
             }
         }
-        /* phase B: consume */
+        /* B: fast path = the k-mer sits in its home slot, is already known to come from several
+         * reads and has passed the logging ranks: one RED.  Everything else is queued. */
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
-            bool need_log = false;
-            u64 stamp = 0;
-            Slot1 *slot = nullptr;
-            if (idx[u] != NIL32) {
-                u64 hi; u32 fl;
-                tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, stamp);
-                const u64 r = stamp / (u64)g.w;
-                slot = a.table + idx[u];
-                u64 q2 = m2[u];
-                bool found = (k0[u] == lo[u] && k1[u] == hi);
-                if (!found) found = pass1_probe(a, lo[u], hi, idx[u], slot, q2);
-                if (!found) {
-                    atomicExch(&a.ctr->overflow, 1u);
-                } else {
-                    const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
-                    u32 first_rec = (u32)(q2 >> 32);
-                    u32 rank = NIL32;
-                    if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u) & CNT_MASK; /* arrival rank decides logging */
-                    else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                 /* result unused: RED, no stall */
-                    if (!(cw & CNT_MULTI)) {
-                        if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
-                        if (first_rec != NIL32 && first_rec != (u32)r &&
-                            !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
-                            atomicOr(&slot->count, CNT_MULTI);
-                    }
-                    need_log = rank < a.nb_ranks;
-                }
-            }
-            /* warp-converged log allocation out of per-warp chunks */
-            u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
-            if (ballot) {
-                u32 n = __popc(ballot);
-                if (chunk_used + n > LOG_CHUNK) {
-                    u32 base = 0;
-                    if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
-                    chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    chunk_used = 0;
-                }
-                u32 e = chunk_base + chunk_used + __popc(ballot & ((1u << lane) - 1));
-                chunk_used += n;
-                if (need_log) {
-                    if (e < a.log_cap) {
-                        u32 prev = atomicExch(&slot->head, e);
-                        LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
-                        a.log[e] = le;
-                    } else {
-                        atomicExch(&a.ctr->overflow, 2u);
-                    }
-                }
-            }
+            const bool valid = idx[u] != NIL32;
+            const u32 cw = (u32)m2[u], cnt = cw & CNT_MASK;
+            const bool fast = valid && k0[u] == lo[u] && k1[u] == (w1[u] & hmask) && (cw & CNT_MULTI) && cnt >= a.nb_ranks;
+            if (fast && cnt < CNT_CAP) atomicAdd(&a.table[idx[u]].count, 1u);
+            qn = q.push(qn, valid && !fast, lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
         }
+        if (qn >= QFLUSH) { pass1_drain<WIDE>(a, g, pt, q, qn, lc); qn = 0; }
     }
+    pass1_drain<WIDE>(a, g, pt, q, qn, lc);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -745,8 +821,11 @@ k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters
         ld_sector(&t1[i], q0, q1, q2, q3);
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
         if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
-        if (t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.slice2), q0, q1) == INF64)
-            atomicExch(&ctr->overflow, 3u);
+        const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.slice2), q0, q1);
+        if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
+        /* the gated occurrences are N-free occurrences: seed node->frequency with them */
+        const u32 cnt = (u32)q2 & CNT_MASK;
+        t2[at].count = cnt > CNT_CAP ? CNT_CAP : cnt;
     }
 }
 
@@ -768,67 +847,119 @@ struct Pass2Args {
     Counters *ctr;
 };
 
+/* reductions of one pass-2 hit; c2/c3/o are the loaded count word, first_any and out_first[c] */
+__device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2, u64 c3, u64 o, bool has_next, u32 c, u64 stamp) {
+    if (count_it && (u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
+    if (stamp < c3) atomicMin(&slot->first_any, stamp);
+    if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
+}
+
+/* slow path of pass 2: tuples whose home slot holds a different k-mer; queue entries carry the
+ * tuple, its home slot and (top bit of idx) whether the tuple is from the ungated region */
+template <bool WIDE>
+__device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, const WarpQueue<WIDE> &q, u32 qn) {
+    const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    u32 next = 0, n_hits = 0;
+    bool have = false, count_it = false;
+    u64 lo = 0, hi = 0, stamp = 0;
+    u32 idx = 0, probe = 0, fl = 0;
+    __syncwarp();
+    for (;;) {
+        const u32 need = __ballot_sync(0xFFFFFFFFu, !have);
+        const u32 avail = qn - next;
+        if (need == 0xFFFFFFFFu && avail == 0) break;
+        if (need && avail) {
+            const u32 my = __popc(need & lt);
+            if (!have && my < avail) {
+                const u32 e = next + my;
+                lo = q.lo[e];
+                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, stamp);
+                idx = q.idx[e];
+                count_it = idx >> 31;
+                idx &= 0x7FFFFFFFu;
+                probe = 0;
+                have = true;
+            }
+            next += min((u32)__popc(need), avail);
+        }
+        if (have) {
+            if (++idx == (u32)a.cap) idx = 0;
+            Slot2 *slot = a.table + idx;
+            u64 q0, q1, q2, q3;
+            ld_sector(slot, q0, q1, q2, q3);
+            if (q0 == lo && q1 == hi) {
+                const bool has_next = fl & 1u;
+                const u32 c = fl >> 1;
+                u64 o = 0;
+                if (has_next) o = ld_cg_u64(&slot->out_first[c]);
+                pass2_update(slot, count_it, q2, q3, o, has_next, c, stamp);
+                n_hits++;
+                have = false;
+            } else if ((q0 == EMPTY64 && q1 == EMPTY64) || ++probe >= MAX_PROBE) {
+                have = false;
+            }
+        }
+    }
+    __syncwarp();
+    return n_hits;
+}
+
 template <bool WIDE>
 __global__ void __launch_bounds__(THREADS, 3)
 k_pass2(Pass2Args a, Geom g, Part pt) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    WarpQueue<WIDE> q;
+    q.setup(smem);
     const u32 lane = threadIdx.x & 31;
     const u64 span = (u64)THREADS * BATCH;
     const u64 n_blk = (pt.n_valid + span - 1) / span;
-    u32 n_hits = 0;
+    const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
+    u32 n_hits = 0, qn = 0;
     for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
         const u64 t0 = blk * span + threadIdx.x;
-        /* phase A: BATCH independent probes per thread: the hot sector of the home slot and,
-         * speculatively, the out_first word this window would update */
         u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
         u32 idx[BATCH];
+        /* A1: tuples */
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const u64 t = t0 + (u64)u * THREADS;
-            idx[u] = NIL32;
-            of[u] = 0;
-            if (t < pt.n_valid) {
-                tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
-                u64 hi = pt.hb ? (w1[u] & ((1ull << pt.hb) - 1)) : 0ull;
-                u32 fl = (u32)(w1[u] >> pt.hb) & 15u;
-                idx[u] = (u32)home_slot(hash_key(lo[u], hi), pt.pbits, pt.slice2);
+            lo[u] = w1[u] = 0; if (WIDE) w2[u] = 0;
+            idx[u] = t < pt.n_valid ? 0u : NIL32;
+            if (t < pt.n_valid) tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
+        }
+        /* A2: the hot sector of the home slot and, speculatively, the out_first word this
+         * window would update */
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            q0[u] = q1[u] = q2[u] = q3[u] = of[u] = 0;
+            if (idx[u] != NIL32) {
+                const u32 fl = (u32)(w1[u] >> pt.hb) & 15u;
+                idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice2);
                 const Slot2 *s = a.table + idx[u];
                 ld_sector(s, q0[u], q1[u], q2[u], q3[u]);
                 if (fl & 1u) of[u] = ld_cg_u64(&s->out_first[fl >> 1]);
             }
         }
-        /* phase B: consume.  No `continue`/early exits: with independent thread scheduling a
-         * lane that leaves the unrolled body early is not guaranteed to rejoin its warp, and a
-         * fragmented warp issues every later instruction once per fragment. */
+        /* B: hit at home -> reductions; empty home -> the k-mer did not survive; otherwise queue.
+         * node->frequency counts every N-free occurrence; the gated ones were already counted by
+         * pass 1 (k_build_table2 seeds count with them), so only ungated tuples add to it. */
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
+            const bool valid = idx[u] != NIL32;
+            const bool ungated = t0 + (u64)u * THREADS >= pt.n_gated;
             u64 hi, stamp; u32 fl;
             tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, stamp);
-            const bool has_next = fl & 1u;
-            const u32 c = fl >> 1;
-            u64 id = idx[u], c2 = q2[u], c3 = q3[u], o = of[u];
-            bool hit = idx[u] != NIL32;
-            if (hit && !(q0[u] == lo[u] && q1[u] == hi)) {
-                hit = false;
-                if (!(q0[u] == EMPTY64 && q1[u] == EMPTY64)) {
-                    /* collision at the home slot: probe on (rare at load <= 0.5) */
-                    if (++id == a.cap) id = 0;
-                    id = t2_probe_from(a.table, a.cap, id, lo[u], hi, c2, c3);
-                    if (id != INF64) {
-                        hit = true;
-                        if (has_next) o = ld_cg_u64(&a.table[id].out_first[c]);
-                    }
-                }
-            }
+            const bool hit = valid && q0[u] == lo[u] && q1[u] == hi;
+            const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
             if (hit) {
+                pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, fl >> 1, stamp);
                 n_hits++;
-                Slot2 *slot = a.table + id;
-                if ((u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
-                if (stamp < c3) atomicMin(&slot->first_any, stamp);
-                if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
             }
-            __syncwarp();
+            qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
         }
+        if (qn >= QFLUSH) { n_hits += pass2_drain<WIDE>(a, pt, q, qn); qn = 0; }
     }
+    n_hits += pass2_drain<WIDE>(a, pt, q, qn);
     for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
     if (lane == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
 }

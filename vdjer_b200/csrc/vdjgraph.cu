@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -45,6 +46,12 @@ int fail(int code, const char *fmt, ...) {
             return fail(VDJGRAPH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
                         __FILE__, __LINE__);                                                      \
     } while (0)
+
+/* performance knobs, overridable from the environment for tuning runs (results never depend on them) */
+double env_double(const char *name, double dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atof(v) : dflt;
+}
 
 double wall_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -519,7 +526,8 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     for (int i = 0; i < HB; i++) { n_gated += hist[i]; n_ungated += hist[HB + i]; }
     const uint64_t n_valid = n_gated + n_ungated;
     double est = std::min<double>(hll_estimate(c->h_hll.as<uint32_t>()), (double)n_gated);
-    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(est * 1.06 / 0.5) + 1024;
+    const double load1 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD1", 0.5)));
+    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(est * 1.06 / load1) + 1024;
     cap1 = std::max<uint64_t>(cap1, 1024);
 
     /* ---- partitioning: table-1 slices of at most SLICE_BYTES so that a slice is L2-resident ---- */
@@ -530,7 +538,8 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         if (c->prm.partitions) {
             while ((1u << pbits) < c->prm.partitions && pbits < HIST_BITS) pbits++;
         } else {
-            while (pbits < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits) > SLICE_BYTES) pbits++;
+            const uint64_t slice_bytes = (uint64_t)(env_double("VDJGRAPH_SLICE_MB", (double)(SLICE_BYTES >> 20)) * 1048576.0);
+            while (pbits < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits) > slice_bytes) pbits++;
         }
         pt.pbits = pbits;
         pt.hb = std::max(0, 2 * g.k - 64);
@@ -573,10 +582,11 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     CK(cudaEventRecord(c->ev[11], s));
 
     const uint64_t span = (uint64_t)THREADS * BATCH;
+    const size_t smem_q = WARPS * (pt.wide ? WarpQueue<true>::bytes() : WarpQueue<false>::bytes());
     const int grid_p1 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_gated + span - 1) / span,
-                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, 0)));
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, smem_q)));
     const int grid_p2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_valid + span - 1) / span,
-                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, 0)));
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, smem_q)));
 
     /* ---- K2 + K3: pass 1 and prune (retried with a larger table if it overflows) ---- */
     for (int attempt = 0;; attempt++) {
@@ -605,8 +615,8 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
         a1.log = c->d_log.as<LogEntry>(); a1.log_cap = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
         a1.ctr = d_ctr;
-        if (pt.wide) k_pass1<true><<<grid_p1, THREADS, 0, s>>>(a1, g, pt);
-        else k_pass1<false><<<grid_p1, THREADS, 0, s>>>(a1, g, pt);
+        if (pt.wide) k_pass1<true><<<grid_p1, THREADS, smem_q, s>>>(a1, g, pt);
+        else k_pass1<false><<<grid_p1, THREADS, smem_q, s>>>(a1, g, pt);
         CK(cudaEventRecord(c->ev[3], s));
         PruneArgs ap;
         ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<LogEntry>();
@@ -628,9 +638,10 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     const uint64_t n_distinct = h_ctr->n_distinct;
 
     /* ---- survivor table + pass 2 ---- */
-    pt.slice2 = (std::max<uint64_t>(1024, n_surv * 2 + 64) + P - 1) / P;
+    const double load2 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD2", 0.5)));
+    pt.slice2 = (std::max<uint64_t>(1024, (uint64_t)((double)n_surv / load2) + 64) + P - 1) / P;
     const uint64_t cap2 = pt.slice2 * (uint64_t)P;
-    if (cap2 > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
+    if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
     if ((rc = c->d_t2.ensure(cap2 * sizeof(Slot2)))) return rc;
     c->cap2 = cap2;
     c->part = pt;
@@ -656,8 +667,8 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     Pass2Args a2;
     a2.tuples = c->d_tuples.as<u64>();
     a2.table = c->d_t2.as<Slot2>(); a2.cap = cap2; a2.ctr = d_ctr;
-    if (pt.wide) k_pass2<true><<<grid_p2, THREADS, 0, s>>>(a2, g, pt);
-    else k_pass2<false><<<grid_p2, THREADS, 0, s>>>(a2, g, pt);
+    if (pt.wide) k_pass2<true><<<grid_p2, THREADS, smem_q, s>>>(a2, g, pt);
+    else k_pass2<false><<<grid_p2, THREADS, smem_q, s>>>(a2, g, pt);
     CK(cudaEventRecord(c->ev[7], s));
     launches += 3;
 
