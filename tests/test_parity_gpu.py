@@ -62,10 +62,30 @@ def test_partition_count_and_tuple_format_do_not_change_the_result(built, partit
     with GraphBuilder(L, k, mf, mq, partitions=partitions, wide_tuples=wide) as gb:
         got = gb.build(primary, secondary)
         pre = gb.pre_table()
-    assert got.stats["partitions"] == partitions and got.stats["tuple_bytes"] == (24 if wide else 16)
+    # narrow tuples need room for the stamp and a few read-fingerprint bits; k=50 leaves none
+    assert got.stats["partitions"] == partitions and got.stats["tuple_bytes"] == (24 if wide or k == 50 else 16)
     assert_pre_table_equal(pre, want, primary, secondary, L, k, f"P{partitions}")
     assert_graph_equal(got, want, f"P{partitions} wide{wide}")
     assert got.stats["n_hits"] == want["n_hits"] and got.stats["n_gated"] == want["n_gated"]
+
+
+@pytest.mark.parametrize("fp_bits", ["0", "2"])
+def test_weak_read_fingerprints_fall_back_to_the_exact_comparison(built, fp_bits, monkeypatch):
+    """hasMultipleUniqueReads (:349-352) is decided by a read fingerprint carried in the tuples and,
+    when fingerprints are equal, by comparing the packed reads.  With 0 or 2 fingerprint bits almost
+    every decision takes the exact path; the result must not change.  Duplicated reads included."""
+    monkeypatch.setenv("VDJGRAPH_FP_BITS", fp_bits)
+    primary, secondary = synth.generate(n_pairs=12000, read_length=50, seed=77, n_clones=150, threads=4)
+    rl = 2 * 50 + 1
+    body = primary[:-1].reshape(-1, rl)
+    primary = np.concatenate([body, body[:4000], body[1000:2000]]).reshape(-1)   # duplicated records
+    primary = np.concatenate([primary, np.zeros(1, np.uint8)])
+    want = loader.build(primary, secondary, 50, 35, 2, 60, kind="port")
+    with GraphBuilder(50, 35, 2, 60) as gb:
+        got = gb.build(primary, secondary)
+        pre = gb.pre_table()
+    assert_pre_table_equal(pre, want, primary, secondary, 50, 35, f"fp{fp_bits}")
+    assert_graph_equal(got, want, f"fp{fp_bits}")
 
 
 def test_context_reuse_and_param_changes(built):

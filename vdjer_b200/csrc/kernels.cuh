@@ -40,12 +40,12 @@ constexpr u32 CNT_CAP = 32765;   /* MAX_FREQUENCY-1, :66, :262, :345 */
 constexpr int GATE_Q = 20;       /* MIN_BASE_QUALITY, :76 */
 constexpr int QSUM_SAT = 214;    /* MAX_QUAL_SUM-41, :356 */
 constexpr int MAX_LOG_RANKS = 11;/* ceil(214/20) */
-constexpr u32 CNT_MULTI = 0x80000000u; /* top bit of Slot1::count = hasMultipleUniqueReads */
-constexpr u32 CNT_MASK = 0x7FFFFFFFu;
-constexpr u32 FLAG_SURV = 2u;
+constexpr u32 CNT_MULTI = 0x80000000u; /* bit 31 of Slot1::count = hasMultipleUniqueReads */
+constexpr u32 CNT_SURV = 0x40000000u;  /* bit 30: survived prune_pre_graph (set by k_prune) */
+constexpr u32 CNT_MASK = 0x3FFFFFFFu;
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr u32 LOG_CHUNK = 128;   /* log entries a warp reserves per global atomic */
+constexpr u32 LOG_CHUNK = 64;    /* log blocks a warp reserves per global atomic */
 constexpr u32 MAX_PROBE = 1u << 14;
 constexpr int HLL_BITS = 12;     /* 4096 registers, sigma ~ 1.6 % */
 constexpr int HIST_BITS = 8;     /* k_count histograms the top 8 hash bits; P <= 256 partitions */
@@ -54,11 +54,12 @@ constexpr int BATCH = 4;         /* independent table probes a thread keeps in f
 /* pass-1 table slot: exactly one 32-byte sector */
 struct __align__(32) Slot1 {
     u64 klo, khi;     /* packed k-mer; all ones = empty */
-    u32 count;        /* bits 0..30: gated occurrences (stops counting a little above CNT_CAP);
-                         bit 31 (CNT_MULTI): hasMultipleUniqueReads :349-352 */
+    u32 count;        /* bits 0..29: gated occurrences (stops counting a little above CNT_CAP);
+                         bit 30 CNT_SURV; bit 31 CNT_MULTI: hasMultipleUniqueReads :349-352 */
+    u32 head;         /* this k-mer's block of NB log entries (stamps of its first NB arrivals);
+                         NIL32 until the thread that claimed the slot has published it */
     u32 first_rec;    /* record of the first ARRIVING gated occurrence: contributingRead :335 */
-    u32 head;         /* list of the first <= NB occurrences (log entry index) */
-    u32 flags;        /* FLAG_SURV set by prune */
+    u32 first_fp;     /* fingerprint of that record's sequence (as carried by the tuples) */
 };
 static_assert(sizeof(Slot1) == 32, "Slot1 must be one sector");
 
@@ -72,7 +73,6 @@ struct __align__(64) Slot2 {
 };
 static_assert(sizeof(Slot2) == 64, "Slot2 must be two sectors");
 
-struct __align__(16) LogEntry { u64 stamp; u32 next; u32 pad; };
 
 struct Geom {
     int L, k, w, nb, nm;
@@ -90,7 +90,7 @@ struct Part {
     int pbits;          /* P = 1 << pbits partitions by the top hash bits */
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
     int wide;           /* 1: 24-byte tuples (stamp in a third word) */
-    int pad;
+    int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
     u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
     u64 n_gated, n_valid; /* tuples in the gated region / in both regions */
 };
@@ -124,6 +124,21 @@ __device__ __forceinline__ void ld_cg_v2(const void *p, u64 &a, u64 &b) {
 __device__ __forceinline__ u64 ld_cg_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+/* L1-cached variants for the fast paths of the table passes.  Ig reads are extremely skewed
+ * (every read that touches the constant region repeats the same few hundred k-mers), so a dozen
+ * slots per partition take half of all probes; L1 absorbs them.  L1 is not coherent across SMs:
+ * the fast paths only test MONOTONIC facts on the loaded words (key present, MULTI set, count
+ * past a threshold, a min-stamp already <= ours), so a stale line can only send a tuple to the
+ * slow path or cost a redundant RED, never change a result. */
+__device__ __forceinline__ void ld_sector_ca(const void *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.global.ca.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ u64 ld_ca_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.ca.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 /* streaming (touched-once) tuple traffic: evict-first so it does not push the L2-resident
@@ -235,16 +250,20 @@ __device__ __forceinline__ u32 div_w(u32 win, const Geom &g) { return g.div_magi
 
 /* ------------------------------------------------------------------------------------------ */
 /* tuples: one per N-free window.  word0 = k-mer bits 0..63; word1 = k-mer bits 64.. (hb bits)  */
-/* | has_next << hb | next_base << (hb+1) | stamp << (hb+4)   (narrow, 16 B), or the stamp in a  */
-/* third word (wide, 24 B) when it does not fit.  The gate bit is implied by the region.        */
+/* | has_next << hb | next_base << (hb+1) | fp << (hb+4) | stamp << (hb+4+fb)  (narrow, 16 B);   */
+/* when fewer than 4 fingerprint bits would fit the stamp moves to a third word (wide, 24 B)    */
+/* and fb = 32.  fp = fingerprint of the record's whole sequence: two records with different    */
+/* fingerprints hold different reads, which settles hasMultipleUniqueReads without touching the */
+/* reads again (equal fingerprints fall back to the exact comparison).  The gate bit is implied */
+/* by the region the tuple lies in.                                                              */
 /* ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void tuple_store(u64 *base, u64 t, const Part &pt, u64 lo, u64 hi, u32 fl, u64 stamp) {
-    u64 w1 = hi | ((u64)fl << pt.hb);
+__device__ __forceinline__ void tuple_store(u64 *base, u64 t, const Part &pt, u64 lo, u64 hi, u32 fl, u32 fp, u64 stamp) {
+    u64 w1 = hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + 4));
     if (pt.wide) {
         u64 *p = base + t * 3;
         st_stream_u64(p, lo); st_stream_u64(p + 1, w1); st_stream_u64(p + 2, stamp);
     } else {
-        st_stream_v2(base + t * 2, lo, w1 | (stamp << (pt.hb + 4)));
+        st_stream_v2(base + t * 2, lo, w1 | (stamp << (pt.hb + 4 + pt.fb)));
     }
 }
 template <bool WIDE>
@@ -258,10 +277,16 @@ __device__ __forceinline__ void tuple_load(const u64 *base, u64 t, u64 &lo, u64 
     }
 }
 template <bool WIDE>
-__device__ __forceinline__ void tuple_decode(const Part &pt, u64 w1, u64 w2, u64 &hi, u32 &fl, u64 &stamp) {
+__device__ __forceinline__ void tuple_decode(const Part &pt, u64 w1, u64 w2, u64 &hi, u32 &fl, u32 &fp, u64 &stamp) {
     hi = pt.hb ? (w1 & ((1ull << pt.hb) - 1)) : 0ull;
     fl = (u32)(w1 >> pt.hb) & 15u;
-    stamp = WIDE ? w2 : (w1 >> (pt.hb + 4));
+    fp = (u32)(w1 >> (pt.hb + 4)) & (u32)((1ull << pt.fb) - 1);
+    stamp = WIDE ? w2 : (w1 >> (pt.hb + 4 + pt.fb));
+}
+/* all operands must be computed before anything after this point is issued: keeps independent
+ * loads of a batch back to back instead of interleaved with the address arithmetic of the next */
+__device__ __forceinline__ void issue_fence(u32 &a, u32 &b, u32 &c, u32 &d) {
+    asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -384,7 +409,8 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
 /* written with streaming stores.                                                                */
 /* ------------------------------------------------------------------------------------------ */
 __host__ __device__ inline size_t scatter_head_bytes(const Geom &g) {
-    size_t b = 512 * sizeof(u32) + 512 * sizeof(u64) + (size_t)((g.tile_win + 31) / 32) * THREADS * sizeof(u32);
+    size_t b = 512 * sizeof(u32) + 512 * sizeof(u64) + (size_t)((g.tile_win + 31) / 32) * THREADS * sizeof(u32) +
+               (size_t)WARPS * g.tile_rec * sizeof(u32);
     return (b + 127) & ~(size_t)127;
 }
 struct ScatterArgs {
@@ -403,6 +429,8 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
     u32 *cnt = reinterpret_cast<u32 *>(smem);          /* [512] */
     u64 *gbase = reinterpret_cast<u64 *>(cnt + 512);   /* [512] */
     u32 *meta = reinterpret_cast<u32 *>(gbase + 512);  /* [per_lane][THREADS] */
+    u32 *sfp = meta + per_lane * THREADS + (threadIdx.x >> 5) * g.tile_rec;  /* [tile_rec] read fingerprints of this warp's tile */
+    const u32 fpmask = (u32)((1ull << pt.fb) - 1);
     WarpTiles t = tile_setup(smem + scatter_head_bytes(g), g, 2);
     const u32 lane = threadIdx.x & 31;
     const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
@@ -419,6 +447,13 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
         }
         const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf);
+        if (have)
+            for (u32 rec = lane; rec < g.tile_rec; rec += 32) {
+                u64 h = 0x9E3779B97F4A7C15ull;
+                for (int i = 0; i < g.nb; i++) h = hash_key(sb[(size_t)rec * g.nb + i], h);
+                for (int i = 0; i < g.nm; i++) h = hash_key(sv[(size_t)rec * g.nm + i], h);
+                sfp[rec] = (u32)(h >> 32) & fpmask;
+            }
         /* phase A: bucket and rank of every window this lane owns (packed bucket<<20 | rank) */
         for (u32 j = 0; j < per_lane; j++) {
             u32 m = NIL32;
@@ -465,7 +500,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             if (i + 1 < g.w && bit_at(sv + (size_t)rec * g.nm, i + g.k)) fl = 1u | (base_at(bb, i + g.k) << 1);
             const u64 stamp = (tile * g.tile_rec + rec) * (u64)g.w + (u64)i;
             const u64 b = gbase[m >> 20];
-            if (b != INF64) tuple_store(a.tuples, b + (m & 0xFFFFFu), pt, lo, hi, fl, stamp);
+            if (b != INF64) tuple_store(a.tuples, b + (m & 0xFFFFFu), pt, lo, hi, fl, sfp[rec], stamp);
         }
         __syncthreads();
     }
@@ -477,7 +512,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
 __global__ void k_init_table1(Slot1 *t, u64 cap) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
     for (; i < cap; i += stride)
-        st_sector(&t[i], EMPTY64, EMPTY64, (u64)0 | ((u64)NIL32 << 32), (u64)NIL32 | ((u64)0 << 32));
+        st_sector(&t[i], EMPTY64, EMPTY64, (u64)0 | ((u64)NIL32 << 32), (u64)NIL32);
 }
 __global__ void k_init_table2(Slot2 *t, u64 cap) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
@@ -516,9 +551,9 @@ struct Pass1Args {
     const u8 *strand;
     Slot1 *table;
     u64 cap;
-    LogEntry *log;
-    u32 log_cap;
-    u32 nb_ranks;   /* NB: arrivals with rank < NB are logged */
+    u64 *log;         /* [log_blocks][NB] stamps */
+    u32 log_blocks;
+    u32 nb_ranks;     /* NB: arrivals with rank < NB are logged */
     Counters *ctr;
 };
 
@@ -555,17 +590,19 @@ struct WarpQueue {
     }
 };
 
-struct LogCursor { u32 base, used; };   /* warp-uniform: the warp's current log chunk */
+struct LogCursor { u32 base, used; };   /* warp-uniform: the warp's current chunk of log blocks */
 
-/* slow path of pass 1 for `qn` queued tuples */
+/* slow path of pass 1 for `qn` queued tuples.  One loop iteration = at most two dependent
+ * round trips to L2 per lane: (1) the probe (sector load, plus the 128-bit CAS when the slot is
+ * empty), (2) the arrival-rank atomicAdd and the first-record CAS, issued together. */
 template <bool WIDE>
 __device__ __forceinline__ void pass1_drain(const Pass1Args &a, const Geom &g, const Part &pt, const WarpQueue<WIDE> &q,
-                                         u32 qn, LogCursor &lc) {
+                                            u32 qn, LogCursor &lc) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     u32 next = 0;
     bool have = false;
     u64 lo = 0, hi = 0, stamp = 0;
-    u32 idx = 0, probe = 0;
+    u32 idx = 0, probe = 0, fp = 0;
     __syncwarp();
     for (;;) {
         /* refill idle lanes */
@@ -578,71 +615,75 @@ __device__ __forceinline__ void pass1_drain(const Pass1Args &a, const Geom &g, c
                 const u32 e = next + my;
                 u32 fl;
                 lo = q.lo[e];
-                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, stamp);
+                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, fp, stamp);
                 idx = q.idx[e];
                 probe = 0;
                 have = true;
             }
             next += min((u32)__popc(need), avail);
         }
-        /* one probe step: find or claim the slot of (lo,hi) */
-        bool found = false;
-        u64 q2 = 0;
+        /* probe step: find or claim the slot of (lo,hi) */
+        bool found = false, claimed = false;
+        u64 q2 = 0, q3 = 0;
         Slot1 *slot = a.table + idx;
         if (have) {
-            u64 q0, q1, q3;
+            u64 q0, q1;
             ld_sector(slot, q0, q1, q2, q3);
             if (q0 == EMPTY64 && q1 == EMPTY64) {
                 cas128(slot, EMPTY64, EMPTY64, lo, hi, q0, q1);
-                if (q0 == EMPTY64 && q1 == EMPTY64) { found = true; q2 = (u64)NIL32 << 32; }   /* claimed: initial fields */
-                else if (q0 == lo && q1 == hi) { found = true; q2 = ld_cg_u64(reinterpret_cast<const u64 *>(slot) + 2); }
+                if (q0 == EMPTY64 && q1 == EMPTY64) { found = claimed = true; q2 = (u64)NIL32 << 32; q3 = (u64)NIL32; }
+                else if (q0 == lo && q1 == hi) q2 = (u64)NIL32 << 32;   /* lost the race to the same k-mer: look again */
             } else if (q0 == lo && q1 == hi) {
-                found = true;
+                /* a slot whose log block is not published yet is looked at again next iteration */
+                found = a.nb_ranks == 0 || (u32)(q2 >> 32) != NIL32;
             }
-            if (!found) {
+            if (!found && !(q0 == lo && q1 == hi)) {
                 if (++idx == (u32)a.cap) idx = 0;
                 if (++probe >= MAX_PROBE) { atomicExch(&a.ctr->overflow, 1u); have = false; }
             }
         }
+        /* the claiming lane reserves the k-mer's log block (warp-aggregated) and publishes it */
+        u32 blk = (u32)(q2 >> 32);
+        if (a.nb_ranks) {
+            const u32 ballot = __ballot_sync(0xFFFFFFFFu, claimed);
+            if (ballot) {
+                const u32 n = __popc(ballot);
+                if (lc.used + n > LOG_CHUNK) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
+                    lc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    lc.used = 0;
+                }
+                if (claimed) {
+                    blk = lc.base + lc.used + __popc(ballot & lt);
+                    if (blk < a.log_blocks) slot->head = blk;
+                    else { atomicExch(&a.ctr->overflow, 2u); blk = NIL32; slot->head = 0; }
+                }
+                lc.used += n;
+            }
+        }
         /* update the slot (:334-352) */
-        bool need_log = false;
         if (found) {
-            const u64 r = stamp / (u64)g.w;
+            const u32 r = (u32)(stamp / (u64)g.w);
             const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
-            u32 first_rec = (u32)(q2 >> 32);
+            u32 first_rec = (u32)q3, first_fp = (u32)(q3 >> 32);
+            /* the arrival-rank add and the first-record CAS go out together (one round trip) */
             u32 rank = NIL32;
-            if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u) & CNT_MASK; /* arrival rank decides logging */
-            else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                 /* result unused: RED */
+            u64 old = q3;
+            const bool want_first = !(cw & CNT_MULTI) && first_rec == NIL32;
+            if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u);              /* arrival rank decides logging */
+            else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                   /* result unused: RED */
+            if (want_first) old = atomicCAS(reinterpret_cast<u64 *>(&slot->first_rec), (u64)NIL32, (u64)r | ((u64)fp << 32));
+            rank = rank == NIL32 ? NIL32 : (rank & CNT_MASK);
             if (!(cw & CNT_MULTI)) {
-                if (first_rec == NIL32) first_rec = atomicCAS(&slot->first_rec, NIL32, (u32)r);
-                if (first_rec != NIL32 && first_rec != (u32)r &&
-                    !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm))
+                first_rec = (u32)old; first_fp = (u32)(old >> 32);
+                /* different fingerprints: different reads.  Equal ones: compare the reads (:142-144) */
+                if (first_rec != NIL32 && first_rec != r &&
+                    (first_fp != fp || !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm)))
                     atomicOr(&slot->count, CNT_MULTI);
             }
-            need_log = rank < a.nb_ranks;
+            if (rank < a.nb_ranks && blk != NIL32) a.log[(u64)blk * a.nb_ranks + rank] = stamp;
             have = false;
-        }
-        /* warp-converged log allocation out of per-warp chunks */
-        const u32 ballot = __ballot_sync(0xFFFFFFFFu, need_log);
-        if (ballot) {
-            const u32 n = __popc(ballot);
-            if (lc.used + n > LOG_CHUNK) {
-                u32 base = 0;
-                if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
-                lc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                lc.used = 0;
-            }
-            const u32 e = lc.base + lc.used + __popc(ballot & lt);
-            lc.used += n;
-            if (need_log) {
-                if (e < a.log_cap) {
-                    u32 prev = atomicExch(&slot->head, e);
-                    LogEntry le; le.stamp = stamp; le.next = prev; le.pad = 0;
-                    a.log[e] = le;
-                } else {
-                    atomicExch(&a.ctr->overflow, 2u);
-                }
-            }
         }
     }
     __syncwarp();
@@ -659,6 +700,7 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
     const u64 span = (u64)THREADS * BATCH;
     const u64 n_blk = (pt.n_gated + span - 1) / span;
     const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
+    static_assert(BATCH == 4, "issue_fence takes four operands");
     for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
         const u64 t0 = blk * span + threadIdx.x;
         u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], k0[BATCH], k1[BATCH], m2[BATCH];
@@ -671,15 +713,17 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
             idx[u] = t < pt.n_gated ? 0u : NIL32;
             if (t < pt.n_gated) tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
         }
-        /* A2: their home slots */
+        /* A2: their home slots, again all in flight together */
+#pragma unroll
+        for (int u = 0; u < BATCH; u++)
+            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice1);
+        issue_fence(idx[0], idx[1], idx[2], idx[3]);
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             k0[u] = k1[u] = m2[u] = 0;
             if (idx[u] != NIL32) {
-                idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice1);
-                const Slot1 *s = a.table + idx[u];
-                ld_cg_v2(s, k0[u], k1[u]);
-                m2[u] = ld_cg_u64(reinterpret_cast<const u64 *>(s) + 2);
+                u64 unused;
+                ld_sector_ca(a.table + idx[u], k0[u], k1[u], m2[u], unused);
             }
         }
         /* B: fast path = the k-mer sits in its home slot, is already known to come from several
@@ -710,7 +754,8 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
 struct PruneArgs {
     Slot1 *table;
     u64 cap;
-    const LogEntry *log;
+    const u64 *log;
+    u32 nb_ranks;
     const u8 *qual;
     int mf, T;
     Counters *ctr;
@@ -721,31 +766,28 @@ k_prune(PruneArgs a, Geom g) {
     /* lane = one slot; slots whose quality sums must be evaluated are then handled by the whole
      * warp: lane j owns k-mer positions j and j+32, so each occurrence's k quality bytes are one
      * coalesced read */
-    __shared__ u64 s_st[THREADS / 32][32][MAX_LOG_RANKS];
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 lane = threadIdx.x & 31;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 n_iter = (a.cap + stride - 1) / stride;
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 n_distinct = 0, n_surv = 0;
     for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
-        u32 cnt = 0, flags = 0;
+        u32 cnt = 0, cw = 0, head = NIL32;
         bool pass = false, border = false;
         if (i < a.cap) {
             u64 q0, q1, q2, q3;
             ld_sector(&a.table[i], q0, q1, q2, q3);
             if (!(q0 == EMPTY64 && q1 == EMPTY64)) {
                 n_distinct++;
-                const bool multi = ((u32)q2 & CNT_MULTI) != 0;
-                cnt = (u32)q2 & CNT_MASK; flags = (u32)(q3 >> 32);
-                u32 head = (u32)q3;
+                cw = (u32)q2;
+                cnt = cw & CNT_MASK;
+                head = (u32)(q2 >> 32);
                 if (cnt > CNT_CAP) cnt = CNT_CAP;
-                if ((int)cnt >= a.mf && multi) {
+                if ((int)cnt >= a.mf && (cw & CNT_MULTI)) {
                     pass = true;
                     if (GATE_Q * ((int)cnt - 1) < a.T) {
                         border = true;
-                        int n = 0;
-                        for (u32 e = head; e != NIL32 && n < MAX_LOG_RANKS; e = a.log[e].next) s_st[wid][lane][n++] = a.log[e].stamp;
-                        if (n != (int)cnt) { atomicExch(&a.ctr->internal, 1u); border = false; pass = false; }
+                        if (cnt > a.nb_ranks || head == NIL32) { atomicExch(&a.ctr->internal, 1u); border = false; pass = false; }
                     }
                 }
             }
@@ -755,24 +797,26 @@ k_prune(PruneArgs a, Geom g) {
             const int b = __ffs(todo) - 1;
             todo &= todo - 1;
             const int n = (int)__shfl_sync(0xFFFFFFFFu, cnt, b);
-            __syncwarp();
-            u64 first = INF64;
-            for (int e = 0; e < n; e++) first = min(first, s_st[wid][b][e]);
+            const u32 hd = __shfl_sync(0xFFFFFFFFu, head, b);
+            /* lane e < n holds occurrence e */
+            u64 st = (int)lane < n ? a.log[(u64)hd * a.nb_ranks + lane] : INF64;
+            u64 first = st;
+            for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
             int s0 = 0, s1 = 0;
             for (int e = 0; e < n; e++) {
-                u64 st = s_st[wid][b][e];
-                u64 r = st / (u64)g.w;
-                u64 o = st == first ? 0 : st - r * (u64)g.w;   /* first occurrence reads q_r0[j], :337-339 */
-                const u8 *q = a.qual + r * (u64)g.L + o;
-                if ((int)lane < g.k) s0 += q[lane];
-                if ((int)lane + 32 < g.k) s1 += q[lane + 32];
+                const u64 se = __shfl_sync(0xFFFFFFFFu, st, e);
+                const u64 r = se / (u64)g.w;
+                const u64 o = se == first ? 0 : se - r * (u64)g.w;   /* first occurrence reads q_r0[j], :337-339 */
+                const u8 *qp = a.qual + r * (u64)g.L + o;
+                if ((int)lane < g.k) s0 += qp[lane];
+                if ((int)lane + 32 < g.k) s1 += qp[lane + 32];
             }
-            bool bad = ((int)lane < g.k && s0 < a.T) || ((int)lane + 32 < g.k && s1 < a.T);
-            u32 any_bad = __ballot_sync(0xFFFFFFFFu, bad);
+            const bool bad = ((int)lane < g.k && s0 < a.T) || ((int)lane + 32 < g.k && s1 < a.T);
+            const u32 any_bad = __ballot_sync(0xFFFFFFFFu, bad);
             if ((int)lane == b && any_bad) pass = false;
         }
         if (pass) {
-            a.table[i].flags = flags | FLAG_SURV;
+            a.table[i].count = cw | CNT_SURV;
             n_surv++;
         }
     }
@@ -820,7 +864,7 @@ k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters
         u64 q0, q1, q2, q3;
         ld_sector(&t1[i], q0, q1, q2, q3);
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
-        if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
+        if (!((u32)q2 & CNT_SURV)) continue;
         const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.slice2), q0, q1);
         if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
         /* the gated occurrences are N-free occurrences: seed node->frequency with them */
@@ -873,7 +917,8 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, c
             if (!have && my < avail) {
                 const u32 e = next + my;
                 lo = q.lo[e];
-                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, stamp);
+                u32 fp;
+                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, fp, stamp);
                 idx = q.idx[e];
                 count_it = idx >> 31;
                 idx &= 0x7FFFFFFFu;
@@ -928,16 +973,19 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             if (t < pt.n_valid) tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
         }
         /* A2: the hot sector of the home slot and, speculatively, the out_first word this
-         * window would update */
+         * window would update; all loads of the batch in flight together */
+#pragma unroll
+        for (int u = 0; u < BATCH; u++)
+            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice2);
+        issue_fence(idx[0], idx[1], idx[2], idx[3]);
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             q0[u] = q1[u] = q2[u] = q3[u] = of[u] = 0;
             if (idx[u] != NIL32) {
                 const u32 fl = (u32)(w1[u] >> pt.hb) & 15u;
-                idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice2);
                 const Slot2 *s = a.table + idx[u];
-                ld_sector(s, q0[u], q1[u], q2[u], q3[u]);
-                if (fl & 1u) of[u] = ld_cg_u64(&s->out_first[fl >> 1]);
+                ld_sector_ca(s, q0[u], q1[u], q2[u], q3[u]);
+                if (fl & 1u) of[u] = ld_ca_u64(&s->out_first[fl >> 1]);
             }
         }
         /* B: hit at home -> reductions; empty home -> the k-mer did not survive; otherwise queue.
@@ -947,8 +995,8 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
         for (int u = 0; u < BATCH; u++) {
             const bool valid = idx[u] != NIL32;
             const bool ungated = t0 + (u64)u * THREADS >= pt.n_gated;
-            u64 hi, stamp; u32 fl;
-            tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, stamp);
+            u64 hi, stamp; u32 fl, fp;
+            tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, fp, stamp);
             const bool hit = valid && q0[u] == lo[u] && q1[u] == hi;
             const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
             if (hit) {
@@ -1071,7 +1119,7 @@ k_export_pre(const Slot1 *t, u64 cap, u64 *klo, u64 *khi, u16 *freq, u64 *n_out)
         u64 q0, q1, q2, q3;
         ld_sector(&t[i], q0, q1, q2, q3);
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
-        if (!((u32)(q3 >> 32) & FLAG_SURV)) continue;
+        if (!((u32)q2 & CNT_SURV)) continue;
         u64 o = atomicAdd(n_out, 1ull);
         u32 cnt = (u32)q2 & CNT_MASK;
         klo[o] = q0; khi[o] = q1; freq[o] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);

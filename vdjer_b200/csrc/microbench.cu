@@ -84,6 +84,41 @@ __global__ void __launch_bounds__(256) k_rand(char *table, u64 n_slots, u64 ops_
     if (acc == 0x123456789ull) *sink = acc;
 }
 
+/* skew probe: every operation goes to one of `n_hot` slots (spread over the table) */
+template <int OP>
+__global__ void __launch_bounds__(256) k_hot(char *table, u64 n_slots, u64 n_hot, u64 ops_per_thread, u64 *sink) {
+    u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 nthreads = (u64)gridDim.x * blockDim.x;
+    u64 acc = 0;
+    for (u64 it = 0; it < ops_per_thread; it++) {
+        u64 h = mix(it * nthreads + tid + 0x9E3779B97F4A7C15ull);
+        u64 idx = __umul64hi(mix((h % n_hot) + 77), n_slots);
+        if (OP == OP_LOAD) { u64 a, b, c, d; ld_sector(table + idx * 32, a, b, c, d); acc += a ^ d; }
+        else if (OP == OP_RED) atomicAdd(reinterpret_cast<u32 *>(table + idx * 32 + 16), 1u);
+        else if (OP == OP_ATOM) acc += atomicAdd(reinterpret_cast<u32 *>(table + idx * 32 + 16), 1u);
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+}
+template <int OP>
+double run_hot(char *table, u64 n_slots, u64 n_hot, u64 *sink, int sms) {
+    const u64 total_ops = 1ull << 24;
+    int grid = sms * 8;
+    u64 per_thread = total_ops / ((u64)grid * 256);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(e0));
+        k_hot<OP><<<grid, 256>>>(table, n_slots, n_hot, per_thread, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    return (double)per_thread * grid * 256 / (best * 1e-3) / 1e9;
+}
+
 template <int OP, int ILP>
 double run(char *table, u64 n_slots, u64 window, u64 *sink, int sms, int blocks_per_sm) {
     const u64 total_ops = 1ull << 28;
@@ -116,9 +151,11 @@ int main(int argc, char **argv) {
     CK(cudaMemset(table, 0xFF, max_bytes));
     FILE *out = argc > 1 ? fopen(argv[1], "w") : stdout;
     fprintf(out, "{\"gpu\": \"%s\", \"sms\": %d, \"l2_bytes\": %d, \"unit\": \"G ops/s\", \"rows\": [\n", prop.name, sms, prop.l2CacheSize);
+    const bool quick = argc > 2;
     const size_t sizes[] = { 32ull << 20, 96ull << 20, 256ull << 20, 512ull << 20, 1ull << 30, 2ull << 30, 8ull << 30 };
     bool first = true;
     for (size_t bytes : sizes) {
+        if (quick && bytes != (32ull << 20)) continue;
         u64 n = bytes / 32;
         double load1 = run<OP_LOAD, 1>(table, n, 0, sink, sms, 8);
         double load4 = run<OP_LOAD, 4>(table, n, 0, sink, sms, 8);
@@ -141,6 +178,20 @@ int main(int argc, char **argv) {
         fflush(out);
         first = false;
         CK(cudaMemset(table, 0xFF, max_bytes));
+    }
+    fprintf(out, "\n],\n\"hot_addresses\": [\n");
+    {
+        const u64 n = (32ull << 20) / 32;
+        const u64 hots[] = { 1, 4, 16, 64, 256, 1024, 4096, 65536 };
+        bool f2 = true;
+        for (u64 nh : hots) {
+            double l = run_hot<OP_LOAD>(table, n, nh, sink, sms);
+            double r = run_hot<OP_RED>(table, n, nh, sink, sms);
+            double a = run_hot<OP_ATOM>(table, n, nh, sink, sms);
+            fprintf(out, "%s{\"n_hot\": %llu, \"load\": %.3f, \"red\": %.3f, \"atom\": %.3f}", f2 ? "" : ",\n", nh, l, r, a);
+            fflush(out);
+            f2 = false;
+        }
     }
     fprintf(out, "\n]}\n");
     if (out != stdout) fclose(out);

@@ -544,7 +544,11 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         pt.pbits = pbits;
         pt.hb = std::max(0, 2 * g.k - 64);
         const int sbits = bits_for(g.R * (uint64_t)g.w);
-        pt.wide = (pt.hb + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
+        /* narrow tuples need room for at least 4 read-fingerprint bits beside the stamp */
+        pt.wide = (pt.hb + 4 + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
+        pt.fb = pt.wide ? 32 : std::min(32, 64 - pt.hb - 4 - sbits);
+        /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
+        pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
         pt.n_gated = n_gated;
         pt.n_valid = n_valid;
     }
@@ -593,15 +597,15 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         if (attempt > 6) return fail(VDJGRAPH_ERR_INTERNAL, "pass-1 table kept overflowing (capacity %llu)", (unsigned long long)cap1);
         pt.slice1 = (cap1 + P - 1) / P;
         cap1 = pt.slice1 * (uint64_t)P;
-        /* log: at most NB entries per distinct k-mer and never more than the gated windows,
-         * plus one partially used chunk per warp */
+        /* log: one block of NB stamps per distinct k-mer (<= table slots, <= gated windows), plus
+         * one partially used chunk of blocks per warp */
         uint64_t warps = (uint64_t)grid_p1 * WARPS;
-        uint64_t log_cap = std::min<uint64_t>(n_gated, (uint64_t)NB * (uint64_t)(0.75 * (double)cap1)) + warps * LOG_CHUNK + LOG_CHUNK;
-        if (NB == 0) log_cap = LOG_CHUNK;
-        if (log_cap > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "occurrence log would need %llu entries", (unsigned long long)log_cap);
+        uint64_t log_cap = std::min<uint64_t>(n_gated, cap1) + warps * LOG_CHUNK + LOG_CHUNK;
+        if (NB == 0) log_cap = 1;
+        if (log_cap > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "occurrence log would need %llu blocks", (unsigned long long)log_cap);
         if (cap1 > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "pass-1 table would need %llu slots", (unsigned long long)cap1);
         if ((rc = c->d_t1.ensure(cap1 * sizeof(Slot1)))) return rc;
-        if ((rc = c->d_log.ensure(log_cap * sizeof(LogEntry)))) return rc;
+        if ((rc = c->d_log.ensure(log_cap * (uint64_t)std::max(NB, 1) * sizeof(uint64_t)))) return rc;
         c->cap1 = cap1; c->log_cap = (uint32_t)log_cap;
 
         CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
@@ -613,13 +617,13 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         a1.bases = c->d_bases.as<u64>(); a1.valid = c->d_valid.as<u64>();
         a1.strand = c->any_strand1 ? c->d_strand.as<u8>() : nullptr;
         a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
-        a1.log = c->d_log.as<LogEntry>(); a1.log_cap = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
+        a1.log = c->d_log.as<u64>(); a1.log_blocks = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
         a1.ctr = d_ctr;
         if (pt.wide) k_pass1<true><<<grid_p1, THREADS, smem_q, s>>>(a1, g, pt);
         else k_pass1<false><<<grid_p1, THREADS, smem_q, s>>>(a1, g, pt);
         CK(cudaEventRecord(c->ev[3], s));
         PruneArgs ap;
-        ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<LogEntry>();
+        ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<u64>(); ap.nb_ranks = (uint32_t)NB;
         ap.qual = c->d_qual.as<u8>(); ap.mf = c->prm.min_node_freq; ap.T = T; ap.ctr = d_ctr;
         k_prune<<<grid_flat, THREADS, 0, s>>>(ap, g);
         CK(cudaEventRecord(c->ev[4], s));
