@@ -256,6 +256,8 @@ def main():
                        "gated_fraction": stats["n_gated"] / W, "pass2_hit_fraction_h": h,
                        "table1_slots": stats["table1_slots"], "table2_slots": stats["table2_slots"],
                        "hash_partitions": stats["partitions"], "tuple_bytes": stats["tuple_bytes"],
+                       "slow_path_fraction_pass1": stats["n_slow1"] / max(1, stats["n_gated"]),
+                       "slow_path_fraction_pass2": stats["n_slow2"] / max(1, W),
                        "generator_s": round(t_gen, 2)},
             "e2e": {"value": W_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": e2e_stats["h2d_bytes"], "d2h_bytes_per_step": e2e_stats["d2h_bytes"],

@@ -91,6 +91,7 @@ typedef struct vdjgraph_result {
     uint64_t n_pre_total;      /* "Pre Num nodes": distinct gated k-mers */
     uint64_t n_pre;            /* "pre nodes after pruning" (= n_nodes) */
     uint64_t n_hits;           /* pass-2 windows whose k-mer survived (uncapped) */
+    uint64_t n_slow1, n_slow2; /* diagnostics: tuples that took the slow (queued) path of pass 1 / pass 2 */
 
     /* timings of the last build, milliseconds */
     float ms_stage;            /* host pack + H2D (wall clock) */

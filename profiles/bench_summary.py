@@ -15,5 +15,8 @@ for line in sys.stdin:
     print("kernel_ms", {k: round(v, 3) for k, v in d["kernel_ms"].items()})
     print("roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), "path", round(d["roofline_path"]["frac"], 3),
           "clocks", d["clocks"])
+    c = d["config"]
+    print("slow-path fractions", round(c.get("slow_path_fraction_pass1", -1), 3), round(c.get("slow_path_fraction_pass2", -1), 3),
+          "partitions", c.get("hash_partitions"), "h", round(c["pass2_hit_fraction_h"], 3), "gated", round(c["gated_fraction"], 3))
     if "cpu_baseline" in d:
         print("cpu", d["cpu_baseline"]["value"] / 1e6, "M windows/s")

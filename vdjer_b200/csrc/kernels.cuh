@@ -76,9 +76,8 @@ static_assert(sizeof(Slot2) == 64, "Slot2 must be two sectors");
 
 struct Geom {
     int L, k, w, nb, nm;
-    u32 tile_rec;       /* records per warp tile (even) */
-    u32 tile_win;       /* tile_rec * w */
-    u32 div_magic;      /* ceil(2^32 / w), 0 when w == 1 */
+    int segs;           /* thread segments per record: ceil(w / SEG) */
+    u32 tile_rec;       /* records per block tile (even): THREADS / segs */
     u64 R;              /* real records */
     u64 n_tiles;
     u64 kmask_lo, kmask_hi; /* 2k ones */
@@ -101,6 +100,7 @@ struct Counters {
     u64 n_surv;
     u64 n_hits;
     u64 n_nodes;
+    u64 n_slow1, n_slow2; /* tuples that took the slow path of pass 1 / pass 2 */
     u32 log_used;
     u32 overflow;     /* table full / probe bound hit / region overrun */
     u32 internal;     /* invariant violated */
@@ -245,9 +245,6 @@ __device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
     return (u32)(bit < 64 ? lo >> bit : hi >> (bit - 64)) & 3u;
 }
 
-/* window index within a tile -> record within the tile (w == 1 has no 32-bit magic) */
-__device__ __forceinline__ u32 div_w(u32 win, const Geom &g) { return g.div_magic ? __umulhi(win, g.div_magic) : win; }
-
 /* ------------------------------------------------------------------------------------------ */
 /* tuples: one per N-free window.  word0 = k-mer bits 0..63; word1 = k-mer bits 64.. (hb bits)  */
 /* | has_next << hb | next_base << (hb+1) | fp << (hb+4) | stamp << (hb+4+fb)  (narrow, 16 B);   */
@@ -257,15 +254,6 @@ __device__ __forceinline__ u32 div_w(u32 win, const Geom &g) { return g.div_magi
 /* reads again (equal fingerprints fall back to the exact comparison).  The gate bit is implied */
 /* by the region the tuple lies in.                                                              */
 /* ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void tuple_store(u64 *base, u64 t, const Part &pt, u64 lo, u64 hi, u32 fl, u32 fp, u64 stamp) {
-    u64 w1 = hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + 4));
-    if (pt.wide) {
-        u64 *p = base + t * 3;
-        st_stream_u64(p, lo); st_stream_u64(p + 1, w1); st_stream_u64(p + 2, stamp);
-    } else {
-        st_stream_v2(base + t * 2, lo, w1 | (stamp << (pt.hb + 4 + pt.fb)));
-    }
-}
 template <bool WIDE>
 __device__ __forceinline__ void tuple_load(const u64 *base, u64 t, u64 &lo, u64 &w1, u64 &w2) {
     if (WIDE) {
@@ -290,42 +278,34 @@ __device__ __forceinline__ void issue_fence(u32 &a, u32 &b, u32 &c, u32 &d) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Warp-private two-stage TMA tile loader for the kernels that stream the packed reads.        */
-/* Every warp owns two shared-memory buffers and two mbarriers and walks the tiles warp-stride: */
-/* arrays a (nb words/record), b and c (nm words/record) of one tile land in buffer `buf`;     */
-/* lane 0 issues, all lanes wait on the mbarrier.                                               */
+/* Streaming the packed reads (k_count, k_scatter).  A block walks tiles of g.tile_rec records   */
+/* block-stride; the three arrays of a tile are brought into shared memory by TMA bulk copies    */
+/* (double buffered, one elected thread issues, everybody waits on the mbarrier).  Thread t owns */
+/* one SEGMENT of a record: SEG consecutive windows, whose k-mer and gate/N masks it ROLLS (one  */
+/* new base and one new mask bit per window) instead of re-extracting them.                      */
 /* ------------------------------------------------------------------------------------------ */
-struct WarpTiles {
-    u64 *base;  /* warp's region: [buf][a | b | c] */
+constexpr int SEG = 16;                 /* windows per thread segment */
+constexpr u32 MAX_STAGE = THREADS * SEG; /* tuples a block can produce per tile */
+
+struct BlockTiles {
+    u64 *buf;   /* [2][a | b | c] */
     u64 *bar;   /* [2] */
-    u32 words;  /* per buffer */
-    u32 off_b, off_c;
-    __device__ __forceinline__ const u64 *a(int buf) const { return base + buf * words; }
-    __device__ __forceinline__ const u64 *b(int buf) const { return base + buf * words + off_b; }
-    __device__ __forceinline__ const u64 *c(int buf) const { return base + buf * words + off_c; }
+    u32 words, off_b, off_c;
+    __device__ __forceinline__ const u64 *a(int i) const { return buf + i * words; }
+    __device__ __forceinline__ const u64 *b(int i) const { return buf + i * words + off_b; }
+    __device__ __forceinline__ const u64 *c(int i) const { return buf + i * words + off_c; }
 };
-__host__ __device__ inline size_t warp_tile_bytes(u32 tile_rec, int nb, int nm, int n_masks) {
-    return (size_t)2 * tile_rec * (size_t)(nb + n_masks * nm) * 8 + 16;
+__host__ __device__ inline size_t block_tile_bytes(const Geom &g) {
+    return (size_t)2 * g.tile_rec * (size_t)(g.nb + 2 * g.nm) * 8 + 16;
 }
-__device__ __forceinline__ void tile_issue(const WarpTiles &t, int buf, const Geom &g, u64 tile,
-                                           const u64 *ga, const u64 *gb, const u64 *gc) {
-    const u32 bytes_a = g.tile_rec * (u32)g.nb * 8u, bytes_m = g.tile_rec * (u32)g.nm * 8u;
-    u64 *bar = t.bar + buf;
-    u64 *dst = t.base + buf * t.words;
-    mbar_expect_tx(bar, bytes_a + bytes_m + (gc ? bytes_m : 0u));
-    tma_load_1d(dst, ga + tile * g.tile_rec * (u64)g.nb, bytes_a, bar);
-    tma_load_1d(dst + t.off_b, gb + tile * g.tile_rec * (u64)g.nm, bytes_m, bar);
-    if (gc) tma_load_1d(dst + t.off_c, gc + tile * g.tile_rec * (u64)g.nm, bytes_m, bar);
-}
-__device__ __forceinline__ WarpTiles tile_setup(unsigned char *smem, const Geom &g, int n_masks) {
-    WarpTiles t;
-    const u32 wid = threadIdx.x >> 5;
-    t.words = g.tile_rec * (u32)(g.nb + n_masks * g.nm);
+__device__ __forceinline__ BlockTiles tiles_setup(unsigned char *smem, const Geom &g) {
+    BlockTiles t;
+    t.words = g.tile_rec * (u32)(g.nb + 2 * g.nm);
     t.off_b = g.tile_rec * (u32)g.nb;
     t.off_c = t.off_b + g.tile_rec * (u32)g.nm;
-    t.base = reinterpret_cast<u64 *>(smem + wid * warp_tile_bytes(g.tile_rec, g.nb, g.nm, n_masks));
-    t.bar = t.base + 2 * t.words;
-    if ((threadIdx.x & 31) == 0) {
+    t.buf = reinterpret_cast<u64 *>(smem);
+    t.bar = t.buf + 2 * t.words;
+    if (threadIdx.x == 0) {
         mbar_init(&t.bar[0], 1);
         mbar_init(&t.bar[1], 1);
         fence_mbar_init();
@@ -334,9 +314,41 @@ __device__ __forceinline__ WarpTiles tile_setup(unsigned char *smem, const Geom 
     __syncthreads();
     return t;
 }
-static inline size_t tile_smem_bytes(const Geom &g, int n_masks) {
-    return (size_t)WARPS * warp_tile_bytes(g.tile_rec, g.nb, g.nm, n_masks);
+/* one thread: start the three bulk copies of `tile` into buffer i */
+__device__ __forceinline__ void tiles_issue(const BlockTiles &t, int i, const Geom &g, u64 tile,
+                                            const u64 *ga, const u64 *gb, const u64 *gc) {
+    const u32 bytes_a = g.tile_rec * (u32)g.nb * 8u, bytes_m = g.tile_rec * (u32)g.nm * 8u;
+    u64 *dst = t.buf + i * t.words;
+    mbar_expect_tx(&t.bar[i], bytes_a + 2 * bytes_m);
+    tma_load_1d(dst, ga + tile * g.tile_rec * (u64)g.nb, bytes_a, &t.bar[i]);
+    tma_load_1d(dst + t.off_b, gb + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
+    tma_load_1d(dst + t.off_c, gc + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
 }
+
+/* a thread's rolling view of its segment: window i of record `rec` */
+struct Roll {
+    u64 lo, hi;     /* k-mer of the current window */
+    u64 mv, mg;     /* k mask bits: N-free / gate-passing */
+    const u64 *b, *v, *gd;
+    int i;
+    __device__ __forceinline__ void start(const u64 *sb, const u64 *sg, const u64 *sv, u32 rec, int i0, const Geom &g) {
+        b = sb + (size_t)rec * g.nb; gd = sg + (size_t)rec * g.nm; v = sv + (size_t)rec * g.nm;
+        i = i0;
+        extract_kmer(b, g.nb, i0, g.kmask_lo, g.kmask_hi, lo, hi);
+        mv = extract_mask(v, g.nm, i0) & g.kones;
+        mg = extract_mask(gd, g.nm, i0) & g.kones;
+    }
+    /* move to window i+1 (caller guarantees i+1 < w, so base i+k exists) */
+    __device__ __forceinline__ void step(const Geom &g) {
+        const int j = i + g.k;
+        kmer_succ(lo, hi, base_at(b, j), g.k, lo, hi);
+        mv = (mv >> 1) | ((u64)bit_at(v, j) << (g.k - 1));
+        mg = (mg >> 1) | ((u64)bit_at(gd, j) << (g.k - 1));
+        i++;
+    }
+    __device__ __forceinline__ bool valid(const Geom &g) const { return mv == g.kones; }
+    __device__ __forceinline__ bool gated(const Geom &g) const { return mg == g.kones; }
+};
 
 /* ------------------------------------------------------------------------------------------ */
 /* K0 k_count: one streaming pass over the packed reads that sizes everything else:            */
@@ -346,73 +358,75 @@ static inline size_t tile_smem_bytes(const Geom &g, int n_masks) {
 /*     rehashed (the reference's dense_hash_map doubles, internal/densehashtable.h:631-653) nor */
 /*     grossly over-allocated.                                                                   */
 /* ------------------------------------------------------------------------------------------ */
+__host__ __device__ inline size_t count_head_bytes() {
+    return ((size_t)(1 << HLL_BITS) + (size_t)WARPS * 2 * (1 << HIST_BITS)) * sizeof(u32);
+}
 __global__ void __launch_bounds__(THREADS)
 k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *__restrict__ valid,
         Geom g, u32 *hll, u64 *hist /* [2][256] */) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int M = 1 << HLL_BITS, HB = 1 << HIST_BITS;
     u32 *reg = reinterpret_cast<u32 *>(smem);
-    u32 *sh = reg + M;  /* [2][HB] */
-    for (int i = threadIdx.x; i < M + 2 * HB; i += THREADS) reg[i] = 0;
-    WarpTiles t = tile_setup(smem + (M + 2 * HB) * sizeof(u32), g, 2);
-    const u32 lane = threadIdx.x & 31;
-    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
-    const u64 n_iter = (g.n_tiles + gstride - 1) / gstride;
-    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, g, gw, bases, good, valid);
-    u64 tile = gw;
-    for (u64 it = 0; it < n_iter; it++, tile += gstride) {
+    u32 *sh = reg + M;  /* [WARPS][2][HB]: warp-private counters keep shared-memory atomics apart */
+    for (int i = threadIdx.x; i < M + WARPS * 2 * HB; i += THREADS) reg[i] = 0;
+    BlockTiles t = tiles_setup(smem + count_head_bytes(), g);
+    u32 *mine = sh + (threadIdx.x >> 5) * 2 * HB;
+    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG;
+    const int n = rec < g.tile_rec ? min(SEG, g.w - (int)i0) : 0;
+    const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
+    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, bases, good, valid);
+    u64 tile = blockIdx.x;
+    for (u64 it = 0; it < n_iter; it++, tile += gridDim.x) {
         const int buf = (int)(it & 1);
         if (tile < g.n_tiles) {
-            if (lane == 0 && tile + gstride < g.n_tiles) tile_issue(t, buf ^ 1, g, tile + gstride, bases, good, valid);
+            if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, bases, good, valid);
             mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
-            const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf);
-            for (u32 win = lane; win < g.tile_win; win += 32) {
-                u32 rec = div_w(win, g);
-                int i = (int)(win - rec * (u32)g.w);
-                u64 mv = extract_mask(sv + (size_t)rec * g.nm, g.nm, i);
-                if ((mv & g.kones) != g.kones) continue;
-                u64 mg = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
-                const bool gated = (mg & g.kones) == g.kones;
-                u64 lo, hi;
-                extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-                u64 h = hash_key(lo, hi);
-                atomicAdd(&sh[(gated ? 0 : HB) + (u32)(h >> (64 - HIST_BITS))], 1u);
-                if (gated) {
-                    /* HLL uses the low hash bits so that it is independent of the partition bits */
-                    u32 idx = (u32)h & (M - 1);
-                    u32 rho = (u32)__clzll((long long)((h << 8) | (1ull << 20))) + 1;
-                    if (reg[idx] < rho) atomicMax(&reg[idx], rho);
+            if (n > 0) {
+                Roll r;
+                r.start(t.a(buf), t.b(buf), t.c(buf), rec, (int)i0, g);
+                for (int j = 0; j < n; j++) {
+                    if (j) r.step(g);
+                    if (!r.valid(g)) continue;
+                    const bool gated = r.gated(g);
+                    const u64 h = hash_key(r.lo, r.hi);
+                    atomicAdd(&mine[(gated ? 0 : HB) + (u32)(h >> (64 - HIST_BITS))], 1u);
+                    if (gated) {
+                        /* HLL uses the low hash bits so that it is independent of the partition bits */
+                        const u32 idx = (u32)h & (M - 1);
+                        const u32 rho = (u32)__clzll((long long)((h << 8) | (1ull << 20))) + 1;
+                        if (reg[idx] < rho) atomicMax(&reg[idx], rho);
+                    }
                 }
             }
-            __syncwarp();
         }
-        /* u32 block counters: flush long before they can overflow (uniform trip count) */
-        if ((it & 1023) == 1023) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < 2 * HB; i += THREADS) { u32 v = sh[i]; if (v) { atomicAdd(&hist[i], (u64)v); sh[i] = 0; } }
+        __syncthreads();   /* everybody is done with buffer `buf` before it is refilled */
+        /* u32 counters: flush long before they can overflow (uniform trip count) */
+        if ((it & 0xFFFF) == 0xFFFF) {
+            for (int i = threadIdx.x; i < WARPS * 2 * HB; i += THREADS) { u32 v = sh[i]; if (v) { atomicAdd(&hist[i % (2 * HB)], (u64)v); sh[i] = 0; } }
             __syncthreads();
         }
     }
-    __syncthreads();
     for (int i = threadIdx.x; i < M; i += THREADS)
         if (reg[i]) atomicMax(&hll[i], reg[i]);
-    for (int i = threadIdx.x; i < 2 * HB; i += THREADS)
-        if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
+    for (int i = threadIdx.x; i < 2 * HB; i += THREADS) {
+        u64 v = 0;
+        for (int wv = 0; wv < WARPS; wv++) v += sh[wv * 2 * HB + i];
+        if (v) atomicAdd(&hist[i], v);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
 /* K1 k_scatter: every N-free window becomes a tuple in its hash partition's region:           */
 /* regions [gated p=0..P-1][ungated p=0..P-1]; cursor[] starts at the region offsets (exclusive */
-/* scan of k_count's histogram).  A block processes WARPS warp tiles per iteration: windows are */
-/* counted per bucket in shared memory (the returned value is the tuple's rank inside the       */
-/* block's run), one global atomic per non-empty bucket reserves the run, then tuples are       */
-/* written with streaming stores.                                                                */
+/* scan of k_count's histogram).  Per tile a block                                               */
+/*   1. counts its windows per bucket (warp-private shared-memory counters; the value returned  */
+/*      by the atomic is the window's rank among the warp's windows of that bucket),             */
+/*   2. scans the counters into block-local offsets and reserves one run per non-empty bucket   */
+/*      with a single global atomic,                                                             */
+/*   3. re-rolls the windows and writes the tuples into a shared-memory stage in bucket order,   */
+/*   4. copies the stage out: consecutive threads write consecutive tuples of a run, so global  */
+/*      stores are full-sector and coalesced although the destination is a 2P-way scatter.      */
 /* ------------------------------------------------------------------------------------------ */
-__host__ __device__ inline size_t scatter_head_bytes(const Geom &g) {
-    size_t b = 512 * sizeof(u32) + 512 * sizeof(u64) + (size_t)((g.tile_win + 31) / 32) * THREADS * sizeof(u32) +
-               (size_t)WARPS * g.tile_rec * sizeof(u32);
-    return (b + 127) & ~(size_t)127;
-}
 struct ScatterArgs {
     const u64 *bases, *good, *valid;
     u64 *tuples;
@@ -420,87 +434,150 @@ struct ScatterArgs {
     const u64 *limit; /* [2 << pbits] end of each region (overrun check) */
     Counters *ctr;
 };
+struct ScatterSmem {
+    u32 *wcnt;   /* [WARPS][NBK] counters, then warp offsets inside the bucket's run */
+    u32 *boff;   /* [NBK + 1] start of each bucket's run in the stage */
+    u64 *gbase;  /* [NBK] global tuple index of the run */
+    u32 *fp;     /* [tile_rec] read fingerprints */
+    unsigned short *sbk; /* [MAX_STAGE] bucket of a staged tuple */
+    u64 *stage;  /* [MAX_STAGE][2 or 3] */
+    unsigned char *tiles;
+};
+__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *base, const Geom &g, int nbk, int wide) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off = align128(off + bytes); return at; };
+    size_t a_wcnt = take((size_t)WARPS * nbk * 4), a_boff = take((size_t)(nbk + 1) * 4), a_gbase = take((size_t)nbk * 8);
+    size_t a_fp = take((size_t)g.tile_rec * 4), a_sbk = take((size_t)MAX_STAGE * 2);
+    size_t a_stage = take((size_t)MAX_STAGE * (wide ? 24 : 16)), a_tiles = take(block_tile_bytes(g));
+    if (o) {
+        o->wcnt = reinterpret_cast<u32 *>(base + a_wcnt); o->boff = reinterpret_cast<u32 *>(base + a_boff);
+        o->gbase = reinterpret_cast<u64 *>(base + a_gbase); o->fp = reinterpret_cast<u32 *>(base + a_fp);
+        o->sbk = reinterpret_cast<unsigned short *>(base + a_sbk); o->stage = reinterpret_cast<u64 *>(base + a_stage);
+        o->tiles = base + a_tiles;
+    }
+    return off;
+}
 
 __global__ void __launch_bounds__(THREADS)
 k_scatter(ScatterArgs a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int NBK = 2 << pt.pbits;
-    const u32 per_lane = (g.tile_win + 31) / 32;
-    u32 *cnt = reinterpret_cast<u32 *>(smem);          /* [512] */
-    u64 *gbase = reinterpret_cast<u64 *>(cnt + 512);   /* [512] */
-    u32 *meta = reinterpret_cast<u32 *>(gbase + 512);  /* [per_lane][THREADS] */
-    u32 *sfp = meta + per_lane * THREADS + (threadIdx.x >> 5) * g.tile_rec;  /* [tile_rec] read fingerprints of this warp's tile */
+    const int P = 1 << pt.pbits, NBK = 2 * P;
+    ScatterSmem sm;
+    scatter_carve(&sm, smem, g, NBK, pt.wide);
+    BlockTiles t = tiles_setup(sm.tiles, g);
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 *mine = sm.wcnt + wid * NBK;
+    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG;
+    const int n = rec < g.tile_rec ? min(SEG, g.w - (int)i0) : 0;
     const u32 fpmask = (u32)((1ull << pt.fb) - 1);
-    WarpTiles t = tile_setup(smem + scatter_head_bytes(g), g, 2);
-    const u32 lane = threadIdx.x & 31;
-    const u64 gw = (u64)blockIdx.x * WARPS + (threadIdx.x >> 5), gstride = (u64)gridDim.x * WARPS;
-    const u64 n_iter = (g.n_tiles + gstride - 1) / gstride;
-    if (lane == 0 && gw < g.n_tiles) tile_issue(t, 0, g, gw, a.bases, a.good, a.valid);
-    for (int i = threadIdx.x; i < NBK; i += THREADS) cnt[i] = 0;
-    __syncthreads();
-    u64 tile = gw;
-    for (u64 it = 0; it < n_iter; it++, tile += gstride) {
+    const int tw = pt.wide ? 3 : 2;
+    const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
+    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, a.bases, a.good, a.valid);
+    u64 tile = blockIdx.x;
+    for (u64 it = 0; it < n_iter; it++, tile += gridDim.x) {
         const int buf = (int)(it & 1);
-        const bool have = tile < g.n_tiles;
-        if (have) {
-            if (lane == 0 && tile + gstride < g.n_tiles) tile_issue(t, buf ^ 1, g, tile + gstride, a.bases, a.good, a.valid);
-            mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
-        }
+        const bool have = tile < g.n_tiles;   /* block-uniform */
+        if (!have) break;
+        for (int i = threadIdx.x; i < WARPS * NBK; i += THREADS) sm.wcnt[i] = 0;
+        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, a.bases, a.good, a.valid);
+        mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
+        __syncthreads();
         const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf);
-        if (have)
-            for (u32 rec = lane; rec < g.tile_rec; rec += 32) {
-                u64 h = 0x9E3779B97F4A7C15ull;
-                for (int i = 0; i < g.nb; i++) h = hash_key(sb[(size_t)rec * g.nb + i], h);
-                for (int i = 0; i < g.nm; i++) h = hash_key(sv[(size_t)rec * g.nm + i], h);
-                sfp[rec] = (u32)(h >> 32) & fpmask;
-            }
-        /* phase A: bucket and rank of every window this lane owns (packed bucket<<20 | rank) */
-        for (u32 j = 0; j < per_lane; j++) {
-            u32 m = NIL32;
-            const u32 win = j * 32 + lane;
-            if (have && win < g.tile_win) {
-                u32 rec = div_w(win, g);
-                int i = (int)(win - rec * (u32)g.w);
-                u64 mv = extract_mask(sv + (size_t)rec * g.nm, g.nm, i);
-                if ((mv & g.kones) == g.kones) {
-                    u64 mg = extract_mask(sg + (size_t)rec * g.nm, g.nm, i);
-                    const bool gated = (mg & g.kones) == g.kones;
-                    u64 lo, hi;
-                    extract_kmer(sb + (size_t)rec * g.nb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-                    u64 h = hash_key(lo, hi);
-                    u32 bk = (pt.pbits ? (u32)(h >> (64 - pt.pbits)) : 0u) + (gated ? 0u : (1u << pt.pbits));
-                    m = (bk << 20) | atomicAdd(&cnt[bk], 1u);
+        /* read fingerprints of the tile's records */
+        for (u32 r = threadIdx.x; r < g.tile_rec; r += THREADS) {
+            u64 h = 0x9E3779B97F4A7C15ull;
+            for (int i = 0; i < g.nb; i++) h = hash_key(sb[(size_t)r * g.nb + i], h);
+            for (int i = 0; i < g.nm; i++) h = hash_key(sv[(size_t)r * g.nm + i], h);
+            sm.fp[r] = (u32)(h >> 32) & fpmask;
+        }
+        /* 1. bucket and rank of every window of this thread's segment: code = bucket << 16 | rank */
+        u32 code[SEG];
+        {
+            Roll r;
+            if (n > 0) r.start(sb, sg, sv, rec, (int)i0, g);
+#pragma unroll
+            for (int j = 0; j < SEG; j++) {
+                code[j] = NIL32;
+                if (j < n) {
+                    if (j) r.step(g);
+                    if (r.valid(g)) {
+                        const u64 h = hash_key(r.lo, r.hi);
+                        const u32 bk = (pt.pbits ? (u32)(h >> (64 - pt.pbits)) : 0u) + (r.gated(g) ? 0u : (u32)P);
+                        code[j] = (bk << 16) | atomicAdd(&mine[bk], 1u);
+                    }
                 }
             }
-            meta[j * THREADS + threadIdx.x] = m;
         }
         __syncthreads();
-        /* phase B: reserve one run per non-empty bucket */
-        for (int i = threadIdx.x; i < NBK; i += THREADS) {
-            u32 n = cnt[i];
-            if (n) {
-                u64 b = atomicAdd(&a.cursor[i], (u64)n);
-                if (b + n > a.limit[i]) { atomicExch(&a.ctr->overflow, 4u); b = INF64; }
-                gbase[i] = b;
-                cnt[i] = 0;
+        /* 2. offsets.  Every bucket: warp counters -> exclusive prefix over the warps, total */
+        for (int b = threadIdx.x; b < NBK; b += THREADS) {
+            u32 run = 0;
+            for (int wv = 0; wv < WARPS; wv++) { u32 c = sm.wcnt[wv * NBK + b]; sm.wcnt[wv * NBK + b] = run; run += c; }
+            sm.boff[b + 1] = run;
+            u64 gbs = INF64;
+            if (run) {
+                gbs = atomicAdd(&a.cursor[b], (u64)run);
+                if (gbs + run > a.limit[b]) { atomicExch(&a.ctr->overflow, 4u); gbs = INF64; }
+            }
+            sm.gbase[b] = gbs;
+        }
+        __syncthreads();
+        if (wid == 0) {   /* exclusive scan of the totals by one warp: lane owns NBK/32 consecutive buckets */
+            const int per = (NBK + 31) / 32;
+            u32 sum = 0;
+            for (int j = 0; j < per; j++) { int b = lane * per + j; if (b < NBK) sum += sm.boff[b + 1]; }
+            u32 incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
+            u32 run = incl - sum;
+            for (int j = 0; j < per; j++) {
+                int b = lane * per + j;
+                if (b < NBK) { u32 c = sm.boff[b + 1]; sm.boff[b + 1] = run + c; run += c; }
+            }
+            if (lane == 0) sm.boff[0] = 0;
+        }
+        __syncthreads();
+        /* 3. stage the tuples in bucket order */
+        if (n > 0) {
+            Roll r;
+            r.start(sb, sg, sv, rec, (int)i0, g);
+            const u32 fp = sm.fp[rec];
+            const u64 stamp0 = (tile * g.tile_rec + rec) * (u64)g.w;
+#pragma unroll
+            for (int j = 0; j < SEG; j++) {
+                if (j < n) {
+                    if (j) r.step(g);
+                    if (code[j] != NIL32) {
+                        const u32 bk = code[j] >> 16;
+                        const u32 pos = sm.boff[bk] + mine[bk] + (code[j] & 0xFFFFu);
+                        u32 fl = 0;
+                        if (r.i + 1 < g.w && bit_at(r.v, r.i + g.k)) fl = 1u | (base_at(r.b, r.i + g.k) << 1);
+                        const u64 w1 = r.hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + 4));
+                        const u64 stamp = stamp0 + (u64)r.i;
+                        u64 *dst = sm.stage + (size_t)pos * tw;
+                        dst[0] = r.lo;
+                        if (pt.wide) { dst[1] = w1; dst[2] = stamp; }
+                        else dst[1] = w1 | (stamp << (pt.hb + 4 + pt.fb));
+                        sm.sbk[pos] = (unsigned short)bk;
+                    }
+                }
             }
         }
         __syncthreads();
-        /* phase C: write the tuples */
-        for (u32 j = 0; j < per_lane; j++) {
-            const u32 m = meta[j * THREADS + threadIdx.x];
-            if (m == NIL32) continue;
-            const u32 win = j * 32 + lane;
-            u32 rec = div_w(win, g);
-            int i = (int)(win - rec * (u32)g.w);
-            const u64 *bb = sb + (size_t)rec * g.nb;
-            u64 lo, hi;
-            extract_kmer(bb, g.nb, i, g.kmask_lo, g.kmask_hi, lo, hi);
-            u32 fl = 0;
-            if (i + 1 < g.w && bit_at(sv + (size_t)rec * g.nm, i + g.k)) fl = 1u | (base_at(bb, i + g.k) << 1);
-            const u64 stamp = (tile * g.tile_rec + rec) * (u64)g.w + (u64)i;
-            const u64 b = gbase[m >> 20];
-            if (b != INF64) tuple_store(a.tuples, b + (m & 0xFFFFFu), pt, lo, hi, fl, sfp[rec], stamp);
+        /* 4. copy out */
+        const u32 total = sm.boff[NBK];
+        for (u32 e = threadIdx.x; e < total; e += THREADS) {
+            const u32 bk = sm.sbk[e];
+            const u64 gbs = sm.gbase[bk];
+            if (gbs == INF64) continue;
+            const u64 dst = gbs + (e - sm.boff[bk]);
+            const u64 *src = sm.stage + (size_t)e * tw;
+            if (pt.wide) {
+                u64 *p = a.tuples + dst * 3;
+                st_stream_u64(p, src[0]); st_stream_u64(p + 1, src[1]); st_stream_u64(p + 2, src[2]);
+            } else {
+                st_stream_v2(a.tuples + dst * 2, src[0], src[1]);
+            }
         }
         __syncthreads();
     }
@@ -696,7 +773,7 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
     WarpQueue<WIDE> q;
     q.setup(smem);
     LogCursor lc; lc.base = 0; lc.used = LOG_CHUNK;
-    u32 qn = 0;
+    u32 qn = 0, n_slow = 0;   /* warp-uniform */
     const u64 span = (u64)THREADS * BATCH;
     const u64 n_blk = (pt.n_gated + span - 1) / span;
     const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
@@ -736,9 +813,11 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
             if (fast && cnt < CNT_CAP) atomicAdd(&a.table[idx[u]].count, 1u);
             qn = q.push(qn, valid && !fast, lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
         }
-        if (qn >= QFLUSH) { pass1_drain<WIDE>(a, g, pt, q, qn, lc); qn = 0; }
+        if (qn >= QFLUSH) { n_slow += qn; pass1_drain<WIDE>(a, g, pt, q, qn, lc); qn = 0; }
     }
+    n_slow += qn;
     pass1_drain<WIDE>(a, g, pt, q, qn, lc);
+    if ((threadIdx.x & 31) == 0 && n_slow) atomicAdd(&a.ctr->n_slow1, (u64)n_slow);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -959,7 +1038,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
     const u64 span = (u64)THREADS * BATCH;
     const u64 n_blk = (pt.n_valid + span - 1) / span;
     const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
-    u32 n_hits = 0, qn = 0;
+    u32 n_hits = 0, qn = 0, n_slow = 0;
     for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
         const u64 t0 = blk * span + threadIdx.x;
         u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
@@ -1005,9 +1084,11 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             }
             qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
         }
-        if (qn >= QFLUSH) { n_hits += pass2_drain<WIDE>(a, pt, q, qn); qn = 0; }
+        if (qn >= QFLUSH) { n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn); qn = 0; }
     }
+    n_slow += qn;
     n_hits += pass2_drain<WIDE>(a, pt, q, qn);
+    if (lane == 0 && n_slow) atomicAdd(&a.ctr->n_slow2, (u64)n_slow);
     for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
     if (lane == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
 }

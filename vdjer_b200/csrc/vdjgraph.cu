@@ -159,13 +159,11 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     g.w = g.L - g.k + 1;
     g.nb = (g.L + 31) / 32;
     g.nm = (g.L + 63) / 64;
-    /* warp tile: about 32 lanes x BATCH probes x 8 batches of windows, an even record count */
-    uint32_t tr = (32u * BATCH * 8u) / (uint32_t)g.w;
-    tr &= ~1u;
-    tr = std::max(2u, std::min(128u, tr));
+    /* block tile: every thread owns one segment of SEG windows of one record */
+    g.segs = (g.w + SEG - 1) / SEG;
+    uint32_t tr = (uint32_t)THREADS / (uint32_t)g.segs;
+    tr &= ~1u;   /* even: TMA bulk copies need 16-byte sizes and addresses */
     g.tile_rec = tr;
-    g.tile_win = tr * (uint32_t)g.w;
-    g.div_magic = g.w == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)g.w - 1) / (uint64_t)g.w);
     g.R = R;
     g.n_tiles = (R + tr - 1) / tr;
     int bits = 2 * g.k;
@@ -475,7 +473,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     uint64_t launches = 0;
     memset(&c->ctr, 0, sizeof(c->ctr));
     vdjgraph_result &res = c->res;
-    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = 0;
+    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = res.n_slow1 = res.n_slow2 = 0;
     res.ms_device = res.ms_estimate = res.ms_scatter = res.ms_init1 = res.ms_pass1 = res.ms_prune = 0;
     res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
     res.table1_slots = res.table2_slots = 0;
@@ -501,11 +499,8 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     Counters *d_ctr = c->d_ctr.as<Counters>();
     Counters *h_ctr = c->h_ctr.as<Counters>();
 
-    const size_t smem_count = tile_smem_bytes(g, 2) + ((sizeof(uint32_t) << HLL_BITS) + 2 * HB * sizeof(uint32_t));
-    const size_t smem_scatter = tile_smem_bytes(g, 2) + scatter_head_bytes(g);
-    const uint64_t tile_blocks = (g.n_tiles + WARPS - 1) / WARPS;
-    const int grid_count = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
-    const int grid_scatter = (int)std::min<uint64_t>(tile_blocks, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
+    const size_t smem_count = count_head_bytes() + block_tile_bytes(g);
+    const int grid_count = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
     const int grid_flat = c->sm_count * 8;
 
     /* ---- K0: window counts per hash bucket + cardinality estimate ---- */
@@ -579,6 +574,8 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         as.tuples = c->d_tuples.as<u64>();
         as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + 2 * HB;
         as.ctr = d_ctr;
+        const size_t smem_scatter = scatter_carve(nullptr, nullptr, g, 2 * P, pt.wide);
+        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
         k_scatter<<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
         launches++;
         CK(cudaGetLastError());
@@ -639,6 +636,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     if (h_ctr->n_distinct > REF_MAX_NODES)
         return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu distinct gated k-mers exceed MAX_NODES (assembler2_vdj.c:73)", (unsigned long long)h_ctr->n_distinct);
     const uint64_t n_surv = h_ctr->n_surv;
+    res.n_slow1 = h_ctr->n_slow1;
     const uint64_t n_distinct = h_ctr->n_distinct;
 
     /* ---- survivor table + pass 2 ---- */
@@ -707,6 +705,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     res.n_pre_total = n_distinct;
     res.n_pre = n_surv;
     res.n_hits = h_ctr->n_hits;
+    res.n_slow2 = h_ctr->n_slow2;
     res.table1_slots = cap1; res.table2_slots = cap2;
     res.partitions = (uint32_t)P; res.tuple_bytes = (uint32_t)tuple_bytes;
     res.kernel_launches = launches;
