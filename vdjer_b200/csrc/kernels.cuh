@@ -90,6 +90,8 @@ struct Part {
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
     int wide;           /* 1: 24-byte tuples (stamp in a third word) */
     int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
+    u32 l1_refresh;     /* 0 never, 1 after every slow-path drain, 2 once per batch by warp 0 (see l1_invalidate) */
+    u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
     u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
     u64 n_gated, n_valid; /* tuples in the gated region / in both regions */
 };
@@ -140,6 +142,14 @@ __device__ __forceinline__ u64 ld_ca_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.global.ca.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+/* Drop this SM's L1 lines (CCTL.IVALL, emitted after an acquire load): the fast paths then see
+ * what the slow path has just established (a k-mer inserted, MULTI set, ranks used up) instead
+ * of a stale line that would keep sending the k-mer's tuples to the slow path. */
+__device__ __forceinline__ void l1_invalidate(const void *any) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(any) : "memory");
+    asm volatile("" :: "r"(v));
 }
 /* streaming (touched-once) tuple traffic: evict-first so it does not push the L2-resident
  * table slice out */
@@ -275,6 +285,79 @@ __device__ __forceinline__ void tuple_decode(const Part &pt, u64 w1, u64 w2, u64
  * loads of a batch back to back instead of interleaved with the address arithmetic of the next */
 __device__ __forceinline__ void issue_fence(u32 &a, u32 &b, u32 &c, u32 &d) {
     asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K-1 k_pack: the reference's text records (bam_read.c:206-244: strand char, L bases, L         */
+/* phred+33 qualities) -> the packed layout described at the top of this file.  One warp per     */
+/* record; lane j looks at bases j, j+32, ...: the masks are warp ballots, the 2-bit codes two   */
+/* ballots interleaved.  Also validates what the reference only trips over later: the strand     */
+/* byte (exit(-1) at :383-391) and the alphabet (seq_to_int exit(-1), seq_to_kmer.c:23-25).      */
+/* ------------------------------------------------------------------------------------------ */
+struct PackArgs {
+    const unsigned char *text;   /* records r0 .. r0+n of the concatenated primary+secondary text */
+    u64 r0, n;
+    u64 *bases, *good, *valid;
+    u8 *qual, *strand;
+    u64 *bad;                    /* [0] first record with a bad strand byte, [1] with a bad base (atomicMin), [2] any strand '1' */
+};
+/* bits of a (bit i -> bit 2i) */
+__device__ __forceinline__ u64 spread_bits(u32 a) {
+    u64 x = a;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+__global__ void __launch_bounds__(THREADS)
+k_pack(PackArgs a, Geom g) {
+    const u32 lane = threadIdx.x & 31;
+    const u64 warp = ((u64)blockIdx.x * THREADS + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * THREADS) >> 5;
+    const u64 rec_len = 2ull * g.L + 1;
+    for (u64 i = warp; i < a.n; i += n_warps) {
+        const unsigned char *rec = a.text + i * rec_len;
+        const u64 r = a.r0 + i;
+        if (lane == 0) {
+            const unsigned sc = rec[0];
+            if (sc != '0' && sc != '1') atomicMin(&a.bad[0], r);
+            if (sc == '1') a.bad[2] = 1;
+            a.strand[r] = (u8)(sc - '0');
+        }
+        u64 vword = 0, gword = 0;
+        for (int j0 = 0; j0 < g.L; j0 += 32) {
+            const int j = j0 + (int)lane;
+            unsigned code = 4;   /* beyond the read: neither valid nor an error */
+            bool okq = false;
+            if (j < g.L) {
+                const unsigned ch = rec[1 + j];
+                code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
+                const u8 q = (u8)(rec[1 + g.L + j] - '!');
+                a.qual[r * (u64)g.L + j] = q;
+                okq = q >= GATE_Q;
+            }
+            const u32 b0 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 1u));
+            const u32 b1 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 2u));
+            const u32 bv = __ballot_sync(0xFFFFFFFFu, code < 4);
+            const u32 bg = __ballot_sync(0xFFFFFFFFu, code < 4 && okq);
+            const u32 be = __ballot_sync(0xFFFFFFFFu, code == 5);
+            if (lane == 0) {
+                if (be) atomicMin(&a.bad[1], r);
+                a.bases[r * (u64)g.nb + (j0 >> 5)] = spread_bits(b0) | (spread_bits(b1) << 1);
+                if (j0 & 32) {
+                    a.valid[r * (u64)g.nm + (j0 >> 6)] = vword | ((u64)bv << 32);
+                    a.good[r * (u64)g.nm + (j0 >> 6)] = gword | ((u64)bg << 32);
+                } else {
+                    vword = bv; gword = bg;
+                    if (j0 + 32 >= g.L) {   /* last, half-filled mask word */
+                        a.valid[r * (u64)g.nm + (j0 >> 6)] = vword;
+                        a.good[r * (u64)g.nm + (j0 >> 6)] = gword;
+                    }
+                }
+            }
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -640,8 +723,11 @@ struct Pass1Args {
  * ranks, read comparison, logging) for the rest.  Slow tuples are queued and drained by a lane
  * state machine in which every lane always holds a tuple: a lane that finishes takes the next
  * queue entry, so probe chains of different length do not idle the warp. */
-constexpr u32 QFLUSH = 64;                       /* drain when at least this many are queued */
+constexpr u32 QFLUSH = 96;                       /* drain when at least this many are queued */
 constexpr u32 QCAP = 32 * BATCH + QFLUSH;        /* a batch can add 32*BATCH entries */
+constexpr u32 QDENSE = 20;                       /* a non-final drain stops when fewer lanes than this are busy
+                                                    and puts their tuples (with the probe position reached)
+                                                    back in the queue: long probe chains do not idle the warp */
 template <bool WIDE>
 struct WarpQueue {
     u64 *lo, *w1, *w2;
@@ -673,26 +759,26 @@ struct LogCursor { u32 base, used; };   /* warp-uniform: the warp's current chun
  * round trips to L2 per lane: (1) the probe (sector load, plus the 128-bit CAS when the slot is
  * empty), (2) the arrival-rank atomicAdd and the first-record CAS, issued together. */
 template <bool WIDE>
-__device__ __forceinline__ void pass1_drain(const Pass1Args &a, const Geom &g, const Part &pt, const WarpQueue<WIDE> &q,
-                                            u32 qn, LogCursor &lc) {
+__device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, const Part &pt, WarpQueue<WIDE> &q,
+                                           u32 qn, LogCursor &lc, bool final) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     u32 next = 0;
     bool have = false;
-    u64 lo = 0, hi = 0, stamp = 0;
+    u64 lo = 0, hi = 0, stamp = 0, rw1 = 0, rw2 = 0;
     u32 idx = 0, probe = 0, fp = 0;
     __syncwarp();
     for (;;) {
         /* refill idle lanes */
         const u32 need = __ballot_sync(0xFFFFFFFFu, !have);
         const u32 avail = qn - next;
-        if (need == 0xFFFFFFFFu && avail == 0) break;
+        if (avail == 0 && (need == 0xFFFFFFFFu || (!final && 32 - __popc(need) < (int)pt.qdense1))) break;
         if (need && avail) {
             const u32 my = __popc(need & lt);
             if (!have && my < avail) {
                 const u32 e = next + my;
                 u32 fl;
-                lo = q.lo[e];
-                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, fp, stamp);
+                lo = q.lo[e]; rw1 = q.w1[e]; rw2 = WIDE ? q.w2[e] : 0ull;
+                tuple_decode<WIDE>(pt, rw1, rw2, hi, fl, fp, stamp);
                 idx = q.idx[e];
                 probe = 0;
                 have = true;
@@ -763,7 +849,11 @@ __device__ __forceinline__ void pass1_drain(const Pass1Args &a, const Geom &g, c
             have = false;
         }
     }
+    /* unfinished tuples go back to the (now empty) queue with the slot they have reached */
     __syncwarp();
+    const u32 left = q.push(0, have, lo, rw1, rw2, idx);
+    __syncwarp();
+    return left;
 }
 
 template <bool WIDE>
@@ -813,10 +903,14 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
             if (fast && cnt < CNT_CAP) atomicAdd(&a.table[idx[u]].count, 1u);
             qn = q.push(qn, valid && !fast, lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
         }
-        if (qn >= QFLUSH) { n_slow += qn; pass1_drain<WIDE>(a, g, pt, q, qn, lc); qn = 0; }
+        if (qn >= pt.qflush1) {
+            n_slow += qn; qn = pass1_drain<WIDE>(a, g, pt, q, qn, lc, false); n_slow -= qn;
+            if (pt.l1_refresh == 1 && (threadIdx.x & 31) == 0) l1_invalidate(&a.ctr->overflow);
+        }
+        if (pt.l1_refresh == 2 && threadIdx.x == 0) l1_invalidate(&a.ctr->overflow);
     }
     n_slow += qn;
-    pass1_drain<WIDE>(a, g, pt, q, qn, lc);
+    pass1_drain<WIDE>(a, g, pt, q, qn, lc, true);
     if ((threadIdx.x & 31) == 0 && n_slow) atomicAdd(&a.ctr->n_slow1, (u64)n_slow);
 }
 
@@ -980,24 +1074,24 @@ __device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2,
 /* slow path of pass 2: tuples whose home slot holds a different k-mer; queue entries carry the
  * tuple, its home slot and (top bit of idx) whether the tuple is from the ungated region */
 template <bool WIDE>
-__device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, const WarpQueue<WIDE> &q, u32 qn) {
+__device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, WarpQueue<WIDE> &q, u32 &qn, bool final) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     u32 next = 0, n_hits = 0;
     bool have = false, count_it = false;
-    u64 lo = 0, hi = 0, stamp = 0;
+    u64 lo = 0, hi = 0, stamp = 0, rw1 = 0, rw2 = 0;
     u32 idx = 0, probe = 0, fl = 0;
     __syncwarp();
     for (;;) {
         const u32 need = __ballot_sync(0xFFFFFFFFu, !have);
         const u32 avail = qn - next;
-        if (need == 0xFFFFFFFFu && avail == 0) break;
+        if (avail == 0 && (need == 0xFFFFFFFFu || (!final && 32 - __popc(need) < (int)pt.qdense2))) break;
         if (need && avail) {
             const u32 my = __popc(need & lt);
             if (!have && my < avail) {
                 const u32 e = next + my;
-                lo = q.lo[e];
+                lo = q.lo[e]; rw1 = q.w1[e]; rw2 = WIDE ? q.w2[e] : 0ull;
                 u32 fp;
-                tuple_decode<WIDE>(pt, q.w1[e], WIDE ? q.w2[e] : 0ull, hi, fl, fp, stamp);
+                tuple_decode<WIDE>(pt, rw1, rw2, hi, fl, fp, stamp);
                 idx = q.idx[e];
                 count_it = idx >> 31;
                 idx &= 0x7FFFFFFFu;
@@ -1024,6 +1118,9 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, c
             }
         }
     }
+    /* unfinished tuples go back to the (now empty) queue with the slot they have reached */
+    __syncwarp();
+    qn = q.push(0, have, lo, rw1, rw2, idx | (count_it ? 0x80000000u : 0u));
     __syncwarp();
     return n_hits;
 }
@@ -1084,10 +1181,14 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             }
             qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
         }
-        if (qn >= QFLUSH) { n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn); qn = 0; }
+        if (qn >= pt.qflush2) {
+            n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false); n_slow -= qn;
+            if (pt.l1_refresh == 1 && lane == 0) l1_invalidate(&a.ctr->overflow);
+        }
+        if (pt.l1_refresh == 2 && threadIdx.x == 0) l1_invalidate(&a.ctr->overflow);
     }
     n_slow += qn;
-    n_hits += pass2_drain<WIDE>(a, pt, q, qn);
+    n_hits += pass2_drain<WIDE>(a, pt, q, qn, true);
     if (lane == 0 && n_slow) atomicAdd(&a.ctr->n_slow2, (u64)n_slow);
     for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
     if (lane == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);

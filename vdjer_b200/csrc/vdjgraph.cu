@@ -105,7 +105,7 @@ struct StageWorker {
     bool busy[2] = { false, false };
 };
 
-constexpr uint32_t STAGE_CHUNK = 32768; /* records per staging chunk */
+constexpr uint32_t STAGE_CHUNK = 32768; /* records per staging chunk (3.3 MB of text at L=50) */
 constexpr uint64_t REF_MAX_NODES = 900000000ull; /* MAX_NODES, assembler2_vdj.c:73 */
 constexpr uint64_t SLICE_BYTES = 24ull << 20;   /* table-1 bytes one hash partition addresses: L2-resident */
 
@@ -123,7 +123,8 @@ struct vdjgraph_ctx {
     cudaEvent_t ev[12] = {};
     std::vector<StageWorker> workers;
 
-    DevBuf d_bases, d_good, d_valid, d_qual, d_strand;
+    DevBuf d_text, d_bad, d_bases, d_good, d_valid, d_qual, d_strand;
+    PinBuf h_bad;
     DevBuf d_t1, d_log, d_t2, d_hll, d_ctr, d_hist, d_cursor, d_tuples;
     DevBuf d_keys[2], d_vals[2], d_cub;
     DevBuf d_first_pos, d_freq, d_odeg, d_ideg, d_osucc, d_ipred, d_klo, d_khi;
@@ -176,74 +177,6 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
 /* ---------------------------------------------------------------------------------------- */
 /* staging: text records (bam_read.c:206-244) -> packed arrays, chunked through pinned memory */
 /* ---------------------------------------------------------------------------------------- */
-struct PackLut {
-    uint8_t v[256];
-    PackLut() {
-        memset(v, 0xFF, sizeof(v));
-        v[(unsigned char)'A'] = 0; v[(unsigned char)'C'] = 1; v[(unsigned char)'G'] = 2; v[(unsigned char)'T'] = 3;
-        v[(unsigned char)'N'] = 4;
-    }
-};
-const PackLut g_lut;
-
-struct ChunkPtrs {
-    uint64_t *bases, *good, *valid;
-    uint8_t *qual, *strand;
-};
-
-ChunkPtrs carve(void *base, const Geom &g, uint32_t n) {
-    ChunkPtrs c;
-    char *p = (char *)base;
-    c.bases = (uint64_t *)p; p += (size_t)n * g.nb * 8;
-    c.good = (uint64_t *)p;  p += (size_t)n * g.nm * 8;
-    c.valid = (uint64_t *)p; p += (size_t)n * g.nm * 8;
-    c.qual = (uint8_t *)p;   p += (size_t)n * g.L;
-    c.strand = (uint8_t *)p;
-    return c;
-}
-size_t chunk_bytes(const Geom &g, uint32_t n) { return (size_t)n * ((size_t)g.nb * 8 + (size_t)g.nm * 16 + g.L + 1); }
-
-/* returns 0 or a vdjgraph_status; *bad_rec receives the offending record */
-int pack_records(const char *primary, uint64_t np, const char *secondary, const Geom &g,
-                 uint64_t r_lo, uint64_t r_hi, const ChunkPtrs &out, bool *any_strand1, uint64_t *bad_rec) {
-    const int L = g.L;
-    const size_t rec_len = (size_t)2 * L + 1;
-    for (uint64_t r = r_lo; r < r_hi; r++) {
-        const char *rec = r < np ? primary + r * rec_len : secondary + (r - np) * rec_len;
-        const uint64_t o = r - r_lo;
-        unsigned sc = (unsigned char)rec[0];
-        if (sc != '0' && sc != '1') { *bad_rec = r; return VDJGRAPH_ERR_STRAND; }
-        out.strand[o] = (uint8_t)(sc - '0');
-        if (sc == '1') *any_strand1 = true;
-        const unsigned char *seq = (const unsigned char *)rec + 1;
-        const unsigned char *ql = seq + L;
-        uint64_t *bw = out.bases + o * g.nb, *gw = out.good + o * g.nm, *vw = out.valid + o * g.nm;
-        uint8_t *qo = out.qual + o * (size_t)L;
-        unsigned err = 0;
-        for (int j0 = 0; j0 < L; j0 += 64) {
-            uint64_t good = 0, valid = 0, b0 = 0, b1 = 0;
-            int jn = std::min(64, L - j0);
-            for (int j = 0; j < jn; j++) {
-                unsigned code = g_lut.v[seq[j0 + j]];
-                err |= code;
-                uint8_t q = (uint8_t)(ql[j0 + j] - '!');
-                qo[j0 + j] = q;
-                uint64_t isv = code < 4;
-                valid |= isv << j;
-                good |= (isv & (uint64_t)(q >= GATE_Q)) << j;
-                uint64_t two = (uint64_t)(code & 3u);
-                if (j < 32) b0 |= two << (2 * j); else b1 |= two << (2 * (j - 32));
-            }
-            gw[j0 >> 6] = good;
-            vw[j0 >> 6] = valid;
-            bw[j0 >> 5] = b0;
-            if ((j0 >> 5) + 1 < g.nb) bw[(j0 >> 5) + 1] = b1;
-        }
-        if (err & 0x80) { *bad_rec = r; return VDJGRAPH_ERR_BASE; }
-    }
-    return 0;
-}
-
 int ensure_workers(vdjgraph_ctx *c, int n) {
     if ((int)c->workers.size() >= n) return 0;
     size_t old = c->workers.size();
@@ -256,15 +189,15 @@ int ensure_workers(vdjgraph_ctx *c, int n) {
     return 0;
 }
 
+/* Staging = raw text to the device + k_pack there.  The host only moves bytes: worker threads
+ * copy chunks of the caller's (pageable) buffers into their page-locked buffers and queue the
+ * H2D copy and the chunk's k_pack launch on their own stream, double buffered. */
 struct StageShared {
     vdjgraph_ctx *c;
     const char *primary, *secondary;
     uint64_t np, R;
     std::atomic<uint64_t> next_chunk{0};
     std::atomic<int> status{0};
-    std::atomic<uint64_t> bad_rec{0};
-    std::atomic<bool> any_strand1{false};
-    std::string err;
 };
 
 void stage_worker(StageShared *s, int wi) {
@@ -272,28 +205,32 @@ void stage_worker(StageShared *s, int wi) {
     StageWorker &w = c->workers[wi];
     const Geom &g = c->g;
     if (cudaSetDevice(c->device) != cudaSuccess) { s->status = VDJGRAPH_ERR_CUDA; return; }
+    const size_t rec_len = (size_t)2 * g.L + 1;
     const uint64_t n_chunks = (s->R + STAGE_CHUNK - 1) / STAGE_CHUNK;
     int b = 0;
-    bool any1 = false;
     for (;;) {
         uint64_t ch = s->next_chunk.fetch_add(1);
         if (ch >= n_chunks || s->status.load() != 0) break;
-        uint64_t r_lo = ch * STAGE_CHUNK, r_hi = std::min<uint64_t>(s->R, r_lo + STAGE_CHUNK);
-        uint32_t n = (uint32_t)(r_hi - r_lo);
+        const uint64_t r_lo = ch * STAGE_CHUNK, r_hi = std::min<uint64_t>(s->R, r_lo + STAGE_CHUNK);
+        const uint64_t n = r_hi - r_lo;
         if (w.busy[b]) { cudaEventSynchronize(w.ev[b]); w.busy[b] = false; }
-        ChunkPtrs cp = carve(w.buf[b].p, g, n);
-        uint64_t bad = 0;
-        int rc = pack_records(s->primary, s->np, s->secondary, g, r_lo, r_hi, cp, &any1, &bad);
-        if (rc) { s->bad_rec = bad; s->status = rc; break; }
-        cudaError_t e = cudaSuccess;
-        auto cpy = [&](void *dst, const void *src, size_t bytes) {
-            if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, w.stream);
-        };
-        cpy(c->d_bases.as<uint64_t>() + r_lo * g.nb, cp.bases, (size_t)n * g.nb * 8);
-        cpy(c->d_good.as<uint64_t>() + r_lo * g.nm, cp.good, (size_t)n * g.nm * 8);
-        cpy(c->d_valid.as<uint64_t>() + r_lo * g.nm, cp.valid, (size_t)n * g.nm * 8);
-        cpy(c->d_qual.as<uint8_t>() + r_lo * (size_t)g.L, cp.qual, (size_t)n * g.L);
-        cpy(c->d_strand.as<uint8_t>() + r_lo, cp.strand, (size_t)n);
+        char *pin = w.buf[b].as<char>();
+        /* records [r_lo, r_hi) of primary ++ secondary */
+        const uint64_t np_part = r_lo < s->np ? std::min<uint64_t>(r_hi, s->np) - r_lo : 0;
+        if (np_part) memcpy(pin, s->primary + r_lo * rec_len, np_part * rec_len);
+        if (np_part < n) memcpy(pin + np_part * rec_len, s->secondary + (r_lo + np_part - s->np) * rec_len, (n - np_part) * rec_len);
+        unsigned char *dst = c->d_text.as<unsigned char>() + r_lo * rec_len;
+        cudaError_t e = cudaMemcpyAsync(dst, pin, n * rec_len, cudaMemcpyHostToDevice, w.stream);
+        if (e == cudaSuccess) {
+            PackArgs pa;
+            pa.text = dst; pa.r0 = r_lo; pa.n = n;
+            pa.bases = c->d_bases.as<u64>(); pa.good = c->d_good.as<u64>(); pa.valid = c->d_valid.as<u64>();
+            pa.qual = c->d_qual.as<u8>(); pa.strand = c->d_strand.as<u8>();
+            pa.bad = c->d_bad.as<u64>();
+            const int grid = (int)std::min<uint64_t>((n + WARPS - 1) / WARPS, (uint64_t)c->sm_count * 8);
+            k_pack<<<grid, THREADS, 0, w.stream>>>(pa, g);
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaEventRecord(w.ev[b], w.stream);
         if (e != cudaSuccess) { s->status = VDJGRAPH_ERR_CUDA; break; }
         w.busy[b] = true;
@@ -301,7 +238,6 @@ void stage_worker(StageShared *s, int wi) {
     }
     if (cudaStreamSynchronize(w.stream) != cudaSuccess) s->status = VDJGRAPH_ERR_CUDA;
     w.busy[0] = w.busy[1] = false;
-    if (any1) s->any_strand1 = true;
 }
 
 int blocks_per_sm(const void *kernel, size_t smem) {
@@ -375,12 +311,12 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_text, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
     for (DevBuf *b : db) b->release();
-    PinBuf *pb[] = { &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+    PinBuf *pb[] = { &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
     for (int i = 0; i < 12; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -426,14 +362,21 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
     uint64_t h2d = 0;
     c->any_strand1 = false;
     if (R) {
+        const size_t rec_len = (size_t)2 * g.L + 1;
+        if ((rc = c->d_text.ensure(R * rec_len))) return rc;
+        if ((rc = c->d_bad.ensure(3 * sizeof(uint64_t))) || (rc = c->h_bad.ensure(3 * sizeof(uint64_t)))) return rc;
+        uint64_t *hb = c->h_bad.as<uint64_t>();
+        hb[0] = hb[1] = ~0ull; hb[2] = 0;
+        CK(cudaMemcpyAsync(c->d_bad.p, hb, 3 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   /* padding memsets and the flags are in place before the workers start */
         const uint64_t n_chunks = (R + STAGE_CHUNK - 1) / STAGE_CHUNK;
-        int nt = c->prm.host_threads > 0 ? c->prm.host_threads : (int)std::thread::hardware_concurrency();
+        int nt = c->prm.host_threads > 0 ? c->prm.host_threads : (int)std::min(16u, std::thread::hardware_concurrency());
         nt = std::max(1, std::min<int>(nt, 64));
         nt = (int)std::min<uint64_t>((uint64_t)nt, n_chunks);
         if ((rc = ensure_workers(c, nt))) return rc;
         for (int i = 0; i < nt; i++)
             for (int b = 0; b < 2; b++)
-                if ((rc = c->workers[i].buf[b].ensure(chunk_bytes(g, STAGE_CHUNK)))) return rc;
+                if ((rc = c->workers[i].buf[b].ensure((size_t)STAGE_CHUNK * rec_len))) return rc;
         StageShared sh;
         sh.c = c; sh.primary = primary; sh.secondary = secondary; sh.np = np; sh.R = R;
         std::vector<std::thread> th;
@@ -441,15 +384,17 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
         stage_worker(&sh, 0);
         for (auto &t : th) t.join();
         if (int st = sh.status.load()) {
-            if (st == VDJGRAPH_ERR_STRAND)
-                return fail(st, "record %llu does not start with '0' or '1' (assembler2_vdj.c:383-391)", (unsigned long long)sh.bad_rec.load());
-            if (st == VDJGRAPH_ERR_BASE)
-                return fail(st, "record %llu holds a base outside ACGTN", (unsigned long long)sh.bad_rec.load());
             cudaError_t e = cudaGetLastError();
             return fail(st, "staging failed: %s", cudaGetErrorString(e));
         }
-        c->any_strand1 = sh.any_strand1.load();
-        h2d = R * ((uint64_t)g.nb * 8 + (uint64_t)g.nm * 16 + (uint64_t)g.L + 1);
+        CK(cudaMemcpyAsync(hb, c->d_bad.p, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (hb[0] != ~0ull)
+            return fail(VDJGRAPH_ERR_STRAND, "record %llu does not start with '0' or '1' (assembler2_vdj.c:383-391)", (unsigned long long)hb[0]);
+        if (hb[1] != ~0ull)
+            return fail(VDJGRAPH_ERR_BASE, "record %llu holds a base outside ACGTN", (unsigned long long)hb[1]);
+        c->any_strand1 = hb[2] != 0;
+        h2d = R * rec_len;
     }
     CK(cudaStreamSynchronize(c->stream));
     memset(&c->res, 0, sizeof(c->res));
@@ -544,6 +489,11 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         pt.fb = pt.wide ? 32 : std::min(32, 64 - pt.hb - 4 - sbits);
         /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
         pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
+        pt.qflush1 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 64)));
+        pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
+        pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
+        pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
+        pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
         pt.n_gated = n_gated;
         pt.n_valid = n_valid;
     }
@@ -640,7 +590,7 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     const uint64_t n_distinct = h_ctr->n_distinct;
 
     /* ---- survivor table + pass 2 ---- */
-    const double load2 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD2", 0.5)));
+    const double load2 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD2", 0.25)));
     pt.slice2 = (std::max<uint64_t>(1024, (uint64_t)((double)n_surv / load2) + 64) + P - 1) / P;
     const uint64_t cap2 = pt.slice2 * (uint64_t)P;
     if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
