@@ -53,7 +53,7 @@ typedef struct vdjgraph_params {
     int32_t min_node_freq;    /* p.min_node_freq = --mf */
     int32_t min_base_quality; /* p.min_base_quality = --mq; values > 254 are clamped like main() :1514-1516 */
     int32_t device;           /* CUDA device ordinal; -1 = the calling thread's current device */
-    int32_t host_threads;     /* staging threads for text -> packed conversion; 0 = auto */
+    int32_t host_threads;     /* staging threads (pageable text -> pinned chunks -> H2D; packing runs on the device); 0 = auto */
     uint64_t table_capacity;  /* pass-1 table slots; 0 = auto (cardinality estimate on device) */
     uint32_t flags;           /* VDJGRAPH_FLAG_* */
     uint32_t partitions;      /* hash partitions (power of two <= 256); 0 = auto (table slice ~24 MB, L2-resident) */
@@ -94,7 +94,7 @@ typedef struct vdjgraph_result {
     uint64_t n_slow1, n_slow2; /* diagnostics: tuples that took the slow (queued) path of pass 1 / pass 2 */
 
     /* timings of the last build, milliseconds */
-    float ms_stage;            /* host pack + H2D (wall clock) */
+    float ms_stage;            /* H2D of the text + device packing (wall clock) */
     float ms_device;           /* whole vdjgraph_run, CUDA events on the build stream (includes the
                                   two small counter read-backs that size the tables) */
     /* per-kernel CUDA-event times: k_count (window histogram + cardinality estimate), k_scatter,
@@ -139,7 +139,8 @@ int vdjgraph_build(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_reco
                    const char *secondary, size_t n_secondary_records, vdjgraph_result *out);
 
 /* The same in three steps, so that callers (and bench.py) can keep a read set resident in HBM. */
-/* 1. host staging: pack to 2-bit bases + gate/N masks + quality bytes, copy to the device */
+/* 1. staging: the text goes to the device in pinned chunks and is packed there (2-bit bases, gate/N
+ *    masks, quality bytes); validates strand bytes and the alphabet */
 int vdjgraph_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
                    const char *secondary, size_t n_secondary_records);
 /* 2. device only: estimate -> pass 1 -> prune -> pass 2 -> rank/edges/compaction; blocks until done */

@@ -114,3 +114,46 @@ def diff(a: dict, b: dict, keys=GRAPH_KEYS) -> list[str]:
         if not same:
             bad.append(k)
     return bad
+
+
+# --------------------------------------------------------------------------------------------
+# glue check: the reference's downstream code (identify_root_nodes, condense_graph, dump_graph)
+# on a graph rebuilt by glue/vdjgraph_glue.inc from vdjgraph_result arrays
+# --------------------------------------------------------------------------------------------
+GLUE_LIB = os.path.join(HERE, "_ref", "libvdjglue.so")
+
+
+def have_glue() -> bool:
+    return os.path.exists(GLUE_LIB)
+
+
+def glue_dot(primary, secondary, read_length: int, k: int, mf: int, mq: int, dot_path: str,
+             graph=None, scratch_dir: str | None = None):
+    """Write the reference's vdjer.dot for these records.  graph=None: built by the reference's own
+    functions; otherwise an object/dict with first_pos, frequency, out_deg, in_deg, out_succ,
+    in_pred (the vdjgraph_result arrays), rebuilt through the glue.  Returns (n_nodes, n_roots)."""
+    from vdjer_b200.graph import _Result   # struct layout of include/vdjgraph.h
+    p, s = _cbuf(primary), _cbuf(secondary)
+    lib = C.CDLL(GLUE_LIB)
+    lib.vdjglue_dot.restype = C.c_long
+    lib.vdjglue_dot.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
+    res_ptr, keep = None, []
+    if graph is not None:
+        get = (lambda n: graph[n]) if isinstance(graph, dict) else (lambda n: getattr(graph, n))
+        r = _Result()
+        r.n_nodes = len(get("first_pos"))
+        for name, dt in [("first_pos", np.uint64), ("frequency", np.uint16), ("out_deg", np.uint8),
+                         ("in_deg", np.uint8), ("out_succ", np.uint32), ("in_pred", np.uint32)]:
+            a = np.ascontiguousarray(get(name), dtype=dt)
+            keep.append(a)
+            setattr(r, name, a.ctypes.data_as(type(getattr(r, name))))
+        keep.append(r)
+        res_ptr = C.addressof(r)
+    n_roots = C.c_long(0)
+    scratch = scratch_dir or os.path.join(HERE, "_ref")
+    n = lib.vdjglue_dot(p.ctypes.data, s.ctypes.data, read_length, k, mf, mq, scratch.encode(), res_ptr,
+                        dot_path.encode(), C.byref(n_roots))
+    if n < 0:
+        raise RuntimeError(f"vdjglue_dot failed with {n}")
+    return int(n), int(n_roots.value)

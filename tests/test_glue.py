@@ -1,0 +1,55 @@
+"""The drop-in seam: glue/vdjgraph_glue.inc rebuilds the reference's `nodes` map, node pool and
+toNodes/fromNodes lists from vdjgraph_result arrays; the reference's OWN downstream code
+(identify_root_nodes :653, condense_graph :598, dump_graph :1133) must then write a vdjer.dot that
+is byte-identical to the one it writes after its own build_pre_graph/prune_pre_graph/build_graph2.
+
+CPU test: arrays from the oracle (same layout).  GPU test: arrays from libvdjgraph.
+Needs oracle/_ref/libvdjglue.so (compiled from /root/reference by oracle/Makefile; travels to the
+GPU box prebuilt)."""
+import os
+
+import pytest
+
+from oracle import loader
+from tests.cases import CASES, make_inputs
+
+needs_glue = pytest.mark.skipif(not loader.have_glue(), reason="oracle/_ref/libvdjglue.so not built (no /root/reference)")
+
+# k = 50 is left out: dump_graph copies k characters + NUL into char buf[50] (:1179-1181)
+DOT_CASES = ["igh_default_k35", "igh_sensitive_k25", "permissive_k25", "igk_2x75_k35", "pooled_2x100_k35",
+             "k16", "k33", "noisy", "mq0", "secondary_only", "hand_edges"]
+
+
+def _dots(tmp_path, name, graph):
+    case = CASES[name]
+    primary, secondary = make_inputs(case)
+    a, b = str(tmp_path / "ref.dot"), str(tmp_path / "glue.dot")
+    want = loader.glue_dot(primary, secondary, case["L"], case["k"], case["mf"], case["mq"], a)
+    g = graph(primary, secondary, case)
+    got = loader.glue_dot(primary, secondary, case["L"], case["k"], case["mf"], case["mq"], b, graph=g)
+    return want, got, open(a, "rb").read(), open(b, "rb").read()
+
+
+@needs_glue
+@pytest.mark.parametrize("name", DOT_CASES)
+def test_vdjer_dot_identical_from_oracle_arrays(tmp_path, built, name):
+    want, got, ref_dot, glue_dot = _dots(
+        tmp_path, name, lambda p, s, c: loader.build(p, s, c["L"], c["k"], c["mf"], c["mq"], kind="port"))
+    assert got == want, f"{name}: (nodes, roots) {got} != {want}"
+    assert glue_dot == ref_dot, f"{name}: vdjer.dot differs"
+    assert len(ref_dot) > 40 or want[0] == 0
+
+
+@needs_glue
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DOT_CASES)
+def test_vdjer_dot_identical_from_cuda_graph(tmp_path, built, name):
+    from vdjer_b200 import GraphBuilder
+
+    def cuda(p, s, c):
+        with GraphBuilder(c["L"], c["k"], c["mf"], c["mq"]) as gb:
+            return gb.build(p, s)
+
+    want, got, ref_dot, glue_dot = _dots(tmp_path, name, cuda)
+    assert got == want, f"{name}: (nodes, roots) {got} != {want}"
+    assert glue_dot == ref_dot, f"{name}: vdjer.dot differs"

@@ -127,11 +127,13 @@ class PreTable:
     frequency: np.ndarray
 
 
-def _np_from(ptr, n, dtype, cols=1):
+def _np_from(ptr, n, dtype, cols=1, copy=True):
     if n == 0 or not ptr:
         shape = (0, cols) if cols > 1 else (0,)
         return np.zeros(shape, dtype=dtype)
-    a = np.ctypeslib.as_array(ptr, shape=(n * cols,)).copy()
+    a = np.ctypeslib.as_array(ptr, shape=(n * cols,))
+    if copy:
+        a = a.copy()
     return a.reshape(n, cols) if cols > 1 else a
 
 
@@ -195,10 +197,10 @@ class GraphBuilder:
     def run(self):
         self._check(self._lib.vdjgraph_run(self._ctx))
 
-    def fetch(self) -> Graph:
+    def fetch(self, copy: bool = True) -> Graph:
         r = _Result()
         self._check(self._lib.vdjgraph_fetch(self._ctx, C.byref(r)))
-        return self._graph(r)
+        return self._graph(r, copy)
 
     def fetch_stats(self) -> dict:
         """Counters and timings of the last run() without the device-to-host copy of the graph."""
@@ -206,12 +208,15 @@ class GraphBuilder:
         self._check(self._lib.vdjgraph_stats(self._ctx, C.byref(r)))
         return self._stats(r)
 
-    def build(self, primary, secondary=b"") -> Graph:
-        """vdjgraph_build: HOST buffers in, graph out (stage + run + fetch)."""
+    def build(self, primary, secondary=b"", copy: bool = True) -> Graph:
+        """vdjgraph_build: HOST buffers in, graph out (stage + run + fetch).
+
+        copy=False returns views of the library's page-locked result arrays, exactly what a C
+        caller gets: valid until the next stage/build/close on this builder."""
         p, s, n_p, n_s = self._counts(primary, secondary)
         r = _Result()
         self._check(self._lib.vdjgraph_build(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
-        return self._graph(r)
+        return self._graph(r, copy)
 
     def pre_table(self) -> PreTable:
         t = _PreTable()
@@ -226,12 +231,12 @@ class GraphBuilder:
                 for k, _ in _Result._fields_
                 if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple"))}
 
-    def _graph(self, r: _Result) -> Graph:
+    def _graph(self, r: _Result, copy: bool = True) -> Graph:
         n = int(r.n_nodes)
         stats = self._stats(r)
         return Graph(
-            n, _np_from(r.first_pos, n, np.uint64), _np_from(r.frequency, n, np.uint16),
-            _np_from(r.out_deg, n, np.uint8), _np_from(r.in_deg, n, np.uint8),
-            _np_from(r.out_succ, n, np.uint32, 4), _np_from(r.in_pred, n, np.uint32, 4),
-            _np_from(r.kmer_lo, n, np.uint64) if r.kmer_lo else None,
-            _np_from(r.kmer_hi, n, np.uint64) if r.kmer_hi else None, stats)
+            n, _np_from(r.first_pos, n, np.uint64, 1, copy), _np_from(r.frequency, n, np.uint16, 1, copy),
+            _np_from(r.out_deg, n, np.uint8, 1, copy), _np_from(r.in_deg, n, np.uint8, 1, copy),
+            _np_from(r.out_succ, n, np.uint32, 4, copy), _np_from(r.in_pred, n, np.uint32, 4, copy),
+            _np_from(r.kmer_lo, n, np.uint64, 1, copy) if r.kmer_lo else None,
+            _np_from(r.kmer_hi, n, np.uint64, 1, copy) if r.kmer_hi else None, stats)
