@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VDJGRAPH_ABI_VERSION 1
+#define VDJGRAPH_ABI_VERSION 2
 
 typedef enum vdjgraph_status {
     VDJGRAPH_OK = 0,
@@ -147,6 +147,54 @@ int vdjgraph_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_reco
 int vdjgraph_run(vdjgraph_ctx *ctx);
 /* 3. copy the compacted graph to host memory */
 int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
+
+/*
+ * Sharded build over G = 1, 2, 4 or 8 devices: records are split into contiguous
+ * ranges, k-mers are owner-computed (hash partition p belongs to device p mod G).  The caller
+ * runs one context per device (one process per GPU, or several contexts in one process) and
+ * drives the phases below on all of them, exchanging three small host messages in between.  The
+ * bulk exchange is done by the scatter kernel itself, which writes every tuple into the owner's
+ * buffer through peer-mapped memory (NVLink); survivors are gathered once, on rank 0, which ranks
+ * the nodes and builds the edge lists.  Results are identical to the one-device build.
+ *
+ *   all ranks : vdjgraph_shard_stage -> vdjgraph_shard_count                      -> hist, hll
+ *   exchange  : all-gather hist and record counts, element-wise max of hll
+ *   all ranks : vdjgraph_shard_plan  -> vdjgraph_shard_buffers                    -> device pointers
+ *   exchange  : all-gather the pointers (vdjgraph_ipc_export/open across processes)
+ *   all ranks : vdjgraph_shard_set_peers ; BARRIER ; vdjgraph_shard_scatter ; BARRIER
+ *   all ranks : vdjgraph_shard_passes                                             -> survivor count
+ *   exchange  : all-gather the survivor counts
+ *   all ranks : vdjgraph_shard_gather_plan ; rank 0's GATHER pointer to everybody ; set_peers
+ *   all ranks : vdjgraph_shard_send ; BARRIER
+ *   rank 0    : vdjgraph_shard_finish -> vdjgraph_fetch
+ */
+#define VDJGRAPH_SHARD_NBUF 6       /* bases, valid, qual, strand, tuples, gather */
+#define VDJGRAPH_SHARD_HIST 512     /* uint64 per rank: [gated | N-free ungated][256 hash buckets] */
+#define VDJGRAPH_SHARD_HLL 4096     /* uint32 HyperLogLog registers */
+
+typedef struct vdjgraph_shard_info {
+    uint32_t n_ranks, rank;
+    uint64_t record_base;      /* global number of this rank's first record (primary ++ secondary of all ranks, in rank order) */
+    uint64_t total_records;    /* over all ranks */
+} vdjgraph_shard_info;
+
+int vdjgraph_shard_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
+                         const char *secondary, size_t n_secondary_records, const vdjgraph_shard_info *info);
+int vdjgraph_shard_count(vdjgraph_ctx *ctx, uint64_t *hist /*[512]*/, uint32_t *hll /*[4096]*/);
+int vdjgraph_shard_plan(vdjgraph_ctx *ctx, const uint64_t *hist_all /*[n_ranks][512]*/,
+                        const uint32_t *hll_merged /*[4096]*/, const uint64_t *record_counts /*[n_ranks]*/);
+int vdjgraph_shard_buffers(vdjgraph_ctx *ctx, void **ptrs /*[NBUF]*/, size_t *bytes /*[NBUF] or NULL*/);
+int vdjgraph_shard_set_peers(vdjgraph_ctx *ctx, void *const *ptrs /*[n_ranks][NBUF]; this rank's row is ignored*/);
+int vdjgraph_shard_scatter(vdjgraph_ctx *ctx);
+int vdjgraph_shard_passes(vdjgraph_ctx *ctx, uint64_t *n_survivors);
+int vdjgraph_shard_gather_plan(vdjgraph_ctx *ctx, const uint64_t *survivors_all /*[n_ranks]*/);
+int vdjgraph_shard_send(vdjgraph_ctx *ctx);
+int vdjgraph_shard_finish(vdjgraph_ctx *ctx);
+/* peer mapping helpers: CUDA IPC handles (64 opaque bytes) between processes, peer access within one */
+int vdjgraph_ipc_export(const void *device_ptr, unsigned char *handle64);
+int vdjgraph_ipc_open(const unsigned char *handle64, void **device_ptr);
+int vdjgraph_ipc_close(void *device_ptr);
+int vdjgraph_enable_peer_access(int device, int peer_device);
 
 /* Counters and timings of the last run without copying the graph (array pointers are NULL). */
 int vdjgraph_stats(vdjgraph_ctx *ctx, vdjgraph_result *out);

@@ -1,0 +1,133 @@
+"""CPU, world_size 2 over gloo: the host plumbing of the sharded build (vdjer_b200/shard.py).
+No GPU here, so the library's phases are played by a recording stand-in; what is checked is what
+the plumbing is responsible for: every rank hands the SAME merged inputs to the plan phase, record
+bases follow rank order, peer tables are complete and exclude nobody, the gather pointer of rank 0
+reaches everybody, phases run in the documented order and nobody deadlocks.
+The device side of the same flow is covered on a GPU by tests/test_shard_gpu.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from vdjer_b200 import shard  # noqa: E402
+from vdjer_b200.graph import BUF_GATHER, SHARD_HIST, SHARD_HLL, SHARD_NBUF  # noqa: E402
+
+
+class FakeBuilder:
+    """Stands in for GraphBuilder's shard_* methods; pointers are tagged integers."""
+
+    def __init__(self, rank, n_records):
+        self.rank, self.n, self.log = rank, n_records, []
+        self.gather = 0
+
+    def _n_records(self, primary, secondary):
+        return self.n
+
+    def shard_stage(self, p, s, G, rank, base, total):
+        self.log.append(("stage", G, rank, base, total))
+
+    def shard_count(self):
+        rng = np.random.default_rng(100 + self.rank)
+        self.hist = rng.integers(0, 1000, SHARD_HIST).astype(np.uint64)
+        self.hll = rng.integers(0, 30, SHARD_HLL).astype(np.uint32)
+        self.log.append(("count",))
+        return self.hist, self.hll
+
+    def shard_plan(self, hist_all, hll, counts):
+        self.log.append(("plan", hist_all.copy(), hll.copy(), counts.copy()))
+
+    def shard_buffers(self):
+        ptrs = [1000 * (self.rank + 1) + i for i in range(SHARD_NBUF)]
+        ptrs[BUF_GATHER] = self.gather
+        return ptrs, [0] * SHARD_NBUF
+
+    def shard_set_peers(self, table):
+        self.log.append(("peers", [list(r) for r in table]))
+
+    def shard_scatter(self):
+        self.log.append(("scatter",))
+
+    def shard_passes(self):
+        self.log.append(("passes",))
+        return 10 + self.rank
+
+    def shard_gather_plan(self, surv):
+        self.log.append(("gather_plan", list(surv)))
+        if self.rank == 0:
+            self.gather = 777
+
+    def shard_send(self):
+        self.log.append(("send",))
+
+    def shard_finish(self):
+        self.log.append(("finish",))
+
+    def fetch(self, copy=True):
+        return "graph"
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # identity "IPC": a handle is the pointer's decimal text
+    shard._Peers.export = lambda self, ptr: str(ptr).encode() if ptr else b""
+    shard._Peers.map = lambda self, h: int(h) + 5 if h else 0      # +5: a mapping is a different address
+    shard._Peers.close = lambda self: None
+    b = FakeBuilder(rank, 100 + 20 * rank)
+    g = shard.build_distributed(b, None, None, dist=dist)
+    np.save(os.path.join(out_dir, f"log{rank}.npy"), np.array([b.log, g], dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_plumbing_over_gloo(tmp_path):
+    world, port = 2, 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    logs = [np.load(tmp_path / f"log{r}.npy", allow_pickle=True) for r in range(world)]
+    (l0, g0), (l1, g1) = logs
+    assert g0 == "graph" and g1 is None
+    order = ["stage", "count", "plan", "peers", "scatter", "passes", "gather_plan", "peers", "send"]
+    assert [e[0] for e in l0] == order + ["finish"] and [e[0] for e in l1] == order
+    # record bases follow rank order; totals agree
+    assert l0[0] == ("stage", 2, 0, 0, 220) and l1[0] == ("stage", 2, 1, 100, 220)
+    # both ranks plan from identical merged inputs
+    for a, b in zip(l0[2][1:], l1[2][1:]):
+        assert np.array_equal(a, b)
+    hist_all, hll, counts = l0[2][1:]
+    assert hist_all.shape == (2, SHARD_HIST) and list(counts) == [100, 120]
+    rng0, rng1 = np.random.default_rng(100), np.random.default_rng(101)
+    h0, m0 = rng0.integers(0, 1000, SHARD_HIST), rng0.integers(0, 30, SHARD_HLL)
+    h1, m1 = rng1.integers(0, 1000, SHARD_HIST), rng1.integers(0, 30, SHARD_HLL)
+    assert np.array_equal(hist_all[0], h0) and np.array_equal(hist_all[1], h1)
+    assert np.array_equal(hll, np.maximum(m0, m1))           # HyperLogLog registers merge by max
+    # peer tables: the other rank's buffers mapped (pointer + 5), own row left to the library
+    t0, t1 = l0[3][1], l1[3][1]
+    assert t0[0] == [0] * SHARD_NBUF and t1[1] == [0] * SHARD_NBUF
+    assert t0[1][:BUF_GATHER] == [2000 + i + 5 for i in range(BUF_GATHER)]
+    assert t1[0][:BUF_GATHER] == [1000 + i + 5 for i in range(BUF_GATHER)]
+    # survivor counts all-gathered; rank 0's gather buffer reaches rank 1
+    assert l0[6][1] == [10, 11] and l1[6][1] == [10, 11]
+    assert l1[7][1][0][BUF_GATHER] == 777 + 5 and l0[7][1][1][BUF_GATHER] == 0
+
+
+def test_shard_ranges_and_split():
+    assert shard.shard_ranges(10, 4) == [(0, 4), (4, 8), (8, 10), (10, 10)]
+    for total, G in [(0, 2), (7, 8), (1000, 8), (1001, 4)]:
+        r = shard.shard_ranges(total, G)
+        assert r[0][0] == 0 and r[-1][1] == total and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(lo % 2 == 0 for lo, hi in r if hi > lo)   # a read and its reverse complement stay together
+    L = 3
+    rb = 2 * L + 1
+    p = np.arange(4 * rb, dtype=np.uint8)
+    s = np.arange(100, 100 + 3 * rb, dtype=np.uint8)
+    parts = [shard.split_records(p, s, L, lo, hi) for lo, hi in [(0, 2), (2, 6), (6, 7)]]
+    assert np.array_equal(np.concatenate([a for a, _ in parts]), p)
+    assert np.array_equal(np.concatenate([b for _, b in parts]), s)
+    assert parts[1][0].size == 2 * rb and parts[1][1].size == 2 * rb

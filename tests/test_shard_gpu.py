@@ -1,0 +1,81 @@
+"""GPU: the sharded build gives exactly the single-device result.
+
+G ranks run as G contexts inside this process on ONE GPU (peer buffers are plain device pointers;
+across processes the same phases run over CUDA IPC mappings, see vdjer_b200/shard.py and
+tests/test_shard_dist.py): every tuple is written by the scatter kernel into the buffer of the
+rank that owns its hash partition, reads are compared and quality rows fetched across ranks, and
+rank 0 finishes over the gathered survivor records."""
+import numpy as np
+import pytest
+
+from oracle import loader
+from tests.util import assert_graph_equal
+from vdjer_b200 import GraphBuilder, shard, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded(primary, secondary, L, k, mf, mq, G, **kw):
+    rb = 2 * L + 1
+    total = (primary.size // rb) + (secondary.size // rb)
+    parts = [shard.split_records(primary, secondary, L, lo, hi) for lo, hi in shard.shard_ranges(total, G)]
+    builders = [GraphBuilder(L, k, mf, mq, device=0, **kw) for _ in range(G)]
+    try:
+        g = shard.build_local(builders, parts)
+        stats = [b.fetch_stats() for b in builders]
+    finally:
+        for b in builders:
+            b.close()
+    return g, stats
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+@pytest.mark.parametrize("L,k,mf,mq,pairs,clones,seed", [
+    (50, 35, 3, 90, 40000, 800, 201),
+    (50, 25, 1, 20, 20000, 150, 202),      # heavy branching: edge order across owners
+    (100, 50, 2, 120, 10000, 300, 203),    # wide tuples
+])
+def test_sharded_equals_single_device_and_oracle(built, G, L, k, mf, mq, pairs, clones, seed):
+    primary, secondary = synth.generate(n_pairs=pairs, read_length=L, seed=seed, n_clones=clones, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    got, stats = _sharded(primary, secondary, L, k, mf, mq, G)
+    assert_graph_equal(got, want, f"G={G}")
+    assert sum(s["n_pre_total"] for s in stats) == want["n_pre_total"]      # k-mers are owned by exactly one rank
+    assert sum(s["n_gated"] for s in stats) == want["n_gated"]
+    assert sum(s["n_hits"] for s in stats) == want["n_hits"]
+    with GraphBuilder(L, k, mf, mq) as gb:
+        single = gb.build(primary, secondary)
+    for name in ["first_pos", "frequency", "out_deg", "in_deg", "out_succ", "in_pred"]:
+        assert np.array_equal(getattr(got, name), getattr(single, name)), name
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_sharded_duplicates_and_strand_across_ranks(built, G):
+    """Identical reads that land on different ranks must still count as ONE read for
+    hasMultipleUniqueReads (:349-352): the exact comparison reads the peer's packed reads."""
+    L, k = 50, 35
+    primary, secondary = synth.generate(n_pairs=6000, read_length=L, seed=205, n_clones=60, threads=4)
+    rb = 2 * L + 1
+    body = primary[:-1].reshape(-1, rb)
+    primary = np.concatenate([body, body, body[::-1]]).reshape(-1)      # every record three times, far apart
+    primary = np.concatenate([primary, np.zeros(1, np.uint8)])
+    want = loader.build(primary, secondary, L, k, 2, 60, kind="port")
+    got, _ = _sharded(primary, secondary, L, k, 2, 60, G)
+    assert_graph_equal(got, want, f"dups G={G}")
+
+
+def test_sharded_empty_rank(built):
+    """A rank without records (fewer records than ranks) takes part in every phase."""
+    L, k = 50, 35
+    primary, secondary = synth.generate(n_pairs=3000, read_length=L, seed=206, n_clones=30, threads=2)
+    want = loader.build(primary, secondary, L, k, 2, 60, kind="port")
+    rb = 2 * L + 1
+    total = primary.size // rb + secondary.size // rb
+    parts = [shard.split_records(primary, secondary, L, 0, total)] + [(np.zeros(0, np.uint8), np.zeros(0, np.uint8))] * 3
+    builders = [GraphBuilder(L, k, 2, 60, device=0) for _ in range(4)]
+    try:
+        got = shard.build_local(builders, parts)
+    finally:
+        for b in builders:
+            b.close()
+    assert_graph_equal(got, want, "empty ranks")

@@ -87,6 +87,8 @@ struct Geom {
 /* hash partitioning + tuple format */
 struct Part {
     int pbits;          /* P = 1 << pbits partitions by the top hash bits */
+    int gbits;          /* sharded build over G = 1 << gbits devices: partition p belongs to device p & (G-1) and
+                           is that device's local partition p >> gbits (tables hold the local partitions only) */
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
     int wide;           /* 1: 24-byte tuples (stamp in a third word) */
     int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
@@ -94,6 +96,23 @@ struct Part {
     u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
     u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
     u64 n_gated, n_valid; /* tuples in the gated region / in both regions */
+};
+
+/* The packed reads of all devices of a sharded build (one entry when there is one device).
+ * Record numbers are global: device d holds records [rec_base[d], rec_base[d+1]).  Peer arrays
+ * are read through NVLink (peer-mapped memory); only the rare exact read comparison and the
+ * quality rows of border k-mers ever touch them. */
+constexpr int MAX_DEV = 8;
+struct Reads {
+    const u64 *bases[MAX_DEV], *valid[MAX_DEV];
+    const u8 *qual[MAX_DEV], *strand[MAX_DEV];
+    u64 rec_base[MAX_DEV + 1];
+    int n_dev, any_strand;
+    __device__ __forceinline__ int dev_of(u64 r) const {
+        int d = 0;
+        while (d + 1 < n_dev && r >= rec_base[d + 1]) d++;
+        return d;
+    }
 };
 
 struct Counters {
@@ -214,9 +233,9 @@ __device__ __forceinline__ u64 hash_key(u64 lo, u64 hi) {
 }
 /* home slot: the top pbits of the hash select the partition (= a contiguous slice of the
  * table), the remaining bits a slot inside it */
-__device__ __forceinline__ u64 home_slot(u64 h, int pbits, u64 slice) {
+__device__ __forceinline__ u64 home_slot(u64 h, int pbits, int gbits, u64 slice) {
     if (pbits == 0) return __umul64hi(h, slice);
-    return (h >> (64 - pbits)) * slice + __umul64hi(h << pbits, slice);
+    return ((h >> (64 - pbits)) >> gbits) * slice + __umul64hi(h << pbits, slice);
 }
 
 /* bits [2i, 2i+2k) of a record's base words */
@@ -512,9 +531,11 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
 /* ------------------------------------------------------------------------------------------ */
 struct ScatterArgs {
     const u64 *bases, *good, *valid;
-    u64 *tuples;
-    u64 *cursor;      /* [2 << pbits] */
-    const u64 *limit; /* [2 << pbits] end of each region (overrun check) */
+    u64 *const *tbase; /* [2 << pbits] tuple buffer of the device that owns the bucket's partition (peer-mapped
+                          when that is another device: the scatter IS the all-to-all of a sharded build) */
+    u64 *cursor;       /* [2 << pbits] next free tuple of this device's share of the bucket's region */
+    const u64 *limit;  /* [2 << pbits] end of that share (overrun check) */
+    u64 rec_base;      /* global number of this device's first record */
     Counters *ctr;
 };
 struct ScatterSmem {
@@ -625,7 +646,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             Roll r;
             r.start(sb, sg, sv, rec, (int)i0, g);
             const u32 fp = sm.fp[rec];
-            const u64 stamp0 = (tile * g.tile_rec + rec) * (u64)g.w;
+            const u64 stamp0 = (a.rec_base + tile * g.tile_rec + rec) * (u64)g.w;
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 if (j < n) {
@@ -655,11 +676,12 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             if (gbs == INF64) continue;
             const u64 dst = gbs + (e - sm.boff[bk]);
             const u64 *src = sm.stage + (size_t)e * tw;
+            u64 *out = a.tbase[bk];
             if (pt.wide) {
-                u64 *p = a.tuples + dst * 3;
+                u64 *p = out + dst * 3;
                 st_stream_u64(p, src[0]); st_stream_u64(p + 1, src[1]); st_stream_u64(p + 2, src[2]);
             } else {
-                st_stream_v2(a.tuples + dst * 2, src[0], src[1]);
+                st_stream_v2(out + dst * 2, src[0], src[1]);
             }
         }
         __syncthreads();
@@ -684,13 +706,14 @@ __global__ void k_init_table2(Slot2 *t, u64 cap) {
 
 /* do records r1 and r2 hold the same L-character sequence and strand?
  * compare_read :142-144 (strncmp over read_length) and the strand test :350 */
-__device__ __noinline__ bool same_read(const u64 *__restrict__ bases, const u64 *__restrict__ valid,
-                                       const u8 *__restrict__ strand, u64 r1, u64 r2, int nb, int nm) {
-    const u64 *b1 = bases + r1 * nb, *b2 = bases + r2 * nb;
+__device__ __noinline__ bool same_read(const Reads &rd, u64 r1, u64 r2, int nb, int nm) {
+    const int d1 = rd.dev_of(r1), d2 = rd.dev_of(r2);
+    const u64 l1 = r1 - rd.rec_base[d1], l2 = r2 - rd.rec_base[d2];
+    const u64 *b1 = rd.bases[d1] + l1 * nb, *b2 = rd.bases[d2] + l2 * nb;
     for (int i = 0; i < nb; i++) if (b1[i] != b2[i]) return false;
-    const u64 *v1 = valid + r1 * nm, *v2 = valid + r2 * nm;
+    const u64 *v1 = rd.valid[d1] + l1 * nm, *v2 = rd.valid[d2] + l2 * nm;
     for (int i = 0; i < nm; i++) if (v1[i] != v2[i]) return false;
-    if (strand && strand[r1] != strand[r2]) return false;
+    if (rd.any_strand && rd.strand[d1][l1] != rd.strand[d2][l2]) return false;
     return true;
 }
 
@@ -707,8 +730,7 @@ __device__ __noinline__ bool same_read(const u64 *__restrict__ bases, const u64 
 /* ------------------------------------------------------------------------------------------ */
 struct Pass1Args {
     const u64 *tuples;
-    const u64 *bases, *valid;
-    const u8 *strand;
+    Reads rd;
     Slot1 *table;
     u64 cap;
     u64 *log;         /* [log_blocks][NB] stamps */
@@ -842,7 +864,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
                 first_rec = (u32)old; first_fp = (u32)(old >> 32);
                 /* different fingerprints: different reads.  Equal ones: compare the reads (:142-144) */
                 if (first_rec != NIL32 && first_rec != r &&
-                    (first_fp != fp || !same_read(a.bases, a.valid, a.strand, first_rec, r, g.nb, g.nm)))
+                    (first_fp != fp || !same_read(a.rd, first_rec, r, g.nb, g.nm)))
                     atomicOr(&slot->count, CNT_MULTI);
             }
             if (rank < a.nb_ranks && blk != NIL32) a.log[(u64)blk * a.nb_ranks + rank] = stamp;
@@ -883,7 +905,7 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
         /* A2: their home slots, again all in flight together */
 #pragma unroll
         for (int u = 0; u < BATCH; u++)
-            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice1);
+            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.gbits, pt.slice1);
         issue_fence(idx[0], idx[1], idx[2], idx[3]);
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
@@ -929,7 +951,7 @@ struct PruneArgs {
     u64 cap;
     const u64 *log;
     u32 nb_ranks;
-    const u8 *qual;
+    Reads rd;
     int mf, T;
     Counters *ctr;
 };
@@ -980,7 +1002,8 @@ k_prune(PruneArgs a, Geom g) {
                 const u64 se = __shfl_sync(0xFFFFFFFFu, st, e);
                 const u64 r = se / (u64)g.w;
                 const u64 o = se == first ? 0 : se - r * (u64)g.w;   /* first occurrence reads q_r0[j], :337-339 */
-                const u8 *qp = a.qual + r * (u64)g.L + o;
+                const int d = a.rd.dev_of(r);
+                const u8 *qp = a.rd.qual[d] + (r - a.rd.rec_base[d]) * (u64)g.L + o;
                 if ((int)lane < g.k) s0 += qp[lane];
                 if ((int)lane + 32 < g.k) s1 += qp[lane + 32];
             }
@@ -1027,7 +1050,7 @@ __device__ __forceinline__ u64 t2_probe_from(const Slot2 *t, u64 cap, u64 idx, u
     return INF64;
 }
 __device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, const Part &pt, u64 lo, u64 hi, u64 &q2, u64 &q3) {
-    return t2_probe_from(t, cap, home_slot(hash_key(lo, hi), pt.pbits, pt.slice2), lo, hi, q2, q3);
+    return t2_probe_from(t, cap, home_slot(hash_key(lo, hi), pt.pbits, pt.gbits, pt.slice2), lo, hi, q2, q3);
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -1038,11 +1061,51 @@ k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters
         ld_sector(&t1[i], q0, q1, q2, q3);
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
         if (!((u32)q2 & CNT_SURV)) continue;
-        const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.slice2), q0, q1);
+        const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.gbits, pt.slice2), q0, q1);
         if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
         /* the gated occurrences are N-free occurrences: seed node->frequency with them */
         const u32 cnt = (u32)q2 & CNT_MASK;
         t2[at].count = cnt > CNT_CAP ? CNT_CAP : cnt;
+    }
+}
+
+/* Sharded build: a device's survivors as dense Slot2 records (sent to the finishing device), and
+ * the finishing device's table over the records of all devices. */
+__global__ void __launch_bounds__(THREADS)
+k_compact_table2(const Slot2 *t, u64 cap, Slot2 *out, u64 *n_out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    const u32 lane = threadIdx.x & 31;
+    const u64 n_iter = (cap + stride - 1) / stride;
+    for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
+        bool occ = false;
+        u64 q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (i < cap) { ld_sector(&t[i], q0, q1, q2, q3); occ = !(q0 == EMPTY64 && q1 == EMPTY64); }
+        const u32 ballot = __ballot_sync(0xFFFFFFFFu, occ);
+        if (!ballot) continue;
+        u64 base = 0;
+        if (lane == 0) base = atomicAdd(n_out, (u64)__popc(ballot));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (occ) {
+            Slot2 *o = out + base + __popc(ballot & ((1u << lane) - 1));
+            u64 r0, r1, r2, r3;
+            ld_sector(reinterpret_cast<const char *>(&t[i]) + 32, r0, r1, r2, r3);
+            st_sector(o, q0, q1, q2, q3);
+            st_sector(reinterpret_cast<char *>(o) + 32, r0, r1, r2, r3);
+        }
+    }
+}
+__global__ void __launch_bounds__(THREADS)
+k_table2_from_records(const Slot2 *rec, u64 n, Slot2 *t2, u64 cap2, Part pt, Counters *ctr) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 q0, q1, q2, q3, r0, r1, r2, r3;
+        ld_sector(&rec[i], q0, q1, q2, q3);
+        ld_sector(reinterpret_cast<const char *>(&rec[i]) + 32, r0, r1, r2, r3);
+        const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.gbits, pt.slice2), q0, q1);
+        if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
+        Slot2 *o = t2 + at;
+        o->count = (u32)q2; o->rank = 0; o->first_any = q3;
+        st_sector(reinterpret_cast<char *>(o) + 32, r0, r1, r2, r3);
     }
 }
 
@@ -1152,7 +1215,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
          * window would update; all loads of the batch in flight together */
 #pragma unroll
         for (int u = 0; u < BATCH; u++)
-            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.slice2);
+            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.gbits, pt.slice2);
         issue_fence(idx[0], idx[1], idx[2], idx[3]);
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {

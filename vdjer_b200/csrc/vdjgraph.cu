@@ -111,6 +111,24 @@ constexpr uint64_t SLICE_BYTES = 24ull << 20;   /* table-1 bytes one hash partit
 
 } // namespace
 
+/* buffers other devices of a sharded build read or write (vdjgraph_shard_buffers order) */
+enum { BUF_BASES = 0, BUF_VALID, BUF_QUAL, BUF_STRAND, BUF_TUPLES, BUF_GATHER, NBUF };
+static_assert(NBUF == VDJGRAPH_SHARD_NBUF, "header and library disagree");
+
+struct Shard {
+    int G = 1, rank = 0, gbits = 0;
+    uint64_t rec_base[MAX_DEV + 1] = {};
+    uint64_t total_records = 0;
+    std::vector<uint64_t> cnt;                    /* [G][2][P] windows per device, class, partition */
+    void *peer[MAX_DEV][NBUF] = {};
+    bool peers_set = false;
+    uint64_t n_gated_own = 0, n_valid_own = 0;    /* tuples this device receives */
+    uint64_t n_gated_src = 0, n_valid_src = 0;    /* windows this device produces */
+    double est_distinct = 0;
+    uint64_t surv_all[MAX_DEV] = {}, surv_off[MAX_DEV + 1] = {};
+    int phase = 0;  /* 0 staged, 1 counted, 2 planned, 3 scattered, 4 passes done, 5 gather planned, 6 sent, 7 finished */
+};
+
 struct vdjgraph_ctx {
     vdjgraph_params prm;
     int device = 0;
@@ -120,7 +138,7 @@ struct vdjgraph_ctx {
     bool any_strand1 = false;
     bool staged = false, ran = false;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[12] = {};
+    cudaEvent_t ev[13] = {};
     std::vector<StageWorker> workers;
 
     DevBuf d_text, d_bad, d_bases, d_good, d_valid, d_qual, d_strand;
@@ -133,6 +151,10 @@ struct vdjgraph_ctx {
     Part part;
     PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
+
+    DevBuf d_tbase, d_rec, d_gather, d_t2m;
+    PinBuf h_tbase;
+    Shard sh;
 
     uint64_t cap1 = 0, cap2 = 0;
     uint32_t log_cap = 0;
@@ -295,7 +317,7 @@ extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out
     memset(&c->res, 0, sizeof(c->res));
     memset(&c->ctr, 0, sizeof(c->ctr));
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 12 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 13 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) { delete c; return fail(VDJGRAPH_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return 0;
@@ -311,15 +333,15 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_text, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_text, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
     for (DevBuf *b : db) b->release();
-    PinBuf *pb[] = { &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+    PinBuf *pb[] = { &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
-    for (int i = 0; i < 12; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 13; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -402,20 +424,36 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
     c->res.h2d_bytes = h2d;
     c->res.n_records = R;
     c->res.n_windows = R * (uint64_t)g.w;
+    c->sh = Shard();
+    c->sh.total_records = R;
+    c->sh.rec_base[1] = R;
     c->staged = true;
     return 0;
 }
 
-extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
+/* ========================================================================================== */
+/* The build, in phases.  One device: vdjgraph_run() runs them back to back.  Sharded over G     */
+/* devices (one process per GPU, or G contexts in one process): the caller interleaves them with */
+/* three tiny host exchanges (window histograms, peer pointers, survivor counts); the only bulk  */
+/* data movement between devices is done by the kernels themselves through peer-mapped memory:  */
+/* k_scatter writes each tuple straight into the buffer of the device that owns its partition.  */
+/* ========================================================================================== */
+namespace {
+
+constexpr int HB = 1 << HIST_BITS;
+
+int phase_check(vdjgraph_ctx *c, int want, const char *what) {
     if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
-    if (!c->staged) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_run before vdjgraph_stage");
-    CK(cudaSetDevice(c->device));
-    c->ran = false;
-    make_geom(c, c->g.R);
+    if (!c->staged) return fail(VDJGRAPH_ERR_STATE, "%s before vdjgraph_stage", what);
+    if (c->sh.phase != want) return fail(VDJGRAPH_ERR_STATE, "%s called in phase %d (expected %d)", what, c->sh.phase, want);
+    return 0;
+}
+
+/* K0: window counts per hash bucket + HyperLogLog of the gated k-mers -> h_hist, h_hll */
+int run_count(vdjgraph_ctx *c) {
     const Geom g = c->g;
     cudaStream_t s = c->stream;
     int rc;
-    uint64_t launches = 0;
     memset(&c->ctr, 0, sizeof(c->ctr));
     vdjgraph_result &res = c->res;
     res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = res.n_slow1 = res.n_slow2 = 0;
@@ -424,113 +462,211 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     res.table1_slots = res.table2_slots = 0;
     res.partitions = 0; res.tuple_bytes = 0;
     res.kernel_launches = 0;
-    if (g.R == 0) { c->ran = true; return 0; }
+    if ((rc = c->d_ctr.ensure(sizeof(Counters)))) return rc;
+    if ((rc = c->d_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
+    if ((rc = c->d_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
+    if ((rc = c->d_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
+    if ((rc = c->d_tbase.ensure(2 * HB * sizeof(void *)))) return rc;
+    if ((rc = c->h_ctr.ensure(sizeof(Counters)))) return rc;
+    if ((rc = c->h_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
+    if ((rc = c->h_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
+    if ((rc = c->h_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
+    if ((rc = c->h_tbase.ensure(2 * HB * sizeof(void *)))) return rc;
+    CK(cudaEventRecord(c->ev[0], s));
+    CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), s));
+    CK(cudaMemsetAsync(c->d_hll.p, 0, sizeof(uint32_t) << HLL_BITS, s));
+    CK(cudaMemsetAsync(c->d_hist.p, 0, 2 * HB * sizeof(uint64_t), s));
+    if (g.R) {
+        const size_t smem_count = count_head_bytes() + block_tile_bytes(g);
+        const int grid_count = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
+        k_count<<<grid_count, THREADS, smem_count, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g,
+                                                         c->d_hll.as<u32>(), c->d_hist.as<u64>());
+        res.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev[1], s));
+    CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, 2 * HB * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, sizeof(uint32_t) << HLL_BITS, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->sh.phase = 1;
+    return 0;
+}
+
+/* partitioning, tuple format, table sizes, this device's tuple buffer.
+ * hist_all: [G][2][HB] window counts of every device; hll: registers merged (max) over the devices */
+int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
+    Shard &sh = c->sh;
+    const Geom &g = c->g;
+    const int G = sh.G;
+    uint64_t gated_total = 0;
+    for (int d = 0; d < G; d++)
+        for (int i = 0; i < HB; i++) gated_total += hist_all[(size_t)d * 2 * HB + i];
+    sh.est_distinct = std::min<double>(hll_estimate(hll), (double)gated_total);
+    const double load1 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD1", 0.5)));
+    /* capacity of the whole (all devices) pass-1 table */
+    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(sh.est_distinct * 1.06 / load1) + 1024;
+    cap1 = std::max<uint64_t>(cap1, 1024);
+
+    Part pt;
+    memset(&pt, 0, sizeof(pt));
+    int pbits = 0;
+    if (c->prm.partitions) {
+        while ((1u << pbits) < c->prm.partitions && pbits < HIST_BITS) pbits++;
+    } else {
+        /* table-1 slices of at most SLICE_BYTES so that a slice is L2-resident */
+        const uint64_t slice_bytes = (uint64_t)(env_double("VDJGRAPH_SLICE_MB", (double)(SLICE_BYTES >> 20)) * 1048576.0);
+        while (pbits < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits) > slice_bytes) pbits++;
+    }
+    pbits = std::max(pbits, sh.gbits);   /* every device owns at least one partition */
+    pt.pbits = pbits;
+    pt.gbits = sh.gbits;
+    pt.hb = std::max(0, 2 * g.k - 64);
+    const int sbits = bits_for(sh.total_records * (uint64_t)g.w);
+    /* narrow tuples need room for at least 4 read-fingerprint bits beside the stamp */
+    pt.wide = (pt.hb + 4 + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
+    pt.fb = pt.wide ? 32 : std::min(32, 64 - pt.hb - 4 - sbits);
+    /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
+    pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
+    pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
+    pt.qflush1 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 64)));
+    pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
+    pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
+    pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
+
+    /* fold the 256-bucket histograms to P partitions: cnt[d][cls][p] */
+    const int P = 1 << pbits, fold = HB / P;
+    sh.cnt.assign((size_t)G * 2 * P, 0);
+    for (int d = 0; d < G; d++)
+        for (int cls = 0; cls < 2; cls++)
+            for (int pp = 0; pp < P; pp++) {
+                uint64_t n = 0;
+                for (int j = 0; j < fold; j++) n += hist_all[((size_t)d * 2 + cls) * HB + pp * fold + j];
+                sh.cnt[((size_t)d * 2 + cls) * P + pp] = n;
+            }
+    /* what this device receives (its partitions, from every device) and what it produces */
+    sh.n_gated_own = sh.n_valid_own = sh.n_gated_src = sh.n_valid_src = 0;
+    for (int cls = 0; cls < 2; cls++)
+        for (int pp = 0; pp < P; pp++) {
+            for (int d = 0; d < G; d++) {
+                const uint64_t n = sh.cnt[((size_t)d * 2 + cls) * P + pp];
+                if ((pp & (G - 1)) == sh.rank) { sh.n_valid_own += n; if (cls == 0) sh.n_gated_own += n; }
+            }
+            const uint64_t mine = sh.cnt[((size_t)sh.rank * 2 + cls) * P + pp];
+            sh.n_valid_src += mine; if (cls == 0) sh.n_gated_src += mine;
+        }
+    pt.n_gated = sh.n_gated_own;
+    pt.n_valid = sh.n_valid_own;
+    c->part = pt;
+    c->cap1 = std::max<uint64_t>(1024, (cap1 >> sh.gbits) + 1024);
+    const size_t tuple_bytes = pt.wide ? 24 : 16;
+    int rc;
+    if ((rc = c->d_tuples.ensure(std::max<size_t>(16, sh.n_valid_own * tuple_bytes)))) return rc;
+    c->res.partitions = (uint32_t)P;
+    c->res.tuple_bytes = (uint32_t)tuple_bytes;
+    c->res.n_gated = sh.n_gated_src;
+    sh.peers_set = false;
+    sh.phase = 2;
+    return 0;
+}
+
+void own_buffers(vdjgraph_ctx *c, void **ptrs, size_t *bytes) {
+    DevBuf *b[NBUF] = { &c->d_bases, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_tuples, &c->d_gather };
+    for (int i = 0; i < NBUF; i++) { ptrs[i] = b[i]->p; if (bytes) bytes[i] = b[i]->cap; }
+}
+
+void set_self_peers(vdjgraph_ctx *c) {
+    own_buffers(c, c->sh.peer[c->sh.rank], nullptr);
+    c->sh.peers_set = true;
+}
+
+/* K1: scatter this device's windows into the tuple buffers of the partitions' owners */
+int run_scatter(vdjgraph_ctx *c) {
+    Shard &sh = c->sh;
+    if (!sh.peers_set) return fail(VDJGRAPH_ERR_STATE, "peer buffers not set");
+    const Geom g = c->g;
+    const Part pt = c->part;
+    cudaStream_t s = c->stream;
+    const int G = sh.G, P = 1 << pt.pbits, PL = P >> sh.gbits;
+    /* region start of (cls, local partition) in every owner's buffer, then this device's share */
+    uint64_t *cur = c->h_cursor.as<uint64_t>(), *lim = cur + 2 * HB;
+    void **tb = c->h_tbase.as<void *>();
+    for (int o = 0; o < G; o++) {
+        uint64_t off = 0;
+        for (int cls = 0; cls < 2; cls++)
+            for (int lp = 0; lp < PL; lp++) {
+                const int pp = (lp << sh.gbits) | o;
+                uint64_t before = 0, total = 0;
+                for (int d = 0; d < G; d++) {
+                    const uint64_t n = sh.cnt[((size_t)d * 2 + cls) * P + pp];
+                    if (d < sh.rank) before += n;
+                    total += n;
+                }
+                const int b = cls * P + pp;
+                cur[b] = off + before;
+                lim[b] = cur[b] + sh.cnt[((size_t)sh.rank * 2 + cls) * P + pp];
+                tb[b] = sh.peer[o][BUF_TUPLES];
+                if (!tb[b] && lim[b] > cur[b]) return fail(VDJGRAPH_ERR_STATE, "no tuple buffer for device %d", o);
+                off += total;
+            }
+    }
+    CK(cudaMemcpyAsync(c->d_cursor.p, cur, 4 * HB * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_tbase.p, tb, 2 * HB * sizeof(void *), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(c->ev[10], s));
+    if (g.R) {
+        ScatterArgs as;
+        as.bases = c->d_bases.as<u64>(); as.good = c->d_good.as<u64>(); as.valid = c->d_valid.as<u64>();
+        as.tbase = c->d_tbase.as<u64 *>();
+        as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + 2 * HB;
+        as.rec_base = sh.rec_base[sh.rank];
+        as.ctr = c->d_ctr.as<Counters>();
+        const size_t smem_scatter = scatter_carve(nullptr, nullptr, g, 2 * P, pt.wide);
+        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
+        k_scatter<<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
+        c->res.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev[11], s));
+    if (G > 1) CK(cudaStreamSynchronize(s));   /* the peers' tuples are complete once every device got here */
+    sh.phase = 3;
+    return 0;
+}
+
+Reads make_reads(vdjgraph_ctx *c) {
+    Reads rd;
+    memset(&rd, 0, sizeof(rd));
+    const Shard &sh = c->sh;
+    rd.n_dev = sh.G;
+    rd.any_strand = c->any_strand1 || sh.G > 1;   /* peers may hold strand-'1' records */
+    for (int d = 0; d < sh.G; d++) {
+        rd.bases[d] = (const u64 *)sh.peer[d][BUF_BASES];
+        rd.valid[d] = (const u64 *)sh.peer[d][BUF_VALID];
+        rd.qual[d] = (const u8 *)sh.peer[d][BUF_QUAL];
+        rd.strand[d] = (const u8 *)sh.peer[d][BUF_STRAND];
+    }
+    for (int d = 0; d <= sh.G; d++) rd.rec_base[d] = sh.rec_base[d];
+    return rd;
+}
+
+/* K2..K4 on this device's partitions: pass 1, prune, survivor table, pass 2 */
+int run_passes(vdjgraph_ctx *c) {
+    Shard &sh = c->sh;
+    const Geom g = c->g;
+    Part pt = c->part;
+    cudaStream_t s = c->stream;
+    int rc;
+    vdjgraph_result &res = c->res;
+    Counters *d_ctr = c->d_ctr.as<Counters>();
+    Counters *h_ctr = c->h_ctr.as<Counters>();
+    const int PL = (1 << pt.pbits) >> sh.gbits;
+    const uint64_t n_gated = pt.n_gated, n_valid = pt.n_valid;
+    const Reads rd = make_reads(c);
+    const int grid_flat = c->sm_count * 8;
 
     /* pruning constants: T = min(mq, 214) after the <=254 clamp (:1514-1516, :356-360);
      * NB = ceil(T/20) = largest count whose quality sums can still fail */
     int mq = std::min(c->prm.min_base_quality, 254);
     int T = std::min(mq, QSUM_SAT);
     int NB = T > 0 ? (T + GATE_Q - 1) / GATE_Q : 0;
-
-    constexpr int HB = 1 << HIST_BITS;
-    if ((rc = c->d_ctr.ensure(sizeof(Counters)))) return rc;
-    if ((rc = c->d_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
-    if ((rc = c->d_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->d_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->h_ctr.ensure(sizeof(Counters)))) return rc;
-    if ((rc = c->h_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
-    if ((rc = c->h_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->h_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
-    Counters *d_ctr = c->d_ctr.as<Counters>();
-    Counters *h_ctr = c->h_ctr.as<Counters>();
-
-    const size_t smem_count = count_head_bytes() + block_tile_bytes(g);
-    const int grid_count = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
-    const int grid_flat = c->sm_count * 8;
-
-    /* ---- K0: window counts per hash bucket + cardinality estimate ---- */
-    CK(cudaEventRecord(c->ev[0], s));
-    CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
-    CK(cudaMemsetAsync(c->d_hll.p, 0, sizeof(uint32_t) << HLL_BITS, s));
-    CK(cudaMemsetAsync(c->d_hist.p, 0, 2 * HB * sizeof(uint64_t), s));
-    k_count<<<grid_count, THREADS, smem_count, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g,
-                                                     c->d_hll.as<u32>(), c->d_hist.as<u64>());
-    launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev[1], s));
-    CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, 2 * HB * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, sizeof(uint32_t) << HLL_BITS, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const uint64_t *hist = c->h_hist.as<uint64_t>();
-    uint64_t n_gated = 0, n_ungated = 0;
-    for (int i = 0; i < HB; i++) { n_gated += hist[i]; n_ungated += hist[HB + i]; }
-    const uint64_t n_valid = n_gated + n_ungated;
-    double est = std::min<double>(hll_estimate(c->h_hll.as<uint32_t>()), (double)n_gated);
-    const double load1 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD1", 0.5)));
-    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(est * 1.06 / load1) + 1024;
-    cap1 = std::max<uint64_t>(cap1, 1024);
-
-    /* ---- partitioning: table-1 slices of at most SLICE_BYTES so that a slice is L2-resident ---- */
-    Part pt;
-    memset(&pt, 0, sizeof(pt));
-    {
-        int pbits = 0;
-        if (c->prm.partitions) {
-            while ((1u << pbits) < c->prm.partitions && pbits < HIST_BITS) pbits++;
-        } else {
-            const uint64_t slice_bytes = (uint64_t)(env_double("VDJGRAPH_SLICE_MB", (double)(SLICE_BYTES >> 20)) * 1048576.0);
-            while (pbits < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits) > slice_bytes) pbits++;
-        }
-        pt.pbits = pbits;
-        pt.hb = std::max(0, 2 * g.k - 64);
-        const int sbits = bits_for(g.R * (uint64_t)g.w);
-        /* narrow tuples need room for at least 4 read-fingerprint bits beside the stamp */
-        pt.wide = (pt.hb + 4 + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
-        pt.fb = pt.wide ? 32 : std::min(32, 64 - pt.hb - 4 - sbits);
-        /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
-        pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
-        pt.qflush1 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 64)));
-        pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
-        pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
-        pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
-        pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
-        pt.n_gated = n_gated;
-        pt.n_valid = n_valid;
-    }
-    const int P = 1 << pt.pbits;
-    const size_t tuple_bytes = pt.wide ? 24 : 16;
-    if ((rc = c->d_tuples.ensure(std::max<size_t>(16, n_valid * tuple_bytes)))) return rc;
-    {
-        /* region offsets: [gated p=0..P-1][ungated p=0..P-1] */
-        uint64_t *cur = c->h_cursor.as<uint64_t>(), *lim = cur + 2 * HB;
-        const int fold = HB / P;
-        uint64_t off = 0;
-        for (int cls = 0; cls < 2; cls++)
-            for (int p = 0; p < P; p++) {
-                uint64_t n = 0;
-                for (int j = 0; j < fold; j++) n += hist[cls * HB + p * fold + j];
-                cur[cls * P + p] = off;
-                off += n;
-                lim[cls * P + p] = off;
-            }
-        CK(cudaMemcpyAsync(c->d_cursor.p, cur, 4 * HB * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    }
-
-    /* ---- K1: scatter the windows into their partitions ---- */
-    CK(cudaEventRecord(c->ev[10], s));
-    {
-        ScatterArgs as;
-        as.bases = c->d_bases.as<u64>(); as.good = c->d_good.as<u64>(); as.valid = c->d_valid.as<u64>();
-        as.tuples = c->d_tuples.as<u64>();
-        as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + 2 * HB;
-        as.ctr = d_ctr;
-        const size_t smem_scatter = scatter_carve(nullptr, nullptr, g, 2 * P, pt.wide);
-        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
-        k_scatter<<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
-        launches++;
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(c->ev[11], s));
 
     const uint64_t span = (uint64_t)THREADS * BATCH;
     const size_t smem_q = WARPS * (pt.wide ? WarpQueue<true>::bytes() : WarpQueue<false>::bytes());
@@ -540,10 +676,11 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
                                                 (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, smem_q)));
 
     /* ---- K2 + K3: pass 1 and prune (retried with a larger table if it overflows) ---- */
+    uint64_t cap1 = c->cap1;
     for (int attempt = 0;; attempt++) {
         if (attempt > 6) return fail(VDJGRAPH_ERR_INTERNAL, "pass-1 table kept overflowing (capacity %llu)", (unsigned long long)cap1);
-        pt.slice1 = (cap1 + P - 1) / P;
-        cap1 = pt.slice1 * (uint64_t)P;
+        pt.slice1 = (cap1 + PL - 1) / PL;
+        cap1 = pt.slice1 * (uint64_t)PL;
         /* log: one block of NB stamps per distinct k-mer (<= table slots, <= gated windows), plus
          * one partially used chunk of blocks per warp */
         uint64_t warps = (uint64_t)grid_p1 * WARPS;
@@ -555,14 +692,15 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         if ((rc = c->d_log.ensure(log_cap * (uint64_t)std::max(NB, 1) * sizeof(uint64_t)))) return rc;
         c->cap1 = cap1; c->log_cap = (uint32_t)log_cap;
 
+        Counters zero;
+        memset(&zero, 0, sizeof(zero));
         CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
         CK(cudaEventRecord(c->ev[9], s));
         k_init_table1<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1);
         CK(cudaEventRecord(c->ev[2], s));
         Pass1Args a1;
         a1.tuples = c->d_tuples.as<u64>();
-        a1.bases = c->d_bases.as<u64>(); a1.valid = c->d_valid.as<u64>();
-        a1.strand = c->any_strand1 ? c->d_strand.as<u8>() : nullptr;
+        a1.rd = rd;
         a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
         a1.log = c->d_log.as<u64>(); a1.log_blocks = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
         a1.ctr = d_ctr;
@@ -571,10 +709,10 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         CK(cudaEventRecord(c->ev[3], s));
         PruneArgs ap;
         ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<u64>(); ap.nb_ranks = (uint32_t)NB;
-        ap.qual = c->d_qual.as<u8>(); ap.mf = c->prm.min_node_freq; ap.T = T; ap.ctr = d_ctr;
+        ap.rd = rd; ap.mf = c->prm.min_node_freq; ap.T = T; ap.ctr = d_ctr;
         k_prune<<<grid_flat, THREADS, 0, s>>>(ap, g);
         CK(cudaEventRecord(c->ev[4], s));
-        launches += 3;
+        res.kernel_launches += 3;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -587,31 +725,17 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
         return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu distinct gated k-mers exceed MAX_NODES (assembler2_vdj.c:73)", (unsigned long long)h_ctr->n_distinct);
     const uint64_t n_surv = h_ctr->n_surv;
     res.n_slow1 = h_ctr->n_slow1;
-    const uint64_t n_distinct = h_ctr->n_distinct;
+    res.n_pre_total = h_ctr->n_distinct;
+    res.n_pre = n_surv;
 
     /* ---- survivor table + pass 2 ---- */
     const double load2 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD2", 0.25)));
-    pt.slice2 = (std::max<uint64_t>(1024, (uint64_t)((double)n_surv / load2) + 64) + P - 1) / P;
-    const uint64_t cap2 = pt.slice2 * (uint64_t)P;
+    pt.slice2 = (std::max<uint64_t>(1024, (uint64_t)((double)n_surv / load2) + 64) + PL - 1) / PL;
+    const uint64_t cap2 = pt.slice2 * (uint64_t)PL;
     if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
     if ((rc = c->d_t2.ensure(cap2 * sizeof(Slot2)))) return rc;
     c->cap2 = cap2;
     c->part = pt;
-    const size_t na = std::max<uint64_t>(n_surv, 1);
-    if ((rc = c->d_keys[0].ensure(na * 8)) || (rc = c->d_keys[1].ensure(na * 8)) ||
-        (rc = c->d_vals[0].ensure(na * 4)) || (rc = c->d_vals[1].ensure(na * 4)) ||
-        (rc = c->d_first_pos.ensure(na * 8)) || (rc = c->d_freq.ensure(na * 2)) ||
-        (rc = c->d_odeg.ensure(na)) || (rc = c->d_ideg.ensure(na)) ||
-        (rc = c->d_osucc.ensure(na * 16)) || (rc = c->d_ipred.ensure(na * 16)))
-        return rc;
-    const bool want_keys = c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS;
-    if (want_keys && ((rc = c->d_klo.ensure(na * 8)) || (rc = c->d_khi.ensure(na * 8)))) return rc;
-    const int end_bit = bits_for(g.R * (uint64_t)g.w);
-    size_t cub_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[1].as<u64>(),
-                                       c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_surv, 0, end_bit, s));
-    if ((rc = c->d_cub.ensure(std::max<size_t>(cub_bytes, 16)))) return rc;
-
     CK(cudaEventRecord(c->ev[5], s));
     k_init_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2);
     k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, pt, d_ctr);
@@ -622,23 +746,86 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     if (pt.wide) k_pass2<true><<<grid_p2, THREADS, smem_q, s>>>(a2, g, pt);
     else k_pass2<false><<<grid_p2, THREADS, smem_q, s>>>(a2, g, pt);
     CK(cudaEventRecord(c->ev[7], s));
-    launches += 3;
+    res.kernel_launches += 3;
+    CK(cudaGetLastError());
+    res.table1_slots = cap1; res.table2_slots = cap2;
+    sh.surv_all[sh.rank] = n_surv;
+    if (sh.G > 1) {
+        /* the survivors as dense records, ready to be sent to the finishing device */
+        if ((rc = c->d_rec.ensure(std::max<uint64_t>(n_surv, 1) * sizeof(Slot2)))) return rc;
+        CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
+        k_compact_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2, c->d_rec.as<Slot2>(), &d_ctr->n_nodes);
+        res.kernel_launches++;
+        CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_ctr->overflow) return fail(VDJGRAPH_ERR_INTERNAL, "survivor table overflow (code %u)", h_ctr->overflow);
+        if (h_ctr->n_nodes != n_surv) return fail(VDJGRAPH_ERR_INTERNAL, "compacted %llu survivors, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
+        res.n_hits = h_ctr->n_hits;
+        res.n_slow2 = h_ctr->n_slow2;
+    }
+    sh.phase = 4;
+    return 0;
+}
 
-    /* ---- export ---- */
+/* K5: creation ranks and edge lists.  One device: straight from its survivor table.  Sharded: the
+ * finishing device first builds one table over the survivor records gathered from all devices. */
+int run_finish(vdjgraph_ctx *c) {
+    Shard &sh = c->sh;
+    const Geom g = c->g;
+    cudaStream_t s = c->stream;
+    int rc;
+    vdjgraph_result &res = c->res;
+    Counters *d_ctr = c->d_ctr.as<Counters>();
+    Counters *h_ctr = c->h_ctr.as<Counters>();
+    const int grid_flat = c->sm_count * 8;
+    Part pt = c->part;
+    uint64_t n_surv = sh.surv_all[sh.rank];
+    uint64_t cap2 = c->cap2;
+    Slot2 *table = c->d_t2.as<Slot2>();
+    CK(cudaEventRecord(c->ev[12], s));
+    if (sh.G > 1) {
+        n_surv = sh.surv_off[sh.G];
+        /* merged table: its own partitioning (locality does not matter here), no device split */
+        pt.gbits = 0;
+        pt.pbits = 0;
+        pt.slice2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
+        cap2 = pt.slice2;
+        if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "merged survivor table too large");
+        if ((rc = c->d_t2m.ensure(cap2 * sizeof(Slot2)))) return rc;
+        table = c->d_t2m.as<Slot2>();
+        CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
+        k_init_table2<<<grid_flat, THREADS, 0, s>>>(table, cap2);
+        k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(c->d_gather.as<Slot2>(), n_surv, table, cap2, pt, d_ctr);
+        res.kernel_launches += 2;
+    }
+    const size_t na = std::max<uint64_t>(n_surv, 1);
+    if ((rc = c->d_keys[0].ensure(na * 8)) || (rc = c->d_keys[1].ensure(na * 8)) ||
+        (rc = c->d_vals[0].ensure(na * 4)) || (rc = c->d_vals[1].ensure(na * 4)) ||
+        (rc = c->d_first_pos.ensure(na * 8)) || (rc = c->d_freq.ensure(na * 2)) ||
+        (rc = c->d_odeg.ensure(na)) || (rc = c->d_ideg.ensure(na)) ||
+        (rc = c->d_osucc.ensure(na * 16)) || (rc = c->d_ipred.ensure(na * 16)))
+        return rc;
+    const bool want_keys = c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS;
+    if (want_keys && ((rc = c->d_klo.ensure(na * 8)) || (rc = c->d_khi.ensure(na * 8)))) return rc;
+    const int end_bit = bits_for(sh.total_records * (uint64_t)g.w);
+    size_t cub_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[1].as<u64>(),
+                                       c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_surv, 0, end_bit, s));
+    if ((rc = c->d_cub.ensure(std::max<size_t>(cub_bytes, 16)))) return rc;
     if (n_surv) {
-        k_collect<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2, c->d_keys[0].as<u64>(), c->d_vals[0].as<u32>(), d_ctr);
+        k_collect<<<grid_flat, THREADS, 0, s>>>(table, cap2, c->d_keys[0].as<u64>(), c->d_vals[0].as<u32>(), d_ctr);
         CK(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[1].as<u64>(),
                                            c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_surv, 0, end_bit, s));
         const int gb = (int)((n_surv + THREADS - 1) / THREADS);
-        k_assign_rank<<<gb, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), c->d_vals[1].as<u32>(), n_surv);
+        k_assign_rank<<<gb, THREADS, 0, s>>>(table, c->d_vals[1].as<u32>(), n_surv);
         ExportArgs ae;
-        ae.table = c->d_t2.as<Slot2>(); ae.cap = cap2; ae.keys = c->d_keys[1].as<u64>(); ae.vals = c->d_vals[1].as<u32>();
+        ae.table = table; ae.cap = cap2; ae.keys = c->d_keys[1].as<u64>(); ae.vals = c->d_vals[1].as<u32>();
         ae.n = n_surv; ae.first_pos = c->d_first_pos.as<u64>(); ae.frequency = c->d_freq.as<u16>();
         ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
         ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
         ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
         k_export<<<gb, THREADS, 0, s>>>(ae, g, pt);
-        launches += 3;
+        res.kernel_launches += 3;
     }
     CK(cudaEventRecord(c->ev[8], s));
     CK(cudaGetLastError());
@@ -649,17 +836,14 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     if (n_surv && h_ctr->n_nodes != n_surv)
         return fail(VDJGRAPH_ERR_INTERNAL, "collected %llu nodes, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
     c->ctr = *h_ctr;
-
     res.n_nodes = n_surv;
-    res.n_gated = n_gated;
-    res.n_pre_total = n_distinct;
-    res.n_pre = n_surv;
-    res.n_hits = h_ctr->n_hits;
-    res.n_slow2 = h_ctr->n_slow2;
-    res.table1_slots = cap1; res.table2_slots = cap2;
-    res.partitions = (uint32_t)P; res.tuple_bytes = (uint32_t)tuple_bytes;
-    res.kernel_launches = launches;
-    cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
+    if (sh.G == 1) {
+        res.n_hits = h_ctr->n_hits;
+        res.n_slow2 = h_ctr->n_slow2;
+    } else {
+        res.n_pre = n_surv;
+    }
+    /* per-kernel times of this device's share */
     cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&res.ms_scatter, c->ev[10], c->ev[11]);
     cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
@@ -667,8 +851,202 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&res.ms_table2, c->ev[5], c->ev[6]);
     cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
-    cudaEventElapsedTime(&res.ms_export, c->ev[7], c->ev[8]);
+    cudaEventElapsedTime(&res.ms_export, c->ev[12], c->ev[8]);
+    if (sh.G == 1) cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
+    else res.ms_device = res.ms_estimate + res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
+    sh.phase = 7;
     c->ran = true;
+    return 0;
+}
+
+void fill_times_nonfinisher(vdjgraph_ctx *c) {
+    vdjgraph_result &res = c->res;
+    cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&res.ms_scatter, c->ev[10], c->ev[11]);
+    cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
+    cudaEventElapsedTime(&res.ms_pass1, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&res.ms_table2, c->ev[5], c->ev[6]);
+    cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
+    res.ms_export = 0;
+    res.ms_device = res.ms_estimate + res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2;
+}
+
+} // namespace
+
+extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
+    if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
+    if (!c->staged) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_run before vdjgraph_stage");
+    if (c->sh.G != 1) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_run on a sharded context; use the vdjgraph_shard_* phases");
+    CK(cudaSetDevice(c->device));
+    c->ran = false;
+    make_geom(c, c->g.R);
+    int rc;
+    if ((rc = run_count(c))) return rc;
+    if (c->g.R == 0) { c->ran = true; return 0; }
+    if ((rc = run_plan(c, c->h_hist.as<uint64_t>(), c->h_hll.as<uint32_t>()))) return rc;
+    set_self_peers(c);
+    if ((rc = run_scatter(c))) return rc;
+    if ((rc = run_passes(c))) return rc;
+    return run_finish(c);
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* sharded build: the same phases, driven by the caller                                       */
+/* ---------------------------------------------------------------------------------------- */
+extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns,
+                                    const vdjgraph_shard_info *info) {
+    if (!c || !info) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    const uint32_t G = info->n_ranks;
+    if (G < 1 || G > (uint32_t)MAX_DEV || (G & (G - 1)) || info->rank >= G)
+        return fail(VDJGRAPH_ERR_PARAM, "n_ranks %u must be 1, 2, 4 or 8 and rank %u below it", G, info->rank);
+    if (info->record_base + np + ns > info->total_records)
+        return fail(VDJGRAPH_ERR_PARAM, "record range exceeds total_records");
+    if (info->total_records > 0xFFFFFFFEull)
+        return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu records exceed the 2^32-2 record limit", (unsigned long long)info->total_records);
+    int rc = vdjgraph_stage(c, primary, np, secondary, ns);
+    if (rc) return rc;
+    Shard &sh = c->sh;
+    sh.G = (int)G; sh.rank = (int)info->rank;
+    sh.gbits = 0;
+    while ((1u << sh.gbits) < G) sh.gbits++;
+    sh.total_records = info->total_records;
+    memset(sh.rec_base, 0, sizeof(sh.rec_base));
+    sh.rec_base[sh.rank] = info->record_base;   /* the others arrive with vdjgraph_shard_plan */
+    sh.rec_base[sh.rank + 1] = info->record_base + np + ns;
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_count(vdjgraph_ctx *c, uint64_t *hist, uint32_t *hll) {
+    int rc = phase_check(c, 0, "vdjgraph_shard_count");
+    if (rc) return rc;
+    if (!hist || !hll) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    c->ran = false;
+    make_geom(c, c->g.R);
+    if ((rc = run_count(c))) return rc;
+    memcpy(hist, c->h_hist.p, 2 * HB * sizeof(uint64_t));
+    memcpy(hll, c->h_hll.p, sizeof(uint32_t) << HLL_BITS);
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll_merged,
+                                   const uint64_t *record_counts) {
+    int rc = phase_check(c, 1, "vdjgraph_shard_plan");
+    if (rc) return rc;
+    if (!hist_all || !hll_merged || !record_counts) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    Shard &sh = c->sh;
+    uint64_t base = 0;
+    for (int d = 0; d < sh.G; d++) { sh.rec_base[d] = base; base += record_counts[d]; }
+    sh.rec_base[sh.G] = base;
+    if (base != sh.total_records || record_counts[sh.rank] != c->g.R)
+        return fail(VDJGRAPH_ERR_PARAM, "record counts do not add up to total_records / this rank's staged records");
+    return run_plan(c, hist_all, hll_merged);
+}
+
+extern "C" int vdjgraph_shard_buffers(vdjgraph_ctx *c, void **ptrs, size_t *bytes) {
+    if (!c || !ptrs) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    own_buffers(c, ptrs, bytes);
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_set_peers(vdjgraph_ctx *c, void *const *ptrs) {
+    if (!c || !ptrs) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if (c->sh.phase < 2) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_shard_set_peers before vdjgraph_shard_plan");
+    Shard &sh = c->sh;
+    for (int d = 0; d < sh.G; d++)
+        for (int i = 0; i < NBUF; i++) sh.peer[d][i] = ptrs[d * NBUF + i];
+    own_buffers(c, sh.peer[sh.rank], nullptr);
+    sh.peers_set = true;
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_scatter(vdjgraph_ctx *c) {
+    int rc = phase_check(c, 2, "vdjgraph_shard_scatter");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    return run_scatter(c);
+}
+
+extern "C" int vdjgraph_shard_passes(vdjgraph_ctx *c, uint64_t *n_survivors) {
+    int rc = phase_check(c, 3, "vdjgraph_shard_passes");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    if ((rc = run_passes(c))) return rc;
+    if (c->sh.G == 1) { CK(cudaStreamSynchronize(c->stream)); }
+    if (n_survivors) *n_survivors = c->sh.surv_all[c->sh.rank];
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_gather_plan(vdjgraph_ctx *c, const uint64_t *survivors_all) {
+    int rc = phase_check(c, 4, "vdjgraph_shard_gather_plan");
+    if (rc) return rc;
+    if (!survivors_all) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    Shard &sh = c->sh;
+    uint64_t off = 0;
+    for (int d = 0; d < sh.G; d++) { sh.surv_all[d] = survivors_all[d]; sh.surv_off[d] = off; off += survivors_all[d]; }
+    sh.surv_off[sh.G] = off;
+    if (sh.rank == 0 && sh.G > 1 && (rc = c->d_gather.ensure(std::max<uint64_t>(off, 1) * sizeof(Slot2)))) return rc;
+    sh.phase = 5;
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_send(vdjgraph_ctx *c) {
+    int rc = phase_check(c, 5, "vdjgraph_shard_send");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    Shard &sh = c->sh;
+    if (sh.G > 1) {
+        Slot2 *dst = (Slot2 *)sh.peer[0][BUF_GATHER];
+        if (!dst) return fail(VDJGRAPH_ERR_STATE, "the finishing device's gather buffer is not set");
+        const uint64_t n = sh.surv_all[sh.rank];
+        /* peer-mapped destination: a plain device-to-device copy over NVLink */
+        if (n) CK(cudaMemcpyAsync(dst + sh.surv_off[sh.rank], c->d_rec.p, n * sizeof(Slot2), cudaMemcpyDefault, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (sh.rank != 0) fill_times_nonfinisher(c);
+    }
+    sh.phase = 6;
+    return 0;
+}
+
+extern "C" int vdjgraph_shard_finish(vdjgraph_ctx *c) {
+    int rc = phase_check(c, 6, "vdjgraph_shard_finish");
+    if (rc) return rc;
+    if (c->sh.rank != 0) return fail(VDJGRAPH_ERR_STATE, "only rank 0 finishes");
+    CK(cudaSetDevice(c->device));
+    return run_finish(c);
+}
+
+/* opaque CUDA IPC handles for callers that run one process per GPU (64 bytes each) */
+extern "C" int vdjgraph_ipc_export(const void *dptr, unsigned char *out64) {
+    if (!dptr || !out64) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    memcpy(out64, &h, 64);
+    return 0;
+}
+extern "C" int vdjgraph_ipc_open(const unsigned char *in64, void **dptr) {
+    if (!in64 || !dptr) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in64, 64);
+    CK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int vdjgraph_ipc_close(void *dptr) {
+    if (!dptr) return 0;
+    CK(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+/* same-process peers (G contexts on several devices of one process) */
+extern "C" int vdjgraph_enable_peer_access(int device, int peer_device) {
+    if (device == peer_device) return 0;
+    CK(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    CK(e);
     return 0;
 }
 
@@ -719,7 +1097,7 @@ extern "C" int vdjgraph_fetch(vdjgraph_ctx *c, vdjgraph_result *out) {
 
 extern "C" int vdjgraph_stats(vdjgraph_ctx *c, vdjgraph_result *out) {
     if (!c || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
-    if (!c->ran) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_stats before vdjgraph_run");
+    if (!c->ran && c->sh.phase < 6) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_stats before vdjgraph_run");
     *out = c->res;
     out->first_pos = nullptr; out->frequency = nullptr; out->out_deg = out->in_deg = nullptr;
     out->out_succ = out->in_pred = nullptr; out->kmer_lo = out->kmer_hi = nullptr;

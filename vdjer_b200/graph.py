@@ -64,7 +64,18 @@ EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
     "vdjgraph_set_params", "vdjgraph_build", "vdjgraph_stage", "vdjgraph_run", "vdjgraph_fetch",
     "vdjgraph_fetch_pre_table", "vdjgraph_stats",
+    "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_buffers",
+    "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
+    "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
+    "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
 ]
+
+SHARD_NBUF, SHARD_HIST, SHARD_HLL = 6, 512, 4096
+BUF_GATHER = 5
+
+
+class _ShardInfo(C.Structure):
+    _fields_ = [("n_ranks", C.c_uint32), ("rank", C.c_uint32), ("record_base", C.c_uint64), ("total_records", C.c_uint64)]
 
 _lib = None
 
@@ -91,6 +102,20 @@ def load_library():
     lib.vdjgraph_fetch.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.vdjgraph_stats.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.vdjgraph_fetch_pre_table.argtypes = [C.c_void_p, C.POINTER(_PreTable)]
+    lib.vdjgraph_shard_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_ShardInfo)]
+    lib.vdjgraph_shard_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vdjgraph_shard_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vdjgraph_shard_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.vdjgraph_shard_set_peers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.vdjgraph_shard_scatter.argtypes = [C.c_void_p]
+    lib.vdjgraph_shard_passes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.vdjgraph_shard_gather_plan.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vdjgraph_shard_send.argtypes = [C.c_void_p]
+    lib.vdjgraph_shard_finish.argtypes = [C.c_void_p]
+    lib.vdjgraph_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vdjgraph_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.vdjgraph_ipc_close.argtypes = [C.c_void_p]
+    lib.vdjgraph_enable_peer_access.argtypes = [C.c_int, C.c_int]
     _lib = lib
     return lib
 
@@ -189,6 +214,10 @@ class GraphBuilder:
         # a trailing NUL (the reference's buffers are C strings) is not a record
         return p, s, p.size // rec, s.size // rec
 
+    def _n_records(self, primary, secondary) -> int:
+        _, _, n_p, n_s = self._counts(primary, secondary)
+        return n_p + n_s
+
     def stage(self, primary, secondary=b""):
         p, s, n_p, n_s = self._counts(primary, secondary)
         self._keep = (p, s)
@@ -217,6 +246,54 @@ class GraphBuilder:
         r = _Result()
         self._check(self._lib.vdjgraph_build(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
         return self._graph(r, copy)
+
+    # ---- sharded build phases (see include/vdjgraph.h and vdjer_b200/shard.py) -------------------
+    def shard_stage(self, primary, secondary, n_ranks: int, rank: int, record_base: int, total_records: int):
+        p, s, n_p, n_s = self._counts(primary, secondary)
+        self._keep = (p, s)
+        info = _ShardInfo(n_ranks, rank, record_base, total_records)
+        self._check(self._lib.vdjgraph_shard_stage(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(info)))
+
+    def shard_count(self):
+        hist = np.zeros(SHARD_HIST, np.uint64)
+        hll = np.zeros(SHARD_HLL, np.uint32)
+        self._check(self._lib.vdjgraph_shard_count(self._ctx, hist.ctypes.data, hll.ctypes.data))
+        return hist, hll
+
+    def shard_plan(self, hist_all: np.ndarray, hll_merged: np.ndarray, record_counts: np.ndarray):
+        h = np.ascontiguousarray(hist_all, np.uint64)
+        m = np.ascontiguousarray(hll_merged, np.uint32)
+        r = np.ascontiguousarray(record_counts, np.uint64)
+        self._check(self._lib.vdjgraph_shard_plan(self._ctx, h.ctypes.data, m.ctypes.data, r.ctypes.data))
+
+    def shard_buffers(self):
+        ptrs = (C.c_void_p * SHARD_NBUF)()
+        sizes = (C.c_size_t * SHARD_NBUF)()
+        self._check(self._lib.vdjgraph_shard_buffers(self._ctx, ptrs, sizes))
+        return [int(x or 0) for x in ptrs], [int(x) for x in sizes]
+
+    def shard_set_peers(self, table):
+        """table[rank][buffer] = device pointer (ints; 0 = none)."""
+        flat = (C.c_void_p * (len(table) * SHARD_NBUF))(*[C.c_void_p(p or None) for row in table for p in row])
+        self._check(self._lib.vdjgraph_shard_set_peers(self._ctx, flat))
+
+    def shard_scatter(self):
+        self._check(self._lib.vdjgraph_shard_scatter(self._ctx))
+
+    def shard_passes(self) -> int:
+        n = C.c_uint64(0)
+        self._check(self._lib.vdjgraph_shard_passes(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    def shard_gather_plan(self, survivors_all):
+        a = np.ascontiguousarray(survivors_all, np.uint64)
+        self._check(self._lib.vdjgraph_shard_gather_plan(self._ctx, a.ctypes.data))
+
+    def shard_send(self):
+        self._check(self._lib.vdjgraph_shard_send(self._ctx))
+
+    def shard_finish(self):
+        self._check(self._lib.vdjgraph_shard_finish(self._ctx))
 
     def pre_table(self) -> PreTable:
         t = _PreTable()
