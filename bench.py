@@ -17,9 +17,10 @@ synthetic read set.  Unit: windows (k-mer positions) per second, W = records * (
             reference: assembler2_vdj.c:1381-1415; --t only sizes the traversal pool :1287-1299)
 
 --impl reference times that CPU path alone with the same metric/config.
-N > 1 (torchrun): every rank builds the graph of its own equal share of the read set (weak
-scaling, per-GPU work fixed = the N=1 workload with a rank-specific seed); no cross-GPU merge
-yet (see DESIGN.md "Multi-GPU").
+N > 1 (torchrun): ONE graph over the reads of all ranks (weak scaling: every rank contributes the
+N=1 workload generated with a rank-specific seed).  k-mers are hash-sharded, the scatter kernel
+writes each tuple into the owning GPU's buffer through peer-mapped memory, survivors are gathered
+on rank 0 which ranks the nodes and builds the edge lists (DESIGN.md "Multi-GPU").
 """
 from __future__ import annotations
 
@@ -216,17 +217,29 @@ def main():
     t_gen = time.perf_counter() - t0
 
     gb = GraphBuilder(L, k, mf, mq, device=local_rank)
+    sharded = world > 1
+    if sharded:
+        # one graph over the reads of all ranks: k-mers hash-sharded, tuples exchanged by the scatter
+        # kernel through peer-mapped memory, survivors gathered on rank 0 (vdjer_b200/shard.py)
+        from vdjer_b200 import shard
+        host_group = dist.new_group(backend="gloo")   # small host exchanges (histograms, handles, counts)
+        db = shard.DistributedBuilder(gb, dist, group=host_group)
+        stage, run = (lambda: db.stage(primary, secondary)), db.run
+        build = lambda: db.build(primary, secondary, copy=False)  # noqa: E731
+    else:
+        stage, run = (lambda: gb.stage(primary, secondary)), gb.run
+        build = lambda: gb.build(primary, secondary, copy=False)  # noqa: E731
     # ---- device-resident metric ------------------------------------------------------------
-    gb.stage(primary, secondary)
+    stage()
     for _ in range(args.warmup):
-        gb.run()
+        run()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, per_kernel = [], []
     for _ in range(args.steps):
-        gb.run()
+        run()
         g = gb.fetch_stats()
         dev_ms.append(g["ms_device"])
         per_kernel.append(g)
@@ -235,32 +248,42 @@ def main():
     clocks = sampler.stop()
     stats = per_kernel[-1]
     W = stats["n_windows"]
-    ms_dev = float(np.mean(dev_ms))
+    # one device: CUDA events on the library's stream.  Sharded: a step spans several devices and
+    # the host exchanges between its phases, so it is timed between barriers (device-synchronised)
+    ms_dev = wall_dev * 1e3 if sharded else float(np.mean(dev_ms))
 
     # ---- end to end through the C ABI on host buffers ------------------------------------------
     for _ in range(min(args.warmup, 2)):
-        gb.build(primary, secondary, copy=False)
+        build()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        graph = gb.build(primary, secondary, copy=False)   # the C caller's view: result arrays in pinned host memory
-        checksum = int(graph.frequency[:: max(1, graph.n_nodes // 1024)].sum())   # the result is read on the host
+        graph = build()   # the C caller's view: result arrays in pinned host memory
+        if graph is not None:
+            checksum = int(graph.frequency[:: max(1, graph.n_nodes // 1024)].sum())   # the result is read on the host
     barrier()
     ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
-    e2e_stats = graph.stats
+    e2e_stats = gb.fetch_stats()
+    if graph is not None:
+        e2e_stats.update(graph.stats)
 
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, float(W)], device="cuda", dtype=torch.float64)
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_dev, ms_e2e, W_total = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    # max over ranks of the times, sums of the counters
+    sums = {}
+    if sharded:
+        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+        names = ["n_windows", "n_hits", "n_gated", "n_pre_total", "n_slow1", "n_slow2", "kernel_launches", "h2d_bytes"]
+        t = torch.tensor([float(stats[n]) for n in names[:-1]] + [float(e2e_stats["h2d_bytes"])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sums = {n: float(v) for n, v in zip(names, t)}
+        W_total = sums["n_windows"]
     else:
         W_total = float(W)
 
     if rank == 0:
         peak, peak_src = peaks()
-        h = stats["n_hits"] / W
+        h = (sums["n_hits"] / W_total) if sharded else stats["n_hits"] / W
         a1, a2, a_all = algorithmic_bytes(L, k, h)
         kern = {n: float(np.mean([s[n] for s in per_kernel])) for n in
                 ["ms_estimate", "ms_scatter", "ms_init1", "ms_pass1", "ms_prune", "ms_table2", "ms_pass2", "ms_export"]}
@@ -275,19 +298,23 @@ def main():
             "config": {"workload": args.workload, "read_length": L, "k": k, "mf": mf, "mq": mq,
                        "pairs_per_gpu": wl["n_pairs"], "records_per_gpu": stats["n_records"], "windows_per_gpu": W,
                        "l2_policy": "inputs_larger_than_L2 (packed reads + tables >> 126 MB, tables re-initialised every step)",
-                       "parallelism": f"independent shard per GPU x{world}" if world > 1 else "1 GPU",
-                       "distinct_gated_kmers": stats["n_pre_total"], "nodes": stats["n_nodes"],
-                       "gated_fraction": stats["n_gated"] / W, "pass2_hit_fraction_h": h,
+                       "parallelism": (f"one graph over {world} GPUs: k-mers hash-sharded (partition p -> GPU p mod {world}), "
+                                       "scatter kernel writes tuples into the owner's peer-mapped buffer, survivors gathered on rank 0; "
+                                       "step timed between barriers") if sharded else "1 GPU",
+                       "distinct_gated_kmers": int(sums["n_pre_total"]) if sharded else stats["n_pre_total"],
+                       "nodes": stats["n_nodes"],
+                       "gated_fraction": (sums["n_gated"] / W_total) if sharded else stats["n_gated"] / W, "pass2_hit_fraction_h": h,
                        "table1_slots": stats["table1_slots"], "table2_slots": stats["table2_slots"],
                        "hash_partitions": stats["partitions"], "tuple_bytes": stats["tuple_bytes"],
                        "slow_path_fraction_pass1": stats["n_slow1"] / max(1, stats["n_gated"]),
                        "slow_path_fraction_pass2": stats["n_slow2"] / max(1, W),
                        "generator_s": round(t_gen, 2)},
             "e2e": {"value": W_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": e2e_stats["h2d_bytes"], "d2h_bytes_per_step": e2e_stats["d2h_bytes"],
+                    "h2d_bytes_per_step": int(sums["h2d_bytes"]) if sharded else e2e_stats["h2d_bytes"],
+                    "d2h_bytes_per_step": e2e_stats["d2h_bytes"],
                     "ms_stage": e2e_stats["ms_stage"], "ms_device": e2e_stats["ms_device"], "ms_fetch": e2e_stats["ms_fetch"],
                     "host_text_bytes": int(primary.size + secondary.size)},
-            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
+            "gpu_launches": int(sums["kernel_launches"] if sharded else stats["kernel_launches"]) * args.steps,
             "kernel_ms": kern, "wall_ms_per_step_device_loop": wall_dev * 1e3,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -297,10 +324,14 @@ def main():
                               "frac": W * a_all / (ms_dev * 1e-3) / 1e9 / peak},
             "clocks": clocks,
         }
+        if sharded:
+            line["shard_phase_ms_rank0"] = {k2: round(v, 3) for k2, v in db.phase_ms.items()}
         if not args.no_cpu_baseline:
             cb = cpu_baseline(wl, args.cpu_sample_pairs)
             line["cpu_baseline"] = {k2: v for k2, v in cb.items() if not k2.startswith("_")}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        db.close()
     gb.close()
     if world > 1:
         dist.destroy_process_group()

@@ -161,7 +161,7 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
  *   exchange  : all-gather hist and record counts, element-wise max of hll
  *   all ranks : vdjgraph_shard_plan  -> vdjgraph_shard_buffers                    -> device pointers
  *   exchange  : all-gather the pointers (vdjgraph_ipc_export/open across processes)
- *   all ranks : vdjgraph_shard_set_peers ; BARRIER ; vdjgraph_shard_scatter ; BARRIER
+ *   all ranks : vdjgraph_shard_set_peers ; BARRIER ; vdjgraph_shard_release_retired ; vdjgraph_shard_scatter ; BARRIER
  *   all ranks : vdjgraph_shard_passes                                             -> survivor count
  *   exchange  : all-gather the survivor counts
  *   all ranks : vdjgraph_shard_gather_plan ; rank 0's GATHER pointer to everybody ; set_peers
@@ -190,6 +190,9 @@ int vdjgraph_shard_passes(vdjgraph_ctx *ctx, uint64_t *n_survivors);
 int vdjgraph_shard_gather_plan(vdjgraph_ctx *ctx, const uint64_t *survivors_all /*[n_ranks]*/);
 int vdjgraph_shard_send(vdjgraph_ctx *ctx);
 int vdjgraph_shard_finish(vdjgraph_ctx *ctx);
+/* Peers may keep their mappings across builds.  A buffer that had to grow is replaced, not freed;
+ * call this after a barrier that follows vdjgraph_shard_set_peers to free the replaced ones. */
+int vdjgraph_shard_release_retired(vdjgraph_ctx *ctx);
 /* peer mapping helpers: CUDA IPC handles (64 opaque bytes) between processes, peer access within one */
 int vdjgraph_ipc_export(const void *device_ptr, unsigned char *handle64);
 int vdjgraph_ipc_open(const unsigned char *handle64, void **device_ptr);

@@ -18,5 +18,7 @@ for line in sys.stdin:
     c = d["config"]
     print("slow-path fractions", round(c.get("slow_path_fraction_pass1", -1), 3), round(c.get("slow_path_fraction_pass2", -1), 3),
           "partitions", c.get("hash_partitions"), "h", round(c["pass2_hit_fraction_h"], 3), "gated", round(c["gated_fraction"], 3))
+    if "shard_phase_ms_rank0" in d:
+        print("shard phases (rank 0, wall ms)", d["shard_phase_ms_rank0"])
     if "cpu_baseline" in d:
         print("cpu", d["cpu_baseline"]["value"] / 1e6, "M windows/s")

@@ -69,6 +69,9 @@ class FakeBuilder:
     def shard_finish(self):
         self.log.append(("finish",))
 
+    def shard_release_retired(self):
+        self.log.append(("release",))
+
     def fetch(self, copy=True):
         return "graph"
 
@@ -78,7 +81,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     # identity "IPC": a handle is the pointer's decimal text
     shard._Peers.export = lambda self, ptr: str(ptr).encode() if ptr else b""
-    shard._Peers.map = lambda self, h: int(h) + 5 if h else 0      # +5: a mapping is a different address
+    shard._Peers.map = lambda self, r, i, h: int(h) + 5 if h else 0      # +5: a mapping is a different address
     shard._Peers.close = lambda self: None
     b = FakeBuilder(rank, 100 + 20 * rank)
     g = shard.build_distributed(b, None, None, dist=dist)
@@ -93,7 +96,7 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     logs = [np.load(tmp_path / f"log{r}.npy", allow_pickle=True) for r in range(world)]
     (l0, g0), (l1, g1) = logs
     assert g0 == "graph" and g1 is None
-    order = ["stage", "count", "plan", "peers", "scatter", "passes", "gather_plan", "peers", "send"]
+    order = ["stage", "count", "plan", "peers", "release", "scatter", "passes", "gather_plan", "peers", "send", "release"]
     assert [e[0] for e in l0] == order + ["finish"] and [e[0] for e in l1] == order
     # record bases follow rank order; totals agree
     assert l0[0] == ("stage", 2, 0, 0, 220) and l1[0] == ("stage", 2, 1, 100, 220)
@@ -113,8 +116,8 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     assert t0[1][:BUF_GATHER] == [2000 + i + 5 for i in range(BUF_GATHER)]
     assert t1[0][:BUF_GATHER] == [1000 + i + 5 for i in range(BUF_GATHER)]
     # survivor counts all-gathered; rank 0's gather buffer reaches rank 1
-    assert l0[6][1] == [10, 11] and l1[6][1] == [10, 11]
-    assert l1[7][1][0][BUF_GATHER] == 777 + 5 and l0[7][1][1][BUF_GATHER] == 0
+    assert l0[7][1] == [10, 11] and l1[7][1] == [10, 11]
+    assert l1[8][1][0][BUF_GATHER] == 777 + 5 and l0[8][1][1][BUF_GATHER] == 0
 
 
 def test_shard_ranges_and_split():

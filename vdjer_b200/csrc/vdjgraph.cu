@@ -60,9 +60,13 @@ double wall_ms() {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    /* buffers that other devices map (sharded build) are not freed when they grow: peers may still
+     * have the old allocation mapped.  It is parked here until vdjgraph_shard_release_retired(). */
+    bool exported = false;
+    std::vector<void *> retired;
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
+        if (p) { if (exported) retired.push_back(p); else cudaFree(p); }
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 16 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -73,7 +77,8 @@ struct DevBuf {
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release_retired() { for (void *q : retired) cudaFree(q); retired.clear(); }
+    void release() { release_retired(); if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -904,6 +909,10 @@ extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t
         return fail(VDJGRAPH_ERR_PARAM, "record range exceeds total_records");
     if (info->total_records > 0xFFFFFFFEull)
         return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu records exceed the 2^32-2 record limit", (unsigned long long)info->total_records);
+    {
+        DevBuf *ex[NBUF] = { &c->d_bases, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_tuples, &c->d_gather };
+        for (DevBuf *b : ex) b->exported = G > 1;
+    }
     int rc = vdjgraph_stage(c, primary, np, secondary, ns);
     if (rc) return rc;
     Shard &sh = c->sh;
@@ -918,6 +927,7 @@ extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t
 }
 
 extern "C" int vdjgraph_shard_count(vdjgraph_ctx *c, uint64_t *hist, uint32_t *hll) {
+    if (c && c->staged && c->sh.phase >= 6) c->sh.phase = 0;   /* another build of the same staged records */
     int rc = phase_check(c, 0, "vdjgraph_shard_count");
     if (rc) return rc;
     if (!hist || !hll) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
@@ -1017,6 +1027,16 @@ extern "C" int vdjgraph_shard_finish(vdjgraph_ctx *c) {
     if (c->sh.rank != 0) return fail(VDJGRAPH_ERR_STATE, "only rank 0 finishes");
     CK(cudaSetDevice(c->device));
     return run_finish(c);
+}
+
+/* Frees allocations that were replaced by larger ones while peers could still have them mapped.
+ * Call it once every rank has installed (and mapped) the current buffers. */
+extern "C" int vdjgraph_shard_release_retired(vdjgraph_ctx *c) {
+    if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    DevBuf *ex[NBUF] = { &c->d_bases, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_tuples, &c->d_gather };
+    for (DevBuf *b : ex) b->release_retired();
+    return 0;
 }
 
 /* opaque CUDA IPC handles for callers that run one process per GPU (64 bytes each) */

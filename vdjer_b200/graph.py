@@ -66,7 +66,7 @@ EXPORTS = [
     "vdjgraph_fetch_pre_table", "vdjgraph_stats",
     "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_buffers",
     "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
-    "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
+    "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
     "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
 ]
 
@@ -112,6 +112,7 @@ def load_library():
     lib.vdjgraph_shard_gather_plan.argtypes = [C.c_void_p, C.c_void_p]
     lib.vdjgraph_shard_send.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_finish.argtypes = [C.c_void_p]
+    lib.vdjgraph_shard_release_retired.argtypes = [C.c_void_p]
     lib.vdjgraph_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
     lib.vdjgraph_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.vdjgraph_ipc_close.argtypes = [C.c_void_p]
@@ -294,6 +295,9 @@ class GraphBuilder:
 
     def shard_finish(self):
         self._check(self._lib.vdjgraph_shard_finish(self._ctx))
+
+    def shard_release_retired(self):
+        self._check(self._lib.vdjgraph_shard_release_retired(self._ctx))
 
     def pre_table(self) -> PreTable:
         t = _PreTable()

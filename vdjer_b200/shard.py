@@ -97,11 +97,14 @@ def build_local(builders: list[GraphBuilder], parts: list[tuple], devices: list[
 # one process per GPU
 # ------------------------------------------------------------------------------------------------
 class _Peers:
-    """CUDA IPC mappings of the other ranks' buffers, closed before the owners may free them."""
+    """CUDA IPC mappings of the other ranks' buffers.  Mapping a multi-GB allocation costs far more
+    than a build step, so mappings are kept across builds: a (rank, buffer) is re-mapped only when
+    its handle changes, i.e. when the owner had to grow the buffer (the owner parks the old
+    allocation until vdjgraph_shard_release_retired, so closing it late is safe)."""
 
     def __init__(self):
         self.lib = load_library()
-        self.open = []
+        self.cache = {}   # (rank, buffer) -> (handle, mapped pointer)
 
     def export(self, ptr: int) -> bytes:
         if not ptr:
@@ -111,70 +114,137 @@ class _Peers:
             raise RuntimeError("vdjgraph_ipc_export: " + self.lib.vdjgraph_last_error().decode())
         return bytes(h)
 
-    def map(self, handle: bytes) -> int:
+    def map(self, rank: int, buf: int, handle: bytes) -> int:
+        old = self.cache.get((rank, buf))
+        if old and old[0] == handle:
+            return old[1]
+        if old:
+            self.lib.vdjgraph_ipc_close(C.c_void_p(old[1]))
+            del self.cache[(rank, buf)]
         if not handle:
             return 0
         out = C.c_void_p()
-        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
-        if self.lib.vdjgraph_ipc_open(buf, C.byref(out)):
+        raw = (C.c_ubyte * 64).from_buffer_copy(handle)
+        if self.lib.vdjgraph_ipc_open(raw, C.byref(out)):
             raise RuntimeError("vdjgraph_ipc_open: " + self.lib.vdjgraph_last_error().decode())
-        self.open.append(out.value)
+        self.cache[(rank, buf)] = (handle, int(out.value))
         return int(out.value)
 
     def close(self):
-        for p in self.open:
-            self.lib.vdjgraph_ipc_close(C.c_void_p(p))
-        self.open = []
+        for _, ptr in self.cache.values():
+            self.lib.vdjgraph_ipc_close(C.c_void_p(ptr))
+        self.cache = {}
 
 
-def _all_gather(obj, dist):
-    out = [None] * dist.get_world_size()
-    dist.all_gather_object(out, obj)
-    return out
+class DistributedBuilder:
+    """One rank of the sharded build (one process per GPU).  `dist`: torch.distributed (initialised)
+    or an object with get_rank / get_world_size / all_gather_object / barrier; `group`: the
+    process group for the small host exchanges (a gloo group keeps them off the GPU).  This
+    process' records are its `primary` / `secondary`; rank order = record order.  close() before
+    the GraphBuilder is closed: it unmaps the peers' buffers."""
+
+    def __init__(self, builder: GraphBuilder, dist=None, group=None):
+        if dist is None:
+            import torch.distributed as dist  # noqa: PLW0642
+        self.b, self.dist, self.group = builder, dist, group
+        self.G = dist.get_world_size(group) if group is not None else dist.get_world_size()
+        self.rank = dist.get_rank(group) if group is not None else dist.get_rank()
+        self.counts = None
+        self.peers = _Peers()
+        self.table = [[0] * SHARD_NBUF for _ in range(self.G)]
+
+    def _gather(self, obj):
+        out = [None] * self.G
+        if self.group is not None:
+            self.dist.all_gather_object(out, obj, group=self.group)
+        else:
+            self.dist.all_gather_object(out, obj)
+        return out
+
+    def _barrier(self):
+        if self.group is not None:
+            self.dist.barrier(group=self.group)
+        else:
+            self.dist.barrier()
+
+    def _exchange(self, only):
+        """all-gather the IPC handles of this rank's buffers in `only`; map the peers'."""
+        ptrs, _ = self.b.shard_buffers()
+        mine = {i: self.peers.export(ptrs[i]) for i in only}
+        handles = self._gather(mine)
+        for r in range(self.G):
+            if r != self.rank:
+                for i in only:
+                    self.table[r][i] = self.peers.map(r, i, handles[r][i])
+        self.b.shard_set_peers(self.table)
+
+    def stage(self, primary, secondary=b""):
+        n_local = self.b._n_records(primary, secondary)
+        self.counts = self._gather(n_local)
+        base = int(sum(self.counts[:self.rank]))
+        self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)))
+
+    def run(self):
+        """count -> plan -> scatter (= the all-to-all) -> passes -> gather -> finish on the staged
+        records.  Every phase returns with its stream synchronised, so the host barriers order the
+        devices.  The graph then sits on rank 0's device: fetch() copies it to the host.
+        self.phase_ms holds the wall time of each phase of the last run."""
+        import time
+        b = self.b
+        t = [time.perf_counter()]
+
+        def mark():
+            t.append(time.perf_counter())
+
+        hist, hll = b.shard_count()
+        mark()
+        pieces = self._gather((hist, hll))
+        mark()
+        hist_all, hll_m, cnt = plan_inputs([x[0] for x in pieces], [x[1] for x in pieces], self.counts)
+        b.shard_plan(hist_all, hll_m, cnt)
+        mark()
+        self._exchange([i for i in range(SHARD_NBUF) if i != BUF_GATHER])
+        self._barrier()                     # every peer buffer exists and is mapped everywhere
+        b.shard_release_retired()
+        mark()
+        b.shard_scatter()
+        self._barrier()                     # every rank's tuples have arrived
+        mark()
+        n_surv = b.shard_passes()
+        mark()
+        surv = self._gather(n_surv)
+        b.shard_gather_plan(surv)
+        self._exchange([BUF_GATHER])
+        mark()
+        b.shard_send()
+        self._barrier()                     # rank 0 holds every survivor record
+        mark()
+        b.shard_release_retired()
+        if self.rank == 0:
+            b.shard_finish()
+        mark()
+        names = ["count", "x_hist", "plan", "x_peers", "scatter+barrier", "passes", "x_surv", "send+barrier", "finish"]
+        self.phase_ms = {n: (t[i + 1] - t[i]) * 1e3 for i, n in enumerate(names)}
+
+    def fetch(self, copy: bool = True):
+        """The graph on rank 0 (None elsewhere)."""
+        return self.b.fetch(copy=copy) if self.rank == 0 else None
+
+    def build(self, primary, secondary=b"", copy: bool = True):
+        self.stage(primary, secondary)
+        self.run()
+        return self.fetch(copy=copy)
+
+    def close(self):
+        self._barrier()                     # nobody is still reading a peer buffer
+        self.peers.close()
+        self._barrier()                     # everything is unmapped before the owners free
 
 
-def build_distributed(builder: GraphBuilder, primary, secondary, dist=None, copy: bool = True, timings: dict | None = None):
-    """One rank of the sharded build: this process' records are `primary`/`secondary`, rank order =
-    record order.  Returns the Graph on rank 0 and None elsewhere.  `dist`: torch.distributed
-    (initialised) or any object with get_rank/get_world_size/all_gather_object/barrier."""
-    if dist is None:
-        import torch.distributed as dist  # noqa: PLW0642
-    G, rank = dist.get_world_size(), dist.get_rank()
-    peers = _Peers()
+def build_distributed(builder: GraphBuilder, primary, secondary, dist=None, copy: bool = True):
+    """stage + run of one rank; see DistributedBuilder."""
+    db = DistributedBuilder(builder, dist)
     try:
-        n_local = builder._n_records(primary, secondary)
-        counts = _all_gather(n_local, dist)
-        base = int(sum(counts[:rank]))
-        builder.shard_stage(primary, secondary, G, rank, base, int(sum(counts)))
-        hist, hll = builder.shard_count()
-        pieces = _all_gather((hist, hll), dist)
-        hist_all, hll_m, cnt = plan_inputs([x[0] for x in pieces], [x[1] for x in pieces], counts)
-        builder.shard_plan(hist_all, hll_m, cnt)
-
-        def exchange(only=None):
-            ptrs, _ = builder.shard_buffers()
-            mine = [peers.export(p) if (only is None or i in only) else b"" for i, p in enumerate(ptrs)]
-            handles = _all_gather(mine, dist)
-            return [[0] * SHARD_NBUF if r == rank else [peers.map(h) for h in handles[r]] for r in range(G)]
-
-        table = exchange(only=set(range(SHARD_NBUF)) - {BUF_GATHER})
-        builder.shard_set_peers(table)
-        dist.barrier()                      # every peer buffer exists and is mapped
-        builder.shard_scatter()
-        dist.barrier()                      # every rank's tuples have arrived
-        surv = _all_gather(builder.shard_passes(), dist)
-        builder.shard_gather_plan(surv)
-        gather = exchange(only={BUF_GATHER})
-        for r in range(G):
-            table[r][BUF_GATHER] = gather[r][BUF_GATHER]
-        builder.shard_set_peers(table)
-        builder.shard_send()
-        dist.barrier()                      # rank 0 holds every survivor record
-        graph = None
-        if rank == 0:
-            builder.shard_finish()
-            graph = builder.fetch(copy=copy)
-        dist.barrier()                      # peers stay mapped until everybody is done with them
-        return graph
+        return db.build(primary, secondary, copy=copy)
     finally:
-        peers.close()
+        db.close()
