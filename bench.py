@@ -222,8 +222,7 @@ def main():
         # one graph over the reads of all ranks: k-mers hash-sharded, tuples exchanged by the scatter
         # kernel through peer-mapped memory, survivors gathered on rank 0 (vdjer_b200/shard.py)
         from vdjer_b200 import shard
-        host_group = dist.new_group(backend="gloo")   # small host exchanges (histograms, handles, counts)
-        db = shard.DistributedBuilder(gb, dist, group=host_group)
+        db = shard.DistributedBuilder(gb, dist, device=f"cuda:{local_rank}")   # small exchanges ride NCCL
         stage, run = (lambda: db.stage(primary, secondary)), db.run
         build = lambda: db.build(primary, secondary, copy=False)  # noqa: E731
     else:

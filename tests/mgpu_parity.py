@@ -25,7 +25,6 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    host = dist.new_group(backend="gloo")   # the small host exchanges stay off the GPU
     ok = True
     for (L, k, mf, mq, pairs, clones, seed) in [(50, 35, 3, 90, 200000, 3000, 301), (50, 25, 1, 20, 40000, 300, 302),
                                                 (100, 50, 2, 120, 30000, 500, 303)]:
@@ -35,7 +34,7 @@ def main():
         lo, hi = shard.shard_ranges(total, world)[rank]
         p, s = shard.split_records(primary, secondary, L, lo, hi)
         gb = GraphBuilder(L, k, mf, mq, device=local)
-        db = shard.DistributedBuilder(gb, dist, group=host)
+        db = shard.DistributedBuilder(gb, dist, device=f"cuda:{local}")
         g = db.build(p, s)
         t0 = time.perf_counter()
         for _ in range(3):

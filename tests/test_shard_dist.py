@@ -80,7 +80,7 @@ def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     # identity "IPC": a handle is the pointer's decimal text
-    shard._Peers.export = lambda self, ptr: str(ptr).encode() if ptr else b""
+    shard._Peers.export = lambda self, ptr: str(ptr).encode().ljust(64, b" ") if ptr else b""
     shard._Peers.map = lambda self, r, i, h: int(h) + 5 if h else 0      # +5: a mapping is a different address
     shard._Peers.close = lambda self: None
     b = FakeBuilder(rank, 100 + 20 * rank)

@@ -17,6 +17,7 @@
  * Packed read layout in HBM (written by the host staging code in vdjgraph.cu):
  *   bases [R][nb] u64 : 2 bits/base, A=0 C=1 G=2 T=3 (N stored as 0), base j at bits 2j of the record
  *   good  [R][nm] u64 : bit j = base j is ACGT and phred >= 20      (pass-1 gate, :240-259)
+ *   hiq   [R][nm] u64 : bit j = base j is ACGT and phred >= 30      (prune's quality-sum bound)
  *   valid [R][nm] u64 : bit j = base j is ACGT                      (pass 2 has no quality gate, :272-274)
  *   qual  [R][L]  u8  : (unsigned char)(ch - '!')                   (phred33 :150-152)
  *   strand[R]     u8  : strand char - '0'                           (contributing_strand :336, :350)
@@ -38,6 +39,10 @@ constexpr u64 INF64 = ~0ull;
 constexpr u32 NIL32 = 0xFFFFFFFFu;
 constexpr u32 CNT_CAP = 32765;   /* MAX_FREQUENCY-1, :66, :262, :345 */
 constexpr int GATE_Q = 20;       /* MIN_BASE_QUALITY, :76 */
+constexpr int HIQ = 30;          /* "high quality": windows whose phreds are all >= HIQ let prune bound the quality
+                                    sums without reading quality rows (k_prune) */
+constexpr int FLB = 5;           /* tuple flag bits: has-next, next base (2), window all >= HIQ, record start all >= HIQ */
+constexpr u64 LOG_A = 1ull << 62, LOG_B = 1ull << 63;   /* those two flags in a log entry, above the stamp */
 constexpr int QSUM_SAT = 214;    /* MAX_QUAL_SUM-41, :356 */
 constexpr int MAX_LOG_RANKS = 11;/* ceil(214/20) */
 constexpr u32 CNT_MULTI = 0x80000000u; /* bit 31 of Slot1::count = hasMultipleUniqueReads */
@@ -276,7 +281,7 @@ __device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
 
 /* ------------------------------------------------------------------------------------------ */
 /* tuples: one per N-free window.  word0 = k-mer bits 0..63; word1 = k-mer bits 64.. (hb bits)  */
-/* | has_next << hb | next_base << (hb+1) | fp << (hb+4) | stamp << (hb+4+fb)  (narrow, 16 B);   */
+/* | flags << hb (FLB bits) | fp << (hb+FLB) | stamp << (hb+FLB+fb)              (narrow, 16 B);   */
 /* when fewer than 4 fingerprint bits would fit the stamp moves to a third word (wide, 24 B)    */
 /* and fb = 32.  fp = fingerprint of the record's whole sequence: two records with different    */
 /* fingerprints hold different reads, which settles hasMultipleUniqueReads without touching the */
@@ -296,9 +301,9 @@ __device__ __forceinline__ void tuple_load(const u64 *base, u64 t, u64 &lo, u64 
 template <bool WIDE>
 __device__ __forceinline__ void tuple_decode(const Part &pt, u64 w1, u64 w2, u64 &hi, u32 &fl, u32 &fp, u64 &stamp) {
     hi = pt.hb ? (w1 & ((1ull << pt.hb) - 1)) : 0ull;
-    fl = (u32)(w1 >> pt.hb) & 15u;
-    fp = (u32)(w1 >> (pt.hb + 4)) & (u32)((1ull << pt.fb) - 1);
-    stamp = WIDE ? w2 : (w1 >> (pt.hb + 4 + pt.fb));
+    fl = (u32)(w1 >> pt.hb) & ((1u << FLB) - 1);
+    fp = (u32)(w1 >> (pt.hb + FLB)) & (u32)((1ull << pt.fb) - 1);
+    stamp = WIDE ? w2 : (w1 >> (pt.hb + FLB + pt.fb));
 }
 /* all operands must be computed before anything after this point is issued: keeps independent
  * loads of a batch back to back instead of interleaved with the address arithmetic of the next */
@@ -316,7 +321,7 @@ __device__ __forceinline__ void issue_fence(u32 &a, u32 &b, u32 &c, u32 &d) {
 struct PackArgs {
     const unsigned char *text;   /* records r0 .. r0+n of the concatenated primary+secondary text */
     u64 r0, n;
-    u64 *bases, *good, *valid;
+    u64 *bases, *good, *valid, *hiq;
     u8 *qual, *strand;
     u64 *bad;                    /* [0] first record with a bad strand byte, [1] with a bad base (atomicMin), [2] any strand '1' */
 };
@@ -344,22 +349,24 @@ k_pack(PackArgs a, Geom g) {
             if (sc == '1') a.bad[2] = 1;
             a.strand[r] = (u8)(sc - '0');
         }
-        u64 vword = 0, gword = 0;
+        u64 vword = 0, gword = 0, hword = 0;
         for (int j0 = 0; j0 < g.L; j0 += 32) {
             const int j = j0 + (int)lane;
             unsigned code = 4;   /* beyond the read: neither valid nor an error */
-            bool okq = false;
+            bool okq = false, hiq = false;
             if (j < g.L) {
                 const unsigned ch = rec[1 + j];
                 code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
                 const u8 q = (u8)(rec[1 + g.L + j] - '!');
                 a.qual[r * (u64)g.L + j] = q;
                 okq = q >= GATE_Q;
+                hiq = q >= HIQ;
             }
             const u32 b0 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 1u));
             const u32 b1 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 2u));
             const u32 bv = __ballot_sync(0xFFFFFFFFu, code < 4);
             const u32 bg = __ballot_sync(0xFFFFFFFFu, code < 4 && okq);
+            const u32 bh = __ballot_sync(0xFFFFFFFFu, code < 4 && hiq);
             const u32 be = __ballot_sync(0xFFFFFFFFu, code == 5);
             if (lane == 0) {
                 if (be) atomicMin(&a.bad[1], r);
@@ -367,11 +374,13 @@ k_pack(PackArgs a, Geom g) {
                 if (j0 & 32) {
                     a.valid[r * (u64)g.nm + (j0 >> 6)] = vword | ((u64)bv << 32);
                     a.good[r * (u64)g.nm + (j0 >> 6)] = gword | ((u64)bg << 32);
+                    a.hiq[r * (u64)g.nm + (j0 >> 6)] = hword | ((u64)bh << 32);
                 } else {
-                    vword = bv; gword = bg;
+                    vword = bv; gword = bg; hword = bh;
                     if (j0 + 32 >= g.L) {   /* last, half-filled mask word */
                         a.valid[r * (u64)g.nm + (j0 >> 6)] = vword;
                         a.good[r * (u64)g.nm + (j0 >> 6)] = gword;
+                        a.hiq[r * (u64)g.nm + (j0 >> 6)] = hword;
                     }
                 }
             }
@@ -390,21 +399,24 @@ constexpr int SEG = 16;                 /* windows per thread segment */
 constexpr u32 MAX_STAGE = THREADS * SEG; /* tuples a block can produce per tile */
 
 struct BlockTiles {
-    u64 *buf;   /* [2][a | b | c] */
+    u64 *buf;   /* [2][a | b | c | d] */
     u64 *bar;   /* [2] */
-    u32 words, off_b, off_c;
+    u32 words, off_b, off_c, off_d;
     __device__ __forceinline__ const u64 *a(int i) const { return buf + i * words; }
     __device__ __forceinline__ const u64 *b(int i) const { return buf + i * words + off_b; }
     __device__ __forceinline__ const u64 *c(int i) const { return buf + i * words + off_c; }
+    __device__ __forceinline__ const u64 *d(int i) const { return buf + i * words + off_d; }
 };
-__host__ __device__ inline size_t block_tile_bytes(const Geom &g) {
-    return (size_t)2 * g.tile_rec * (size_t)(g.nb + 2 * g.nm) * 8 + 16;
+/* n_masks = 2 (good, valid) or 3 (+ hiq) */
+__host__ __device__ inline size_t block_tile_bytes(const Geom &g, int n_masks) {
+    return (size_t)2 * g.tile_rec * (size_t)(g.nb + n_masks * g.nm) * 8 + 16;
 }
-__device__ __forceinline__ BlockTiles tiles_setup(unsigned char *smem, const Geom &g) {
+__device__ __forceinline__ BlockTiles tiles_setup(unsigned char *smem, const Geom &g, int n_masks) {
     BlockTiles t;
-    t.words = g.tile_rec * (u32)(g.nb + 2 * g.nm);
+    t.words = g.tile_rec * (u32)(g.nb + n_masks * g.nm);
     t.off_b = g.tile_rec * (u32)g.nb;
     t.off_c = t.off_b + g.tile_rec * (u32)g.nm;
+    t.off_d = t.off_c + g.tile_rec * (u32)g.nm;
     t.buf = reinterpret_cast<u64 *>(smem);
     t.bar = t.buf + 2 * t.words;
     if (threadIdx.x == 0) {
@@ -418,27 +430,31 @@ __device__ __forceinline__ BlockTiles tiles_setup(unsigned char *smem, const Geo
 }
 /* one thread: start the three bulk copies of `tile` into buffer i */
 __device__ __forceinline__ void tiles_issue(const BlockTiles &t, int i, const Geom &g, u64 tile,
-                                            const u64 *ga, const u64 *gb, const u64 *gc) {
+                                            const u64 *ga, const u64 *gb, const u64 *gc, const u64 *gd = nullptr) {
     const u32 bytes_a = g.tile_rec * (u32)g.nb * 8u, bytes_m = g.tile_rec * (u32)g.nm * 8u;
     u64 *dst = t.buf + i * t.words;
-    mbar_expect_tx(&t.bar[i], bytes_a + 2 * bytes_m);
+    mbar_expect_tx(&t.bar[i], bytes_a + (gd ? 3 : 2) * bytes_m);
     tma_load_1d(dst, ga + tile * g.tile_rec * (u64)g.nb, bytes_a, &t.bar[i]);
     tma_load_1d(dst + t.off_b, gb + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
     tma_load_1d(dst + t.off_c, gc + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
+    if (gd) tma_load_1d(dst + t.off_d, gd + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
 }
 
 /* a thread's rolling view of its segment: window i of record `rec` */
 struct Roll {
     u64 lo, hi;     /* k-mer of the current window */
-    u64 mv, mg;     /* k mask bits: N-free / gate-passing */
-    const u64 *b, *v, *gd;
+    u64 mv, mg, mh; /* k mask bits: N-free / gate-passing / all phreds >= HIQ (only when started with a hiq array) */
+    const u64 *b, *v, *gd, *hq;
     int i;
-    __device__ __forceinline__ void start(const u64 *sb, const u64 *sg, const u64 *sv, u32 rec, int i0, const Geom &g) {
+    __device__ __forceinline__ void start(const u64 *sb, const u64 *sg, const u64 *sv, u32 rec, int i0, const Geom &g,
+                                          const u64 *sh = nullptr) {
         b = sb + (size_t)rec * g.nb; gd = sg + (size_t)rec * g.nm; v = sv + (size_t)rec * g.nm;
+        hq = sh ? sh + (size_t)rec * g.nm : nullptr;
         i = i0;
         extract_kmer(b, g.nb, i0, g.kmask_lo, g.kmask_hi, lo, hi);
         mv = extract_mask(v, g.nm, i0) & g.kones;
         mg = extract_mask(gd, g.nm, i0) & g.kones;
+        mh = hq ? extract_mask(hq, g.nm, i0) & g.kones : 0ull;
     }
     /* move to window i+1 (caller guarantees i+1 < w, so base i+k exists) */
     __device__ __forceinline__ void step(const Geom &g) {
@@ -446,6 +462,7 @@ struct Roll {
         kmer_succ(lo, hi, base_at(b, j), g.k, lo, hi);
         mv = (mv >> 1) | ((u64)bit_at(v, j) << (g.k - 1));
         mg = (mg >> 1) | ((u64)bit_at(gd, j) << (g.k - 1));
+        if (hq) mh = (mh >> 1) | ((u64)bit_at(hq, j) << (g.k - 1));
         i++;
     }
     __device__ __forceinline__ bool valid(const Geom &g) const { return mv == g.kones; }
@@ -471,7 +488,7 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
     u32 *reg = reinterpret_cast<u32 *>(smem);
     u32 *sh = reg + M;  /* [WARPS][2][HB]: warp-private counters keep shared-memory atomics apart */
     for (int i = threadIdx.x; i < M + WARPS * 2 * HB; i += THREADS) reg[i] = 0;
-    BlockTiles t = tiles_setup(smem + count_head_bytes(), g);
+    BlockTiles t = tiles_setup(smem + count_head_bytes(), g, 2);
     u32 *mine = sh + (threadIdx.x >> 5) * 2 * HB;
     const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG;
     const int n = rec < g.tile_rec ? min(SEG, g.w - (int)i0) : 0;
@@ -530,7 +547,7 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
 /*      stores are full-sector and coalesced although the destination is a 2P-way scatter.      */
 /* ------------------------------------------------------------------------------------------ */
 struct ScatterArgs {
-    const u64 *bases, *good, *valid;
+    const u64 *bases, *good, *valid, *hiq;
     u64 *const *tbase; /* [2 << pbits] tuple buffer of the device that owns the bucket's partition (peer-mapped
                           when that is another device: the scatter IS the all-to-all of a sharded build) */
     u64 *cursor;       /* [2 << pbits] next free tuple of this device's share of the bucket's region */
@@ -553,7 +570,7 @@ __host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *b
     auto take = [&](size_t bytes) { size_t at = off; off = align128(off + bytes); return at; };
     size_t a_wcnt = take((size_t)WARPS * nbk * 4), a_boff = take((size_t)(nbk + 1) * 4), a_gbase = take((size_t)nbk * 8);
     size_t a_fp = take((size_t)g.tile_rec * 4), a_sbk = take((size_t)MAX_STAGE * 2);
-    size_t a_stage = take((size_t)MAX_STAGE * (wide ? 24 : 16)), a_tiles = take(block_tile_bytes(g));
+    size_t a_stage = take((size_t)MAX_STAGE * (wide ? 24 : 16)), a_tiles = take(block_tile_bytes(g, 3));
     if (o) {
         o->wcnt = reinterpret_cast<u32 *>(base + a_wcnt); o->boff = reinterpret_cast<u32 *>(base + a_boff);
         o->gbase = reinterpret_cast<u64 *>(base + a_gbase); o->fp = reinterpret_cast<u32 *>(base + a_fp);
@@ -569,7 +586,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
     const int P = 1 << pt.pbits, NBK = 2 * P;
     ScatterSmem sm;
     scatter_carve(&sm, smem, g, NBK, pt.wide);
-    BlockTiles t = tiles_setup(sm.tiles, g);
+    BlockTiles t = tiles_setup(sm.tiles, g, 3);
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u32 *mine = sm.wcnt + wid * NBK;
     const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG;
@@ -577,17 +594,17 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
     const u32 fpmask = (u32)((1ull << pt.fb) - 1);
     const int tw = pt.wide ? 3 : 2;
     const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
-    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, a.bases, a.good, a.valid);
+    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, a.bases, a.good, a.valid, a.hiq);
     u64 tile = blockIdx.x;
     for (u64 it = 0; it < n_iter; it++, tile += gridDim.x) {
         const int buf = (int)(it & 1);
         const bool have = tile < g.n_tiles;   /* block-uniform */
         if (!have) break;
         for (int i = threadIdx.x; i < WARPS * NBK; i += THREADS) sm.wcnt[i] = 0;
-        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, a.bases, a.good, a.valid);
+        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, a.bases, a.good, a.valid, a.hiq);
         mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
         __syncthreads();
-        const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf);
+        const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf), *sh = t.d(buf);
         /* read fingerprints of the tile's records */
         for (u32 r = threadIdx.x; r < g.tile_rec; r += THREADS) {
             u64 h = 0x9E3779B97F4A7C15ull;
@@ -644,8 +661,11 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
         /* 3. stage the tuples in bucket order */
         if (n > 0) {
             Roll r;
-            r.start(sb, sg, sv, rec, (int)i0, g);
+            r.start(sb, sg, sv, rec, (int)i0, g, sh);
             const u32 fp = sm.fp[rec];
+            /* are the record's first k phreds all >= HIQ?  (the first occurrence of a k-mer contributes
+             * the RECORD's first k qualities to the sums, :337-339) */
+            const u32 rec_hi = (extract_mask(sh + (size_t)rec * g.nm, g.nm, 0) & g.kones) == g.kones ? 16u : 0u;
             const u64 stamp0 = (a.rec_base + tile * g.tile_rec + rec) * (u64)g.w;
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
@@ -654,14 +674,14 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
                     if (code[j] != NIL32) {
                         const u32 bk = code[j] >> 16;
                         const u32 pos = sm.boff[bk] + mine[bk] + (code[j] & 0xFFFFu);
-                        u32 fl = 0;
-                        if (r.i + 1 < g.w && bit_at(r.v, r.i + g.k)) fl = 1u | (base_at(r.b, r.i + g.k) << 1);
-                        const u64 w1 = r.hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + 4));
+                        u32 fl = rec_hi | (r.mh == g.kones ? 8u : 0u);
+                        if (r.i + 1 < g.w && bit_at(r.v, r.i + g.k)) fl |= 1u | (base_at(r.b, r.i + g.k) << 1);
+                        const u64 w1 = r.hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + FLB));
                         const u64 stamp = stamp0 + (u64)r.i;
                         u64 *dst = sm.stage + (size_t)pos * tw;
                         dst[0] = r.lo;
                         if (pt.wide) { dst[1] = w1; dst[2] = stamp; }
-                        else dst[1] = w1 | (stamp << (pt.hb + 4 + pt.fb));
+                        else dst[1] = w1 | (stamp << (pt.hb + FLB + pt.fb));
                         sm.sbk[pos] = (unsigned short)bk;
                     }
                 }
@@ -787,7 +807,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
     u32 next = 0;
     bool have = false;
     u64 lo = 0, hi = 0, stamp = 0, rw1 = 0, rw2 = 0;
-    u32 idx = 0, probe = 0, fp = 0;
+    u32 idx = 0, probe = 0, fp = 0, fl = 0;
     __syncwarp();
     for (;;) {
         /* refill idle lanes */
@@ -798,7 +818,6 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
             const u32 my = __popc(need & lt);
             if (!have && my < avail) {
                 const u32 e = next + my;
-                u32 fl;
                 lo = q.lo[e]; rw1 = q.w1[e]; rw2 = WIDE ? q.w2[e] : 0ull;
                 tuple_decode<WIDE>(pt, rw1, rw2, hi, fl, fp, stamp);
                 idx = q.idx[e];
@@ -867,7 +886,8 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
                     (first_fp != fp || !same_read(a.rd, first_rec, r, g.nb, g.nm)))
                     atomicOr(&slot->count, CNT_MULTI);
             }
-            if (rank < a.nb_ranks && blk != NIL32) a.log[(u64)blk * a.nb_ranks + rank] = stamp;
+            if (rank < a.nb_ranks && blk != NIL32)
+                a.log[(u64)blk * a.nb_ranks + rank] = stamp | ((fl & 8u) ? LOG_A : 0ull) | ((fl & 16u) ? LOG_B : 0ull);
             have = false;
         }
     }
@@ -968,6 +988,7 @@ k_prune(PruneArgs a, Geom g) {
     u32 n_distinct = 0, n_surv = 0;
     for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
         u32 cnt = 0, cw = 0, head = NIL32;
+        int lb_first = 0;
         bool pass = false, border = false;
         if (i < a.cap) {
             u64 q0, q1, q2, q3;
@@ -984,6 +1005,23 @@ k_prune(PruneArgs a, Geom g) {
                         border = true;
                         if (cnt > a.nb_ranks || head == NIL32) { atomicExch(&a.ctr->internal, 1u); border = false; pass = false; }
                     }
+                    if (border) {
+                        /* lower bound of every quality sum from the flags logged with the stamps: a later
+                         * occurrence adds >= HIQ at every position when its window is all-HIQ, else >= 20
+                         * (it passed the gate); the first one adds its RECORD's first k qualities: >= HIQ
+                         * when those are all-HIQ, else nothing is known.  Bound >= T: no rows needed. */
+                        const u64 *lg = a.log + (u64)head * a.nb_ranks;
+                        u64 first = INF64;
+                        int lb = 0;
+                        bool first_b = false;
+                        for (u32 e = 0; e < cnt; e++) {
+                            const u64 en = lg[e], st = en & ~(LOG_A | LOG_B);
+                            lb += (en & LOG_A) ? HIQ : GATE_Q;
+                            if (st < first) { first = st; first_b = en & LOG_B; lb_first = (en & LOG_A) ? HIQ : GATE_Q; }
+                        }
+                        lb += (first_b ? HIQ : 0) - lb_first;
+                        if (lb >= a.T) border = false;
+                    }
                 }
             }
         }
@@ -994,7 +1032,7 @@ k_prune(PruneArgs a, Geom g) {
             const int n = (int)__shfl_sync(0xFFFFFFFFu, cnt, b);
             const u32 hd = __shfl_sync(0xFFFFFFFFu, head, b);
             /* lane e < n holds occurrence e */
-            u64 st = (int)lane < n ? a.log[(u64)hd * a.nb_ranks + lane] : INF64;
+            u64 st = (int)lane < n ? (a.log[(u64)hd * a.nb_ranks + lane] & ~(LOG_A | LOG_B)) : INF64;
             u64 first = st;
             for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
             int s0 = 0, s1 = 0;
@@ -1170,7 +1208,7 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, W
             ld_sector(slot, q0, q1, q2, q3);
             if (q0 == lo && q1 == hi) {
                 const bool has_next = fl & 1u;
-                const u32 c = fl >> 1;
+                const u32 c = (fl >> 1) & 3u;
                 u64 o = 0;
                 if (has_next) o = ld_cg_u64(&slot->out_first[c]);
                 pass2_update(slot, count_it, q2, q3, o, has_next, c, stamp);
@@ -1221,7 +1259,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
         for (int u = 0; u < BATCH; u++) {
             q0[u] = q1[u] = q2[u] = q3[u] = of[u] = 0;
             if (idx[u] != NIL32) {
-                const u32 fl = (u32)(w1[u] >> pt.hb) & 15u;
+                const u32 fl = (u32)(w1[u] >> pt.hb) & 7u;
                 const Slot2 *s = a.table + idx[u];
                 ld_sector_ca(s, q0[u], q1[u], q2[u], q3[u]);
                 if (fl & 1u) of[u] = ld_ca_u64(&s->out_first[fl >> 1]);
@@ -1239,7 +1277,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             const bool hit = valid && q0[u] == lo[u] && q1[u] == hi;
             const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
             if (hit) {
-                pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, fl >> 1, stamp);
+                pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
                 n_hits++;
             }
             qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));

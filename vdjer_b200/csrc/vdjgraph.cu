@@ -146,7 +146,7 @@ struct vdjgraph_ctx {
     cudaEvent_t ev[13] = {};
     std::vector<StageWorker> workers;
 
-    DevBuf d_text, d_bad, d_bases, d_good, d_valid, d_qual, d_strand;
+    DevBuf d_text, d_bad, d_bases, d_good, d_valid, d_hiq, d_qual, d_strand;
     PinBuf h_bad;
     DevBuf d_t1, d_log, d_t2, d_hll, d_ctr, d_hist, d_cursor, d_tuples;
     DevBuf d_keys[2], d_vals[2], d_cub;
@@ -252,6 +252,7 @@ void stage_worker(StageShared *s, int wi) {
             PackArgs pa;
             pa.text = dst; pa.r0 = r_lo; pa.n = n;
             pa.bases = c->d_bases.as<u64>(); pa.good = c->d_good.as<u64>(); pa.valid = c->d_valid.as<u64>();
+            pa.hiq = c->d_hiq.as<u64>();
             pa.qual = c->d_qual.as<u8>(); pa.strand = c->d_strand.as<u8>();
             pa.bad = c->d_bad.as<u64>();
             const int grid = (int)std::min<uint64_t>((n + WARPS - 1) / WARPS, (uint64_t)c->sm_count * 8);
@@ -338,7 +339,7 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_text, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_text, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
@@ -378,6 +379,7 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
     if ((rc = c->d_bases.ensure(std::max<size_t>(16, c->R_pad * g.nb * 8)))) return rc;
     if ((rc = c->d_good.ensure(std::max<size_t>(16, c->R_pad * g.nm * 8)))) return rc;
     if ((rc = c->d_valid.ensure(std::max<size_t>(16, c->R_pad * g.nm * 8)))) return rc;
+    if ((rc = c->d_hiq.ensure(std::max<size_t>(16, c->R_pad * g.nm * 8)))) return rc;
     if ((rc = c->d_qual.ensure(std::max<size_t>(16, c->R_pad * (size_t)g.L)))) return rc;
     if ((rc = c->d_strand.ensure(std::max<size_t>(16, c->R_pad)))) return rc;
     /* zero the padding records of the last tile: no window of theirs is gated or N-free */
@@ -385,6 +387,7 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
         CK(cudaMemsetAsync(c->d_bases.as<uint64_t>() + R * g.nb, 0, (c->R_pad - R) * g.nb * 8, c->stream));
         CK(cudaMemsetAsync(c->d_good.as<uint64_t>() + R * g.nm, 0, (c->R_pad - R) * g.nm * 8, c->stream));
         CK(cudaMemsetAsync(c->d_valid.as<uint64_t>() + R * g.nm, 0, (c->R_pad - R) * g.nm * 8, c->stream));
+        CK(cudaMemsetAsync(c->d_hiq.as<uint64_t>() + R * g.nm, 0, (c->R_pad - R) * g.nm * 8, c->stream));
     }
     uint64_t h2d = 0;
     c->any_strand1 = false;
@@ -482,7 +485,7 @@ int run_count(vdjgraph_ctx *c) {
     CK(cudaMemsetAsync(c->d_hll.p, 0, sizeof(uint32_t) << HLL_BITS, s));
     CK(cudaMemsetAsync(c->d_hist.p, 0, 2 * HB * sizeof(uint64_t), s));
     if (g.R) {
-        const size_t smem_count = count_head_bytes() + block_tile_bytes(g);
+        const size_t smem_count = count_head_bytes() + block_tile_bytes(g, 2);
         const int grid_count = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
         k_count<<<grid_count, THREADS, smem_count, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g,
                                                          c->d_hll.as<u32>(), c->d_hist.as<u64>());
@@ -528,8 +531,8 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     pt.hb = std::max(0, 2 * g.k - 64);
     const int sbits = bits_for(sh.total_records * (uint64_t)g.w);
     /* narrow tuples need room for at least 4 read-fingerprint bits beside the stamp */
-    pt.wide = (pt.hb + 4 + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
-    pt.fb = pt.wide ? 32 : std::min(32, 64 - pt.hb - 4 - sbits);
+    pt.wide = (pt.hb + FLB + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
+    pt.fb = pt.wide ? std::min(32, 64 - pt.hb - FLB) : std::min(32, 64 - pt.hb - FLB - sbits);
     /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
     pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
     pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
@@ -620,6 +623,7 @@ int run_scatter(vdjgraph_ctx *c) {
     if (g.R) {
         ScatterArgs as;
         as.bases = c->d_bases.as<u64>(); as.good = c->d_good.as<u64>(); as.valid = c->d_valid.as<u64>();
+        as.hiq = c->d_hiq.as<u64>();
         as.tbase = c->d_tbase.as<u64 *>();
         as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + 2 * HB;
         as.rec_base = sh.rec_base[sh.rank];
