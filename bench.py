@@ -115,6 +115,21 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
+    ncu --set full capture (profiles/ncu_r1_summary.json, made by profiles/prof_r1.sh on the default
+    workload); None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_r1_summary.json")
+    try:
+        ks = json.load(open(path))["kernels"]
+        for name, d in ks.items():
+            if name.startswith(kernel):
+                return d["dram_traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def algorithmic_bytes(L, k, h):
     """bytes per window of each pass and of the whole path."""
     w = L - k + 1
@@ -180,7 +195,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--pairs", type=int, default=0, help="override the workload's pair count (debug)")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=150_000)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -316,7 +331,11 @@ def main():
             "gpu_launches": int(sums["kernel_launches"] if sharded else stats["kernel_launches"]) * args.steps,
             "kernel_ms": kern, "wall_ms_per_step_device_loop": wall_dev * 1e3,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic(dom) if (args.workload == DEFAULT_WORKLOAD and not args.pairs and not sharded) else None,
+                         "traffic_source": "profiles/ncu_r1_summary.json (ncu --set full, same workload, one launch)",
+                         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_window": a1 if dom == "k_pass1" else a2,
                          "windows_per_launch": W},
             "roofline_path": {"algorithmic_bytes_per_window": a_all, "achieved": W * a_all / (ms_dev * 1e-3) / 1e9,

@@ -440,29 +440,46 @@ __device__ __forceinline__ void tiles_issue(const BlockTiles &t, int i, const Ge
     if (gd) tma_load_1d(dst + t.off_d, gd + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
 }
 
-/* a thread's rolling view of its segment: window i of record `rec` */
+/* a thread's rolling view of its segment: window i of record `rec`.  start() pulls everything the
+ * segment will need out of shared memory into registers (the k-mer of the first window and, for
+ * each of the SEG-1 steps, the base and mask bits that enter the window), so that a step is a
+ * handful of shifts. */
 struct Roll {
     u64 lo, hi;     /* k-mer of the current window */
     u64 mv, mg, mh; /* k mask bits: N-free / gate-passing / all phreds >= HIQ (only when started with a hiq array) */
-    const u64 *b, *v, *gd, *hq;
+    u32 nbase;      /* 2-bit codes of the bases i+k, i+k+1, ... (next to enter) */
+    u32 nv, ng, nh; /* their mask bits; bit 0 = position i+k */
     int i;
+    bool has_h;
     __device__ __forceinline__ void start(const u64 *sb, const u64 *sg, const u64 *sv, u32 rec, int i0, const Geom &g,
                                           const u64 *sh = nullptr) {
-        b = sb + (size_t)rec * g.nb; gd = sg + (size_t)rec * g.nm; v = sv + (size_t)rec * g.nm;
-        hq = sh ? sh + (size_t)rec * g.nm : nullptr;
+        const u64 *b = sb + (size_t)rec * g.nb, *gd = sg + (size_t)rec * g.nm, *v = sv + (size_t)rec * g.nm;
         i = i0;
+        has_h = sh != nullptr;
         extract_kmer(b, g.nb, i0, g.kmask_lo, g.kmask_hi, lo, hi);
         mv = extract_mask(v, g.nm, i0) & g.kones;
         mg = extract_mask(gd, g.nm, i0) & g.kones;
-        mh = hq ? extract_mask(hq, g.nm, i0) & g.kones : 0ull;
+        mh = has_h ? extract_mask(sh + (size_t)rec * g.nm, g.nm, i0) & g.kones : 0ull;
+        /* positions i0+k .. i0+k+SEG-1 (beyond the read: zero words / zero bits) */
+        const int j = i0 + g.k;
+        u64 nl, nhi;
+        extract_kmer(b, g.nb, j < 32 * g.nb ? j : 32 * g.nb - 1, ~0ull, 0ull, nl, nhi);
+        nbase = j < 32 * g.nb ? (u32)nl : 0u;
+        const bool in = j < 64 * g.nm;
+        nv = in ? (u32)extract_mask(v, g.nm, j) : 0u;
+        ng = in ? (u32)extract_mask(gd, g.nm, j) : 0u;
+        nh = in && has_h ? (u32)extract_mask(sh + (size_t)rec * g.nm, g.nm, j) : 0u;
     }
+    /* is there a window i+1, i.e. does base i+k exist and is it ACGT / what is it */
+    __device__ __forceinline__ bool next_valid() const { return nv & 1u; }
+    __device__ __forceinline__ u32 next_base() const { return nbase & 3u; }
     /* move to window i+1 (caller guarantees i+1 < w, so base i+k exists) */
     __device__ __forceinline__ void step(const Geom &g) {
-        const int j = i + g.k;
-        kmer_succ(lo, hi, base_at(b, j), g.k, lo, hi);
-        mv = (mv >> 1) | ((u64)bit_at(v, j) << (g.k - 1));
-        mg = (mg >> 1) | ((u64)bit_at(gd, j) << (g.k - 1));
-        if (hq) mh = (mh >> 1) | ((u64)bit_at(hq, j) << (g.k - 1));
+        kmer_succ(lo, hi, nbase & 3u, g.k, lo, hi);
+        mv = (mv >> 1) | ((u64)(nv & 1u) << (g.k - 1));
+        mg = (mg >> 1) | ((u64)(ng & 1u) << (g.k - 1));
+        if (has_h) mh = (mh >> 1) | ((u64)(nh & 1u) << (g.k - 1));
+        nbase >>= 2; nv >>= 1; ng >>= 1; nh >>= 1;
         i++;
     }
     __device__ __forceinline__ bool valid(const Geom &g) const { return mv == g.kones; }
@@ -675,7 +692,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
                         const u32 bk = code[j] >> 16;
                         const u32 pos = sm.boff[bk] + mine[bk] + (code[j] & 0xFFFFu);
                         u32 fl = rec_hi | (r.mh == g.kones ? 8u : 0u);
-                        if (r.i + 1 < g.w && bit_at(r.v, r.i + g.k)) fl |= 1u | (base_at(r.b, r.i + g.k) << 1);
+                        if (r.i + 1 < g.w && r.next_valid()) fl |= 1u | (r.next_base() << 1);
                         const u64 w1 = r.hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + FLB));
                         const u64 stamp = stamp0 + (u64)r.i;
                         u64 *dst = sm.stage + (size_t)pos * tw;
@@ -725,16 +742,19 @@ __global__ void k_init_table2(Slot2 *t, u64 cap) {
 }
 
 /* do records r1 and r2 hold the same L-character sequence and strand?
- * compare_read :142-144 (strncmp over read_length) and the strand test :350 */
-__device__ __noinline__ bool same_read(const Reads &rd, u64 r1, u64 r2, int nb, int nm) {
+ * compare_read :142-144 (strncmp over read_length) and the strand test :350.
+ * The words of both records are fetched together (one round trip, possibly to a peer device). */
+__device__ __noinline__ bool same_words(const u64 *b1, const u64 *b2, int nb, const u64 *v1, const u64 *v2, int nm) {
+    u64 diff = 0;
+    for (int i = 0; i < nb; i++) diff |= b1[i] ^ b2[i];
+    for (int i = 0; i < nm; i++) diff |= v1[i] ^ v2[i];
+    return diff == 0;
+}
+__device__ __forceinline__ bool same_read(const Reads &rd, u64 r1, u64 r2, int nb, int nm) {
     const int d1 = rd.dev_of(r1), d2 = rd.dev_of(r2);
     const u64 l1 = r1 - rd.rec_base[d1], l2 = r2 - rd.rec_base[d2];
-    const u64 *b1 = rd.bases[d1] + l1 * nb, *b2 = rd.bases[d2] + l2 * nb;
-    for (int i = 0; i < nb; i++) if (b1[i] != b2[i]) return false;
-    const u64 *v1 = rd.valid[d1] + l1 * nm, *v2 = rd.valid[d2] + l2 * nm;
-    for (int i = 0; i < nm; i++) if (v1[i] != v2[i]) return false;
     if (rd.any_strand && rd.strand[d1][l1] != rd.strand[d2][l2]) return false;
-    return true;
+    return same_words(rd.bases[d1] + l1 * nb, rd.bases[d2] + l2 * nb, nb, rd.valid[d1] + l1 * nm, rd.valid[d2] + l2 * nm, nm);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -899,7 +919,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 k_pass1(Pass1Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
     WarpQueue<WIDE> q;
@@ -1227,7 +1247,7 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, W
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 k_pass2(Pass2Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
     WarpQueue<WIDE> q;

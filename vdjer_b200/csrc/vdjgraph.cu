@@ -536,7 +536,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
     pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
     pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
-    pt.qflush1 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 64)));
+    pt.qflush1 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 8)));
     pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
     pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
     pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
