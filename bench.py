@@ -20,7 +20,8 @@ synthetic read set.  Unit: windows (k-mer positions) per second, W = records * (
 N > 1 (torchrun): ONE graph over the reads of all ranks (weak scaling: every rank contributes the
 N=1 workload generated with a rank-specific seed).  k-mers are hash-sharded, the scatter kernel
 writes each tuple into the owning GPU's buffer through peer-mapped memory, survivors are gathered
-on rank 0 which ranks the nodes and builds the edge lists (DESIGN.md "Multi-GPU").
+on rank 0 which ranks the nodes and builds the edge lists (DESIGN.md "Multi-GPU").  All ranks draw
+disjoint reads from the SAME clone library (one pooled repertoire sequenced N times deeper).
 """
 from __future__ import annotations
 
@@ -228,7 +229,9 @@ def main():
     L, k, mf, mq = wl["read_length"], wl["k"], wl["mf"], wl["mq"]
     gen = {kk: v for kk, v in wl.items() if kk not in ("k", "mf", "mq")}
     t0 = time.perf_counter()
-    primary, secondary = synth.generate(seed=12345 + rank, **gen)
+    # N > 1: ONE repertoire (same seed = same clone library), every rank draws its own disjoint
+    # n_pairs reads from it: the pooled repertoire of BASELINE configs[4], sequenced N times deeper
+    primary, secondary = synth.generate(seed=12345, pair_offset=rank * wl["n_pairs"], **gen)
     t_gen = time.perf_counter() - t0
 
     gb = GraphBuilder(L, k, mf, mq, device=local_rank)
@@ -261,6 +264,7 @@ def main():
     wall_dev = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
     stats = per_kernel[-1]
+    phase_ms = dict(db.phase_ms) if sharded else None
     W = stats["n_windows"]
     # one device: CUDA events on the library's stream.  Sharded: a step spans several devices and
     # the host exchanges between its phases, so it is timed between barriers (device-synchronised)
@@ -343,7 +347,7 @@ def main():
             "clocks": clocks,
         }
         if sharded:
-            line["shard_phase_ms_rank0"] = {k2: round(v, 3) for k2, v in db.phase_ms.items()}
+            line["shard_phase_ms_rank0"] = {k2: round(v, 3) for k2, v in phase_ms.items()}
         if not args.no_cpu_baseline:
             cb = cpu_baseline(wl, args.cpu_sample_pairs)
             line["cpu_baseline"] = {k2: v for k2, v in cb.items() if not k2.startswith("_")}

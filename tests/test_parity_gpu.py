@@ -7,7 +7,7 @@ import pytest
 
 from oracle import loader
 from tests.cases import CASES, make_inputs
-from tests.util import GOLDEN_DIR, assert_graph_equal, assert_pre_table_equal, graph_invariants
+from tests.util import GOLDEN_DIR, assert_graph_equal, assert_pre_table_equal, graph_invariants, sha
 from vdjer_b200 import GraphBuilder, VdjGraphError, synth
 
 pytestmark = pytest.mark.gpu
@@ -163,3 +163,62 @@ def test_large_invariants_and_cross_check(built):
     want = loader.build(primary, secondary, L, k, 3, 90, kind="port")
     assert_graph_equal(got, want, "mid-size")
     assert got.stats["n_hits"] == want["n_hits"]
+
+
+def _digest(g):
+    return sha(g.first_pos, g.frequency, g.out_deg, g.in_deg, g.out_succ, g.in_pred)
+
+
+@pytest.mark.parametrize("workload", ["igh_2x50_5M", "igh_sensitive_2x50_5M", "igk_2x75_20M"])
+def test_full_size_baseline_configs_properties(built, workload):
+    """BASELINE.json configs[1..3] at FULL size (the oracle would need minutes there), through
+    size-independent properties:
+      * structural invariants of any correct graph (creation order, edge symmetry, k-1 overlap, ...);
+      * determinism and independence from the performance knobs (partition count);
+      * monotonicity against the oracle on a PREFIX of the records: counts, the multi-read flag and
+        the quality sums only grow with more records and the first occurrence of a k-mer does not
+        move, so every node of the prefix graph is a node of the full graph with the same first_pos,
+        a frequency at least as large, in the same relative creation order, and every prefix edge
+        is an edge of the full graph."""
+    from tests.util import sha  # noqa: F401
+    wl = dict(synth.CONFIGS[workload])
+    L, k, mf, mq = wl["read_length"], wl["k"], wl["mf"], wl["mq"]
+    gen = {kk: v for kk, v in wl.items() if kk not in ("k", "mf", "mq")}
+    primary, secondary = synth.generate(seed=12345, **gen)
+    rb = 2 * L + 1
+    with GraphBuilder(L, k, mf, mq) as gb:
+        full = gb.build(primary, secondary)
+        stats = dict(full.stats)
+        W = stats["n_windows"]
+        assert W == (primary.size // rb + secondary.size // rb) * (L - k + 1)
+        assert 0 < stats["n_gated"] <= W and stats["n_hits"] <= W
+        assert stats["n_nodes"] == stats["n_pre"] <= stats["n_pre_total"] <= stats["n_gated"]
+        # frequency is the capped count of N-free occurrences
+        assert int(full.frequency.astype(np.int64).sum()) <= stats["n_hits"]
+        assert int(full.frequency.max()) <= 32765
+        graph_invariants(full, L, k, primary, secondary)
+        d0 = _digest(full)
+        again = gb.build(primary, secondary)
+        assert _digest(again) == d0, "two builds of the same input differ"
+    with GraphBuilder(L, k, mf, mq, partitions=max(1, stats["partitions"] // 4)) as gb:
+        other = gb.build(primary, secondary)
+        assert other.stats["partitions"] != stats["partitions"]
+        assert _digest(other) == d0, "result depends on the partition count"
+    # prefix monotonicity against the oracle: the first 150k primary records
+    n_pre_rec = min(150_000, (primary.size // rb) & ~1)
+    prefix = np.concatenate([primary[: n_pre_rec * rb], np.zeros(1, np.uint8)])
+    want = loader.build(prefix, np.zeros(1, np.uint8), L, k, mf, mq, kind="port")
+    pos = np.searchsorted(full.first_pos, want["first_pos"])
+    assert np.all(pos < full.n_nodes) and np.array_equal(full.first_pos[pos], want["first_pos"]), \
+        "a node of the prefix graph is missing from the full graph"
+    assert np.all(np.diff(pos.astype(np.int64)) > 0)
+    assert np.all(full.frequency[pos] >= want["frequency"])
+    # prefix edges survive: successor sets (mapped to full node numbers) are subsets
+    nil = 0xFFFFFFFF
+    sel = np.arange(0, want["n_nodes"], max(1, want["n_nodes"] // 200000))
+    for j in range(4):
+        s = want["out_succ"][sel, j]
+        m = s != nil
+        tgt = pos[s[m]]
+        src = pos[sel[m]]
+        assert np.all((full.out_succ[src] == tgt[:, None].astype(np.uint32)).any(axis=1)), "a prefix edge is missing"

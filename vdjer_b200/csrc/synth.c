@@ -38,6 +38,8 @@ typedef struct vdjsynth_params {
     double p_low_base;      /* isolated low-quality bases in good reads */
     double p_n;             /* 'N' rate */
     int32_t threads;
+    uint64_t pair_offset;   /* pairs are numbered pair_offset .. pair_offset + n_pairs - 1 in the (seed-defined) stream:
+                               several callers can draw disjoint read sets from the SAME clone library */
 } vdjsynth_params;
 
 #define V_LEN 300
@@ -160,7 +162,7 @@ static void *worker(void *arg) {
     const size_t rec = (size_t)2 * L + 1;
     char seq[512], qual[512];
     for (uint64_t pair = jb->lo; pair < jb->hi; pair++) {
-        rng r = rng_make(p->seed, 3, pair);
+        rng r = rng_make(p->seed, 3, p->pair_offset + pair);
         double u = rng_unif(&r);
         int lo = 0, hi = lib->n_clones - 1;
         while (lo < hi) { int mid = (lo + hi) >> 1; if (lib->cdf[mid] < u) lo = mid + 1; else hi = mid; }
