@@ -790,18 +790,23 @@ constexpr u32 QCAP = 32 * BATCH + QFLUSH;        /* a batch can add 32*BATCH ent
 constexpr u32 QDENSE = 20;                       /* a non-final drain stops when fewer lanes than this are busy
                                                     and puts their tuples (with the probe position reached)
                                                     back in the queue: long probe chains do not idle the warp */
-template <bool WIDE>
+/* QC = capacity: a batch can add 32*BATCH entries on top of the flush threshold.  Pass 1 drains
+ * almost every batch and keeps its queue small: shared memory it does not take stays L1, which is
+ * what absorbs the probes of the hot k-mers. */
+constexpr u32 QFLUSH1 = 32;
+constexpr u32 QCAP1 = 32 * BATCH + QFLUSH1;
+template <bool WIDE, u32 QC = QCAP>
 struct WarpQueue {
     u64 *lo, *w1, *w2;
     u32 *idx;
     __device__ __forceinline__ void setup(unsigned char *smem) {
         unsigned char *p = smem + (threadIdx.x >> 5) * bytes();
         lo = reinterpret_cast<u64 *>(p);
-        w1 = lo + QCAP;
-        w2 = w1 + QCAP;
-        idx = reinterpret_cast<u32 *>(w1 + (WIDE ? 2 : 1) * QCAP);
+        w1 = lo + QC;
+        w2 = w1 + QC;
+        idx = reinterpret_cast<u32 *>(w1 + (WIDE ? 2 : 1) * QC);
     }
-    __host__ __device__ static constexpr size_t bytes() { return (size_t)QCAP * (WIDE ? 28 : 20); }
+    __host__ __device__ static constexpr size_t bytes() { return (size_t)QC * (WIDE ? 28 : 20); }
     /* warp-converged push of the lanes with `defer` set; returns the new count */
     __device__ __forceinline__ u32 push(u32 qn, bool defer, u64 l, u64 a, u64 b, u32 i) {
         const u32 lane = threadIdx.x & 31;
@@ -821,7 +826,7 @@ struct LogCursor { u32 base, used; };   /* warp-uniform: the warp's current chun
  * round trips to L2 per lane: (1) the probe (sector load, plus the 128-bit CAS when the slot is
  * empty), (2) the arrival-rank atomicAdd and the first-record CAS, issued together. */
 template <bool WIDE>
-__device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, const Part &pt, WarpQueue<WIDE> &q,
+__device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, const Part &pt, WarpQueue<WIDE, QCAP1> &q,
                                            u32 qn, LogCursor &lc, bool final) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     u32 next = 0;
@@ -922,7 +927,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(THREADS, 4)
 k_pass1(Pass1Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
-    WarpQueue<WIDE> q;
+    WarpQueue<WIDE, QCAP1> q;
     q.setup(smem);
     LogCursor lc; lc.base = 0; lc.used = LOG_CHUNK;
     u32 qn = 0, n_slow = 0;   /* warp-uniform */

@@ -536,7 +536,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
     pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
     pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
-    pt.qflush1 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 8)));
+    pt.qflush1 = (u32)std::min<double>(QFLUSH1, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 8)));
     pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
     pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
     pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
@@ -678,9 +678,10 @@ int run_passes(vdjgraph_ctx *c) {
     int NB = T > 0 ? (T + GATE_Q - 1) / GATE_Q : 0;
 
     const uint64_t span = (uint64_t)THREADS * BATCH;
+    const size_t smem_q1 = WARPS * (pt.wide ? WarpQueue<true, QCAP1>::bytes() : WarpQueue<false, QCAP1>::bytes());
     const size_t smem_q = WARPS * (pt.wide ? WarpQueue<true>::bytes() : WarpQueue<false>::bytes());
     const int grid_p1 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_gated + span - 1) / span,
-                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, smem_q)));
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, smem_q1)));
     const int grid_p2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_valid + span - 1) / span,
                                                 (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, smem_q)));
 
@@ -713,8 +714,8 @@ int run_passes(vdjgraph_ctx *c) {
         a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
         a1.log = c->d_log.as<u64>(); a1.log_blocks = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
         a1.ctr = d_ctr;
-        if (pt.wide) k_pass1<true><<<grid_p1, THREADS, smem_q, s>>>(a1, g, pt);
-        else k_pass1<false><<<grid_p1, THREADS, smem_q, s>>>(a1, g, pt);
+        if (pt.wide) k_pass1<true><<<grid_p1, THREADS, smem_q1, s>>>(a1, g, pt);
+        else k_pass1<false><<<grid_p1, THREADS, smem_q1, s>>>(a1, g, pt);
         CK(cudaEventRecord(c->ev[3], s));
         PruneArgs ap;
         ap.table = c->d_t1.as<Slot1>(); ap.cap = cap1; ap.log = c->d_log.as<u64>(); ap.nb_ranks = (uint32_t)NB;
