@@ -81,7 +81,8 @@ static_assert(sizeof(Slot2) == 64, "Slot2 must be two sectors");
 
 struct Geom {
     int L, k, w, nb, nm;
-    int segs;           /* thread segments per record: ceil(w / SEG) */
+    int seg;            /* windows per thread segment (SEG_COUNT or SEG: the two streaming kernels tile differently) */
+    int segs;           /* thread segments per record: ceil(w / seg) */
     u32 tile_rec;       /* records per block tile (even): THREADS / segs */
     u64 R;              /* real records */
     u64 n_tiles;
@@ -395,7 +396,8 @@ k_pack(PackArgs a, Geom g) {
 /* one SEGMENT of a record: SEG consecutive windows, whose k-mer and gate/N masks it ROLLS (one  */
 /* new base and one new mask bit per window) instead of re-extracting them.                      */
 /* ------------------------------------------------------------------------------------------ */
-constexpr int SEG = 16;                 /* windows per thread segment */
+constexpr int SEG_COUNT = 16;           /* windows per thread segment in k_count (fewer, larger tiles) */
+constexpr int SEG = 8;                  /* ... and in k_scatter (smaller stage -> 3 blocks per SM) */
 constexpr u32 MAX_STAGE = THREADS * SEG; /* tuples a block can produce per tile */
 
 struct BlockTiles {
@@ -460,7 +462,7 @@ struct Roll {
         mv = extract_mask(v, g.nm, i0) & g.kones;
         mg = extract_mask(gd, g.nm, i0) & g.kones;
         mh = has_h ? extract_mask(sh + (size_t)rec * g.nm, g.nm, i0) & g.kones : 0ull;
-        /* positions i0+k .. i0+k+SEG-1 (beyond the read: zero words / zero bits) */
+        /* positions i0+k .. i0+k+15 (at most SEG_COUNT = 16 steps; beyond the read: zero words / zero bits) */
         const int j = i0 + g.k;
         u64 nl, nhi;
         extract_kmer(b, g.nb, j < 32 * g.nb ? j : 32 * g.nb - 1, ~0ull, 0ull, nl, nhi);
@@ -507,8 +509,8 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
     for (int i = threadIdx.x; i < M + WARPS * 2 * HB; i += THREADS) reg[i] = 0;
     BlockTiles t = tiles_setup(smem + count_head_bytes(), g, 2);
     u32 *mine = sh + (threadIdx.x >> 5) * 2 * HB;
-    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG;
-    const int n = rec < g.tile_rec ? min(SEG, g.w - (int)i0) : 0;
+    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG_COUNT;
+    const int n = rec < g.tile_rec ? min(SEG_COUNT, g.w - (int)i0) : 0;
     const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
     if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, bases, good, valid);
     u64 tile = blockIdx.x;

@@ -138,7 +138,7 @@ struct vdjgraph_ctx {
     vdjgraph_params prm;
     int device = 0;
     int sm_count = 0;
-    Geom g;
+    Geom g, gc;
     uint64_t R_pad = 0;
     bool any_strand1 = false;
     bool staged = false, ran = false;
@@ -180,6 +180,16 @@ int check_params(const vdjgraph_params *p) {
     return 0;
 }
 
+/* tiling of the packed reads for a streaming kernel whose threads own `seg` windows each */
+void tile_geom(Geom &g, int seg, uint64_t R) {
+    g.seg = seg;
+    g.segs = (g.w + seg - 1) / seg;
+    uint32_t tr = (uint32_t)THREADS / (uint32_t)g.segs;
+    tr &= ~1u;   /* even: TMA bulk copies need 16-byte sizes and addresses */
+    g.tile_rec = tr;
+    g.n_tiles = (R + tr - 1) / tr;
+}
+
 void make_geom(vdjgraph_ctx *c, uint64_t R) {
     Geom &g = c->g;
     g.L = c->prm.read_length;
@@ -187,23 +197,18 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     g.w = g.L - g.k + 1;
     g.nb = (g.L + 31) / 32;
     g.nm = (g.L + 63) / 64;
-    /* block tile: every thread owns one segment of SEG windows of one record */
-    g.segs = (g.w + SEG - 1) / SEG;
-    uint32_t tr = (uint32_t)THREADS / (uint32_t)g.segs;
-    tr &= ~1u;   /* even: TMA bulk copies need 16-byte sizes and addresses */
-    g.tile_rec = tr;
     g.R = R;
-    g.n_tiles = (R + tr - 1) / tr;
     int bits = 2 * g.k;
     g.kmask_lo = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
     g.kmask_hi = bits > 64 ? ((1ull << (bits - 64)) - 1) : 0ull;
     g.kones = (1ull << g.k) - 1;
-    c->R_pad = g.n_tiles * tr;
+    /* c->g tiles for k_scatter, c->gc for k_count; the arrays are padded for both */
+    c->gc = g;
+    tile_geom(c->gc, SEG_COUNT, R);
+    tile_geom(g, SEG, R);
+    c->R_pad = std::max(g.n_tiles * g.tile_rec, c->gc.n_tiles * c->gc.tile_rec);
 }
 
-/* ---------------------------------------------------------------------------------------- */
-/* staging: text records (bam_read.c:206-244) -> packed arrays, chunked through pinned memory */
-/* ---------------------------------------------------------------------------------------- */
 int ensure_workers(vdjgraph_ctx *c, int n) {
     if ((int)c->workers.size() >= n) return 0;
     size_t old = c->workers.size();
@@ -459,7 +464,7 @@ int phase_check(vdjgraph_ctx *c, int want, const char *what) {
 
 /* K0: window counts per hash bucket + HyperLogLog of the gated k-mers -> h_hist, h_hll */
 int run_count(vdjgraph_ctx *c) {
-    const Geom g = c->g;
+    const Geom g = c->gc;
     cudaStream_t s = c->stream;
     int rc;
     memset(&c->ctr, 0, sizeof(c->ctr));
