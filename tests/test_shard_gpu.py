@@ -79,3 +79,23 @@ def test_sharded_empty_rank(built):
         for b in builders:
             b.close()
     assert_graph_equal(got, want, "empty ranks")
+
+
+def test_multi_process_parity_over_nvlink(built):
+    """One process per GPU (torchrun), peer buffers mapped with CUDA IPC, tuples written over NVLink
+    by the scatter kernel: bit-exact against the oracle (tests/mgpu_parity.py).  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on the box")
+    world = 8 if n >= 8 else 4 if n >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_parity.py")],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("PARITY OK") == 3, r.stdout[-2000:]
