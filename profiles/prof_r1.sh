@@ -10,3 +10,8 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/be
 tail -1 gpurun_out/bench_r1.json | python profiles/bench_summary.py
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1.err
 tail -1 gpurun_out/bench_r1_reference.json | python profiles/bench_summary.py
+# the other single-GPU BASELINE configs, for the record (parity for them: tests/test_parity_gpu.py full-size properties)
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload igh_sensitive_2x50_5M > gpurun_out/bench_r1_c3_sensitive.json 2>> gpurun_out/bench_r1.err
+tail -1 gpurun_out/bench_r1_c3_sensitive.json | python profiles/bench_summary.py
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload igk_2x75_20M > gpurun_out/bench_r1_c4_igk_2x75_20M.json 2>> gpurun_out/bench_r1.err
+tail -1 gpurun_out/bench_r1_c4_igk_2x75_20M.json | python profiles/bench_summary.py
