@@ -224,6 +224,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, u32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+/* TMA 1-D bulk copy shared -> global (to this or a peer device), tracked by the bulk async-group */
+__device__ __forceinline__ void tma_store_1d(void *dst_global, const void *src_smem, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst_global), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* the shared-memory source of every committed bulk store has been read */
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -707,9 +715,22 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             }
         }
         __syncthreads();
-        /* 4. copy out */
+        /* 4. copy out.  16-byte tuples: one TMA bulk store per non-empty bucket, straight from the
+         * stage to the bucket's region (on this device or, through peer-mapped memory, on the
+         * owner's): a run is contiguous on both sides.  24-byte tuples keep the per-tuple stores. */
         const u32 total = sm.boff[NBK];
-        for (u32 e = threadIdx.x; e < total; e += THREADS) {
+        if (!pt.wide) {
+            fence_proxy_async();     /* the stage was written with ordinary stores */
+            __syncthreads();
+            for (int b = threadIdx.x; b < NBK; b += THREADS) {
+                const u32 run = sm.boff[b + 1] - sm.boff[b];
+                const u64 gbs = sm.gbase[b];
+                if (run && gbs != INF64) tma_store_1d(a.tbase[b] + gbs * 2, sm.stage + (size_t)sm.boff[b] * 2, run * 16u);
+            }
+            tma_store_commit();
+            tma_store_wait_read();   /* the stage may be overwritten by the next tile */
+        }
+        for (u32 e = threadIdx.x; pt.wide && e < total; e += THREADS) {
             const u32 bk = sm.sbk[e];
             const u64 gbs = sm.gbase[bk];
             if (gbs == INF64) continue;
