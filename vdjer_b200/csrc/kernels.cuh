@@ -98,6 +98,10 @@ struct Part {
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
     int wide;           /* 1: 24-byte tuples (stamp in a third word) */
     int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
+    u32 hot_t, hot_flush; /* pass 1: fast-path increments of k-mers whose count is already >= hot_t are summed in a
+                             small per-warp shared-memory cache and added to the table every hot_flush batches */
+    u32 dbg;            /* TIMING EXPERIMENTS ONLY (wrong results): 1 drop slow tuples, 2 no fast-path RED, 4 slow path claims
+                           but does not update, 8 no log stores */
     u32 l1_refresh;     /* 0 never, 1 after every slow-path drain, 2 once per batch by warp 0 (see l1_invalidate) */
     u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
     u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
@@ -816,6 +820,8 @@ constexpr u32 QDENSE = 20;                       /* a non-final drain stops when
 /* QC = capacity: a batch can add 32*BATCH entries on top of the flush threshold.  Pass 1 drains
  * almost every batch and keeps its queue small: shared memory it does not take stays L1, which is
  * what absorbs the probes of the hot k-mers. */
+constexpr int HOTC_BITS = 6;
+constexpr u32 HOTC = 1u << HOTC_BITS;            /* entries of a warp's hot-k-mer increment cache */
 constexpr u32 QFLUSH1 = 32;
 constexpr u32 QCAP1 = 32 * BATCH + QFLUSH1;
 template <bool WIDE, u32 QC = QCAP>
@@ -915,6 +921,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
             }
         }
         /* update the slot (:334-352) */
+        if (found && (pt.dbg & 4u)) { have = false; found = false; }
         if (found) {
             const u32 r = (u32)(stamp / (u64)g.w);
             const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
@@ -934,7 +941,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
                     (first_fp != fp || !same_read(a.rd, first_rec, r, g.nb, g.nm)))
                     atomicOr(&slot->count, CNT_MULTI);
             }
-            if (rank < a.nb_ranks && blk != NIL32)
+            if (rank < a.nb_ranks && blk != NIL32 && !(pt.dbg & 8u))
                 a.log[(u64)blk * a.nb_ranks + rank] = stamp | ((fl & 8u) ? LOG_A : 0ull) | ((fl & 16u) ? LOG_B : 0ull);
             have = false;
         }
@@ -952,6 +959,12 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
     WarpQueue<WIDE, QCAP1> q;
     q.setup(smem);
+    /* per-warp cache of pending increments for hot k-mers: [HOTC] slot index, [HOTC] count */
+    u32 *hidx = reinterpret_cast<u32 *>(smem + WARPS * WarpQueue<WIDE, QCAP1>::bytes()) + (threadIdx.x >> 5) * 2 * HOTC;
+    u32 *hcnt = hidx + HOTC;
+    for (u32 i = threadIdx.x & 31; i < HOTC; i += 32) { hidx[i] = NIL32; hcnt[i] = 0; }
+    __syncwarp();
+    u32 since_flush = 0;
     LogCursor lc; lc.base = 0; lc.used = LOG_CHUNK;
     u32 qn = 0, n_slow = 0;   /* warp-uniform */
     const u64 span = (u64)THREADS * BATCH;
@@ -980,7 +993,8 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
             k0[u] = k1[u] = m2[u] = 0;
             if (idx[u] != NIL32) {
                 u64 unused;
-                ld_sector_ca(a.table + idx[u], k0[u], k1[u], m2[u], unused);
+                if (pt.dbg & 16u) ld_sector(a.table + idx[u], k0[u], k1[u], m2[u], unused);
+                else ld_sector_ca(a.table + idx[u], k0[u], k1[u], m2[u], unused);
             }
         }
         /* B: fast path = the k-mer sits in its home slot, is already known to come from several
@@ -990,8 +1004,25 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
             const bool valid = idx[u] != NIL32;
             const u32 cw = (u32)m2[u], cnt = cw & CNT_MASK;
             const bool fast = valid && k0[u] == lo[u] && k1[u] == (w1[u] & hmask) && (cw & CNT_MULTI) && cnt >= a.nb_ranks;
-            if (fast && cnt < CNT_CAP) atomicAdd(&a.table[idx[u]].count, 1u);
-            qn = q.push(qn, valid && !fast, lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
+            if (fast && cnt < CNT_CAP && !(pt.dbg & 2u)) {
+                bool cached = false;
+                if (cnt >= pt.hot_t) {
+                    const u32 e = (idx[u] * 0x9E3779B1u) >> (32 - HOTC_BITS);
+                    const u32 old = atomicCAS(&hidx[e], NIL32, idx[u]);
+                    if (old == NIL32 || old == idx[u]) { atomicAdd(&hcnt[e], 1u); cached = true; }
+                }
+                if (!cached) atomicAdd(&a.table[idx[u]].count, 1u);
+            }
+            qn = q.push(qn, valid && !fast && !(pt.dbg & 1u), lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
+        }
+        if (++since_flush >= pt.hot_flush) {
+            since_flush = 0;
+            __syncwarp();
+            for (u32 i = threadIdx.x & 31; i < HOTC; i += 32) {
+                if (hcnt[i]) atomicAdd(&a.table[hidx[i]].count, hcnt[i]);
+                hidx[i] = NIL32; hcnt[i] = 0;
+            }
+            __syncwarp();
         }
         if (qn >= pt.qflush1) {
             n_slow += qn; qn = pass1_drain<WIDE>(a, g, pt, q, qn, lc, false); n_slow -= qn;
@@ -999,6 +1030,9 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
         }
         if (pt.l1_refresh == 2 && threadIdx.x == 0) l1_invalidate(&a.ctr->overflow);
     }
+    __syncwarp();
+    for (u32 i = threadIdx.x & 31; i < HOTC; i += 32)
+        if (hcnt[i]) atomicAdd(&a.table[hidx[i]].count, hcnt[i]);
     n_slow += qn;
     pass1_drain<WIDE>(a, g, pt, q, qn, lc, true);
     if ((threadIdx.x & 31) == 0 && n_slow) atomicAdd(&a.ctr->n_slow1, (u64)n_slow);
