@@ -100,8 +100,8 @@ struct Part {
     int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
     u32 hot_t, hot_flush; /* pass 1: fast-path increments of k-mers whose count is already >= hot_t are summed in a
                              small per-warp shared-memory cache and added to the table every hot_flush batches */
-    u32 dbg;            /* TIMING EXPERIMENTS ONLY (wrong results): 1 drop slow tuples, 2 no fast-path RED, 4 slow path claims
-                           but does not update, 8 no log stores */
+    u32 dbg;            /* TIMING EXPERIMENTS ONLY (wrong results): pass 1: 1 drop slow tuples, 2 no fast-path RED, 4 slow path
+                           claims but does not update, 8 no log stores, 16 no L1; pass 2: 32 drop slow tuples, 64 no reductions */
     u32 l1_refresh;     /* 0 never, 1 after every slow-path drain, 2 once per batch by warp 0 (see l1_invalidate) */
     u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
     u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
@@ -1359,10 +1359,10 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             const bool hit = valid && q0[u] == lo[u] && q1[u] == hi;
             const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
             if (hit) {
-                pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
+                if (!(pt.dbg & 64u)) pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
                 n_hits++;
             }
-            qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
+            qn = q.push(qn, valid && !hit && !empty && !(pt.dbg & 32u), lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
         }
         if (qn >= pt.qflush2) {
             n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false); n_slow -= qn;
