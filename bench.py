@@ -131,16 +131,18 @@ def ncu_traffic(kernel: str):
     return None
 
 
-def algorithmic_bytes(L, k, h, gated=1.0):
+def algorithmic_bytes(L, k, h, gated=1.0, h_rmw=None):
     """Bytes per window of each pass and of the whole path.
-    SURVEY.md 8d charges every window a slot read-modify-write in pass 1 (gated = 1.0).  Only the
-    windows that pass the quality gate ever touch the pass-1 table (include_kmer :240-259), so the
-    figures reported as `roofline` charge the 64 B to the gated fraction only; the SURVEY formula
-    is kept beside them as `survey_formula`."""
+    SURVEY.md 8d charges every window a slot read-modify-write in pass 1 (gated = 1.0) and every
+    pass-2 hit a read-modify-write (h_rmw = h).  In the reference only the windows that pass the
+    quality gate reach the pass-1 table (include_kmer :240-259), and here the gated occurrences
+    are not counted again in pass 2 (its count is seeded from pass 1), so the figures reported as
+    `roofline` charge the pass-1 64 B to the gated fraction and the pass-2 64 B to the UNGATED
+    hits only; the SURVEY formula is kept beside them as `survey_formula`."""
     w = L - k + 1
     b_in = 1.25 * L / (2 * w)
-    p1 = b_in + 64.0 * gated     # packed read bytes + one slot sector read-modify-write per gated window
-    p2 = b_in + 32.0 + 64.0 * h  # packed read bytes + membership probe + hit RMW
+    p1 = b_in + 64.0 * gated                            # packed read bytes + one slot sector RMW per gated window
+    p2 = b_in + 32.0 + 64.0 * (h if h_rmw is None else h_rmw)   # packed read bytes + membership probe + count RMW
     return p1, p2, p1 + p2
 
 
@@ -295,7 +297,7 @@ def main():
         t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = float(t[0]), float(t[1])
-        names = ["n_windows", "n_hits", "n_gated", "n_pre_total", "n_slow1", "n_slow2", "kernel_launches", "h2d_bytes"]
+        names = ["n_windows", "n_hits", "n_gated", "n_pre_total", "n_slow1", "n_slow2", "n_hits_ungated", "kernel_launches", "h2d_bytes"]
         t = torch.tensor([float(stats[n]) for n in names[:-1]] + [float(e2e_stats["h2d_bytes"])], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         sums = {n: float(v) for n, v in zip(names, t)}
@@ -307,7 +309,8 @@ def main():
         peak, peak_src = peaks()
         h = (sums["n_hits"] / W_total) if sharded else stats["n_hits"] / W
         gated = (sums["n_gated"] / W_total) if sharded else stats["n_gated"] / W
-        a1, a2, a_all = algorithmic_bytes(L, k, h, gated)
+        h_u = (sums["n_hits_ungated"] / W_total) if sharded else stats["n_hits_ungated"] / W
+        a1, a2, a_all = algorithmic_bytes(L, k, h, gated, h_u)
         s1, s2, s_all = algorithmic_bytes(L, k, h)
         kern = {n: float(np.mean([s[n] for s in per_kernel])) for n in
                 ["ms_estimate", "ms_scatter", "ms_init1", "ms_pass1", "ms_prune", "ms_table2", "ms_pass2", "ms_export"]}
@@ -329,6 +332,7 @@ def main():
                        "distinct_gated_kmers": int(sums["n_pre_total"]) if sharded else stats["n_pre_total"],
                        "nodes": stats["n_nodes"],
                        "gated_fraction": (sums["n_gated"] / W_total) if sharded else stats["n_gated"] / W, "pass2_hit_fraction_h": h,
+                       "pass2_ungated_hit_fraction": h_u,
                        "table1_slots": stats["table1_slots"], "table2_slots": stats["table2_slots"],
                        "hash_partitions": stats["partitions"], "tuple_bytes": stats["tuple_bytes"],
                        "slow_path_fraction_pass1": stats["n_slow1"] / max(1, stats["n_gated"]),

@@ -92,6 +92,7 @@ typedef struct vdjgraph_result {
     uint64_t n_pre;            /* "pre nodes after pruning" (= n_nodes) */
     uint64_t n_hits;           /* pass-2 windows whose k-mer survived (uncapped) */
     uint64_t n_slow1, n_slow2; /* diagnostics: tuples that took the slow (queued) path of pass 1 / pass 2 */
+    uint64_t n_hits_ungated;   /* pass-2 hits among the windows that failed the quality gate (only those add to node->frequency in pass 2) */
 
     /* timings of the last build, milliseconds */
     float ms_stage;            /* H2D of the text + device packing (wall clock) */

@@ -132,6 +132,7 @@ struct Counters {
     u64 n_hits;
     u64 n_nodes;
     u64 n_slow1, n_slow2; /* tuples that took the slow path of pass 1 / pass 2 */
+    u64 n_hits_ungated;   /* pass-2 hits of windows that did not pass the quality gate (the ones that add to the count) */
     u32 log_used;
     u32 overflow;     /* table full / probe bound hit / region overrun */
     u32 internal;     /* invariant violated */
@@ -409,8 +410,8 @@ k_pack(PackArgs a, Geom g) {
 /* new base and one new mask bit per window) instead of re-extracting them.                      */
 /* ------------------------------------------------------------------------------------------ */
 constexpr int SEG_COUNT = 16;           /* windows per thread segment in k_count (fewer, larger tiles) */
-constexpr int SEG = 8;                  /* ... and in k_scatter (smaller stage -> 3 blocks per SM) */
-constexpr u32 MAX_STAGE = THREADS * SEG; /* tuples a block can produce per tile */
+/* k_scatter<SG>: SG = 8 (2048-tuple stage, 3 blocks per SM) up to 128 partitions, 16 (4096-tuple stage)
+ * beyond, so that a bucket's run in the stage stays >= 8 tuples (one 128-byte bulk store) */
 
 struct BlockTiles {
     u64 *buf;   /* [2][a | b | c | d] */
@@ -591,12 +592,13 @@ struct ScatterSmem {
     u32 *boff;   /* [NBK + 1] start of each bucket's run in the stage */
     u64 *gbase;  /* [NBK] global tuple index of the run */
     u32 *fp;     /* [tile_rec] read fingerprints */
-    unsigned short *sbk; /* [MAX_STAGE] bucket of a staged tuple */
-    u64 *stage;  /* [MAX_STAGE][2 or 3] */
+    unsigned short *sbk; /* [THREADS * SG] bucket of a staged tuple */
+    u64 *stage;  /* [THREADS * SG][2 or 3] */
     unsigned char *tiles;
 };
 __host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *base, const Geom &g, int nbk, int wide) {
+    const size_t MAX_STAGE = (size_t)THREADS * g.seg;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t at = off; off = align128(off + bytes); return at; };
     size_t a_wcnt = take((size_t)WARPS * nbk * 4), a_boff = take((size_t)(nbk + 1) * 4), a_gbase = take((size_t)nbk * 8);
@@ -611,8 +613,10 @@ __host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *b
     return off;
 }
 
+template <int SG>
 __global__ void __launch_bounds__(THREADS)
 k_scatter(ScatterArgs a, Geom g, Part pt) {
+    constexpr int SEG = SG;
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = 1 << pt.pbits, NBK = 2 * P;
     ScatterSmem sm;
@@ -1257,7 +1261,7 @@ __device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2,
 /* slow path of pass 2: tuples whose home slot holds a different k-mer; queue entries carry the
  * tuple, its home slot and (top bit of idx) whether the tuple is from the ungated region */
 template <bool WIDE>
-__device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, WarpQueue<WIDE> &q, u32 &qn, bool final) {
+__device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, WarpQueue<WIDE> &q, u32 &qn, bool final, u32 &n_hits_u) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     u32 next = 0, n_hits = 0;
     bool have = false, count_it = false;
@@ -1295,6 +1299,7 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, W
                 if (has_next) o = ld_cg_u64(&slot->out_first[c]);
                 pass2_update(slot, count_it, q2, q3, o, has_next, c, stamp);
                 n_hits++;
+                n_hits_u += count_it;
                 have = false;
             } else if ((q0 == EMPTY64 && q1 == EMPTY64) || ++probe >= MAX_PROBE) {
                 have = false;
@@ -1318,7 +1323,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
     const u64 span = (u64)THREADS * BATCH;
     const u64 n_blk = (pt.n_valid + span - 1) / span;
     const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
-    u32 n_hits = 0, qn = 0, n_slow = 0;
+    u32 n_hits = 0, qn = 0, n_slow = 0, n_hits_u = 0;
     for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
         const u64 t0 = blk * span + threadIdx.x;
         u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
@@ -1361,20 +1366,22 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             if (hit) {
                 if (!(pt.dbg & 64u)) pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
                 n_hits++;
+                n_hits_u += ungated;
             }
             qn = q.push(qn, valid && !hit && !empty && !(pt.dbg & 32u), lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
         }
         if (qn >= pt.qflush2) {
-            n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false); n_slow -= qn;
+            n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false, n_hits_u); n_slow -= qn;
             if (pt.l1_refresh == 1 && lane == 0) l1_invalidate(&a.ctr->overflow);
         }
         if (pt.l1_refresh == 2 && threadIdx.x == 0) l1_invalidate(&a.ctr->overflow);
     }
     n_slow += qn;
-    n_hits += pass2_drain<WIDE>(a, pt, q, qn, true);
+    n_hits += pass2_drain<WIDE>(a, pt, q, qn, true, n_hits_u);
     if (lane == 0 && n_slow) atomicAdd(&a.ctr->n_slow2, (u64)n_slow);
-    for (int o = 16; o; o >>= 1) n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o);
+    for (int o = 16; o; o >>= 1) { n_hits += __shfl_xor_sync(0xFFFFFFFFu, n_hits, o); n_hits_u += __shfl_xor_sync(0xFFFFFFFFu, n_hits_u, o); }
     if (lane == 0 && n_hits) atomicAdd(&a.ctr->n_hits, (u64)n_hits);
+    if (lane == 0 && n_hits_u) atomicAdd(&a.ctr->n_hits_ungated, (u64)n_hits_u);
 }
 
 /* ------------------------------------------------------------------------------------------ */

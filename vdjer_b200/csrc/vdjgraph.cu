@@ -205,7 +205,7 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     /* c->g tiles for k_scatter, c->gc for k_count; the arrays are padded for both */
     c->gc = g;
     tile_geom(c->gc, SEG_COUNT, R);
-    tile_geom(g, SEG, R);
+    tile_geom(g, 8, R);
     c->R_pad = std::max(g.n_tiles * g.tile_rec, c->gc.n_tiles * c->gc.tile_rec);
 }
 
@@ -469,7 +469,7 @@ int run_count(vdjgraph_ctx *c) {
     int rc;
     memset(&c->ctr, 0, sizeof(c->ctr));
     vdjgraph_result &res = c->res;
-    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = res.n_slow1 = res.n_slow2 = 0;
+    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = res.n_slow1 = res.n_slow2 = res.n_hits_ungated = 0;
     res.ms_device = res.ms_estimate = res.ms_scatter = res.ms_init1 = res.ms_pass1 = res.ms_prune = 0;
     res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
     res.table1_slots = res.table2_slots = 0;
@@ -599,8 +599,10 @@ void set_self_peers(vdjgraph_ctx *c) {
 int run_scatter(vdjgraph_ctx *c) {
     Shard &sh = c->sh;
     if (!sh.peers_set) return fail(VDJGRAPH_ERR_STATE, "peer buffers not set");
-    const Geom g = c->g;
     const Part pt = c->part;
+    /* 8-window segments up to 128 partitions, 16-window segments (k_count's tiling) beyond */
+    const bool seg16 = (2 << pt.pbits) > 256;
+    const Geom g = seg16 ? c->gc : c->g;
     cudaStream_t s = c->stream;
     const int G = sh.G, P = 1 << pt.pbits, PL = P >> sh.gbits;
     /* region start of (cls, local partition) in every owner's buffer, then this device's share */
@@ -637,8 +639,10 @@ int run_scatter(vdjgraph_ctx *c) {
         as.rec_base = sh.rec_base[sh.rank];
         as.ctr = c->d_ctr.as<Counters>();
         const size_t smem_scatter = scatter_carve(nullptr, nullptr, g, 2 * P, pt.wide);
-        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
-        k_scatter<<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
+        const void *fn = seg16 ? (const void *)k_scatter<16> : (const void *)k_scatter<8>;
+        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm(fn, smem_scatter));
+        if (seg16) k_scatter<16><<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
+        else k_scatter<8><<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
         c->res.kernel_launches++;
         CK(cudaGetLastError());
     }
@@ -780,6 +784,7 @@ int run_passes(vdjgraph_ctx *c) {
         if (h_ctr->n_nodes != n_surv) return fail(VDJGRAPH_ERR_INTERNAL, "compacted %llu survivors, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
         res.n_hits = h_ctr->n_hits;
         res.n_slow2 = h_ctr->n_slow2;
+        res.n_hits_ungated = h_ctr->n_hits_ungated;
     }
     sh.phase = 4;
     return 0;
@@ -858,6 +863,7 @@ int run_finish(vdjgraph_ctx *c) {
     if (sh.G == 1) {
         res.n_hits = h_ctr->n_hits;
         res.n_slow2 = h_ctr->n_slow2;
+        res.n_hits_ungated = h_ctr->n_hits_ungated;
     } else {
         res.n_pre = n_surv;
     }

@@ -42,7 +42,7 @@ class _Result(C.Structure):
         ("kmer_lo", C.POINTER(C.c_uint64)), ("kmer_hi", C.POINTER(C.c_uint64)),
         ("n_records", C.c_uint64), ("n_windows", C.c_uint64), ("n_gated", C.c_uint64),
         ("n_pre_total", C.c_uint64), ("n_pre", C.c_uint64), ("n_hits", C.c_uint64),
-        ("n_slow1", C.c_uint64), ("n_slow2", C.c_uint64),
+        ("n_slow1", C.c_uint64), ("n_slow2", C.c_uint64), ("n_hits_ungated", C.c_uint64),
         ("ms_stage", C.c_float), ("ms_device", C.c_float), ("ms_estimate", C.c_float),
         ("ms_scatter", C.c_float), ("ms_init1", C.c_float), ("ms_pass1", C.c_float), ("ms_prune", C.c_float), ("ms_table2", C.c_float),
         ("ms_pass2", C.c_float), ("ms_export", C.c_float), ("ms_fetch", C.c_float),
