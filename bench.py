@@ -240,7 +240,11 @@ def main():
     primary, secondary = synth.generate(seed=12345, pair_offset=rank * wl["n_pairs"], **gen)
     t_gen = time.perf_counter() - t0
 
-    gb = GraphBuilder(L, k, mf, mq, device=local_rank)
+    # staging threads: all cores for one rank; N ranks on one host share them
+    host_threads = 0 if world == 1 else max(2, (os.cpu_count() or 16) // world)
+    if os.environ.get("VDJGRAPH_HOST_THREADS"):
+        host_threads = int(os.environ["VDJGRAPH_HOST_THREADS"])
+    gb = GraphBuilder(L, k, mf, mq, device=local_rank, host_threads=host_threads)
     sharded = world > 1
     if sharded:
         # one graph over the reads of all ranks: k-mers hash-sharded, tuples exchanged by the scatter
