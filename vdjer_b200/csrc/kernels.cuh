@@ -14,7 +14,8 @@
  * partition addresses is a few MB and stays L2-resident, every probe and atomic is an L2 hit,
  * and HBM only sees streaming traffic.
  *
- * Packed read layout in HBM (written by the host staging code in vdjgraph.cu):
+ * Packed read layout in HBM (written by k_pack from the caller's text records, which the host
+ * staging code in vdjgraph.cu streams to the device):
  *   bases [R][nb] u64 : 2 bits/base, A=0 C=1 G=2 T=3 (N stored as 0), base j at bits 2j of the record
  *   good  [R][nm] u64 : bit j = base j is ACGT and phred >= 20      (pass-1 gate, :240-259)
  *   hiq   [R][nm] u64 : bit j = base j is ACGT and phred >= 30      (prune's quality-sum bound)
