@@ -103,7 +103,6 @@ struct Part {
                              small per-warp shared-memory cache and added to the table every hot_flush batches */
     u32 dbg;            /* TIMING EXPERIMENTS ONLY (wrong results): pass 1: 1 drop slow tuples, 2 no fast-path RED, 4 slow path
                            claims but does not update, 8 no log stores, 16 no L1; pass 2: 32 drop slow tuples, 64 no reductions */
-    u32 l1_refresh;     /* 0 never, 1 after every slow-path drain, 2 once per batch by warp 0 (see l1_invalidate) */
     u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
     u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
     u64 n_gated, n_valid; /* tuples in the gated region / in both regions */
@@ -173,14 +172,6 @@ __device__ __forceinline__ u64 ld_ca_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.global.ca.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-/* Drop this SM's L1 lines (CCTL.IVALL, emitted after an acquire load): the fast paths then see
- * what the slow path has just established (a k-mer inserted, MULTI set, ranks used up) instead
- * of a stale line that would keep sending the k-mer's tuples to the slow path. */
-__device__ __forceinline__ void l1_invalidate(const void *any) {
-    u32 v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(any) : "memory");
-    asm volatile("" :: "r"(v));
 }
 /* streaming (touched-once) tuple traffic: evict-first so it does not push the L2-resident
  * table slice out */
@@ -1031,9 +1022,7 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
         }
         if (qn >= pt.qflush1) {
             n_slow += qn; qn = pass1_drain<WIDE>(a, g, pt, q, qn, lc, false); n_slow -= qn;
-            if (pt.l1_refresh == 1 && (threadIdx.x & 31) == 0) l1_invalidate(&a.ctr->overflow);
         }
-        if (pt.l1_refresh == 2 && threadIdx.x == 0) l1_invalidate(&a.ctr->overflow);
     }
     __syncwarp();
     for (u32 i = threadIdx.x & 31; i < HOTC; i += 32)
@@ -1373,9 +1362,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
         }
         if (qn >= pt.qflush2) {
             n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false, n_hits_u); n_slow -= qn;
-            if (pt.l1_refresh == 1 && lane == 0) l1_invalidate(&a.ctr->overflow);
         }
-        if (pt.l1_refresh == 2 && threadIdx.x == 0) l1_invalidate(&a.ctr->overflow);
     }
     n_slow += qn;
     n_hits += pass2_drain<WIDE>(a, pt, q, qn, true, n_hits_u);

@@ -540,7 +540,6 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     pt.fb = pt.wide ? std::min(32, 64 - pt.hb - FLB) : std::min(32, 64 - pt.hb - FLB - sbits);
     /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
     pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
-    pt.l1_refresh = (u32)env_double("VDJGRAPH_L1_REFRESH", 0);
     pt.dbg = (u32)env_double("VDJGRAPH_DBG", 0);
     pt.hot_t = (u32)env_double("VDJGRAPH_HOT_T", 1024);
     pt.hot_flush = (u32)std::max(1.0, env_double("VDJGRAPH_HOT_FLUSH", 3));
