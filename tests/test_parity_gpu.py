@@ -69,6 +69,30 @@ def test_partition_count_and_tuple_format_do_not_change_the_result(built, partit
     assert got.stats["n_hits"] == want["n_hits"] and got.stats["n_gated"] == want["n_gated"]
 
 
+@pytest.mark.parametrize("knobs", [
+    {"VDJGRAPH_HOT_T": "1", "VDJGRAPH_HOT_FLUSH": "1"},           # every fast-path increment goes through the warp cache
+    {"VDJGRAPH_HOT_T": "2000000000"},                               # ... none does
+    {"VDJGRAPH_LOAD1": "0.85", "VDJGRAPH_LOAD2": "0.85"},           # long probe chains in both tables
+    {"VDJGRAPH_SLICE_MB": "0.05"},                                  # as many partitions as there can be
+    {"VDJGRAPH_QFLUSH1": "32", "VDJGRAPH_QDENSE1": "16"},           # pass-1 drains re-queue stragglers
+    {"VDJGRAPH_QFLUSH2": "1", "VDJGRAPH_QDENSE2": "0"},             # pass-2 drains after every batch, to the end
+    {"VDJGRAPH_QFLUSH2": "96", "VDJGRAPH_QDENSE2": "31"},           # ... or give up early and re-queue
+])
+def test_performance_knobs_do_not_change_the_result(built, knobs, monkeypatch):
+    """The environment knobs of DESIGN.md section 4 only move work around."""
+    for k_, v in knobs.items():
+        monkeypatch.setenv(k_, v)
+    for (L, k, mf, mq, seed) in [(50, 35, 3, 90, 81), (50, 25, 1, 20, 82)]:
+        primary, secondary = synth.generate(n_pairs=20000, read_length=L, seed=seed, n_clones=200, threads=4)
+        want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+        with GraphBuilder(L, k, mf, mq) as gb:
+            got = gb.build(primary, secondary)
+            pre = gb.pre_table()
+        assert_pre_table_equal(pre, want, primary, secondary, L, k, str(knobs))
+        assert_graph_equal(got, want, str(knobs))
+        assert got.stats["n_hits"] == want["n_hits"]
+
+
 @pytest.mark.parametrize("fp_bits", ["0", "2"])
 def test_weak_read_fingerprints_fall_back_to_the_exact_comparison(built, fp_bits, monkeypatch):
     """hasMultipleUniqueReads (:349-352) is decided by a read fingerprint carried in the tuples and,
