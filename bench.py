@@ -131,6 +131,16 @@ def ncu_traffic(kernel: str):
     return None
 
 
+def atomic_rates():
+    """L2-resident random load+RED / load / RED rates (G ops/s) measured on this pool by
+    vdjer_b200/microbench (profiles/microbench_r1.json, 32 MB table row); None if absent."""
+    try:
+        row = json.load(open(os.path.join(ROOT, "profiles", "microbench_r1.json")))["rows"][0]
+        return {"load_red": row["load_red_ilp4"], "load": row["load_ilp4"], "red": row["red_ilp4"], "table_mb": row["table_mb"]}
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(L, k, h, gated=1.0, h_rmw=None):
     """Bytes per window of each pass and of the whole path.
     SURVEY.md 8d charges every window a slot read-modify-write in pass 1 (gated = 1.0) and every
@@ -366,6 +376,20 @@ def main():
                               "note": "whole step (all kernels) per GPU against the HBM copy peak"},
             "clocks": clocks,
         }
+        ar = atomic_rates()
+        if ar:
+            # SURVEY 8d "atomic roof": pass 1 = one L2 load + RED per gated window; pass 2 = one L2 load per
+            # N-free window + one RED per ungated hit.  Rates: random sectors in an L2-resident table.
+            n_g = gated * W
+            t1 = n_g / (ar["load_red"] * 1e9) * 1e3
+            n_valid = W   # N-free windows ~ all windows (N rate 0.05 %)
+            t2 = (n_valid / (ar["load"] * 1e9) + h_u * W / (ar["red"] * 1e9)) * 1e3
+            line["roofline_atomic"] = {
+                "source": "profiles/microbench_r1.json (random 32-B sectors, 32 MB table: L2-resident)",
+                "rates_G_ops_per_s": ar,
+                "k_pass1": {"roof_ms": t1, "measured_ms": kern["ms_pass1"], "frac": t1 / kern["ms_pass1"]},
+                "k_pass2": {"roof_ms": t2, "measured_ms": kern["ms_pass2"], "frac": t2 / kern["ms_pass2"]},
+            }
         if sharded:
             line["shard_phase_ms_rank0"] = {k2: round(v, 3) for k2, v in phase_ms.items()}
         if not args.no_cpu_baseline:

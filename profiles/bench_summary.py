@@ -18,6 +18,9 @@ for line in sys.stdin:
     c = d["config"]
     print("slow-path fractions", round(c.get("slow_path_fraction_pass1", -1), 3), round(c.get("slow_path_fraction_pass2", -1), 3),
           "partitions", c.get("hash_partitions"), "h", round(c["pass2_hit_fraction_h"], 3), "gated", round(c["gated_fraction"], 3))
+    if "roofline_atomic" in d:
+        ra = d["roofline_atomic"]
+        print("atomic roof: pass1", round(ra["k_pass1"]["frac"], 3), "pass2", round(ra["k_pass2"]["frac"], 3))
     if "shard_phase_ms_rank0" in d:
         print("shard phases (rank 0, wall ms)", d["shard_phase_ms_rank0"])
     if "cpu_baseline" in d:
