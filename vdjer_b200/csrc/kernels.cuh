@@ -60,11 +60,14 @@ constexpr int BATCH = 4;         /* independent table probes a thread keeps in f
 /* pass-1 table slot: exactly one 32-byte sector */
 struct __align__(32) Slot1 {
     u64 klo, khi;     /* packed k-mer; all ones = empty */
-    u32 count;        /* bits 0..29: gated occurrences (stops counting a little above CNT_CAP);
-                         bit 30 CNT_SURV; bit 31 CNT_MULTI: hasMultipleUniqueReads :349-352 */
+    u32 count;        /* bits 0..29: gated occurrences AFTER the one that claimed the slot (the k-mer's count is
+                         this + 1; stops counting a little above CNT_CAP); bit 30 CNT_SURV; bit 31 CNT_MULTI:
+                         hasMultipleUniqueReads :349-352 */
     u32 head;         /* this k-mer's block of NB log entries (stamps of its first NB arrivals);
                          NIL32 until the thread that claimed the slot has published it */
-    u32 first_rec;    /* record of the first ARRIVING gated occurrence: contributingRead :335 */
+    u32 first_rec;    /* record of the occurrence that claimed the slot: contributingRead :335.  Written (with
+                         first_fp, one 64-bit store) by the claiming thread AFTER head: a slot is usable by
+                         others once they see it */
     u32 first_fp;     /* fingerprint of that record's sequence (as carried by the tuples) */
 };
 static_assert(sizeof(Slot1) == 32, "Slot1 must be one sector");
@@ -188,6 +191,9 @@ __device__ __forceinline__ void st_stream_v2(void *p, u64 a, u64 b) {
 }
 __device__ __forceinline__ void st_stream_u64(void *p, u64 a) {
     asm volatile("st.global.cs.b64 [%0], %1;" :: "l"(p), "l"(a) : "memory");
+}
+__device__ __forceinline__ void st_cg_u64(u64 *p, u64 v) {
+    asm volatile("st.global.cg.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 /* 128-bit compare-and-swap on a 16-byte aligned key (ATOMG.E.CAS.128 on sm_100a) */
 __device__ __forceinline__ void cas128(void *addr, u64 cmp_lo, u64 cmp_hi, u64 val_lo, u64 val_hi,
@@ -888,8 +894,9 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
                 if (q0 == EMPTY64 && q1 == EMPTY64) { found = claimed = true; q2 = (u64)NIL32 << 32; q3 = (u64)NIL32; }
                 else if (q0 == lo && q1 == hi) q2 = (u64)NIL32 << 32;   /* lost the race to the same k-mer: look again */
             } else if (q0 == lo && q1 == hi) {
-                /* a slot whose log block is not published yet is looked at again next iteration */
-                found = a.nb_ranks == 0 || (u32)(q2 >> 32) != NIL32;
+                /* a slot whose claimer has not published its first record (and log block) yet is looked
+                 * at again next iteration */
+                found = (u32)q3 != NIL32 && (a.nb_ranks == 0 || (u32)(q2 >> 32) != NIL32);
             }
             if (!found && !(q0 == lo && q1 == hi)) {
                 if (++idx == (u32)a.cap) idx = 0;
@@ -920,25 +927,24 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
         if (found && (pt.dbg & 4u)) { have = false; found = false; }
         if (found) {
             const u32 r = (u32)(stamp / (u64)g.w);
-            const u32 cw = (u32)q2, cnt = cw & CNT_MASK;
-            u32 first_rec = (u32)q3, first_fp = (u32)(q3 >> 32);
-            /* the arrival-rank add and the first-record CAS go out together (one round trip) */
-            u32 rank = NIL32;
-            u64 old = q3;
-            const bool want_first = !(cw & CNT_MULTI) && first_rec == NIL32;
-            if (cnt < a.nb_ranks) rank = atomicAdd(&slot->count, 1u);              /* arrival rank decides logging */
-            else if (cnt < CNT_CAP) atomicAdd(&slot->count, 1u);                   /* result unused: RED */
-            if (want_first) old = atomicCAS(reinterpret_cast<u64 *>(&slot->first_rec), (u64)NIL32, (u64)r | ((u64)fp << 32));
-            rank = rank == NIL32 ? NIL32 : (rank & CNT_MASK);
-            if (!(cw & CNT_MULTI)) {
-                first_rec = (u32)old; first_fp = (u32)(old >> 32);
+            const u64 entry = stamp | ((fl & 8u) ? LOG_A : 0ull) | ((fl & 16u) ? LOG_B : 0ull);
+            if (claimed) {
+                /* first arrival: arrival rank 0, nothing to compare with, and nobody else touches the slot
+                 * until the first-record word is published: plain stores, no atomics */
+                if (a.nb_ranks && blk != NIL32 && !(pt.dbg & 8u)) a.log[(u64)blk * a.nb_ranks] = entry;
+                st_cg_u64(reinterpret_cast<u64 *>(&slot->first_rec), (u64)r | ((u64)fp << 32));
+            } else {
+                const u32 cw = (u32)q2, cnt = cw & CNT_MASK;       /* arrivals after the claimer seen so far */
+                const u32 first_rec = (u32)q3, first_fp = (u32)(q3 >> 32);
+                u32 rank = NIL32;
+                if (cnt + 1 < a.nb_ranks) rank = (atomicAdd(&slot->count, 1u) & CNT_MASK) + 1;   /* arrival rank decides logging */
+                else if (cnt + 1 < CNT_CAP) atomicAdd(&slot->count, 1u);                          /* result unused: RED */
                 /* different fingerprints: different reads.  Equal ones: compare the reads (:142-144) */
-                if (first_rec != NIL32 && first_rec != r &&
+                if (!(cw & CNT_MULTI) && first_rec != r &&
                     (first_fp != fp || !same_read(a.rd, first_rec, r, g.nb, g.nm)))
                     atomicOr(&slot->count, CNT_MULTI);
+                if (rank < a.nb_ranks && blk != NIL32 && !(pt.dbg & 8u)) a.log[(u64)blk * a.nb_ranks + rank] = entry;
             }
-            if (rank < a.nb_ranks && blk != NIL32 && !(pt.dbg & 8u))
-                a.log[(u64)blk * a.nb_ranks + rank] = stamp | ((fl & 8u) ? LOG_A : 0ull) | ((fl & 16u) ? LOG_B : 0ull);
             have = false;
         }
     }
@@ -999,8 +1005,8 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
         for (int u = 0; u < BATCH; u++) {
             const bool valid = idx[u] != NIL32;
             const u32 cw = (u32)m2[u], cnt = cw & CNT_MASK;
-            const bool fast = valid && k0[u] == lo[u] && k1[u] == (w1[u] & hmask) && (cw & CNT_MULTI) && cnt >= a.nb_ranks;
-            if (fast && cnt < CNT_CAP && !(pt.dbg & 2u)) {
+            const bool fast = valid && k0[u] == lo[u] && k1[u] == (w1[u] & hmask) && (cw & CNT_MULTI) && cnt + 1 >= a.nb_ranks;
+            if (fast && cnt + 1 < CNT_CAP && !(pt.dbg & 2u)) {
                 bool cached = false;
                 if (cnt >= pt.hot_t) {
                     const u32 e = (idx[u] * 0x9E3779B1u) >> (32 - HOTC_BITS);
@@ -1072,7 +1078,7 @@ k_prune(PruneArgs a, Geom g) {
             if (!(q0 == EMPTY64 && q1 == EMPTY64)) {
                 n_distinct++;
                 cw = (u32)q2;
-                cnt = cw & CNT_MASK;
+                cnt = (cw & CNT_MASK) + 1;          /* the claiming occurrence + the others */
                 head = (u32)(q2 >> 32);
                 if (cnt > CNT_CAP) cnt = CNT_CAP;
                 if ((int)cnt >= a.mf && (cw & CNT_MULTI)) {
@@ -1178,7 +1184,7 @@ k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters
         const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.gbits, pt.slice2), q0, q1);
         if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
         /* the gated occurrences are N-free occurrences: seed node->frequency with them */
-        const u32 cnt = (u32)q2 & CNT_MASK;
+        const u32 cnt = ((u32)q2 & CNT_MASK) + 1;
         t2[at].count = cnt > CNT_CAP ? CNT_CAP : cnt;
     }
 }
@@ -1481,7 +1487,7 @@ k_export_pre(const Slot1 *t, u64 cap, u64 *klo, u64 *khi, u16 *freq, u64 *n_out)
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
         if (!((u32)q2 & CNT_SURV)) continue;
         u64 o = atomicAdd(n_out, 1ull);
-        u32 cnt = (u32)q2 & CNT_MASK;
+        u32 cnt = ((u32)q2 & CNT_MASK) + 1;
         klo[o] = q0; khi[o] = q1; freq[o] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);
     }
 }
