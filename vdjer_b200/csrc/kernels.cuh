@@ -1189,24 +1189,39 @@ k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters
     }
 }
 
+/* Position of this thread's element in a global append-only array: warps sum their counts in
+ * shared memory and ONE global atomic per block reserves the block's range (a per-warp atomic on
+ * the single counter serialises: 400 k same-address atomics cost more than the scan itself).
+ * Must be called by all threads of the block; `take` = this thread appends one element. */
+__device__ __forceinline__ u64 block_append(bool take, u64 *counter) {
+    __shared__ u32 s_cnt;
+    __shared__ u64 s_base;
+    const u32 lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const u32 ballot = __ballot_sync(0xFFFFFFFFu, take);
+    u32 wbase = 0;
+    if (lane == 0 && ballot) wbase = atomicAdd(&s_cnt, (u32)__popc(ballot));
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = s_cnt ? atomicAdd(counter, (u64)s_cnt) : 0ull;
+    __syncthreads();
+    return s_base + wbase + __popc(ballot & ((1u << lane) - 1));
+}
+
 /* Sharded build: a device's survivors as dense Slot2 records (sent to the finishing device), and
  * the finishing device's table over the records of all devices. */
 __global__ void __launch_bounds__(THREADS)
 k_compact_table2(const Slot2 *t, u64 cap, Slot2 *out, u64 *n_out) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
-    const u32 lane = threadIdx.x & 31;
     const u64 n_iter = (cap + stride - 1) / stride;
     for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
         bool occ = false;
         u64 q0 = 0, q1 = 0, q2 = 0, q3 = 0;
         if (i < cap) { ld_sector(&t[i], q0, q1, q2, q3); occ = !(q0 == EMPTY64 && q1 == EMPTY64); }
-        const u32 ballot = __ballot_sync(0xFFFFFFFFu, occ);
-        if (!ballot) continue;
-        u64 base = 0;
-        if (lane == 0) base = atomicAdd(n_out, (u64)__popc(ballot));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const u64 at = block_append(occ, n_out);
         if (occ) {
-            Slot2 *o = out + base + __popc(ballot & ((1u << lane) - 1));
+            Slot2 *o = out + at;
             u64 r0, r1, r2, r3;
             ld_sector(reinterpret_cast<const char *>(&t[i]) + 32, r0, r1, r2, r3);
             st_sector(o, q0, q1, q2, q3);
@@ -1385,7 +1400,6 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
 __global__ void __launch_bounds__(THREADS)
 k_collect(const Slot2 *t, u64 cap, u64 *keys, u32 *vals, Counters *ctr) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
-    const u32 lane = threadIdx.x & 31;
     u64 n_iter = (cap + stride - 1) / stride;
     for (u64 itn = 0; itn < n_iter; itn++, i += stride) {
         bool occ = false;
@@ -1394,13 +1408,8 @@ k_collect(const Slot2 *t, u64 cap, u64 *keys, u32 *vals, Counters *ctr) {
             ld_sector(&t[i], q0, q1, q2, q3);
             occ = !(q0 == EMPTY64 && q1 == EMPTY64);
         }
-        u32 ballot = __ballot_sync(0xFFFFFFFFu, occ);
-        if (!ballot) continue;
-        u64 base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->n_nodes, (u64)__popc(ballot));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const u64 o = block_append(occ, &ctr->n_nodes);
         if (occ) {
-            u64 o = base + __popc(ballot & ((1u << lane) - 1));
             keys[o] = q3;            /* first_any */
             vals[o] = (u32)i;
             if (q3 == INF64) atomicExch(&ctr->internal, 2u);
