@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VDJGRAPH_ABI_VERSION 2
+#define VDJGRAPH_ABI_VERSION 3
 
 typedef enum vdjgraph_status {
     VDJGRAPH_OK = 0,
@@ -57,6 +57,12 @@ typedef struct vdjgraph_params {
     uint64_t table_capacity;  /* pass-1 table slots; 0 = auto (cardinality estimate on device) */
     uint32_t flags;           /* VDJGRAPH_FLAG_* */
     uint32_t partitions;      /* hash partitions (power of two <= 256); 0 = auto (table slice ~24 MB, L2-resident) */
+    uint32_t rounds;          /* hash super-partitions processed one after the other (power of two, rounds * devices
+                                 <= 256): the tuple buffer and both tables hold 1/rounds of the hash space at a time
+                                 and the packed reads are streamed once per round -- for inputs whose tuples do not
+                                 fit HBM (BASELINE configs[4]).  0 = auto: the smallest count whose working set fits
+                                 the device (1 for everything up to configs[3]).  Results do not depend on it */
+    uint32_t reserved;        /* 0 */
 } vdjgraph_params;
 
 #define VDJGRAPH_FLAG_EXPORT_KEYS 1u /* also export the packed k-mer of every node (kmer_lo/kmer_hi) */
@@ -105,6 +111,7 @@ typedef struct vdjgraph_result {
     float ms_fetch;            /* D2H of the result (wall clock) */
     uint64_t table1_slots, table2_slots; /* capacities used */
     uint32_t partitions, tuple_bytes;    /* hash partitions and tuple size used */
+    uint32_t rounds, reserved;           /* super-partition rounds used */
     uint64_t h2d_bytes, d2h_bytes;       /* bytes moved by stage / fetch */
     uint64_t kernel_launches;            /* our kernels launched by the last run (CUB's sort passes not counted) */
 } vdjgraph_result;
@@ -164,6 +171,9 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
  *   exchange  : all-gather the pointers (vdjgraph_ipc_export/open across processes)
  *   all ranks : vdjgraph_shard_set_peers ; BARRIER ; vdjgraph_shard_release_retired ; vdjgraph_shard_scatter ; BARRIER
  *   all ranks : vdjgraph_shard_passes                                             -> survivor count
+ *   (more than one round, vdjgraph_shard_rounds() > 1: BARRIER ; vdjgraph_shard_scatter ; BARRIER ;
+ *    vdjgraph_shard_passes again, once per further round: the scatter of round r+1 overwrites the tuple
+ *    buffers that the owners' passes of round r read)
  *   exchange  : all-gather the survivor counts
  *   all ranks : vdjgraph_shard_gather_plan ; rank 0's GATHER pointer to everybody ; set_peers
  *   all ranks : vdjgraph_shard_send ; BARRIER
@@ -184,10 +194,13 @@ int vdjgraph_shard_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primar
 int vdjgraph_shard_count(vdjgraph_ctx *ctx, uint64_t *hist /*[512]*/, uint32_t *hll /*[4096]*/);
 int vdjgraph_shard_plan(vdjgraph_ctx *ctx, const uint64_t *hist_all /*[n_ranks][512]*/,
                         const uint32_t *hll_merged /*[4096]*/, const uint64_t *record_counts /*[n_ranks]*/);
+/* rounds the plan settled on (every rank computes the same number from the all-gathered inputs);
+ * negative status before vdjgraph_shard_plan */
+int vdjgraph_shard_rounds(vdjgraph_ctx *ctx);
 int vdjgraph_shard_buffers(vdjgraph_ctx *ctx, void **ptrs /*[NBUF]*/, size_t *bytes /*[NBUF] or NULL*/);
 int vdjgraph_shard_set_peers(vdjgraph_ctx *ctx, void *const *ptrs /*[n_ranks][NBUF]; this rank's row is ignored*/);
 int vdjgraph_shard_scatter(vdjgraph_ctx *ctx);
-int vdjgraph_shard_passes(vdjgraph_ctx *ctx, uint64_t *n_survivors);
+int vdjgraph_shard_passes(vdjgraph_ctx *ctx, uint64_t *n_survivors /* of this rank, all rounds so far */);
 int vdjgraph_shard_gather_plan(vdjgraph_ctx *ctx, const uint64_t *survivors_all /*[n_ranks]*/);
 int vdjgraph_shard_send(vdjgraph_ctx *ctx);
 int vdjgraph_shard_finish(vdjgraph_ctx *ctx);

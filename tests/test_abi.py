@@ -24,7 +24,7 @@ def test_header_symbols_exported(built):
     assert set(names) == set(graph.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vdjgraph.h but not exported"
-    assert lib.vdjgraph_version() == 2
+    assert lib.vdjgraph_version() == 3
 
 
 def test_struct_layouts_match_header(built):
@@ -67,6 +67,9 @@ def test_param_validation(built):
         assert lib.vdjgraph_create(C.byref(p), C.byref(ctx)) == -1
         assert lib.vdjgraph_last_error()
     assert lib.vdjgraph_create(None, C.byref(ctx)) == -1
+    for rounds in (3, 512):     # not a power of two / more than the 256 hash buckets
+        p = graph._Params(50, 35, 3, 90, -1, 0, 0, 0, 0, rounds, 0)
+        assert lib.vdjgraph_create(C.byref(p), C.byref(ctx)) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

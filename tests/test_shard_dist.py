@@ -23,9 +23,13 @@ from vdjer_b200.graph import BUF_GATHER, SHARD_HIST, SHARD_HLL, SHARD_NBUF  # no
 class FakeBuilder:
     """Stands in for GraphBuilder's shard_* methods; pointers are tagged integers."""
 
-    def __init__(self, rank, n_records):
+    def __init__(self, rank, n_records, rounds=1):
         self.rank, self.n, self.log = rank, n_records, []
         self.gather = 0
+        self.rounds = rounds
+
+    def shard_rounds(self):
+        return self.rounds
 
     def _n_records(self, primary, secondary):
         return self.n
@@ -56,7 +60,8 @@ class FakeBuilder:
 
     def shard_passes(self):
         self.log.append(("passes",))
-        return 10 + self.rank
+        self.surv = getattr(self, "surv", 0) + 10 + self.rank      # survivors accumulate over the rounds
+        return self.surv
 
     def shard_gather_plan(self, surv):
         self.log.append(("gather_plan", list(surv)))
@@ -76,14 +81,14 @@ class FakeBuilder:
         return "graph"
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, rounds=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     # identity "IPC": a handle is the pointer's decimal text
     shard._Peers.export = lambda self, ptr: str(ptr).encode().ljust(64, b" ") if ptr else b""
     shard._Peers.map = lambda self, r, i, h: int(h) + 5 if h else 0      # +5: a mapping is a different address
     shard._Peers.close = lambda self: None
-    b = FakeBuilder(rank, 100 + 20 * rank)
+    b = FakeBuilder(rank, 100 + 20 * rank, rounds)
     g = shard.build_distributed(b, None, None, dist=dist)
     np.save(os.path.join(out_dir, f"log{rank}.npy"), np.array([b.log, g], dtype=object), allow_pickle=True)
     dist.destroy_process_group()
@@ -118,6 +123,20 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     # survivor counts all-gathered; rank 0's gather buffer reaches rank 1
     assert l0[7][1] == [10, 11] and l1[7][1] == [10, 11]
     assert l1[8][1][0][BUF_GATHER] == 777 + 5 and l0[8][1][1][BUF_GATHER] == 0
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_rounds_over_gloo(tmp_path):
+    """Three super-partition rounds: scatter + passes once per round on every rank, the cumulative
+    survivor counts of the LAST round are what is gathered."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), 3), nprocs=world, join=True)
+    logs = [np.load(tmp_path / f"log{r}.npy", allow_pickle=True) for r in range(world)]
+    (l0, _), (l1, _) = logs
+    order = ["stage", "count", "plan", "peers", "release"] + ["scatter", "passes"] * 3 + ["gather_plan", "peers", "send", "release"]
+    assert [e[0] for e in l0] == order + ["finish"] and [e[0] for e in l1] == order
+    gp = order.index("gather_plan")
+    assert l0[gp][1] == [30, 33] and l1[gp][1] == [30, 33]
 
 
 def test_shard_ranges_and_split():

@@ -97,8 +97,12 @@ struct Geom {
 /* hash partitioning + tuple format */
 struct Part {
     int pbits;          /* P = 1 << pbits partitions by the top hash bits */
-    int gbits;          /* sharded build over G = 1 << gbits devices: partition p belongs to device p & (G-1) and
-                           is that device's local partition p >> gbits (tables hold the local partitions only) */
+    int gbits;          /* low partition bits that do not address this device's tables.  A build sharded over G
+                           devices and run in S rounds (hash super-partitions processed one after the other, for
+                           inputs whose tuples exceed HBM) gives partition p to device p & (G-1), round
+                           (p >> log2 G) & (S-1), and makes it local partition p >> gbits, gbits = log2 G + log2 S:
+                           the tables hold the local partitions of ONE round only */
+    u32 rshift, rmask, round; /* k_scatter ships the windows of partitions with ((p >> rshift) & rmask) == round */
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
     int wide;           /* 1: 24-byte tuples (stamp in a third word) */
     int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
@@ -251,8 +255,12 @@ __device__ __forceinline__ u64 hash_key(u64 lo, u64 hi) {
 /* home slot: the top pbits of the hash select the partition (= a contiguous slice of the
  * table), the remaining bits a slot inside it */
 __device__ __forceinline__ u64 home_slot(u64 h, int pbits, int gbits, u64 slice) {
-    if (pbits == 0) return __umul64hi(h, slice);
-    return ((h >> (64 - pbits)) >> gbits) * slice + __umul64hi(h << pbits, slice);
+    /* slices hold fewer than 2^32 slots (the host checks the table capacities): the 32 hash bits
+     * below the partition bits pick the slot with one 32-bit multiply-high */
+    const u32 x = (u32)((h << pbits) >> 32);
+    const u32 in_slice = __umulhi(x, (u32)slice);
+    if (pbits == 0) return in_slice;
+    return (u64)((u32)(h >> (64 - pbits)) >> gbits) * (u32)slice + in_slice;
 }
 
 /* bits [2i, 2i+2k) of a record's base words */
@@ -657,8 +665,11 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
                     if (j) r.step(g);
                     if (r.valid(g)) {
                         const u64 h = hash_key(r.lo, r.hi);
-                        const u32 bk = (pt.pbits ? (u32)(h >> (64 - pt.pbits)) : 0u) + (r.gated(g) ? 0u : (u32)P);
-                        code[j] = (bk << 16) | atomicAdd(&mine[bk], 1u);
+                        const u32 part = pt.pbits ? (u32)(h >> (64 - pt.pbits)) : 0u;
+                        if (((part >> pt.rshift) & pt.rmask) == pt.round) {   /* this round's share of the hash space */
+                            const u32 bk = part + (r.gated(g) ? 0u : (u32)P);
+                            code[j] = (bk << 16) | atomicAdd(&mine[bk], 1u);
+                        }
                     }
                 }
             }

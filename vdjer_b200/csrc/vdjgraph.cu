@@ -77,6 +77,24 @@ struct DevBuf {
         cap = want;
         return 0;
     }
+    /* grow to `bytes`, keeping the first `keep` bytes (survivor records accumulate over the rounds) */
+    int ensure_keep(size_t bytes, size_t keep, cudaStream_t s) {
+        if (bytes <= cap) return 0;
+        void *old = p;
+        const size_t old_cap = cap;
+        const bool was_exported = exported;
+        p = nullptr; cap = 0; exported = false;
+        int rc = ensure(bytes + bytes / 4);
+        exported = was_exported;
+        if (rc) { p = old; cap = old_cap; return rc; }   /* the old buffer and its contents stay */
+        if (old && keep) {
+            cudaError_t e = cudaMemcpyAsync(p, old, keep, cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(old); return fail(VDJGRAPH_ERR_CUDA, "copy into the grown buffer failed: %s", cudaGetErrorString(e)); }
+        }
+        if (old) { if (exported) retired.push_back(old); else cudaFree(old); }
+        return 0;
+    }
     void release_retired() { for (void *q : retired) cudaFree(q); retired.clear(); }
     void release() { release_retired(); if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
@@ -131,6 +149,12 @@ struct Shard {
     uint64_t n_gated_src = 0, n_valid_src = 0;    /* windows this device produces */
     double est_distinct = 0;
     uint64_t surv_all[MAX_DEV] = {}, surv_off[MAX_DEV + 1] = {};
+    /* rounds: hash super-partitions processed one after the other (tuples of one round in HBM at a time) */
+    int S = 1, sbits = 0, rnd = 0;
+    std::vector<uint64_t> own_gated, own_valid;   /* [S] tuples this device receives in each round */
+    uint64_t surv_done = 0;                       /* survivor records of the finished rounds (in d_rec) */
+    float acc[6] = {};                            /* scatter, init1, pass1, prune, table2, pass2 ms summed over the rounds */
+    bool merged() const { return G > 1 || S > 1; } /* the finish builds one table over survivor RECORDS */
     int phase = 0;  /* 0 staged, 1 counted, 2 planned, 3 scattered, 4 passes done, 5 gather planned, 6 sent, 7 finished */
 };
 
@@ -138,6 +162,7 @@ struct vdjgraph_ctx {
     vdjgraph_params prm;
     int device = 0;
     int sm_count = 0;
+    size_t mem_total = 0;
     Geom g, gc;
     uint64_t R_pad = 0;
     bool any_strand1 = false;
@@ -177,6 +202,8 @@ int check_params(const vdjgraph_params *p) {
         return fail(VDJGRAPH_ERR_PARAM, "kmer_size %d outside 1..50 (MAX_KMER_LEN, assembler2_vdj.c:70)", p->kmer_size);
     if (p->kmer_size > p->read_length)
         return fail(VDJGRAPH_ERR_PARAM, "kmer_size %d > read_length %d", p->kmer_size, p->read_length);
+    if (p->rounds & (p->rounds - 1) || p->rounds > (1u << HIST_BITS))
+        return fail(VDJGRAPH_ERR_PARAM, "rounds %u is not a power of two <= %u", p->rounds, 1u << HIST_BITS);
     return 0;
 }
 
@@ -325,6 +352,7 @@ extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out
     c->prm = *params;
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
+    c->mem_total = prop.totalGlobalMem;
     memset(&c->res, 0, sizeof(c->res));
     memset(&c->ctr, 0, sizeof(c->ctr));
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -505,8 +533,10 @@ int run_count(vdjgraph_ctx *c) {
     return 0;
 }
 
-/* partitioning, tuple format, table sizes, this device's tuple buffer.
- * hist_all: [G][2][HB] window counts of every device; hll: registers merged (max) over the devices */
+/* partitioning, rounds, tuple format, table sizes, this device's tuple buffer.
+ * hist_all: [G][2][HB] window counts of every device; hll: registers merged (max) over the devices.
+ * Everything here is a function of the all-gathered inputs only, so every rank of a sharded build
+ * arrives at the same partitioning and the same number of rounds. */
 int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     Shard &sh = c->sh;
     const Geom &g = c->g;
@@ -516,23 +546,20 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
         for (int i = 0; i < HB; i++) gated_total += hist_all[(size_t)d * 2 * HB + i];
     sh.est_distinct = std::min<double>(hll_estimate(hll), (double)gated_total);
     const double load1 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD1", 0.5)));
-    /* capacity of the whole (all devices) pass-1 table */
+    /* capacity of the whole (all devices, all rounds) pass-1 table */
     uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(sh.est_distinct * 1.06 / load1) + 1024;
     cap1 = std::max<uint64_t>(cap1, 1024);
 
     Part pt;
     memset(&pt, 0, sizeof(pt));
-    int pbits = 0;
+    int pbits0 = 0;
     if (c->prm.partitions) {
-        while ((1u << pbits) < c->prm.partitions && pbits < HIST_BITS) pbits++;
+        while ((1u << pbits0) < c->prm.partitions && pbits0 < HIST_BITS) pbits0++;
     } else {
         /* table-1 slices of at most SLICE_BYTES so that a slice is L2-resident */
         const uint64_t slice_bytes = (uint64_t)(env_double("VDJGRAPH_SLICE_MB", (double)(SLICE_BYTES >> 20)) * 1048576.0);
-        while (pbits < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits) > slice_bytes) pbits++;
+        while (pbits0 < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits0) > slice_bytes) pbits0++;
     }
-    pbits = std::max(pbits, sh.gbits);   /* every device owns at least one partition */
-    pt.pbits = pbits;
-    pt.gbits = sh.gbits;
     pt.hb = std::max(0, 2 * g.k - 64);
     const int sbits = bits_for(sh.total_records * (uint64_t)g.w);
     /* narrow tuples need room for at least 4 read-fingerprint bits beside the stamp */
@@ -547,6 +574,66 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
     pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
     pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
+    const size_t tuple_bytes = pt.wide ? 24 : 16;
+
+    /* Layout for S rounds: partition pp (the top pbits hash bits) belongs to device pp & (G-1), round
+     * (pp >> gbits) & (S-1).  own[cls][d][r] = tuples device d receives in round r. */
+    std::vector<uint64_t> own;
+    auto layout = [&](int rb, int &pbits) {
+        pbits = std::max(pbits0, sh.gbits + rb);   /* every (device, round) owns at least one partition */
+        const int P = 1 << pbits, fold = HB / P, S = 1 << rb;
+        own.assign((size_t)2 * G * S, 0);
+        for (int d = 0; d < G; d++)
+            for (int cls = 0; cls < 2; cls++)
+                for (int b = 0; b < HB; b++) {
+                    const int pp = b / fold;
+                    own[((size_t)cls * G + (pp & (G - 1))) * S + ((pp >> sh.gbits) & (S - 1))] += hist_all[((size_t)d * 2 + cls) * HB + b];
+                }
+    };
+    /* Working set of one device with S rounds, against its memory: packed reads (+ the staged text)
+     * stay resident; tuples, both tables and the log hold one round; survivor records and the
+     * finishing device's merged table, sort and export buffers hold the whole graph (~0.6 of the
+     * distinct k-mers survive on repertoire data; an underestimate only costs an allocation error,
+     * and `rounds` can be set by the caller). */
+    int mqc = std::min(std::min(c->prm.min_base_quality, 254), QSUM_SAT);
+    const int NBq = mqc > 0 ? (mqc + GATE_Q - 1) / GATE_Q : 0;
+    uint64_t rec_max = 0;
+    for (int d = 0; d < G; d++) rec_max = std::max(rec_max, sh.rec_base[d + 1] - sh.rec_base[d]);
+    const double reads_bytes = (double)rec_max * ((double)g.nb * 8 + 3.0 * g.nm * 8 + g.L + 1 + 2.0 * g.L + 1);
+    const double budget = env_double("VDJGRAPH_MEM_BUDGET_MB", 0.9 * (double)c->mem_total / 1048576.0) * 1048576.0;
+    auto working_set = [&](int rb) {
+        const int S = 1 << rb;
+        uint64_t tmax = 0, gmax = 0;
+        for (int d = 0; d < G; d++)
+            for (int r = 0; r < S; r++) {
+                const uint64_t gt = own[((size_t)0 * G + d) * S + r], vt = gt + own[((size_t)1 * G + d) * S + r];
+                tmax = std::max(tmax, vt); gmax = std::max(gmax, gt);
+            }
+        const double cap1_dev = (double)cap1 / ((double)G * S) + 1024;
+        const double nodes = 0.6 * sh.est_distinct;
+        return reads_bytes + (double)tmax * tuple_bytes + cap1_dev * sizeof(Slot1)
+             + std::min((double)gmax, cap1_dev) * NBq * 8.0
+             + nodes / ((double)G * S) * 4.0 * sizeof(Slot2)
+             + (G * S > 1 ? nodes * (sizeof(Slot2) / (double)G + 3.0 * sizeof(Slot2)) : 0.0) + nodes * 70.0;
+    };
+    int rb = 0, pbits = 0;
+    const int rb_max = HIST_BITS - sh.gbits;
+    if (c->prm.rounds) {
+        while ((1u << rb) < c->prm.rounds) rb++;
+        if (rb > rb_max) return fail(VDJGRAPH_ERR_PARAM, "rounds %u x %d devices exceed %d partitions", c->prm.rounds, G, HB);
+        layout(rb, pbits);
+    } else {
+        for (;; rb++) {
+            layout(rb, pbits);
+            if (working_set(rb) <= budget || rb == rb_max) break;
+        }
+    }
+    sh.S = 1 << rb; sh.sbits = rb; sh.rnd = 0; sh.surv_done = 0;
+    memset(sh.acc, 0, sizeof(sh.acc));
+    const int S = sh.S;
+    pt.pbits = pbits;
+    pt.gbits = sh.gbits + sh.sbits;
+    pt.rshift = (u32)sh.gbits; pt.rmask = (u32)(S - 1); pt.round = 0;
 
     /* fold the 256-bucket histograms to P partitions: cnt[d][cls][p] */
     const int P = 1 << pbits, fold = HB / P;
@@ -558,26 +645,31 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
                 for (int j = 0; j < fold; j++) n += hist_all[((size_t)d * 2 + cls) * HB + pp * fold + j];
                 sh.cnt[((size_t)d * 2 + cls) * P + pp] = n;
             }
-    /* what this device receives (its partitions, from every device) and what it produces */
-    sh.n_gated_own = sh.n_valid_own = sh.n_gated_src = sh.n_valid_src = 0;
+    /* what this device receives in every round (its partitions, from every device) and what it produces */
+    sh.own_gated.assign(S, 0); sh.own_valid.assign(S, 0);
+    uint64_t valid_max = 0;
+    for (int r = 0; r < S; r++) {
+        sh.own_gated[r] = own[((size_t)0 * G + sh.rank) * S + r];
+        sh.own_valid[r] = sh.own_gated[r] + own[((size_t)1 * G + sh.rank) * S + r];
+        valid_max = std::max(valid_max, sh.own_valid[r]);
+    }
+    sh.n_gated_src = sh.n_valid_src = 0;
     for (int cls = 0; cls < 2; cls++)
         for (int pp = 0; pp < P; pp++) {
-            for (int d = 0; d < G; d++) {
-                const uint64_t n = sh.cnt[((size_t)d * 2 + cls) * P + pp];
-                if ((pp & (G - 1)) == sh.rank) { sh.n_valid_own += n; if (cls == 0) sh.n_gated_own += n; }
-            }
             const uint64_t mine = sh.cnt[((size_t)sh.rank * 2 + cls) * P + pp];
             sh.n_valid_src += mine; if (cls == 0) sh.n_gated_src += mine;
         }
+    sh.n_gated_own = sh.own_gated[0];
+    sh.n_valid_own = sh.own_valid[0];
     pt.n_gated = sh.n_gated_own;
     pt.n_valid = sh.n_valid_own;
     c->part = pt;
-    c->cap1 = std::max<uint64_t>(1024, (cap1 >> sh.gbits) + 1024);
-    const size_t tuple_bytes = pt.wide ? 24 : 16;
+    c->cap1 = std::max<uint64_t>(1024, (cap1 >> (sh.gbits + sh.sbits)) + 1024);
     int rc;
-    if ((rc = c->d_tuples.ensure(std::max<size_t>(16, sh.n_valid_own * tuple_bytes)))) return rc;
+    if ((rc = c->d_tuples.ensure(std::max<size_t>(16, valid_max * tuple_bytes)))) return rc;
     c->res.partitions = (uint32_t)P;
     c->res.tuple_bytes = (uint32_t)tuple_bytes;
+    c->res.rounds = (uint32_t)S;
     c->res.n_gated = sh.n_gated_src;
     sh.peers_set = false;
     sh.phase = 2;
@@ -598,20 +690,25 @@ void set_self_peers(vdjgraph_ctx *c) {
 int run_scatter(vdjgraph_ctx *c) {
     Shard &sh = c->sh;
     if (!sh.peers_set) return fail(VDJGRAPH_ERR_STATE, "peer buffers not set");
+    c->part.round = (u32)sh.rnd;
+    c->part.n_gated = sh.n_gated_own = sh.own_gated[sh.rnd];
+    c->part.n_valid = sh.n_valid_own = sh.own_valid[sh.rnd];
     const Part pt = c->part;
     /* 8-window segments up to 128 partitions, 16-window segments (k_count's tiling) beyond */
     const bool seg16 = (2 << pt.pbits) > 256;
     const Geom g = seg16 ? c->gc : c->g;
     cudaStream_t s = c->stream;
-    const int G = sh.G, P = 1 << pt.pbits, PL = P >> sh.gbits;
-    /* region start of (cls, local partition) in every owner's buffer, then this device's share */
+    const int G = sh.G, P = 1 << pt.pbits, PL = P >> pt.gbits;
+    /* region start of (cls, local partition) of THIS ROUND in every owner's buffer, then this device's
+     * share of it; the buckets of other rounds get no destination (the kernel skips their windows) */
     uint64_t *cur = c->h_cursor.as<uint64_t>(), *lim = cur + 2 * HB;
     void **tb = c->h_tbase.as<void *>();
+    for (int b = 0; b < 2 * HB; b++) { cur[b] = 0; lim[b] = 0; tb[b] = nullptr; }
     for (int o = 0; o < G; o++) {
         uint64_t off = 0;
         for (int cls = 0; cls < 2; cls++)
             for (int lp = 0; lp < PL; lp++) {
-                const int pp = (lp << sh.gbits) | o;
+                const int pp = (lp << pt.gbits) | (sh.rnd << sh.gbits) | o;
                 uint64_t before = 0, total = 0;
                 for (int d = 0; d < G; d++) {
                     const uint64_t n = sh.cnt[((size_t)d * 2 + cls) * P + pp];
@@ -677,7 +774,7 @@ int run_passes(vdjgraph_ctx *c) {
     vdjgraph_result &res = c->res;
     Counters *d_ctr = c->d_ctr.as<Counters>();
     Counters *h_ctr = c->h_ctr.as<Counters>();
-    const int PL = (1 << pt.pbits) >> sh.gbits;
+    const int PL = (1 << pt.pbits) >> pt.gbits;
     const uint64_t n_gated = pt.n_gated, n_valid = pt.n_valid;
     const Reads rd = make_reads(c);
     const int grid_flat = c->sm_count * 8;
@@ -742,12 +839,12 @@ int run_passes(vdjgraph_ctx *c) {
         if (h_ctr->internal && !pt.dbg) return fail(VDJGRAPH_ERR_INTERNAL, "occurrence log inconsistent (code %u)", h_ctr->internal);
         break;
     }
-    if (h_ctr->n_distinct > REF_MAX_NODES)
-        return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu distinct gated k-mers exceed MAX_NODES (assembler2_vdj.c:73)", (unsigned long long)h_ctr->n_distinct);
     const uint64_t n_surv = h_ctr->n_surv;
-    res.n_slow1 = h_ctr->n_slow1;
-    res.n_pre_total = h_ctr->n_distinct;
-    res.n_pre = n_surv;
+    res.n_slow1 += h_ctr->n_slow1;          /* sums over the rounds (zeroed by run_count) */
+    res.n_pre_total += h_ctr->n_distinct;
+    res.n_pre += n_surv;
+    if (res.n_pre_total > REF_MAX_NODES)
+        return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu distinct gated k-mers exceed MAX_NODES (assembler2_vdj.c:73)", (unsigned long long)res.n_pre_total);
 
     /* ---- survivor table + pass 2 ---- */
     const double load2 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD2", 0.25)));
@@ -770,21 +867,35 @@ int run_passes(vdjgraph_ctx *c) {
     res.kernel_launches += 3;
     CK(cudaGetLastError());
     res.table1_slots = cap1; res.table2_slots = cap2;
-    sh.surv_all[sh.rank] = n_surv;
-    if (sh.G > 1) {
-        /* the survivors as dense records, ready to be sent to the finishing device */
-        if ((rc = c->d_rec.ensure(std::max<uint64_t>(n_surv, 1) * sizeof(Slot2)))) return rc;
+    if (sh.merged()) {
+        /* the survivors as dense records: appended to those of the earlier rounds, ready to be sent
+         * to the finishing device */
+        const uint64_t done = sh.surv_done;
+        const uint64_t expect = sh.rnd == 0 && sh.S > 1 ? n_surv * (uint64_t)sh.S + n_surv / 8 : done + n_surv;
+        if ((rc = c->d_rec.ensure_keep(std::max<uint64_t>(done + n_surv, 1) * sizeof(Slot2), done * sizeof(Slot2), s))) return rc;
+        if (expect > done + n_surv) c->d_rec.ensure_keep(expect * sizeof(Slot2), done * sizeof(Slot2), s);   /* best effort */
         CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
-        k_compact_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2, c->d_rec.as<Slot2>(), &d_ctr->n_nodes);
+        k_compact_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2, c->d_rec.as<Slot2>() + done, &d_ctr->n_nodes);
         res.kernel_launches++;
         CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (h_ctr->overflow) return fail(VDJGRAPH_ERR_INTERNAL, "survivor table overflow (code %u)", h_ctr->overflow);
         if (h_ctr->n_nodes != n_surv) return fail(VDJGRAPH_ERR_INTERNAL, "compacted %llu survivors, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
-        res.n_hits = h_ctr->n_hits;
-        res.n_slow2 = h_ctr->n_slow2;
-        res.n_hits_ungated = h_ctr->n_hits_ungated;
+        res.n_hits += h_ctr->n_hits;
+        res.n_slow2 += h_ctr->n_slow2;
+        res.n_hits_ungated += h_ctr->n_hits_ungated;
+        sh.surv_done = done + n_surv;
+        /* this round's kernel times (the stream is idle: every event has completed) */
+        const int pairs[6][2] = { { 10, 11 }, { 9, 2 }, { 2, 3 }, { 3, 4 }, { 5, 6 }, { 6, 7 } };
+        for (int i = 0; i < 6; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[pairs[i][0]], c->ev[pairs[i][1]]);
+            sh.acc[i] += ms;
+        }
+    } else {
+        sh.surv_done = n_surv;
     }
+    sh.surv_all[sh.rank] = sh.surv_done;
     sh.phase = 4;
     return 0;
 }
@@ -805,8 +916,10 @@ int run_finish(vdjgraph_ctx *c) {
     uint64_t cap2 = c->cap2;
     Slot2 *table = c->d_t2.as<Slot2>();
     CK(cudaEventRecord(c->ev[12], s));
-    if (sh.G > 1) {
-        n_surv = sh.surv_off[sh.G];
+    if (sh.merged()) {
+        /* all survivor records: gathered from every device, or this device's own rounds */
+        const Slot2 *records = sh.G > 1 ? c->d_gather.as<Slot2>() : c->d_rec.as<Slot2>();
+        n_surv = sh.G > 1 ? sh.surv_off[sh.G] : sh.surv_done;
         /* merged table: its own partitioning (locality does not matter here), no device split */
         pt.gbits = 0;
         pt.pbits = 0;
@@ -817,7 +930,7 @@ int run_finish(vdjgraph_ctx *c) {
         table = c->d_t2m.as<Slot2>();
         CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
         k_init_table2<<<grid_flat, THREADS, 0, s>>>(table, cap2);
-        k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(c->d_gather.as<Slot2>(), n_surv, table, cap2, pt, d_ctr);
+        k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(records, n_surv, table, cap2, pt, d_ctr);
         res.kernel_launches += 2;
     }
     const size_t na = std::max<uint64_t>(n_surv, 1);
@@ -859,7 +972,7 @@ int run_finish(vdjgraph_ctx *c) {
         return fail(VDJGRAPH_ERR_INTERNAL, "collected %llu nodes, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
     c->ctr = *h_ctr;
     res.n_nodes = n_surv;
-    if (sh.G == 1) {
+    if (!sh.merged()) {
         res.n_hits = h_ctr->n_hits;
         res.n_slow2 = h_ctr->n_slow2;
         res.n_hits_ungated = h_ctr->n_hits_ungated;
@@ -868,12 +981,17 @@ int run_finish(vdjgraph_ctx *c) {
     }
     /* per-kernel times of this device's share */
     cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&res.ms_scatter, c->ev[10], c->ev[11]);
-    cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
-    cudaEventElapsedTime(&res.ms_pass1, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);
-    cudaEventElapsedTime(&res.ms_table2, c->ev[5], c->ev[6]);
-    cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
+    if (sh.merged()) {
+        res.ms_scatter = sh.acc[0]; res.ms_init1 = sh.acc[1]; res.ms_pass1 = sh.acc[2];
+        res.ms_prune = sh.acc[3]; res.ms_table2 = sh.acc[4]; res.ms_pass2 = sh.acc[5];
+    } else {
+        cudaEventElapsedTime(&res.ms_scatter, c->ev[10], c->ev[11]);
+        cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
+        cudaEventElapsedTime(&res.ms_pass1, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&res.ms_table2, c->ev[5], c->ev[6]);
+        cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
+    }
     cudaEventElapsedTime(&res.ms_export, c->ev[12], c->ev[8]);
     if (sh.G == 1) cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
     else res.ms_device = res.ms_estimate + res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
@@ -884,13 +1002,10 @@ int run_finish(vdjgraph_ctx *c) {
 
 void fill_times_nonfinisher(vdjgraph_ctx *c) {
     vdjgraph_result &res = c->res;
+    const Shard &sh = c->sh;
     cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&res.ms_scatter, c->ev[10], c->ev[11]);
-    cudaEventElapsedTime(&res.ms_init1, c->ev[9], c->ev[2]);
-    cudaEventElapsedTime(&res.ms_pass1, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&res.ms_prune, c->ev[3], c->ev[4]);
-    cudaEventElapsedTime(&res.ms_table2, c->ev[5], c->ev[6]);
-    cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
+    res.ms_scatter = sh.acc[0]; res.ms_init1 = sh.acc[1]; res.ms_pass1 = sh.acc[2];
+    res.ms_prune = sh.acc[3]; res.ms_table2 = sh.acc[4]; res.ms_pass2 = sh.acc[5];
     res.ms_export = 0;
     res.ms_device = res.ms_estimate + res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2;
 }
@@ -909,8 +1024,11 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     if (c->g.R == 0) { c->ran = true; return 0; }
     if ((rc = run_plan(c, c->h_hist.as<uint64_t>(), c->h_hll.as<uint32_t>()))) return rc;
     set_self_peers(c);
-    if ((rc = run_scatter(c))) return rc;
-    if ((rc = run_passes(c))) return rc;
+    for (int r = 0; r < c->sh.S; r++) {
+        c->sh.rnd = r;
+        if ((rc = run_scatter(c))) return rc;
+        if ((rc = run_passes(c))) return rc;
+    }
     return run_finish(c);
 }
 
@@ -990,7 +1108,15 @@ extern "C" int vdjgraph_shard_set_peers(vdjgraph_ctx *c, void *const *ptrs) {
     return 0;
 }
 
+extern "C" int vdjgraph_shard_rounds(vdjgraph_ctx *c) {
+    if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
+    if (!c->staged || c->sh.phase < 2) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_shard_rounds before vdjgraph_shard_plan");
+    return c->sh.S;
+}
+
 extern "C" int vdjgraph_shard_scatter(vdjgraph_ctx *c) {
+    /* after the passes of a round that was not the last: the next round */
+    if (c && c->staged && c->sh.phase == 4 && c->sh.rnd + 1 < c->sh.S) { c->sh.rnd++; c->sh.phase = 2; }
     int rc = phase_check(c, 2, "vdjgraph_shard_scatter");
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
@@ -1011,6 +1137,8 @@ extern "C" int vdjgraph_shard_gather_plan(vdjgraph_ctx *c, const uint64_t *survi
     int rc = phase_check(c, 4, "vdjgraph_shard_gather_plan");
     if (rc) return rc;
     if (!survivors_all) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if (c->sh.rnd + 1 < c->sh.S)
+        return fail(VDJGRAPH_ERR_STATE, "vdjgraph_shard_gather_plan after round %d of %d", c->sh.rnd + 1, c->sh.S);
     CK(cudaSetDevice(c->device));
     Shard &sh = c->sh;
     uint64_t off = 0;
@@ -1153,6 +1281,7 @@ extern "C" int vdjgraph_build(vdjgraph_ctx *c, const char *primary, size_t np, c
 extern "C" int vdjgraph_fetch_pre_table(vdjgraph_ctx *c, vdjgraph_pre_table *out) {
     if (!c || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
     if (!c->ran) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_fetch_pre_table before vdjgraph_run");
+    if (c->sh.merged()) return fail(VDJGRAPH_ERR_STATE, "the pruned pass-1 table is only kept by a one-device, one-round build");
     CK(cudaSetDevice(c->device));
     const uint64_t n = c->res.n_pre;
     const size_t na = std::max<uint64_t>(n, 1);

@@ -30,6 +30,7 @@ class _Params(C.Structure):
         ("read_length", C.c_int32), ("kmer_size", C.c_int32), ("min_node_freq", C.c_int32),
         ("min_base_quality", C.c_int32), ("device", C.c_int32), ("host_threads", C.c_int32),
         ("table_capacity", C.c_uint64), ("flags", C.c_uint32), ("partitions", C.c_uint32),
+        ("rounds", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -47,7 +48,7 @@ class _Result(C.Structure):
         ("ms_scatter", C.c_float), ("ms_init1", C.c_float), ("ms_pass1", C.c_float), ("ms_prune", C.c_float), ("ms_table2", C.c_float),
         ("ms_pass2", C.c_float), ("ms_export", C.c_float), ("ms_fetch", C.c_float),
         ("table1_slots", C.c_uint64), ("table2_slots", C.c_uint64),
-        ("partitions", C.c_uint32), ("tuple_bytes", C.c_uint32),
+        ("partitions", C.c_uint32), ("tuple_bytes", C.c_uint32), ("rounds", C.c_uint32), ("reserved", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
     ]
 
@@ -64,7 +65,7 @@ EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
     "vdjgraph_set_params", "vdjgraph_build", "vdjgraph_stage", "vdjgraph_run", "vdjgraph_fetch",
     "vdjgraph_fetch_pre_table", "vdjgraph_stats",
-    "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_buffers",
+    "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_rounds", "vdjgraph_shard_buffers",
     "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
     "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
     "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
@@ -105,6 +106,7 @@ def load_library():
     lib.vdjgraph_shard_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_ShardInfo)]
     lib.vdjgraph_shard_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vdjgraph_shard_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vdjgraph_shard_rounds.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.vdjgraph_shard_set_peers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.vdjgraph_shard_scatter.argtypes = [C.c_void_p]
@@ -168,12 +170,12 @@ class GraphBuilder:
 
     def __init__(self, read_length: int, k: int = 35, mf: int = 3, mq: int = 90, device: int = -1,
                  host_threads: int = 0, table_capacity: int = 0, export_keys: bool = False,
-                 partitions: int = 0, wide_tuples: bool = False):
+                 partitions: int = 0, wide_tuples: bool = False, rounds: int = 0):
         self._lib = load_library()
         self._ctx = C.c_void_p()
         self._p = _Params(read_length, k, mf, mq, device, host_threads, table_capacity,
                           (FLAG_EXPORT_KEYS if export_keys else 0) | (FLAG_WIDE_TUPLES if wide_tuples else 0),
-                          partitions)
+                          partitions, rounds, 0)
         self._check(self._lib.vdjgraph_create(C.byref(self._p), C.byref(self._ctx)))
         self._keep = None
 
@@ -267,6 +269,13 @@ class GraphBuilder:
         r = np.ascontiguousarray(record_counts, np.uint64)
         self._check(self._lib.vdjgraph_shard_plan(self._ctx, h.ctypes.data, m.ctypes.data, r.ctypes.data))
 
+    def shard_rounds(self) -> int:
+        """Super-partition rounds the plan settled on (scatter + passes run once per round)."""
+        n = self._lib.vdjgraph_shard_rounds(self._ctx)
+        if n < 0:
+            self._check(n)
+        return n
+
     def shard_buffers(self):
         ptrs = (C.c_void_p * SHARD_NBUF)()
         sizes = (C.c_size_t * SHARD_NBUF)()
@@ -310,7 +319,7 @@ class GraphBuilder:
     def _stats(r: _Result) -> dict:
         return {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
                 for k, _ in _Result._fields_
-                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple"))}
+                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple", "rounds"))}
 
     def _graph(self, r: _Result, copy: bool = True) -> Graph:
         n = int(r.n_nodes)

@@ -79,9 +79,11 @@ def build_local(builders: list[GraphBuilder], parts: list[tuple], devices: list[
     table = [b.shard_buffers()[0] for b in builders]
     for b in builders:
         b.shard_set_peers(table)
-    for b in builders:
-        b.shard_scatter()
-    surv = [b.shard_passes() for b in builders]
+    # one scatter (= the exchange) + passes per super-partition round; every rank plans the same count
+    for _ in range(builders[0].shard_rounds()):
+        for b in builders:
+            b.shard_scatter()
+        surv = [b.shard_passes() for b in builders]
     for b in builders:
         b.shard_gather_plan(surv)
     table = [b.shard_buffers()[0] for b in builders]
@@ -219,11 +221,19 @@ class DistributedBuilder:
         self._barrier()                     # every peer buffer exists and is mapped everywhere
         b.shard_release_retired()
         mark()
-        b.shard_scatter()
-        self._barrier()                     # every rank's tuples have arrived
-        mark()
-        n_surv = b.shard_passes()
-        mark()
+        t_sc = t_pa = 0.0
+        for rnd in range(b.shard_rounds()):
+            if rnd:
+                self._barrier()             # the owners have consumed the previous round's tuples
+            t0 = time.perf_counter()
+            b.shard_scatter()
+            self._barrier()                 # every rank's tuples of this round have arrived
+            t1 = time.perf_counter()
+            n_surv = b.shard_passes()
+            t_sc += t1 - t0
+            t_pa += time.perf_counter() - t1
+        t.append(t[-1] + t_sc)
+        t.append(t[-1] + t_pa)
         surv = [int(x) for x in self._gather(np.array([n_surv], np.int64))[:, 0]]
         b.shard_gather_plan(surv)
         self._exchange([BUF_GATHER])
