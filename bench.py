@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--pairs", type=int, default=0, help="override the workload's pair count (debug)")
+    ap.add_argument("--rounds", type=int, default=0, help="hash super-partition rounds (0 = auto: 1 unless the tuples exceed HBM)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -254,7 +255,7 @@ def main():
     host_threads = 0 if world == 1 else max(2, (os.cpu_count() or 16) // world)
     if os.environ.get("VDJGRAPH_HOST_THREADS"):
         host_threads = int(os.environ["VDJGRAPH_HOST_THREADS"])
-    gb = GraphBuilder(L, k, mf, mq, device=local_rank, host_threads=host_threads)
+    gb = GraphBuilder(L, k, mf, mq, device=local_rank, host_threads=host_threads, rounds=args.rounds)
     sharded = world > 1
     if sharded:
         # one graph over the reads of all ranks: k-mers hash-sharded, tuples exchanged by the scatter
@@ -348,7 +349,7 @@ def main():
                        "gated_fraction": (sums["n_gated"] / W_total) if sharded else stats["n_gated"] / W, "pass2_hit_fraction_h": h,
                        "pass2_ungated_hit_fraction": h_u,
                        "table1_slots": stats["table1_slots"], "table2_slots": stats["table2_slots"],
-                       "hash_partitions": stats["partitions"], "tuple_bytes": stats["tuple_bytes"],
+                       "hash_partitions": stats["partitions"], "tuple_bytes": stats["tuple_bytes"], "rounds": stats["rounds"],
                        "slow_path_fraction_pass1": stats["n_slow1"] / max(1, stats["n_gated"]),
                        "slow_path_fraction_pass2": stats["n_slow2"] / max(1, W),
                        "generator_s": round(t_gen, 2)},

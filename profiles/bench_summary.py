@@ -17,7 +17,7 @@ for line in sys.stdin:
           "clocks", d["clocks"])
     c = d["config"]
     print("slow-path fractions", round(c.get("slow_path_fraction_pass1", -1), 3), round(c.get("slow_path_fraction_pass2", -1), 3),
-          "partitions", c.get("hash_partitions"), "h", round(c["pass2_hit_fraction_h"], 3), "gated", round(c["gated_fraction"], 3))
+          "partitions", c.get("hash_partitions"), "rounds", c.get("rounds"), "h", round(c["pass2_hit_fraction_h"], 3), "gated", round(c["gated_fraction"], 3))
     if "roofline_atomic" in d:
         ra = d["roofline_atomic"]
         print("atomic roof: pass1", round(ra["k_pass1"]["frac"], 3), "pass2", round(ra["k_pass2"]["frac"], 3))

@@ -228,6 +228,13 @@ def test_full_size_baseline_configs_properties(built, workload):
         other = gb.build(primary, secondary)
         assert other.stats["partitions"] != stats["partitions"]
         assert _digest(other) == d0, "result depends on the partition count"
+    # ... and from the number of super-partition rounds (the route for inputs whose tuples exceed HBM)
+    with GraphBuilder(L, k, mf, mq, rounds=4) as gb:
+        rounds4 = gb.build(primary, secondary)
+        assert rounds4.stats["rounds"] == 4
+        assert _digest(rounds4) == d0, "result depends on the number of rounds"
+        for name in ["n_gated", "n_pre_total", "n_hits", "n_hits_ungated"]:
+            assert rounds4.stats[name] == stats[name], name
     # prefix monotonicity against the oracle: the first 150k primary records
     n_pre_rec = min(150_000, (primary.size // rb) & ~1)
     prefix = np.concatenate([primary[: n_pre_rec * rb], np.zeros(1, np.uint8)])

@@ -120,10 +120,13 @@ struct PinBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-/* one staging worker: a stream and two page-locked chunk buffers (double buffering) */
+/* one staging worker: a stream, two page-locked chunk buffers (double buffering) and the two
+ * device chunk buffers their text lands in (the text is never held on the device as a whole:
+ * k_pack turns a chunk into packed reads right behind its copy, on the same stream) */
 struct StageWorker {
     cudaStream_t stream = nullptr;
     PinBuf buf[2];
+    DevBuf dbuf[2];
     cudaEvent_t ev[2] = { nullptr, nullptr };
     bool busy[2] = { false, false };
 };
@@ -171,7 +174,7 @@ struct vdjgraph_ctx {
     cudaEvent_t ev[13] = {};
     std::vector<StageWorker> workers;
 
-    DevBuf d_text, d_bad, d_bases, d_good, d_valid, d_hiq, d_qual, d_strand;
+    DevBuf d_bad, d_bases, d_good, d_valid, d_hiq, d_qual, d_strand;
     PinBuf h_bad;
     DevBuf d_t1, d_log, d_t2, d_hll, d_ctr, d_hist, d_cursor, d_tuples;
     DevBuf d_keys[2], d_vals[2], d_cub;
@@ -278,7 +281,8 @@ void stage_worker(StageShared *s, int wi) {
         const uint64_t np_part = r_lo < s->np ? std::min<uint64_t>(r_hi, s->np) - r_lo : 0;
         if (np_part) memcpy(pin, s->primary + r_lo * rec_len, np_part * rec_len);
         if (np_part < n) memcpy(pin + np_part * rec_len, s->secondary + (r_lo + np_part - s->np) * rec_len, (n - np_part) * rec_len);
-        unsigned char *dst = c->d_text.as<unsigned char>() + r_lo * rec_len;
+        /* stream order keeps the chunk's previous k_pack ahead of this copy */
+        unsigned char *dst = w.dbuf[b].as<unsigned char>();
         cudaError_t e = cudaMemcpyAsync(dst, pin, n * rec_len, cudaMemcpyHostToDevice, w.stream);
         if (e == cudaSuccess) {
             PackArgs pa;
@@ -368,11 +372,12 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &w : c->workers) {
         w.buf[0].release(); w.buf[1].release();
+        w.dbuf[0].release(); w.dbuf[1].release();
         if (w.ev[0]) cudaEventDestroy(w.ev[0]);
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_text, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
@@ -426,7 +431,6 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
     c->any_strand1 = false;
     if (R) {
         const size_t rec_len = (size_t)2 * g.L + 1;
-        if ((rc = c->d_text.ensure(R * rec_len))) return rc;
         if ((rc = c->d_bad.ensure(3 * sizeof(uint64_t))) || (rc = c->h_bad.ensure(3 * sizeof(uint64_t)))) return rc;
         uint64_t *hb = c->h_bad.as<uint64_t>();
         hb[0] = hb[1] = ~0ull; hb[2] = 0;
@@ -439,7 +443,8 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
         if ((rc = ensure_workers(c, nt))) return rc;
         for (int i = 0; i < nt; i++)
             for (int b = 0; b < 2; b++)
-                if ((rc = c->workers[i].buf[b].ensure((size_t)STAGE_CHUNK * rec_len))) return rc;
+                if ((rc = c->workers[i].buf[b].ensure((size_t)STAGE_CHUNK * rec_len)) ||
+                    (rc = c->workers[i].dbuf[b].ensure((size_t)STAGE_CHUNK * rec_len))) return rc;
         StageShared sh;
         sh.c = c; sh.primary = primary; sh.secondary = secondary; sh.np = np; sh.R = R;
         std::vector<std::thread> th;
@@ -590,8 +595,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
                     own[((size_t)cls * G + (pp & (G - 1))) * S + ((pp >> sh.gbits) & (S - 1))] += hist_all[((size_t)d * 2 + cls) * HB + b];
                 }
     };
-    /* Working set of one device with S rounds, against its memory: packed reads (+ the staged text)
-     * stay resident; tuples, both tables and the log hold one round; survivor records and the
+    /* Working set of one device with S rounds, against its memory: packed reads stay resident; tuples, both tables and the log hold one round; survivor records and the
      * finishing device's merged table, sort and export buffers hold the whole graph (~0.6 of the
      * distinct k-mers survive on repertoire data; an underestimate only costs an allocation error,
      * and `rounds` can be set by the caller). */
@@ -599,7 +603,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     const int NBq = mqc > 0 ? (mqc + GATE_Q - 1) / GATE_Q : 0;
     uint64_t rec_max = 0;
     for (int d = 0; d < G; d++) rec_max = std::max(rec_max, sh.rec_base[d + 1] - sh.rec_base[d]);
-    const double reads_bytes = (double)rec_max * ((double)g.nb * 8 + 3.0 * g.nm * 8 + g.L + 1 + 2.0 * g.L + 1);
+    const double reads_bytes = (double)rec_max * ((double)g.nb * 8 + 3.0 * g.nm * 8 + g.L + 1);
     const double budget = env_double("VDJGRAPH_MEM_BUDGET_MB", 0.9 * (double)c->mem_total / 1048576.0) * 1048576.0;
     auto working_set = [&](int rb) {
         const int S = 1 << rb;
