@@ -146,6 +146,20 @@ int vdjgraph_set_params(vdjgraph_ctx *ctx, const vdjgraph_params *params);
 int vdjgraph_build(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
                    const char *secondary, size_t n_secondary_records, vdjgraph_result *out);
 
+/*
+ * Page-locked memory for the two record buffers.  The reference allocates them with calloc
+ * (bam_read.c:386-388); a caller that takes them from vdjgraph_host_alloc instead (or registers
+ * its own allocation once) lets vdjgraph_stage/vdjgraph_build DMA straight out of them: no host
+ * copy into bounce buffers, no host threads, and N ranks on one host do not compete for cores and
+ * memory bandwidth.  Pageable buffers keep working (bounced through page-locked chunks by
+ * `host_threads` workers).  Unlike calloc's, the memory is not zero-filled: a caller that relies
+ * on the terminating NUL writes it itself.
+ */
+int vdjgraph_host_alloc(size_t bytes, void **out);
+int vdjgraph_host_free(void *ptr);
+int vdjgraph_host_register(void *ptr, size_t bytes);
+int vdjgraph_host_unregister(void *ptr);
+
 /* The same in three steps, so that callers (and bench.py) can keep a read set resident in HBM. */
 /* 1. staging: the text goes to the device in pinned chunks and is packed there (2-bit bases, gate/N
  *    masks, quality bytes); validates strand bytes and the alphabet */

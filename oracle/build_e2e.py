@@ -15,7 +15,8 @@ files that need a patch are patched COPIES in a temporary directory that is dele
   * the worker-exit race of worker_thread (:1099 reads the queue size before the "all roots handed
     out" flag, so up to 5 queued roots per thread can be dropped): the two operands of
     the loop condition are swapped, in BOTH binaries, so that vdj_contigs.fa is reproducible;
-  * vdjer_gpu only: the INTEGRATION.md diff.
+  * vdjer_gpu only: the INTEGRATION.md diffs (the assemble() block; the two record-buffer callocs
+    of bam_read.c:386-388 taken from page-locked memory).
 htslib is compiled from its .c files with plain gcc commands (no reference build system is run).
 """
 from __future__ import annotations
@@ -64,6 +65,11 @@ def patched_sources(tmp: str, gpu: bool) -> list[str]:
             text = sub_once(text, r"(\tvalidate_params\(p\);\n)(\})", r"\1\treturn 0;\n\2", "parse_params return")
         elif tu == "bam_read":
             text = sub_once(text, r"(\toutput\[strlen\(input\)\] = '\\0';\n)(\})", r"\1\treturn 0;\n\2", "rc/reverse return", 2)
+            if gpu:
+                # the record buffers in page-locked memory (bam_read.c:386-388)
+                text = sub_once(text, r"(primary|secondary)_buf = \(char\*\) calloc\(((?:primary|secondary)_reads\.size\(\) \* \(read_len\*8 \+ 4\) \+ 1), sizeof\(char\)\);",
+                                r"\1_buf = (char*) vdjgraph_records_calloc(\2);", "record buffers", 2)
+                text = sub_once(text, r"\nvoid extract\(char\* bam_file,", "\nchar* vdjgraph_records_calloc(size_t);\n\nvoid extract(char* bam_file,", "records_calloc declaration")
         elif tu == "assembler2_vdj":
             text = sub_once(text, r"while \(num_roots_in_thread\(thread\) > 0 \|\| !all_roots_processed\) \{",
                             "while (!all_roots_processed || num_roots_in_thread(thread) > 0) {", "worker exit race")

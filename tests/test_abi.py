@@ -79,6 +79,15 @@ def test_no_cpu_fallback_without_gpu(built):
     assert e.value.code == -5  # VDJGRAPH_ERR_CUDA
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_host_alloc_fails_loudly_without_gpu(built):
+    lib = graph.load_library()
+    p = C.c_void_p()
+    assert lib.vdjgraph_host_alloc(1 << 20, C.byref(p)) < 0 and not p.value
+    assert lib.vdjgraph_last_error()
+    assert lib.vdjgraph_host_free(None) == 0
+
+
 def test_product_never_touches_oracle():
     """Nothing under vdjer_b200/ or include/ may import, link or mention oracle/."""
     for base in ("vdjer_b200", "include"):

@@ -253,3 +253,36 @@ def test_full_size_baseline_configs_properties(built, workload):
         tgt = pos[s[m]]
         src = pos[sel[m]]
         assert np.all((full.out_succ[src] == tgt[:, None].astype(np.uint32)).any(axis=1)), "a prefix edge is missing"
+
+
+def test_page_locked_record_buffers_are_staged_without_bounce_copies(built):
+    """Record buffers from vdjgraph_host_alloc / registered with vdjgraph_host_register are DMAed
+    straight to the device; pageable ones are bounced by the staging threads.
+    Same graph either way, also when the chunk size does not divide the record counts and a chunk
+    spans the primary/secondary boundary."""
+    from vdjer_b200 import PinnedRecords, host_alloc, host_free
+    L, k, mf, mq = 50, 35, 3, 90
+    primary, secondary = synth.generate(n_pairs=150000, read_length=L, seed=91, n_clones=1500, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    with GraphBuilder(L, k, mf, mq) as gb:
+        pageable = gb.build(primary, secondary)
+        assert_graph_equal(pageable, want, "pageable")
+        with PinnedRecords(primary, secondary):
+            registered = gb.build(primary, secondary)
+        assert_graph_equal(registered, want, "registered")
+        p2, s2 = host_alloc(primary.size), host_alloc(secondary.size)
+        try:
+            p2[:] = primary
+            s2[:] = secondary
+            allocated = gb.build(p2, s2)
+            assert_graph_equal(allocated, want, "host_alloc")
+            mixed = gb.build(p2, secondary)          # one pageable buffer: the bounce path takes both
+            assert_graph_equal(mixed, want, "mixed")
+            only_secondary = gb.build(np.zeros(1, np.uint8), s2)
+        finally:
+            host_free(p2)
+            host_free(s2)
+        want_s = loader.build(np.zeros(1, np.uint8), secondary, L, k, mf, mq, kind="port")
+        assert_graph_equal(only_secondary, want_s, "secondary only")
+        for g in (pageable, registered, allocated, mixed):
+            assert g.stats["h2d_bytes"] == (primary.size - 1) + (secondary.size - 1)

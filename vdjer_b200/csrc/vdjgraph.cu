@@ -169,7 +169,7 @@ struct vdjgraph_ctx {
     Geom g, gc;
     uint64_t R_pad = 0;
     bool any_strand1 = false;
-    bool staged = false, ran = false;
+    bool staged = false, ran = false, staged_direct = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[13] = {};
     std::vector<StageWorker> workers;
@@ -304,6 +304,54 @@ void stage_worker(StageShared *s, int wi) {
     w.busy[0] = w.busy[1] = false;
 }
 
+/* is [p, p+bytes) page-locked memory this process registered or allocated through CUDA? */
+bool is_page_locked(const void *p, size_t bytes) {
+    if (!p || !bytes) return true;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+        cudaPointerGetAttributes(&a1, (const char *)p + bytes - 1) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+}
+
+constexpr uint32_t DIRECT_CHUNK = 8 * STAGE_CHUNK;   /* records per DMA when the caller's buffers are page-locked */
+constexpr int DIRECT_STREAMS = 4;
+
+/* Staging from page-locked caller buffers (vdjgraph_host_alloc / vdjgraph_host_register): no host
+ * copy at all.  One thread queues, chunk by chunk on a few streams, the DMA from the caller's
+ * memory into that stream's device chunk buffer and the chunk's k_pack behind it: copies of one
+ * stream overlap the packing of the others, the host cores stay idle (which is what lets N ranks of
+ * one host stage at the same time). */
+int stage_direct(vdjgraph_ctx *c, const char *primary, uint64_t np, const char *secondary, uint64_t R) {
+    const Geom &g = c->g;
+    const size_t rec_len = (size_t)2 * g.L + 1;
+    int rc;
+    if ((rc = ensure_workers(c, DIRECT_STREAMS))) return rc;
+    for (int i = 0; i < DIRECT_STREAMS; i++)
+        if ((rc = c->workers[i].dbuf[0].ensure((size_t)DIRECT_CHUNK * rec_len))) return rc;
+    const uint64_t n_chunks = (R + DIRECT_CHUNK - 1) / DIRECT_CHUNK;
+    for (uint64_t ch = 0; ch < n_chunks; ch++) {
+        StageWorker &w = c->workers[ch % DIRECT_STREAMS];
+        const uint64_t r_lo = ch * DIRECT_CHUNK, r_hi = std::min<uint64_t>(R, r_lo + DIRECT_CHUNK), n = r_hi - r_lo;
+        unsigned char *dst = w.dbuf[0].as<unsigned char>();   /* stream order: its previous k_pack has read it */
+        const uint64_t np_part = r_lo < np ? std::min<uint64_t>(r_hi, np) - r_lo : 0;
+        if (np_part) CK(cudaMemcpyAsync(dst, primary + r_lo * rec_len, np_part * rec_len, cudaMemcpyHostToDevice, w.stream));
+        if (np_part < n)
+            CK(cudaMemcpyAsync(dst + np_part * rec_len, secondary + (r_lo + np_part - np) * rec_len, (n - np_part) * rec_len,
+                               cudaMemcpyHostToDevice, w.stream));
+        PackArgs pa;
+        pa.text = dst; pa.r0 = r_lo; pa.n = n;
+        pa.bases = c->d_bases.as<u64>(); pa.good = c->d_good.as<u64>(); pa.valid = c->d_valid.as<u64>();
+        pa.hiq = c->d_hiq.as<u64>();
+        pa.qual = c->d_qual.as<u8>(); pa.strand = c->d_strand.as<u8>();
+        pa.bad = c->d_bad.as<u64>();
+        const int grid = (int)std::min<uint64_t>((n + WARPS - 1) / WARPS, (uint64_t)c->sm_count * 8);
+        k_pack<<<grid, THREADS, 0, w.stream>>>(pa, g);
+        CK(cudaGetLastError());
+    }
+    for (int i = 0; i < DIRECT_STREAMS; i++) CK(cudaStreamSynchronize(c->workers[i].stream));
+    return 0;
+}
+
 int blocks_per_sm(const void *kernel, size_t smem) {
     int n = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -436,6 +484,10 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
         hb[0] = hb[1] = ~0ull; hb[2] = 0;
         CK(cudaMemcpyAsync(c->d_bad.p, hb, 3 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));   /* padding memsets and the flags are in place before the workers start */
+        const bool direct = is_page_locked(primary, np * rec_len) && is_page_locked(secondary, ns * rec_len);
+        if (direct) {
+            if ((rc = stage_direct(c, primary, np, secondary, R))) return rc;
+        } else {
         const uint64_t n_chunks = (R + STAGE_CHUNK - 1) / STAGE_CHUNK;
         int nt = c->prm.host_threads > 0 ? c->prm.host_threads : (int)std::min(16u, std::thread::hardware_concurrency());
         nt = std::max(1, std::min<int>(nt, 64));
@@ -455,6 +507,8 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
             cudaError_t e = cudaGetLastError();
             return fail(st, "staging failed: %s", cudaGetErrorString(e));
         }
+        }
+        c->staged_direct = direct;
         CK(cudaMemcpyAsync(hb, c->d_bad.p, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         if (hb[0] != ~0ull)
@@ -1217,6 +1271,35 @@ extern "C" int vdjgraph_enable_peer_access(int device, int peer_device) {
     cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
     if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
     CK(e);
+    return 0;
+}
+
+/* Page-locked host memory for the caller's record buffers: staging then DMAs straight out of them. */
+extern "C" int vdjgraph_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(VDJGRAPH_ERR_PARAM, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? VDJGRAPH_ERR_NOMEM : VDJGRAPH_ERR_CUDA,
+                    "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return 0;
+}
+extern "C" int vdjgraph_host_free(void *p) {
+    if (!p) return 0;
+    CK(cudaFreeHost(p));
+    return 0;
+}
+extern "C" int vdjgraph_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail(VDJGRAPH_ERR_PARAM, "NULL or empty buffer");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int vdjgraph_host_unregister(void *p) {
+    if (!p) return 0;
+    CK(cudaHostUnregister(p));
     return 0;
 }
 

@@ -65,6 +65,7 @@ EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
     "vdjgraph_set_params", "vdjgraph_build", "vdjgraph_stage", "vdjgraph_run", "vdjgraph_fetch",
     "vdjgraph_fetch_pre_table", "vdjgraph_stats",
+    "vdjgraph_host_alloc", "vdjgraph_host_free", "vdjgraph_host_register", "vdjgraph_host_unregister",
     "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_rounds", "vdjgraph_shard_buffers",
     "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
     "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
@@ -103,6 +104,10 @@ def load_library():
     lib.vdjgraph_fetch.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.vdjgraph_stats.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.vdjgraph_fetch_pre_table.argtypes = [C.c_void_p, C.POINTER(_PreTable)]
+    lib.vdjgraph_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.vdjgraph_host_free.argtypes = [C.c_void_p]
+    lib.vdjgraph_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.vdjgraph_host_unregister.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_ShardInfo)]
     lib.vdjgraph_shard_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vdjgraph_shard_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -130,6 +135,49 @@ def _as_u8(buf) -> np.ndarray:
             a = a.view(np.uint8)
         return np.ascontiguousarray(a)
     return np.frombuffer(buf, dtype=np.uint8)
+
+
+class PinnedRecords:
+    """Page-locks record buffers for as long as it lives (vdjgraph_host_register): staging then DMAs
+    straight out of them, as it does from buffers a C caller takes from vdjgraph_host_alloc."""
+
+    def __init__(self, *arrays):
+        self._lib = load_library()
+        self._held = []
+        for a in arrays:
+            a = _as_u8(a)
+            if a.size == 0:
+                continue
+            rc = self._lib.vdjgraph_host_register(a.ctypes.data, a.size)
+            if rc != 0:
+                self.close()
+                raise VdjGraphError(rc, (self._lib.vdjgraph_last_error() or b"").decode())
+            self._held.append(a)
+
+    def close(self):
+        for a in self._held:
+            self._lib.vdjgraph_host_unregister(a.ctypes.data)
+        self._held = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def host_alloc(n_bytes: int) -> np.ndarray:
+    """uint8 array in page-locked memory from vdjgraph_host_alloc (freed with host_free)."""
+    lib = load_library()
+    p = C.c_void_p()
+    rc = lib.vdjgraph_host_alloc(n_bytes, C.byref(p))
+    if rc != 0:
+        raise VdjGraphError(rc, (lib.vdjgraph_last_error() or b"").decode())
+    return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n_bytes, 1),))[:n_bytes]
+
+
+def host_free(a: np.ndarray):
+    load_library().vdjgraph_host_free(C.c_void_p(a.ctypes.data))
 
 
 @dataclass
