@@ -15,3 +15,9 @@ python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload igh_sensitive_
 tail -1 gpurun_out/bench_r1_c3_sensitive.json | python profiles/bench_summary.py
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload igk_2x75_20M > gpurun_out/bench_r1_c4_igk_2x75_20M.json 2>> gpurun_out/bench_r1.err
 tail -1 gpurun_out/bench_r1_c4_igk_2x75_20M.json | python profiles/bench_summary.py
+# configs[4]'s per-GPU share at 8 GPUs (50 M pairs 2x100 = 13.2 G windows, 211 GB of tuples): super-partition rounds on one B200
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload pooled_2x100_50M_per_gpu > gpurun_out/bench_r1_c5_50M_per_gpu.json 2>> gpurun_out/bench_r1.err
+tail -1 gpurun_out/bench_r1_c5_50M_per_gpu.json | python profiles/bench_summary.py
+# the bounce path (pageable record buffers, as the unmodified bam_read.c allocates them)
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --pageable > gpurun_out/bench_r1_pageable.json 2>> gpurun_out/bench_r1.err
+tail -1 gpurun_out/bench_r1_pageable.json | python profiles/bench_summary.py | head -1

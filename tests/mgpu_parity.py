@@ -26,14 +26,16 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for (L, k, mf, mq, pairs, clones, seed) in [(50, 35, 3, 90, 200000, 3000, 301), (50, 25, 1, 20, 40000, 300, 302),
-                                                (100, 50, 2, 120, 30000, 500, 303)]:
+    # last column: super-partition rounds (0 = auto = 1 here); with more than one round every rank
+    # scatters and runs its passes once per round, a barrier apart
+    for (L, k, mf, mq, pairs, clones, seed, rounds) in [(50, 35, 3, 90, 200000, 3000, 301, 0), (50, 25, 1, 20, 40000, 300, 302, 4),
+                                                        (100, 50, 2, 120, 30000, 500, 303, 2)]:
         primary, secondary = synth.generate(n_pairs=pairs, read_length=L, seed=seed, n_clones=clones, threads=4)
         rb = 2 * L + 1
         total = primary.size // rb + secondary.size // rb
         lo, hi = shard.shard_ranges(total, world)[rank]
         p, s = shard.split_records(primary, secondary, L, lo, hi)
-        gb = GraphBuilder(L, k, mf, mq, device=local)
+        gb = GraphBuilder(L, k, mf, mq, device=local, rounds=rounds)
         db = shard.DistributedBuilder(gb, dist, device=f"cuda:{local}")
         g = db.build(p, s)
         t0 = time.perf_counter()
@@ -47,7 +49,7 @@ def main():
             want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
             try:
                 assert_graph_equal(g, want, f"world={world} L={L} k={k}")
-                print(f"PARITY OK world={world} L={L} k={k} mf={mf} mq={mq}: {g.n_nodes} nodes, run {dt * 1e3:.2f} ms", flush=True)
+                print(f"PARITY OK world={world} L={L} k={k} mf={mf} mq={mq} rounds={g.stats['rounds']}: {g.n_nodes} nodes, run {dt * 1e3:.2f} ms", flush=True)
             except AssertionError as e:
                 ok = False
                 print("PARITY FAIL", e, flush=True)
