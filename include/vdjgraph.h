@@ -165,6 +165,21 @@ int vdjgraph_host_unregister(void *ptr);
  *    masks, quality bytes); validates strand bytes and the alphabet */
 int vdjgraph_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
                    const char *secondary, size_t n_secondary_records);
+/*
+ * SURVEY 8f-3 (reads handed over where they are extracted): the same staging from FORWARD reads
+ * only.  The reference's buffers hold every read twice, the read and its reverse complement
+ * (add_to_buffer, bam_read.c:206-244; rc/reverse :130-145), so half of the text is redundant.  A
+ * producer that also appends each read once, in the same record format ('0' + bases + qualities),
+ * to a compact buffer passes that one here: text record i becomes packed records 2i (the read) and
+ * 2i+1 (its reverse complement, derived on the device), i.e. exactly the read set of the doubled
+ * buffers, at half the host-to-device bytes.  Stamps and node positions keep referring to the
+ * doubled numbering, so the glue's text buffers stay the ones node->kmer points into.
+ * n_*_reads count forward reads (= half the records of the corresponding doubled buffer).
+ */
+int vdjgraph_stage_forward(vdjgraph_ctx *ctx, const char *primary_reads, size_t n_primary_reads,
+                           const char *secondary_reads, size_t n_secondary_reads);
+int vdjgraph_build_forward(vdjgraph_ctx *ctx, const char *primary_reads, size_t n_primary_reads,
+                           const char *secondary_reads, size_t n_secondary_reads, vdjgraph_result *out);
 /* 2. device only: estimate -> pass 1 -> prune -> pass 2 -> rank/edges/compaction; blocks until done */
 int vdjgraph_run(vdjgraph_ctx *ctx);
 /* 3. copy the compacted graph to host memory */

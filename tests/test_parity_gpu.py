@@ -286,3 +286,65 @@ def test_page_locked_record_buffers_are_staged_without_bounce_copies(built):
         assert_graph_equal(only_secondary, want_s, "secondary only")
         for g in (pageable, registered, allocated, mixed):
             assert g.stats["h2d_bytes"] == (primary.size - 1) + (secondary.size - 1)
+
+
+@pytest.mark.parametrize("L,k,mf,mq,pairs,clones,seed", [
+    (50, 35, 3, 90, 150000, 1500, 92),
+    (100, 50, 2, 120, 20000, 400, 93),     # wide tuples, two mask words
+    (75, 25, 1, 20, 30000, 200, 94),
+])
+def test_forward_reads_only_give_the_graph_of_the_doubled_buffers(built, L, k, mf, mq, pairs, clones, seed):
+    """vdjgraph_build_forward: from the forward reads alone the device derives every
+    reverse-complement record (bam_read.c:230-243) and builds the graph of the reference's doubled
+    buffers: same nodes, same positions in the DOUBLED numbering, same edges."""
+    from vdjer_b200 import PinnedRecords, forward_reads
+    primary, secondary = synth.generate(n_pairs=pairs, read_length=L, seed=seed, n_clones=clones, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    fp, fs = forward_reads(primary, L), forward_reads(secondary, L)
+    assert fp.size - 1 == (primary.size - 1) // 2
+    with GraphBuilder(L, k, mf, mq, export_keys=True) as gb:
+        text = gb.build(primary, secondary)
+        got = gb.build_forward(fp, fs)
+        pre = gb.pre_table()
+        assert_graph_equal(got, want, "forward")
+        assert_pre_table_equal(pre, want, primary, secondary, L, k, "forward")
+        for name in ["first_pos", "frequency", "out_deg", "in_deg", "out_succ", "in_pred", "kmer_lo", "kmer_hi"]:
+            assert np.array_equal(getattr(got, name), getattr(text, name)), name
+        for name in ["n_records", "n_windows", "n_gated", "n_pre_total", "n_hits"]:
+            assert got.stats[name] == text.stats[name], name
+        assert got.stats["h2d_bytes"] * 2 == text.stats["h2d_bytes"]
+        with PinnedRecords(fp, fs):                      # page-locked: the direct-DMA path
+            pinned = gb.build_forward(fp, fs)
+        assert_graph_equal(pinned, want, "forward, page-locked")
+        only_primary = gb.build_forward(fp)
+    want_p = loader.build(primary, np.zeros(1, np.uint8), L, k, mf, mq, kind="port")
+    assert_graph_equal(only_primary, want_p, "forward, primary only")
+
+
+def test_forward_reads_errors(built):
+    """A bad base or strand byte in a forward read is reported with its record number in the doubled
+    numbering; N reads stay N in the derived record."""
+    from vdjer_b200 import forward_reads
+    L, k = 50, 35
+    primary, secondary = synth.generate(n_pairs=4000, read_length=L, seed=95, n_clones=40, threads=2)
+    fp = forward_reads(primary, L)
+    rb = 2 * L + 1
+    with GraphBuilder(L, k, 2, 60) as gb:
+        bad = fp.copy()
+        bad[7 * rb + 5] = ord("X")
+        with pytest.raises(VdjGraphError) as e:
+            gb.build_forward(bad)
+        assert e.value.code == -3 and "record 14 " in str(e.value)
+        bad = fp.copy()
+        bad[3 * rb] = ord("2")
+        with pytest.raises(VdjGraphError) as e:
+            gb.build_forward(bad)
+        assert e.value.code == -2 and "record 6 " in str(e.value)
+        # reads with N: both strands carry it at mirrored positions
+        withn = primary.copy()
+        recs = withn[:-1].reshape(-1, rb)
+        recs[0::2, 1 + 10] = ord("N")
+        recs[1::2, 1 + L - 1 - 10] = ord("N")
+        want = loader.build(withn, np.zeros(1, np.uint8), L, k, 2, 60, kind="port")
+        got = gb.build_forward(forward_reads(withn, L))
+        assert_graph_equal(got, want, "forward with N")

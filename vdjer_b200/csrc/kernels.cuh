@@ -339,8 +339,10 @@ __device__ __forceinline__ void issue_fence(u32 &a, u32 &b, u32 &c, u32 &d) {
 /* byte (exit(-1) at :383-391) and the alphabet (seq_to_int exit(-1), seq_to_kmer.c:23-25).      */
 /* ------------------------------------------------------------------------------------------ */
 struct PackArgs {
-    const unsigned char *text;   /* records r0 .. r0+n of the concatenated primary+secondary text */
+    const unsigned char *text;   /* n text records; packed record numbers start at r0 */
     u64 r0, n;
+    u32 fwd_only;                /* the text holds forward reads only (vdjgraph_stage_forward): every text record
+                                    yields two packed records, the read and its reverse complement */
     u64 *bases, *good, *valid, *hiq;
     u8 *qual, *strand;
     u64 *bad;                    /* [0] first record with a bad strand byte, [1] with a bad base (atomicMin), [2] any strand '1' */
@@ -355,6 +357,55 @@ __device__ __forceinline__ u64 spread_bits(u32 a) {
     x = (x | (x << 1)) & 0x5555555555555555ull;
     return x;
 }
+/* one record by one warp.  rev: emit the record's reverse complement instead (bases complemented
+ * and reversed, qualities reversed, same strand byte: what add_to_buffer writes as the second record
+ * of every read, bam_read.c:230-243 with rc :130-137 / reverse :139-145) */
+__device__ __forceinline__ void pack_record(const PackArgs &a, const Geom &g, const unsigned char *rec, u64 r, bool rev, u32 lane) {
+    if (lane == 0) {
+        const unsigned sc = rec[0];
+        if (sc != '0' && sc != '1') atomicMin(&a.bad[0], r);
+        if (sc == '1') a.bad[2] = 1;
+        a.strand[r] = (u8)(sc - '0');
+    }
+    u64 vword = 0, gword = 0, hword = 0;
+    for (int j0 = 0; j0 < g.L; j0 += 32) {
+        const int j = j0 + (int)lane;
+        unsigned code = 4;   /* beyond the read: neither valid nor an error */
+        bool okq = false, hiq = false;
+        if (j < g.L) {
+            const int sj = rev ? g.L - 1 - j : j;
+            const unsigned ch = rec[1 + sj];
+            code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
+            if (rev && code < 4) code = 3u - code;   /* complement :116-128; N stays N */
+            const u8 q = (u8)(rec[1 + g.L + sj] - '!');
+            a.qual[r * (u64)g.L + j] = q;
+            okq = q >= GATE_Q;
+            hiq = q >= HIQ;
+        }
+        const u32 b0 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 1u));
+        const u32 b1 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 2u));
+        const u32 bv = __ballot_sync(0xFFFFFFFFu, code < 4);
+        const u32 bg = __ballot_sync(0xFFFFFFFFu, code < 4 && okq);
+        const u32 bh = __ballot_sync(0xFFFFFFFFu, code < 4 && hiq);
+        const u32 be = __ballot_sync(0xFFFFFFFFu, code == 5);
+        if (lane == 0) {
+            if (be) atomicMin(&a.bad[1], r);
+            a.bases[r * (u64)g.nb + (j0 >> 5)] = spread_bits(b0) | (spread_bits(b1) << 1);
+            if (j0 & 32) {
+                a.valid[r * (u64)g.nm + (j0 >> 6)] = vword | ((u64)bv << 32);
+                a.good[r * (u64)g.nm + (j0 >> 6)] = gword | ((u64)bg << 32);
+                a.hiq[r * (u64)g.nm + (j0 >> 6)] = hword | ((u64)bh << 32);
+            } else {
+                vword = bv; gword = bg; hword = bh;
+                if (j0 + 32 >= g.L) {   /* last, half-filled mask word */
+                    a.valid[r * (u64)g.nm + (j0 >> 6)] = vword;
+                    a.good[r * (u64)g.nm + (j0 >> 6)] = gword;
+                    a.hiq[r * (u64)g.nm + (j0 >> 6)] = hword;
+                }
+            }
+        }
+    }
+}
 __global__ void __launch_bounds__(THREADS)
 k_pack(PackArgs a, Geom g) {
     const u32 lane = threadIdx.x & 31;
@@ -362,48 +413,11 @@ k_pack(PackArgs a, Geom g) {
     const u64 rec_len = 2ull * g.L + 1;
     for (u64 i = warp; i < a.n; i += n_warps) {
         const unsigned char *rec = a.text + i * rec_len;
-        const u64 r = a.r0 + i;
-        if (lane == 0) {
-            const unsigned sc = rec[0];
-            if (sc != '0' && sc != '1') atomicMin(&a.bad[0], r);
-            if (sc == '1') a.bad[2] = 1;
-            a.strand[r] = (u8)(sc - '0');
-        }
-        u64 vword = 0, gword = 0, hword = 0;
-        for (int j0 = 0; j0 < g.L; j0 += 32) {
-            const int j = j0 + (int)lane;
-            unsigned code = 4;   /* beyond the read: neither valid nor an error */
-            bool okq = false, hiq = false;
-            if (j < g.L) {
-                const unsigned ch = rec[1 + j];
-                code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
-                const u8 q = (u8)(rec[1 + g.L + j] - '!');
-                a.qual[r * (u64)g.L + j] = q;
-                okq = q >= GATE_Q;
-                hiq = q >= HIQ;
-            }
-            const u32 b0 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 1u));
-            const u32 b1 = __ballot_sync(0xFFFFFFFFu, code < 4 && (code & 2u));
-            const u32 bv = __ballot_sync(0xFFFFFFFFu, code < 4);
-            const u32 bg = __ballot_sync(0xFFFFFFFFu, code < 4 && okq);
-            const u32 bh = __ballot_sync(0xFFFFFFFFu, code < 4 && hiq);
-            const u32 be = __ballot_sync(0xFFFFFFFFu, code == 5);
-            if (lane == 0) {
-                if (be) atomicMin(&a.bad[1], r);
-                a.bases[r * (u64)g.nb + (j0 >> 5)] = spread_bits(b0) | (spread_bits(b1) << 1);
-                if (j0 & 32) {
-                    a.valid[r * (u64)g.nm + (j0 >> 6)] = vword | ((u64)bv << 32);
-                    a.good[r * (u64)g.nm + (j0 >> 6)] = gword | ((u64)bg << 32);
-                    a.hiq[r * (u64)g.nm + (j0 >> 6)] = hword | ((u64)bh << 32);
-                } else {
-                    vword = bv; gword = bg; hword = bh;
-                    if (j0 + 32 >= g.L) {   /* last, half-filled mask word */
-                        a.valid[r * (u64)g.nm + (j0 >> 6)] = vword;
-                        a.good[r * (u64)g.nm + (j0 >> 6)] = gword;
-                        a.hiq[r * (u64)g.nm + (j0 >> 6)] = hword;
-                    }
-                }
-            }
+        if (!a.fwd_only) {
+            pack_record(a, g, rec, a.r0 + i, false, lane);
+        } else {   /* text record i is a forward read: packed records r0+2i (the read) and r0+2i+1 (derived here) */
+            pack_record(a, g, rec, a.r0 + 2 * i, false, lane);
+            pack_record(a, g, rec, a.r0 + 2 * i + 1, true, lane);
         }
     }
 }

@@ -257,7 +257,8 @@ int ensure_workers(vdjgraph_ctx *c, int n) {
 struct StageShared {
     vdjgraph_ctx *c;
     const char *primary, *secondary;
-    uint64_t np, R;
+    uint64_t np, R;      /* TEXT records: primary, primary + secondary */
+    uint32_t fwd;        /* 1: forward reads only, every text record packs into two records */
     std::atomic<uint64_t> next_chunk{0};
     std::atomic<int> status{0};
 };
@@ -286,7 +287,7 @@ void stage_worker(StageShared *s, int wi) {
         cudaError_t e = cudaMemcpyAsync(dst, pin, n * rec_len, cudaMemcpyHostToDevice, w.stream);
         if (e == cudaSuccess) {
             PackArgs pa;
-            pa.text = dst; pa.r0 = r_lo; pa.n = n;
+            pa.text = dst; pa.r0 = r_lo << s->fwd; pa.n = n; pa.fwd_only = s->fwd;
             pa.bases = c->d_bases.as<u64>(); pa.good = c->d_good.as<u64>(); pa.valid = c->d_valid.as<u64>();
             pa.hiq = c->d_hiq.as<u64>();
             pa.qual = c->d_qual.as<u8>(); pa.strand = c->d_strand.as<u8>();
@@ -321,7 +322,7 @@ constexpr int DIRECT_STREAMS = 4;
  * memory into that stream's device chunk buffer and the chunk's k_pack behind it: copies of one
  * stream overlap the packing of the others, the host cores stay idle (which is what lets N ranks of
  * one host stage at the same time). */
-int stage_direct(vdjgraph_ctx *c, const char *primary, uint64_t np, const char *secondary, uint64_t R) {
+int stage_direct(vdjgraph_ctx *c, const char *primary, uint64_t np, const char *secondary, uint64_t R, uint32_t fwd) {
     const Geom &g = c->g;
     const size_t rec_len = (size_t)2 * g.L + 1;
     int rc;
@@ -339,7 +340,7 @@ int stage_direct(vdjgraph_ctx *c, const char *primary, uint64_t np, const char *
             CK(cudaMemcpyAsync(dst + np_part * rec_len, secondary + (r_lo + np_part - np) * rec_len, (n - np_part) * rec_len,
                                cudaMemcpyHostToDevice, w.stream));
         PackArgs pa;
-        pa.text = dst; pa.r0 = r_lo; pa.n = n;
+        pa.text = dst; pa.r0 = r_lo << fwd; pa.n = n; pa.fwd_only = fwd;
         pa.bases = c->d_bases.as<u64>(); pa.good = c->d_good.as<u64>(); pa.valid = c->d_valid.as<u64>();
         pa.hiq = c->d_hiq.as<u64>();
         pa.qual = c->d_qual.as<u8>(); pa.strand = c->d_strand.as<u8>();
@@ -451,12 +452,16 @@ extern "C" int vdjgraph_set_params(vdjgraph_ctx *c, const vdjgraph_params *param
     return 0;
 }
 
-extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns) {
+/* np / ns count TEXT records.  fwd = 0: the reference's buffers (every read followed by its reverse
+ * complement).  fwd = 1: forward reads only; the packed read set is the same as if the reverse
+ * complements had been in the text (packed record 2i = read i, 2i+1 = derived by k_pack). */
+static int stage_impl(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns, uint32_t fwd) {
     if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
     if ((np && !primary) || (ns && !secondary)) return fail(VDJGRAPH_ERR_PARAM, "NULL record buffer");
     CK(cudaSetDevice(c->device));
     c->staged = false; c->ran = false;
-    const uint64_t R = (uint64_t)np + (uint64_t)ns;
+    const uint64_t Rt = (uint64_t)np + (uint64_t)ns;   /* text records */
+    const uint64_t R = Rt << fwd;                      /* packed records */
     if (R > 0xFFFFFFFEull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu records exceed the 2^32-2 record limit", (unsigned long long)R);
     double t0 = wall_ms();
     make_geom(c, R);
@@ -486,9 +491,9 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
         CK(cudaStreamSynchronize(c->stream));   /* padding memsets and the flags are in place before the workers start */
         const bool direct = is_page_locked(primary, np * rec_len) && is_page_locked(secondary, ns * rec_len);
         if (direct) {
-            if ((rc = stage_direct(c, primary, np, secondary, R))) return rc;
+            if ((rc = stage_direct(c, primary, np, secondary, Rt, fwd))) return rc;
         } else {
-        const uint64_t n_chunks = (R + STAGE_CHUNK - 1) / STAGE_CHUNK;
+        const uint64_t n_chunks = (Rt + STAGE_CHUNK - 1) / STAGE_CHUNK;
         int nt = c->prm.host_threads > 0 ? c->prm.host_threads : (int)std::min(16u, std::thread::hardware_concurrency());
         nt = std::max(1, std::min<int>(nt, 64));
         nt = (int)std::min<uint64_t>((uint64_t)nt, n_chunks);
@@ -498,7 +503,7 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
                 if ((rc = c->workers[i].buf[b].ensure((size_t)STAGE_CHUNK * rec_len)) ||
                     (rc = c->workers[i].dbuf[b].ensure((size_t)STAGE_CHUNK * rec_len))) return rc;
         StageShared sh;
-        sh.c = c; sh.primary = primary; sh.secondary = secondary; sh.np = np; sh.R = R;
+        sh.c = c; sh.primary = primary; sh.secondary = secondary; sh.np = np; sh.R = Rt; sh.fwd = fwd;
         std::vector<std::thread> th;
         for (int i = 1; i < nt; i++) th.emplace_back(stage_worker, &sh, i);
         stage_worker(&sh, 0);
@@ -516,7 +521,7 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
         if (hb[1] != ~0ull)
             return fail(VDJGRAPH_ERR_BASE, "record %llu holds a base outside ACGTN", (unsigned long long)hb[1]);
         c->any_strand1 = hb[2] != 0;
-        h2d = R * rec_len;
+        h2d = Rt * rec_len;
     }
     CK(cudaStreamSynchronize(c->stream));
     memset(&c->res, 0, sizeof(c->res));
@@ -529,6 +534,13 @@ extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, c
     c->sh.rec_base[1] = R;
     c->staged = true;
     return 0;
+}
+
+extern "C" int vdjgraph_stage(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns) {
+    return stage_impl(c, primary, np, secondary, ns, 0);
+}
+extern "C" int vdjgraph_stage_forward(vdjgraph_ctx *c, const char *primary_reads, size_t np, const char *secondary_reads, size_t ns) {
+    return stage_impl(c, primary_reads, np, secondary_reads, ns, 1);
 }
 
 /* ========================================================================================== */
@@ -1363,6 +1375,14 @@ extern "C" int vdjgraph_stats(vdjgraph_ctx *c, vdjgraph_result *out) {
 extern "C" int vdjgraph_build(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns,
                               vdjgraph_result *out) {
     int rc = vdjgraph_stage(c, primary, np, secondary, ns);
+    if (rc) return rc;
+    if ((rc = vdjgraph_run(c))) return rc;
+    return vdjgraph_fetch(c, out);
+}
+
+extern "C" int vdjgraph_build_forward(vdjgraph_ctx *c, const char *primary_reads, size_t np, const char *secondary_reads, size_t ns,
+                                      vdjgraph_result *out) {
+    int rc = vdjgraph_stage_forward(c, primary_reads, np, secondary_reads, ns);
     if (rc) return rc;
     if ((rc = vdjgraph_run(c))) return rc;
     return vdjgraph_fetch(c, out);

@@ -64,6 +64,7 @@ FLAG_WIDE_TUPLES = 2
 EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
     "vdjgraph_set_params", "vdjgraph_build", "vdjgraph_stage", "vdjgraph_run", "vdjgraph_fetch",
+    "vdjgraph_stage_forward", "vdjgraph_build_forward",
     "vdjgraph_fetch_pre_table", "vdjgraph_stats",
     "vdjgraph_host_alloc", "vdjgraph_host_free", "vdjgraph_host_register", "vdjgraph_host_unregister",
     "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_rounds", "vdjgraph_shard_buffers",
@@ -100,6 +101,8 @@ def load_library():
     lib.vdjgraph_set_params.argtypes = [C.c_void_p, C.POINTER(_Params)]
     lib.vdjgraph_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_Result)]
     lib.vdjgraph_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    lib.vdjgraph_build_forward.argtypes = lib.vdjgraph_build.argtypes
+    lib.vdjgraph_stage_forward.argtypes = lib.vdjgraph_stage.argtypes
     lib.vdjgraph_run.argtypes = [C.c_void_p]
     lib.vdjgraph_fetch.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.vdjgraph_stats.argtypes = [C.c_void_p, C.POINTER(_Result)]
@@ -164,6 +167,19 @@ class PinnedRecords:
 
     def __exit__(self, *a):
         self.close()
+
+
+def forward_reads(records, read_length: int) -> np.ndarray:
+    """The even records (the reads themselves) of a reference-format buffer in which every read is
+    followed by its reverse complement (bam_read.c:206-244): what a producer that appends each read
+    once would hand to vdjgraph_stage_forward.  NUL-terminated like the input."""
+    rb = 2 * read_length + 1
+    a = _as_u8(records)
+    n = a.size // rb
+    if n % 2:
+        raise ValueError("odd number of records: not a read / reverse-complement buffer")
+    fwd = a[: n * rb].reshape(n // 2, 2 * rb)[:, :rb]
+    return np.concatenate([fwd.reshape(-1), np.zeros(1, np.uint8)])
 
 
 def host_alloc(n_bytes: int) -> np.ndarray:
@@ -296,6 +312,20 @@ class GraphBuilder:
         p, s, n_p, n_s = self._counts(primary, secondary)
         r = _Result()
         self._check(self._lib.vdjgraph_build(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
+        return self._graph(r, copy)
+
+    def stage_forward(self, primary_reads, secondary_reads=b""):
+        """vdjgraph_stage_forward: buffers of FORWARD reads only (see forward_reads())."""
+        p, s, n_p, n_s = self._counts(primary_reads, secondary_reads)
+        self._keep = (p, s)
+        self._check(self._lib.vdjgraph_stage_forward(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s))
+
+    def build_forward(self, primary_reads, secondary_reads=b"", copy: bool = True) -> Graph:
+        """vdjgraph_build_forward: the graph of the doubled buffers from their forward reads alone;
+        the reverse-complement records are derived on the device (half the H2D bytes)."""
+        p, s, n_p, n_s = self._counts(primary_reads, secondary_reads)
+        r = _Result()
+        self._check(self._lib.vdjgraph_build_forward(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
         return self._graph(r, copy)
 
     # ---- sharded build phases (see include/vdjgraph.h and vdjer_b200/shard.py) -------------------
