@@ -16,7 +16,7 @@ files that need a patch are patched COPIES in a temporary directory that is dele
     out" flag, so up to 5 queued roots per thread can be dropped): the two operands of
     the loop condition are swapped, in BOTH binaries, so that vdj_contigs.fa is reproducible;
   * vdjer_gpu only: the INTEGRATION.md diffs (the assemble() block; the two record-buffer callocs
-    of bam_read.c:386-388 taken from page-locked memory).
+    of bam_read.c:386-388 taken from page-locked memory; add_to_buffer notes every forward record).
 htslib is compiled from its .c files with plain gcc commands (no reference build system is run).
 """
 from __future__ import annotations
@@ -67,9 +67,18 @@ def patched_sources(tmp: str, gpu: bool) -> list[str]:
             text = sub_once(text, r"(\toutput\[strlen\(input\)\] = '\\0';\n)(\})", r"\1\treturn 0;\n\2", "rc/reverse return", 2)
             if gpu:
                 # the record buffers in page-locked memory (bam_read.c:386-388)
-                text = sub_once(text, r"(primary|secondary)_buf = \(char\*\) calloc\(((?:primary|secondary)_reads\.size\(\) \* \(read_len\*8 \+ 4\) \+ 1), sizeof\(char\)\);",
-                                r"\1_buf = (char*) vdjgraph_records_calloc(\2);", "record buffers", 2)
-                text = sub_once(text, r"\nvoid extract\(char\* bam_file,", "\nchar* vdjgraph_records_calloc(size_t);\n\nvoid extract(char* bam_file,", "records_calloc declaration")
+                text = sub_once(text, r"primary_buf = \(char\*\) calloc\((primary_reads\.size\(\) \* \(read_len\*8 \+ 4\) \+ 1), sizeof\(char\)\);",
+                                r"primary_buf = (char*) vdjgraph_records_calloc(\1, 0);", "primary record buffer")
+                text = sub_once(text, r"secondary_buf = \(char\*\) calloc\((secondary_reads\.size\(\) \* \(read_len\*8 \+ 4\) \+ 1), sizeof\(char\)\);",
+                                r"secondary_buf = (char*) vdjgraph_records_calloc(\1, 1);", "secondary record buffer")
+                # section 3c: every read is also kept once (add_to_buffer, :206-244)
+                text = sub_once(text, r"\nvoid add_to_buffer\(bam1_t \*b, char\*& buf_ptr,",
+                                "\nchar* vdjgraph_records_calloc(size_t, int);\nvoid vdjgraph_records_note_read(const char*, size_t);\n\n"
+                                "void add_to_buffer(bam1_t *b, char*& buf_ptr,", "glue declarations")
+                text = sub_once(text, r"(\tbuf_ptr\[0\] = '0';\n\tbuf_ptr \+= 1;\n\tstrncpy\(buf_ptr, seq, read_len\);)",
+                                r"\tchar* vdjgraph_record_start = buf_ptr;\n\1", "forward record start")
+                text = sub_once(text, r"(\t// Now add the reverse alignment\n)",
+                                r"\tvdjgraph_records_note_read(vdjgraph_record_start, 2 * read_len + 1);\n\1", "forward record noted")
         elif tu == "assembler2_vdj":
             text = sub_once(text, r"while \(num_roots_in_thread\(thread\) > 0 \|\| !all_roots_processed\) \{",
                             "while (!all_roots_processed || num_roots_in_thread(thread) > 0) {", "worker exit race")

@@ -20,10 +20,10 @@ needs_bins = pytest.mark.skipif(not all(os.path.exists(p) for p in BIN.values())
                                 reason="oracle/_ref/vdjer_ref, vdjer_gpu, sam2bam not built (no /root/reference)")
 
 
-def _run(binary, bam, ref, cwd, extra):
+def _run(binary, bam, ref, cwd, extra, env=None):
     os.makedirs(cwd, exist_ok=True)
     r = subprocess.run([binary, "--in", bam, "--t", "1", "--ins", "175", "--chain", "IGH", "--ref-dir", ref] + extra,
-                       cwd=cwd, capture_output=True, text=True, timeout=900)
+                       cwd=cwd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr[-3000:]
     keep = [ln for ln in r.stderr.splitlines()
             if re.match(r"(ROOT_INIT|num root nodes|pre nodes after pruning|Total nodes|Num traversable|Num condensed)", ln)]
@@ -52,6 +52,12 @@ def test_vdjer_binary_with_gpu_graph_matches_reference_binary(built, tmp_path, e
     if expect_contigs:   # the pipeline really produced contigs and mapped reads to them
         assert len(ref["contigs"]) > 100 and ref["sam"].count("\n") > 100
     assert "vdjgraph" not in ref["err"]
+    # vdjer_gpu took the forward-reads path (add_to_buffer keeps every read once,
+    # the reverse-complement records are derived on the device); the text path gives the same files
+    assert "vdjgraph: forward reads only" in gpu["err"]
+    txt = _run(BIN["vdjer_gpu"], bam, os.path.join(work, "ref"), os.path.join(work, "gpu_text"), extra, env={"VDJGRAPH_FORWARD": "0"})
+    assert "vdjgraph: forward reads only" not in txt["err"]
+    assert txt["log"] == ref["log"] and txt["dot"] == ref["dot"] and txt["contigs"] == ref["contigs"] and txt["sam"] == ref["sam"]
 
 
 @needs_bins
