@@ -220,6 +220,10 @@ typedef struct vdjgraph_shard_info {
 
 int vdjgraph_shard_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primary_records,
                          const char *secondary, size_t n_secondary_records, const vdjgraph_shard_info *info);
+/* the same from forward reads only (vdjgraph_stage_forward): n_*_reads count reads; record_base,
+ * total_records and the record counts of vdjgraph_shard_plan stay in the doubled numbering */
+int vdjgraph_shard_stage_forward(vdjgraph_ctx *ctx, const char *primary_reads, size_t n_primary_reads,
+                                 const char *secondary_reads, size_t n_secondary_reads, const vdjgraph_shard_info *info);
 int vdjgraph_shard_count(vdjgraph_ctx *ctx, uint64_t *hist /*[512]*/, uint32_t *hll /*[4096]*/);
 int vdjgraph_shard_plan(vdjgraph_ctx *ctx, const uint64_t *hist_all /*[n_ranks][512]*/,
                         const uint32_t *hll_merged /*[4096]*/, const uint64_t *record_counts /*[n_ranks]*/);

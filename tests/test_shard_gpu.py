@@ -99,3 +99,26 @@ def test_multi_process_parity_over_nvlink(built):
                        capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("PARITY OK") == 3, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_sharded_from_forward_reads_only(built, G):
+    """vdjgraph_shard_stage_forward: every rank stages forward reads only, the reverse-complement
+    records are derived on its device; record numbers stay those of the doubled buffers."""
+    from vdjer_b200 import forward_reads
+    L, k, mf, mq = 50, 35, 3, 90
+    primary, secondary = synth.generate(n_pairs=40000, read_length=L, seed=207, n_clones=600, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    rb = 2 * L + 1
+    total = primary.size // rb + secondary.size // rb
+    parts = []
+    for lo, hi in shard.shard_ranges(total, G):          # even boundaries: a read stays with its reverse complement
+        p, s = shard.split_records(primary, secondary, L, lo, hi)
+        parts.append((forward_reads(p, L), forward_reads(s, L)))
+    builders = [GraphBuilder(L, k, mf, mq, device=0) for _ in range(G)]
+    try:
+        got = shard.build_local(builders, parts, forward=True)
+    finally:
+        for b in builders:
+            b.close()
+    assert_graph_equal(got, want, f"forward G={G}")

@@ -1108,13 +1108,14 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
 /* ---------------------------------------------------------------------------------------- */
 /* sharded build: the same phases, driven by the caller                                       */
 /* ---------------------------------------------------------------------------------------- */
-extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns,
-                                    const vdjgraph_shard_info *info) {
+static int shard_stage_impl(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns,
+                            const vdjgraph_shard_info *info, uint32_t fwd) {
     if (!c || !info) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
     const uint32_t G = info->n_ranks;
     if (G < 1 || G > (uint32_t)MAX_DEV || (G & (G - 1)) || info->rank >= G)
         return fail(VDJGRAPH_ERR_PARAM, "n_ranks %u must be 1, 2, 4 or 8 and rank %u below it", G, info->rank);
-    if (info->record_base + np + ns > info->total_records)
+    const uint64_t n_rec = ((uint64_t)np + (uint64_t)ns) << fwd;   /* packed records of this rank */
+    if (info->record_base + n_rec > info->total_records)
         return fail(VDJGRAPH_ERR_PARAM, "record range exceeds total_records");
     if (info->total_records > 0xFFFFFFFEull)
         return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu records exceed the 2^32-2 record limit", (unsigned long long)info->total_records);
@@ -1122,7 +1123,7 @@ extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t
         DevBuf *ex[NBUF] = { &c->d_bases, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_tuples, &c->d_gather };
         for (DevBuf *b : ex) b->exported = G > 1;
     }
-    int rc = vdjgraph_stage(c, primary, np, secondary, ns);
+    int rc = stage_impl(c, primary, np, secondary, ns, fwd);
     if (rc) return rc;
     Shard &sh = c->sh;
     sh.G = (int)G; sh.rank = (int)info->rank;
@@ -1131,8 +1132,19 @@ extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t
     sh.total_records = info->total_records;
     memset(sh.rec_base, 0, sizeof(sh.rec_base));
     sh.rec_base[sh.rank] = info->record_base;   /* the others arrive with vdjgraph_shard_plan */
-    sh.rec_base[sh.rank + 1] = info->record_base + np + ns;
+    sh.rec_base[sh.rank + 1] = info->record_base + n_rec;
     return 0;
+}
+
+extern "C" int vdjgraph_shard_stage(vdjgraph_ctx *c, const char *primary, size_t np, const char *secondary, size_t ns,
+                                    const vdjgraph_shard_info *info) {
+    return shard_stage_impl(c, primary, np, secondary, ns, info, 0);
+}
+/* forward reads only (vdjgraph_stage_forward); record_base / total_records / the record counts handed
+ * to vdjgraph_shard_plan stay in the doubled numbering (two records per read) */
+extern "C" int vdjgraph_shard_stage_forward(vdjgraph_ctx *c, const char *primary_reads, size_t np, const char *secondary_reads,
+                                            size_t ns, const vdjgraph_shard_info *info) {
+    return shard_stage_impl(c, primary_reads, np, secondary_reads, ns, info, 1);
 }
 
 extern "C" int vdjgraph_shard_count(vdjgraph_ctx *c, uint64_t *hist, uint32_t *hll) {

@@ -67,7 +67,7 @@ EXPORTS = [
     "vdjgraph_stage_forward", "vdjgraph_build_forward",
     "vdjgraph_fetch_pre_table", "vdjgraph_stats",
     "vdjgraph_host_alloc", "vdjgraph_host_free", "vdjgraph_host_register", "vdjgraph_host_unregister",
-    "vdjgraph_shard_stage", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_rounds", "vdjgraph_shard_buffers",
+    "vdjgraph_shard_stage", "vdjgraph_shard_stage_forward", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_rounds", "vdjgraph_shard_buffers",
     "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
     "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
     "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
@@ -112,6 +112,7 @@ def load_library():
     lib.vdjgraph_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.vdjgraph_host_unregister.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_ShardInfo)]
+    lib.vdjgraph_shard_stage_forward.argtypes = lib.vdjgraph_shard_stage.argtypes
     lib.vdjgraph_shard_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vdjgraph_shard_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vdjgraph_shard_rounds.argtypes = [C.c_void_p]
@@ -329,11 +330,15 @@ class GraphBuilder:
         return self._graph(r, copy)
 
     # ---- sharded build phases (see include/vdjgraph.h and vdjer_b200/shard.py) -------------------
-    def shard_stage(self, primary, secondary, n_ranks: int, rank: int, record_base: int, total_records: int):
+    def shard_stage(self, primary, secondary, n_ranks: int, rank: int, record_base: int, total_records: int,
+                    forward: bool = False):
+        """forward: the buffers hold forward reads only (forward_reads()); record_base and total_records
+        stay in the doubled numbering (two records per read)."""
         p, s, n_p, n_s = self._counts(primary, secondary)
         self._keep = (p, s)
         info = _ShardInfo(n_ranks, rank, record_base, total_records)
-        self._check(self._lib.vdjgraph_shard_stage(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(info)))
+        fn = self._lib.vdjgraph_shard_stage_forward if forward else self._lib.vdjgraph_shard_stage
+        self._check(fn(self._ctx, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(info)))
 
     def shard_count(self):
         hist = np.zeros(SHARD_HIST, np.uint64)

@@ -56,12 +56,14 @@ def split_records(primary, secondary, L: int, lo: int, hi: int):
 # ------------------------------------------------------------------------------------------------
 # several ranks in one process
 # ------------------------------------------------------------------------------------------------
-def build_local(builders: list[GraphBuilder], parts: list[tuple], devices: list[int] | None = None, copy: bool = True):
+def build_local(builders: list[GraphBuilder], parts: list[tuple], devices: list[int] | None = None, copy: bool = True,
+                forward: bool = False):
     """Run the sharded build with rank r = builders[r] on parts[r] = (primary, secondary); all in
-    this process.  Returns rank 0's Graph."""
+    this process.  Returns rank 0's Graph.  forward: the parts hold forward reads only (two packed
+    records per read, vdjgraph_shard_stage_forward)."""
     G = len(builders)
     lib = load_library()
-    counts = [b._n_records(p, s) for b, (p, s) in zip(builders, parts)]
+    counts = [b._n_records(p, s) * (2 if forward else 1) for b, (p, s) in zip(builders, parts)]
     total = sum(counts)
     base = np.concatenate([[0], np.cumsum(counts)])
     if devices:
@@ -71,7 +73,7 @@ def build_local(builders: list[GraphBuilder], parts: list[tuple], devices: list[
                 if rc:
                     raise RuntimeError(f"peer access {a}->{b}: {lib.vdjgraph_last_error().decode()}")
     for r, (b, (p, s)) in enumerate(zip(builders, parts)):
-        b.shard_stage(p, s, G, r, int(base[r]), total)
+        b.shard_stage(p, s, G, r, int(base[r]), total, forward=forward)
     pieces = [b.shard_count() for b in builders]
     hist_all, hll, cnt = plan_inputs([x[0] for x in pieces], [x[1] for x in pieces], counts)
     for b in builders:
@@ -191,11 +193,15 @@ class DistributedBuilder:
                     self.table[r][i] = self.peers.map(r, i, hs[i].tobytes() if hv[i] else b"")
         self.b.shard_set_peers(self.table)
 
-    def stage(self, primary, secondary=b""):
-        n_local = self.b._n_records(primary, secondary)
+    def stage(self, primary, secondary=b"", forward: bool = False):
+        """forward: this rank's buffers hold forward reads only (every rank alike)."""
+        n_local = self.b._n_records(primary, secondary) * (2 if forward else 1)
         self.counts = [int(x) for x in self._gather(np.array([n_local], np.int64))[:, 0]]
         base = int(sum(self.counts[:self.rank]))
-        self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)))
+        if forward:
+            self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)), forward=True)
+        else:
+            self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)))
 
     def run(self):
         """count -> plan -> scatter (= the all-to-all) -> passes -> gather -> finish on the staged
