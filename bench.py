@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="override the workload's pair count (debug)")
     ap.add_argument("--pageable", action="store_true",
                     help="leave the record buffers pageable (the reference's calloc): staging bounces them through page-locked chunks")
+    ap.add_argument("--forward-sharded", action="store_true", help="(accepted for old command lines; the forward-reads path is always measured)")
     ap.add_argument("--no-forward", action="store_true", help="skip the forward-reads-only end-to-end measurement")
     ap.add_argument("--rounds", type=int, default=0, help="hash super-partition rounds (0 = auto: 1 unless the tuples exceed HBM)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
@@ -314,27 +315,27 @@ def main():
         e2e_stats.update(graph.stats)
 
     # ---- the same from forward reads only (vdjgraph_build_forward): reported beside e2e ----
-    fwd_line = None
-    if not sharded and not args.no_forward:
+    ms_fwd, fwd_stats = None, None
+    if not args.no_forward:
         from vdjer_b200 import forward_reads
         fp, fs = forward_reads(primary, L), forward_reads(secondary, L)      # what a producer appending each read once holds
         pinned_f = None if args.pageable else PinnedRecords(fp, fs)
+        build_f = (lambda: db.build(fp, fs, copy=False, forward=True)) if sharded else (lambda: gb.build_forward(fp, fs, copy=False))  # noqa: E731
         for _ in range(min(args.warmup, 2)):
-            gb.build_forward(fp, fs, copy=False)
+            build_f()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            g2 = gb.build_forward(fp, fs, copy=False)
-            checksum_f = int(g2.frequency[:: max(1, g2.n_nodes // 1024)].sum())
+            g2 = build_f()
+            if g2 is not None:
+                checksum_f = int(g2.frequency[:: max(1, g2.n_nodes // 1024)].sum())
         barrier()
         ms_fwd = (time.perf_counter() - t0) / args.steps * 1e3
-        if g2.n_nodes != graph.n_nodes or checksum_f != checksum:
+        if g2 is not None and (g2.n_nodes != graph.n_nodes or checksum_f != checksum):
             raise SystemExit("forward-reads build differs from the build on the doubled buffers")
-        fwd_line = {"value": W / (ms_fwd * 1e-3), "unit": UNIT, "ms_per_step": ms_fwd,
-                    "h2d_bytes_per_step": g2.stats["h2d_bytes"], "d2h_bytes_per_step": g2.stats["d2h_bytes"],
-                    "ms_stage": g2.stats["ms_stage"], "ms_device": g2.stats["ms_device"], "ms_fetch": g2.stats["ms_fetch"],
-                    "note": "vdjgraph_build_forward: host buffers hold each read once; the reverse-complement records "
-                            "(half of the reference's text) are derived on the device; same graph"}
+        fwd_stats = gb.fetch_stats()
+        if g2 is not None:
+            fwd_stats.update(g2.stats)
         if pinned_f is not None:
             pinned_f.close()
         del fp, fs
@@ -342,9 +343,10 @@ def main():
     # max over ranks of the times, sums of the counters
     sums = {}
     if sharded:
-        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_e2e, ms_fwd or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = float(t[0]), float(t[1])
+        ms_fwd = float(t[2]) if ms_fwd is not None else None
         names = ["n_windows", "n_hits", "n_gated", "n_pre_total", "n_slow1", "n_slow2", "n_hits_ungated", "kernel_launches", "h2d_bytes"]
         t = torch.tensor([float(stats[n]) for n in names[:-1]] + [float(e2e_stats["h2d_bytes"])], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -426,8 +428,14 @@ def main():
                 "k_pass1": {"roof_ms": t1, "measured_ms": kern["ms_pass1"], "frac": t1 / kern["ms_pass1"]},
                 "k_pass2": {"roof_ms": t2, "measured_ms": kern["ms_pass2"], "frac": t2 / kern["ms_pass2"]},
             }
-        if fwd_line:
-            line["e2e_forward_reads"] = fwd_line
+        if ms_fwd is not None:
+            line["e2e_forward_reads"] = {
+                "value": W_total / (ms_fwd * 1e-3), "unit": UNIT, "ms_per_step": ms_fwd,
+                "h2d_bytes_per_step": int(sums["h2d_bytes"]) // 2 if sharded else fwd_stats["h2d_bytes"],
+                "d2h_bytes_per_step": fwd_stats["d2h_bytes"],
+                "ms_stage": fwd_stats["ms_stage"], "ms_device": fwd_stats["ms_device"], "ms_fetch": fwd_stats["ms_fetch"],
+                "note": "vdjgraph_build_forward: host buffers hold each read once; the reverse-complement records "
+                        "(half of the reference's text) are derived on the device; same graph"}
         if sharded:
             line["shard_phase_ms_rank0"] = {k2: round(v, 3) for k2, v in phase_ms.items()}
         if not args.no_cpu_baseline:

@@ -258,8 +258,8 @@ class DistributedBuilder:
         """The graph on rank 0 (None elsewhere)."""
         return self.b.fetch(copy=copy) if self.rank == 0 else None
 
-    def build(self, primary, secondary=b"", copy: bool = True):
-        self.stage(primary, secondary)
+    def build(self, primary, secondary=b"", copy: bool = True, forward: bool = False):
+        self.stage(primary, secondary, forward=forward)
         self.run()
         return self.fetch(copy=copy)
 
