@@ -37,3 +37,29 @@ def test_pack_helpers():
     lo, hi = pack_codes(codes)
     assert codes.shape == (2, 35) and list(codes[0][:4]) == [0, 1, 2, 3] and list(codes[1][:2]) == [2, 3]
     assert int(lo[0]) & 0xFF == 0b11100100 and int(hi[0]) == (0 | (1 << 2) | (2 << 4))
+
+
+def test_forward_reads_helper_and_oracle_equivalence(built):
+    """forward_reads() keeps the even records; rebuilding the doubled buffer from them (what
+    k_pack does on the device for vdjgraph_stage_forward: bam_read.c:130-145, 230-243) gives back the
+    generator's buffer byte for byte, so the oracle sees the same input either way."""
+    import pytest
+
+    from vdjer_b200 import forward_reads
+    L = 50
+    rb = 2 * L + 1
+    p, s = synth.generate(n_pairs=300, read_length=L, seed=9, n_clones=10, threads=2)
+    for buf in (p, s):
+        f = forward_reads(buf, L)
+        assert f[-1] == 0 and (f.size - 1) * 2 == buf.size - 1
+        fr = f[:-1].reshape(-1, rb)
+        assert np.array_equal(fr, buf[:-1].reshape(-1, rb)[0::2])
+        comp = np.arange(256, dtype=np.uint8)
+        for a, b in zip(b"ACGT", b"TGCA"):
+            comp[a] = b
+        rc = np.concatenate([fr[:, :1], comp[fr[:, 1:1 + L]][:, ::-1], fr[:, 1 + L:][:, ::-1]], axis=1)
+        doubled = np.stack([fr, rc], axis=1).reshape(-1)
+        assert np.array_equal(doubled, buf[:-1])
+    assert forward_reads(np.zeros(1, np.uint8), L).size == 1          # empty buffer: just the NUL
+    with pytest.raises(ValueError):
+        forward_reads(p[: 3 * rb], L)                                  # odd number of records
