@@ -215,6 +215,9 @@ def main():
     ap.add_argument("--pageable", action="store_true",
                     help="leave the record buffers pageable (the reference's calloc): staging bounces them through page-locked chunks")
     ap.add_argument("--forward-sharded", action="store_true", help="(accepted for old command lines; the forward-reads path is always measured)")
+    ap.add_argument("--forward-inputs", action="store_true",
+                    help="generate forward reads only (half the host memory: configs[4] at full size) and run everything, "
+                         "`e2e` included, through vdjgraph_*_forward; the doubled text is never materialised")
     ap.add_argument("--no-forward", action="store_true", help="skip the forward-reads-only end-to-end measurement")
     ap.add_argument("--rounds", type=int, default=0, help="hash super-partition rounds (0 = auto: 1 unless the tuples exceed HBM)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
@@ -252,7 +255,8 @@ def main():
     t0 = time.perf_counter()
     # N > 1: ONE repertoire (same seed = same clone library), every rank draws its own disjoint
     # n_pairs reads from it: the pooled repertoire of BASELINE configs[4], sequenced N times deeper
-    primary, secondary = synth.generate(seed=12345, pair_offset=rank * wl["n_pairs"], **gen)
+    fwd_in = bool(args.forward_inputs)
+    primary, secondary = synth.generate(seed=12345, pair_offset=rank * wl["n_pairs"], forward_only=fwd_in, **gen)
     t_gen = time.perf_counter() - t0
     # The record buffers are page-locked once, outside every timed region: a caller that allocates
     # them with vdjgraph_host_alloc has them page-locked from the start.
@@ -270,8 +274,11 @@ def main():
         # kernel through peer-mapped memory, survivors gathered on rank 0 (vdjer_b200/shard.py)
         from vdjer_b200 import shard
         db = shard.DistributedBuilder(gb, dist, device=f"cuda:{local_rank}")   # small exchanges ride NCCL
-        stage, run = (lambda: db.stage(primary, secondary)), db.run
-        build = lambda: db.build(primary, secondary, copy=False)  # noqa: E731
+        stage, run = (lambda: db.stage(primary, secondary, forward=fwd_in)), db.run
+        build = lambda: db.build(primary, secondary, copy=False, forward=fwd_in)  # noqa: E731
+    elif fwd_in:
+        stage, run = (lambda: gb.stage_forward(primary, secondary)), gb.run
+        build = lambda: gb.build_forward(primary, secondary, copy=False)  # noqa: E731
     else:
         stage, run = (lambda: gb.stage(primary, secondary)), gb.run
         build = lambda: gb.build(primary, secondary, copy=False)  # noqa: E731
@@ -316,7 +323,7 @@ def main():
 
     # ---- the same from forward reads only (vdjgraph_build_forward): reported beside e2e ----
     ms_fwd, fwd_stats = None, None
-    if not args.no_forward:
+    if not args.no_forward and not fwd_in:
         from vdjer_b200 import forward_reads
         fp, fs = forward_reads(primary, L), forward_reads(secondary, L)      # what a producer appending each read once holds
         pinned_f = None if args.pageable else PinnedRecords(fp, fs)
@@ -393,6 +400,8 @@ def main():
                     "d2h_bytes_per_step": e2e_stats["d2h_bytes"],
                     "ms_stage": e2e_stats["ms_stage"], "ms_device": e2e_stats["ms_device"], "ms_fetch": e2e_stats["ms_fetch"],
                     "host_text_bytes": int(primary.size + secondary.size),
+                    "inputs": ("forward reads only (vdjgraph_build_forward): the reverse-complement records are derived on the device"
+                               if fwd_in else "the reference's record buffers (every read and its reverse complement)"),
                     "host_buffers": "pageable, bounced through page-locked chunks by host threads" if args.pageable else
                                     "page-locked (vdjgraph_host_register once, untimed): staging DMAs straight from the caller's records"},
             "gpu_launches": int(sums["kernel_launches"] if sharded else stats["kernel_launches"]) * args.steps,

@@ -63,3 +63,13 @@ def test_forward_reads_helper_and_oracle_equivalence(built):
     assert forward_reads(np.zeros(1, np.uint8), L).size == 1          # empty buffer: just the NUL
     with pytest.raises(ValueError):
         forward_reads(p[: 3 * rb], L)                                  # odd number of records
+
+
+def test_generator_forward_only_is_the_even_records(built):
+    """forward_only=True writes the reads once: exactly the even records of the default output, for
+    any thread count and pair offset."""
+    from vdjer_b200 import forward_reads
+    for L, n, thr in [(50, 1500, 3), (100, 333, 5)]:
+        p, s = synth.generate(n_pairs=n, read_length=L, seed=11, n_clones=40, threads=thr, pair_offset=77)
+        fp, fs = synth.generate(n_pairs=n, read_length=L, seed=11, n_clones=40, threads=2, pair_offset=77, forward_only=True)
+        assert np.array_equal(fp, forward_reads(p, L)) and np.array_equal(fs, forward_reads(s, L))

@@ -40,6 +40,9 @@ typedef struct vdjsynth_params {
     int32_t threads;
     uint64_t pair_offset;   /* pairs are numbered pair_offset .. pair_offset + n_pairs - 1 in the (seed-defined) stream:
                                several callers can draw disjoint read sets from the SAME clone library */
+    int32_t forward_only;   /* 1: only the forward record of every mate (2 records per pair instead of 4): the even
+                               records of the default output, i.e. what vdjgraph_stage_forward takes */
+    int32_t reserved;
 } vdjsynth_params;
 
 #define V_LEN 300
@@ -134,11 +137,12 @@ static void make_read(const vdjsynth_params *p, rng *r, const char *src, int L, 
     }
 }
 
-static void write_records(char *dst, const char *seq, const char *qual, int L) {
+static void write_records(char *dst, const char *seq, const char *qual, int L, int forward_only) {
     /* forward record, then reverse complement with reversed qualities */
     dst[0] = '0';
     memcpy(dst + 1, seq, (size_t)L);
     memcpy(dst + 1 + L, qual, (size_t)L);
+    if (forward_only) return;
     char *d2 = dst + 2 * L + 1;
     d2[0] = '0';
     for (int i = 0; i < L; i++) {
@@ -175,12 +179,13 @@ static void *worker(void *arg) {
         if (ins > 400) ins = 400;
         if (ins > tl) ins = tl;
         int start = (int)rng_below(&r, (uint32_t)(tl - ins + 1));
-        char *dst = pair < jb->n_primary_pairs ? jb->primary + pair * 4 * rec
-                                                : jb->secondary + (pair - jb->n_primary_pairs) * 4 * rec;
+        const size_t per_mate = p->forward_only ? rec : 2 * rec;   /* bytes one mate occupies */
+        char *dst = pair < jb->n_primary_pairs ? jb->primary + pair * 2 * per_mate
+                                                : jb->secondary + (pair - jb->n_primary_pairs) * 2 * per_mate;
         make_read(p, &r, t + start, L, seq, qual);
-        write_records(dst, seq, qual, L);
+        write_records(dst, seq, qual, L, p->forward_only);
         make_read(p, &r, t + start + ins - L, L, seq, qual);
-        write_records(dst + 2 * rec, seq, qual, L);
+        write_records(dst + per_mate, seq, qual, L, p->forward_only);
     }
     return NULL;
 }
@@ -191,8 +196,9 @@ void vdjsynth_sizes(const vdjsynth_params *p, uint64_t *primary_bytes, uint64_t 
     uint64_t n_sec = (uint64_t)((double)p->n_pairs * p->frac_secondary);
     uint64_t n_pri = p->n_pairs - n_sec;
     uint64_t rec = (uint64_t)2 * p->read_length + 1;
-    *primary_records = n_pri * 4; *secondary_records = n_sec * 4;
-    *primary_bytes = n_pri * 4 * rec + 1; *secondary_bytes = n_sec * 4 * rec + 1;
+    uint64_t per_pair = p->forward_only ? 2 : 4;
+    *primary_records = n_pri * per_pair; *secondary_records = n_sec * per_pair;
+    *primary_bytes = n_pri * per_pair * rec + 1; *secondary_bytes = n_sec * per_pair * rec + 1;
 }
 
 int vdjsynth_generate(const vdjsynth_params *p, char *primary, char *secondary) {
@@ -209,7 +215,7 @@ int vdjsynth_generate(const vdjsynth_params *p, char *primary, char *secondary) 
     job jobs[256];
     for (int i = 0; i < nt; i++) {
         jobs[i].p = p; jobs[i].lib = &lib; jobs[i].primary = primary; jobs[i].secondary = secondary;
-        jobs[i].n_primary_pairs = pr / 4;
+        jobs[i].n_primary_pairs = pr / (p->forward_only ? 2 : 4);
         jobs[i].lo = p->n_pairs * (uint64_t)i / (uint64_t)nt;
         jobs[i].hi = p->n_pairs * (uint64_t)(i + 1) / (uint64_t)nt;
         pthread_create(&th[i], NULL, worker, &jobs[i]);
