@@ -79,3 +79,33 @@ extern "C" long vdjglue_dot(const char *primary, const char *secondary, int L, i
     delete nodes;   /* the rest is leaked like in the reference; the harness is short-lived */
     return n;
 }
+
+/* Wall time of vdjgraph_rebuild_nodes alone (milliseconds; < 0 on error): what the glue costs a
+ * caller after vdjgraph_build has returned.  The rebuilt graph is leaked like above. */
+extern "C" double vdjglue_rebuild_ms(const char *primary, const char *secondary, int L, int k,
+                                     const char *scratch_dir, const vdjgraph_result *res) {
+    set_default_params(&p);
+    p.kmer = k;
+    if (!g_vjf_ready) {
+        std::string v = std::string(scratch_dir) + "/empty_v_index";
+        std::string j = std::string(scratch_dir) + "/empty_j_index";
+        FILE *f = fopen(v.c_str(), "w"); if (!f) return -3; fclose(f);
+        f = fopen(j.c_str(), "w"); if (!f) return -3; fclose(f);
+        vjf_init((char *)v.c_str(), (char *)j.c_str(), 4, 10, 90, 'W', 486, 162);
+        g_vjf_ready = true;
+    }
+    read_length = L;
+    kmer_size = k;
+    node_id = 1;
+    struct_pool pool;
+    memset(&pool, 0, sizeof(pool));
+    node_map_t *nodes = new node_map_t();
+    nodes->set_empty_key(NULL);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    int rc = vdjgraph_rebuild_nodes(res, primary, strlen(primary) / (size_t)(2 * L + 1), secondary, nodes, &pool);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    delete nodes;
+    if (rc) return (double)rc;
+    return (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+}

@@ -157,3 +157,27 @@ def glue_dot(primary, secondary, read_length: int, k: int, mf: int, mq: int, dot
     if n < 0:
         raise RuntimeError(f"vdjglue_dot failed with {n}")
     return int(n), int(n_roots.value)
+
+
+def glue_rebuild_ms(primary, secondary, read_length: int, k: int, graph, scratch_dir: str | None = None) -> float:
+    """Wall time (ms) of glue/vdjgraph_glue.inc's vdjgraph_rebuild_nodes on these result arrays:
+    what the reference-side glue costs after vdjgraph_build has returned."""
+    from vdjer_b200.graph import _Result
+    p, s = _cbuf(primary), _cbuf(secondary)
+    lib = C.CDLL(GLUE_LIB)
+    lib.vdjglue_rebuild_ms.restype = C.c_double
+    lib.vdjglue_rebuild_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p]
+    get = (lambda n: graph[n]) if isinstance(graph, dict) else (lambda n: getattr(graph, n))
+    r = _Result()
+    r.n_nodes = len(get("first_pos"))
+    keep = []
+    for name, dt in [("first_pos", np.uint64), ("frequency", np.uint16), ("out_deg", np.uint8),
+                     ("in_deg", np.uint8), ("out_succ", np.uint32), ("in_pred", np.uint32)]:
+        a = np.ascontiguousarray(get(name), dtype=dt)
+        keep.append(a)
+        setattr(r, name, a.ctypes.data_as(type(getattr(r, name))))
+    scratch = scratch_dir or os.path.join(HERE, "_ref")
+    ms = lib.vdjglue_rebuild_ms(p.ctypes.data, s.ctypes.data, read_length, k, scratch.encode(), C.addressof(r))
+    if ms < 0:
+        raise RuntimeError(f"vdjglue_rebuild_ms failed with {ms}")
+    return float(ms)

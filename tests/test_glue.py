@@ -53,3 +53,14 @@ def test_vdjer_dot_identical_from_cuda_graph(tmp_path, built, name):
     want, got, ref_dot, glue_dot = _dots(tmp_path, name, cuda)
     assert got == want, f"{name}: (nodes, roots) {got} != {want}"
     assert glue_dot == ref_dot, f"{name}: vdjer.dot differs"
+
+
+@needs_glue
+def test_glue_rebuild_timer(built):
+    """The measurement hook behind profiles/glue_rebuild_time.py (cost of the reference-side rebuild
+    after the library call) runs and returns a plausible wall time."""
+    case = CASES["igh_default_k35"]
+    primary, secondary = make_inputs(case)
+    g = loader.build(primary, secondary, case["L"], case["k"], case["mf"], case["mq"], kind="port")
+    ms = loader.glue_rebuild_ms(primary, secondary, case["L"], case["k"], g)
+    assert 0 <= ms < 60_000
