@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VDJGRAPH_ABI_VERSION 3
+#define VDJGRAPH_ABI_VERSION 4
 
 typedef enum vdjgraph_status {
     VDJGRAPH_OK = 0,
@@ -114,6 +114,9 @@ typedef struct vdjgraph_result {
     uint32_t rounds, reserved;           /* super-partition rounds used */
     uint64_t h2d_bytes, d2h_bytes;       /* bytes moved by stage / fetch */
     uint64_t kernel_launches;            /* our kernels launched by the last run (CUB's sort passes not counted) */
+    uint64_t n_runs;                     /* run records ("super-k-mers") this device shipped: stretches of consecutive
+                                            N-free windows that share a minimizer bucket, one 32-byte record each */
+    uint32_t run_bytes, reserved2;       /* bytes per run record */
 } vdjgraph_result;
 
 /* Pruned pass-1 table (debug/parity export; unordered): what pre_nodes holds after :1393. */
@@ -209,8 +212,8 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
  *   rank 0    : vdjgraph_shard_finish -> vdjgraph_fetch
  */
 #define VDJGRAPH_SHARD_NBUF 6       /* bases, valid, qual, strand, tuples, gather */
-#define VDJGRAPH_SHARD_HIST 512     /* uint64 per rank: [gated | N-free ungated][256 hash buckets] */
-#define VDJGRAPH_SHARD_HLL 4096     /* uint32 HyperLogLog registers */
+#define VDJGRAPH_SHARD_HIST 768     /* uint64 per rank: [runs | gated windows | N-free windows][256 minimizer buckets] */
+#define VDJGRAPH_SHARD_HLL 32768    /* bytes: 128 HyperLogLog registers per minimizer bucket */
 
 typedef struct vdjgraph_shard_info {
     uint32_t n_ranks, rank;
@@ -224,9 +227,10 @@ int vdjgraph_shard_stage(vdjgraph_ctx *ctx, const char *primary, size_t n_primar
  * total_records and the record counts of vdjgraph_shard_plan stay in the doubled numbering */
 int vdjgraph_shard_stage_forward(vdjgraph_ctx *ctx, const char *primary_reads, size_t n_primary_reads,
                                  const char *secondary_reads, size_t n_secondary_reads, const vdjgraph_shard_info *info);
-int vdjgraph_shard_count(vdjgraph_ctx *ctx, uint64_t *hist /*[512]*/, uint32_t *hll /*[4096]*/);
-int vdjgraph_shard_plan(vdjgraph_ctx *ctx, const uint64_t *hist_all /*[n_ranks][512]*/,
-                        const uint32_t *hll_merged /*[4096]*/, const uint64_t *record_counts /*[n_ranks]*/);
+int vdjgraph_shard_count(vdjgraph_ctx *ctx, uint64_t *hist /*[VDJGRAPH_SHARD_HIST]*/, uint8_t *hll /*[VDJGRAPH_SHARD_HLL]*/);
+int vdjgraph_shard_plan(vdjgraph_ctx *ctx, const uint64_t *hist_all /*[n_ranks][VDJGRAPH_SHARD_HIST]*/,
+                        const uint8_t *hll_merged /*[VDJGRAPH_SHARD_HLL], element-wise max over the ranks*/,
+                        const uint64_t *record_counts /*[n_ranks]*/);
 /* rounds the plan settled on (every rank computes the same number from the all-gathered inputs);
  * negative status before vdjgraph_shard_plan */
 int vdjgraph_shard_rounds(vdjgraph_ctx *ctx);

@@ -19,19 +19,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import loader  # noqa: E402
-from tests.util import GOLDEN_DIR, sha  # noqa: E402
+from tests.util import GOLDEN_DIR, digest_of, sha  # noqa: E402
 from vdjer_b200 import synth  # noqa: E402
 
 OUT = os.path.join(GOLDEN_DIR, "full_digests.json")
-ARRAYS = ["first_pos", "frequency", "out_deg", "in_deg", "out_succ", "in_pred"]
-
-
-def digest_of(get) -> dict:
-    """SHA-256 per result array (little-endian, C order, the dtypes of include/vdjgraph.h)."""
-    dt = dict(first_pos=np.uint64, frequency=np.uint16, out_deg=np.uint8, in_deg=np.uint8,
-              out_succ=np.uint32, in_pred=np.uint32)
-    return {name: sha(np.ascontiguousarray(get(name), dtype=dt[name])) for name in ARRAYS}
-
 
 def main():
     assert loader.have_reference(), "build oracle/_ref first: make -C oracle ref"

@@ -7,7 +7,7 @@ import pytest
 
 from oracle import loader
 from tests.cases import CASES, make_inputs
-from tests.util import GOLDEN_DIR, assert_graph_equal, assert_pre_table_equal, graph_invariants, sha
+from tests.util import GOLDEN_DIR, assert_graph_equal, assert_pre_table_equal, digest_of, graph_invariants, sha
 from vdjer_b200 import GraphBuilder, VdjGraphError, synth
 
 pytestmark = pytest.mark.gpu
@@ -143,6 +143,29 @@ def test_tiny_table_capacity_grows(built):
     assert_graph_equal(got, want, "grown")
 
 
+def test_low_redundancy_input_fills_the_occurrence_log(built):
+    """Random, non-overlapping reads: millions of distinct k-mers that each occur once (per strand), so
+    every gated window claims its own occurrence-log block -- the log, not the table, is the
+    structure under pressure (the log used to be sized for clonal data only)."""
+    rng = np.random.default_rng(77)
+    n, L, k = 350_000, 50, 35
+    codes = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    fwd = np.frombuffer(b"ACGT", np.uint8)[codes]
+    rc = np.frombuffer(b"TGCA", np.uint8)[codes[:, ::-1]]
+    rec = np.empty((n, 2, 2 * L + 1), np.uint8)
+    rec[:, :, 0] = ord("0")
+    rec[:, 0, 1:1 + L] = fwd
+    rec[:, 1, 1:1 + L] = rc
+    rec[:, :, 1 + L:] = ord("I")
+    primary = np.concatenate([rec.reshape(-1), np.zeros(1, np.uint8)])
+    want = loader.build(primary, np.zeros(1, np.uint8), L, k, 1, 40, kind="port")
+    assert want["n_pre_total"] > 5_000_000
+    with GraphBuilder(L, k, 1, 40) as gb:
+        got = gb.build(primary, b"")
+    assert got.stats["n_pre_total"] == want["n_pre_total"]
+    assert_graph_equal(got, want, "low redundancy")
+
+
 def test_empty_and_degenerate_inputs(built):
     with GraphBuilder(50, 35, 3, 90) as gb:
         g = gb.build(b"", b"")
@@ -191,6 +214,31 @@ def test_large_invariants_and_cross_check(built):
 
 def _digest(g):
     return sha(g.first_pos, g.frequency, g.out_deg, g.in_deg, g.out_succ, g.in_pred)
+
+
+def _full_digests():
+    import json
+    path = os.path.join(GOLDEN_DIR, "full_digests.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+@pytest.mark.parametrize("workload", sorted(_full_digests()))
+def test_full_size_matches_reference_digest(built, workload):
+    """BASELINE.json configs at FULL size, bit for bit: the compiled reference ran once on exactly
+    this workload (tests/golden/make_full_digest.py, minutes of CPU) and left the counters and a
+    SHA-256 of every result array in tests/golden/full_digests.json; the CUDA result must hash the
+    same.  This is the workload bench.py times."""
+    want = _full_digests()[workload]
+    wl = dict(synth.CONFIGS[workload])
+    L, k, mf, mq = wl["read_length"], wl["k"], wl["mf"], wl["mq"]
+    gen = {kk: v for kk, v in wl.items() if kk not in ("k", "mf", "mq")}
+    primary, secondary = synth.generate(seed=want["seed"], **gen)
+    assert sha(primary, secondary) == want["input_sha256"], "the generator no longer produces the pinned input"
+    with GraphBuilder(L, k, mf, mq) as gb:
+        got = gb.build(primary, secondary, copy=False)
+        for name in ["n_records", "n_windows", "n_pre_total", "n_pre", "n_nodes"]:
+            assert got.stats[name] == want[name], name
+        assert digest_of(lambda n: getattr(got, n)) == want["sha256"]
 
 
 @pytest.mark.parametrize("workload", ["igh_2x50_5M", "igh_sensitive_2x50_5M", "igk_2x75_20M"])

@@ -49,8 +49,8 @@ def test_auto_rounds_follow_the_memory_budget(built, monkeypatch):
     with GraphBuilder(L, k, mf, mq) as gb:
         one = gb.build(primary, secondary)
     assert one.stats["rounds"] == 1
-    # reads + staged text of 160 k records are ~31 MB, their tuples ~41 MB
-    monkeypatch.setenv("VDJGRAPH_MEM_BUDGET_MB", "48")
+    # the packed reads of 160 k records alone are ~15 MB, their runs ~11 MB, tables and graph ~15 MB
+    monkeypatch.setenv("VDJGRAPH_MEM_BUDGET_MB", "20")
     with GraphBuilder(L, k, mf, mq) as gb:
         many = gb.build(primary, secondary)
     assert many.stats["rounds"] > 1

@@ -40,7 +40,7 @@ class FakeBuilder:
     def shard_count(self):
         rng = np.random.default_rng(100 + self.rank)
         self.hist = rng.integers(0, 1000, SHARD_HIST).astype(np.uint64)
-        self.hll = rng.integers(0, 30, SHARD_HLL).astype(np.uint32)
+        self.hll = rng.integers(0, 30, SHARD_HLL).astype(np.uint8)
         self.log.append(("count",))
         return self.hist, self.hll
 

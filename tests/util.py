@@ -20,6 +20,16 @@ def sha(*bufs) -> str:
     return h.hexdigest()
 
 
+RESULT_ARRAYS = dict(first_pos=np.uint64, frequency=np.uint16, out_deg=np.uint8, in_deg=np.uint8,
+                     out_succ=np.uint32, in_pred=np.uint32)
+
+
+def digest_of(get) -> dict:
+    """SHA-256 per result array (little-endian, C order, the dtypes of include/vdjgraph.h);
+    get(name) returns the array."""
+    return {name: sha(np.ascontiguousarray(get(name), dtype=dt)) for name, dt in RESULT_ARRAYS.items()}
+
+
 def kmer_codes_at(primary, secondary, L, k, stamps):
     """2-bit codes [n,k] of the k-mers whose first base is at the given stamps (r*w + o)."""
     w = L - k + 1

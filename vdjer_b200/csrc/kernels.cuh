@@ -8,11 +8,17 @@
  *
  * Design: a hash table probed at random from 3e8 windows misses L2 on almost
  * every probe, and this B200 sustains only ~20 G random read-modify-writes/s out of HBM
- * (profiles/microbench_r1.json) against ~190 G/s inside its 126 MB L2.  So the windows are
- * first SCATTERED, as 16-byte (key, stamp) tuples, into P hash partitions (one streaming write),
- * and both table passes then walk the tuples partition by partition: the slice of the table a
- * partition addresses is a few MB and stays L2-resident, every probe and atomic is an L2 hit,
- * and HBM only sees streaming traffic.
+ * (profiles/microbench_r1.json) against ~190 G/s inside its 126 MB L2.  So the windows are first
+ * SCATTERED into hash partitions and both table passes then walk them partition by partition: the
+ * slice of the table a partition addresses is a few MB and stays L2-resident, every probe and
+ * atomic is an L2 hit, and HBM only sees streaming traffic.
+ *
+ * What is scattered is not one tuple per window but one RUN per stretch of consecutive windows
+ * ("super-k-mer", KMC2 / Gerbil style): the partition of a k-mer is chosen by its MINIMIZER (the
+ * smallest hashed m-mer inside it, m = 10), which consecutive windows of a read share, so a
+ * stretch of up to 24 windows travels as one 32-byte record (its bases once, two flag bits per
+ * window, the stamp of its first window, the read's fingerprint): 3-5 bytes per window instead of
+ * 16.  The table passes expand a run back into its windows on the fly, in registers.
  *
  * Packed read layout in HBM (written by k_pack from the caller's text records, which the host
  * staging code in vdjgraph.cu streams to the device):
@@ -42,7 +48,7 @@ constexpr u32 CNT_CAP = 32765;   /* MAX_FREQUENCY-1, :66, :262, :345 */
 constexpr int GATE_Q = 20;       /* MIN_BASE_QUALITY, :76 */
 constexpr int HIQ = 30;          /* "high quality": windows whose phreds are all >= HIQ let prune bound the quality
                                     sums without reading quality rows (k_prune) */
-constexpr int FLB = 5;           /* tuple flag bits: has-next, next base (2), window all >= HIQ, record start all >= HIQ */
+constexpr int FLB = 5;           /* window flag bits: has-next, next base (2), window all >= HIQ, record start all >= HIQ */
 constexpr u64 LOG_A = 1ull << 62, LOG_B = 1ull << 63;   /* those two flags in a log entry, above the stamp */
 constexpr int QSUM_SAT = 214;    /* MAX_QUAL_SUM-41, :356 */
 constexpr int MAX_LOG_RANKS = 11;/* ceil(214/20) */
@@ -53,9 +59,15 @@ constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr u32 LOG_CHUNK = 64;    /* log blocks a warp reserves per global atomic */
 constexpr u32 MAX_PROBE = 1u << 14;
-constexpr int HLL_BITS = 12;     /* 4096 registers, sigma ~ 1.6 % */
-constexpr int HIST_BITS = 8;     /* k_count histograms the top 8 hash bits; P <= 256 partitions */
+constexpr int HIST_BITS = 8;     /* minimizer buckets: the finest hash partitioning (<= 256 partitions) */
+constexpr int NBUCKET = 1 << HIST_BITS;
+constexpr int BHLL_BITS = 7;     /* HyperLogLog registers (bytes) per bucket: sigma ~ 9 % per bucket, < 1 % over all */
+constexpr int BHLL = 1 << BHLL_BITS;
 constexpr int BATCH = 4;         /* independent table probes a thread keeps in flight */
+constexpr int MINI_M = 10;       /* minimizer length in bases (m = min(k, MINI_M)) */
+constexpr int RUN_MAX = 24;      /* windows per run: two 24-bit flag fields share one word of the run record */
+constexpr int SEG_MAX = 32;      /* windows per thread segment of the streaming kernels (a run never crosses a segment) */
+constexpr int STAMP_BITS = 40;   /* records < 2^32, windows per record <= 255 */
 
 /* pass-1 table slot: exactly one 32-byte sector */
 struct __align__(32) Slot1 {
@@ -68,7 +80,7 @@ struct __align__(32) Slot1 {
     u32 first_rec;    /* record of the occurrence that claimed the slot: contributingRead :335.  Written (with
                          first_fp, one 64-bit store) by the claiming thread AFTER head: a slot is usable by
                          others once they see it */
-    u32 first_fp;     /* fingerprint of that record's sequence (as carried by the tuples) */
+    u32 first_fp;     /* fingerprint of that record's sequence (as carried by the runs) */
 };
 static_assert(sizeof(Slot1) == 32, "Slot1 must be one sector");
 
@@ -85,34 +97,37 @@ static_assert(sizeof(Slot2) == 64, "Slot2 must be two sectors");
 
 struct Geom {
     int L, k, w, nb, nm;
-    int seg;            /* windows per thread segment (SEG_COUNT or SEG: the two streaming kernels tile differently) */
-    int segs;           /* thread segments per record: ceil(w / seg) */
+    int seg;            /* windows per thread segment: ceil(w / segs) <= SEG_MAX */
+    int segs;           /* thread segments per record: ceil(w / SEG_MAX) */
     u32 tile_rec;       /* records per block tile (even): THREADS / segs */
     u64 R;              /* real records */
     u64 n_tiles;
     u64 kmask_lo, kmask_hi; /* 2k ones */
     u64 kones;          /* k ones */
+    int m, span;        /* minimizer length min(k, MINI_M); m-mers per window: k - m + 1 */
+    u32 mmask;          /* 2m ones */
+    int run_max;        /* windows per run: min(RUN_MAX, 64 - k), so that a run's bases fit 128 bits */
 };
 
-/* hash partitioning + tuple format */
+/* The tables of one device as seen by the kernels: hash unit u (= minimizer bucket >> ushift; a unit
+ * is what is assigned to a device and a round) owns slots [off, off+len) of each table.  A k-mer's
+ * home slot is inside its unit's slice; linear probing may run past the slice's end. */
+struct __align__(16) UnitTab { u32 off1, len1, off2, len2; };
+
+/* hash partitioning + the per-window tuple format of the slow-path queues */
 struct Part {
-    int pbits;          /* P = 1 << pbits partitions by the top hash bits */
-    int gbits;          /* low partition bits that do not address this device's tables.  A build sharded over G
-                           devices and run in S rounds (hash super-partitions processed one after the other, for
-                           inputs whose tuples exceed HBM) gives partition p to device p & (G-1), round
-                           (p >> log2 G) & (S-1), and makes it local partition p >> gbits, gbits = log2 G + log2 S:
-                           the tables hold the local partitions of ONE round only */
-    u32 rshift, rmask, round; /* k_scatter ships the windows of partitions with ((p >> rshift) & rmask) == round */
+    int ushift;         /* unit = bucket >> ushift; NBUCKET >> ushift units */
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
-    int wide;           /* 1: 24-byte tuples (stamp in a third word) */
-    int fb;             /* read-fingerprint bits carried by a tuple (4..32; fewer only via the test hook) */
+    int wide;           /* 1: 24-byte queue tuples (stamp in a third word) */
+    int fb;             /* read-fingerprint bits carried by a tuple (<= 25; fewer only via the test hook) */
     u32 hot_t, hot_flush; /* pass 1: fast-path increments of k-mers whose count is already >= hot_t are summed in a
                              small per-warp shared-memory cache and added to the table every hot_flush batches */
-    u32 dbg;            /* TIMING EXPERIMENTS ONLY (wrong results): pass 1: 1 drop slow tuples, 2 no fast-path RED, 4 slow path
-                           claims but does not update, 8 no log stores, 16 no L1; pass 2: 32 drop slow tuples, 64 no reductions */
     u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
-    u64 slice1, slice2; /* slots per partition in table 1 / table 2 (cap = slice << pbits) */
-    u64 n_gated, n_valid; /* tuples in the gated region / in both regions */
+    u32 flat;           /* 1: one slice [0, flat_len) for every k-mer (the merged table of a sharded / multi-round
+                           finish): no minimizer is computed */
+    u32 flat_len;
+    u64 n_runs;         /* runs in this device's buffer (this round) */
+    const UnitTab *ut;  /* [NBUCKET >> ushift], device memory */
 };
 
 /* The packed reads of all devices of a sharded build (one entry when there is one device).
@@ -138,7 +153,7 @@ struct Counters {
     u64 n_surv;
     u64 n_hits;
     u64 n_nodes;
-    u64 n_slow1, n_slow2; /* tuples that took the slow path of pass 1 / pass 2 */
+    u64 n_slow1, n_slow2; /* windows that took the slow path of pass 1 / pass 2 */
     u64 n_hits_ungated;   /* pass-2 hits of windows that did not pass the quality gate (the ones that add to the count) */
     u32 log_used;
     u32 overflow;     /* table full / probe bound hit / region overrun */
@@ -252,15 +267,24 @@ __device__ __forceinline__ u64 hash_key(u64 lo, u64 hi) {
     h ^= h >> 32;
     return h;
 }
-/* home slot: the top pbits of the hash select the partition (= a contiguous slice of the
- * table), the remaining bits a slot inside it */
-__device__ __forceinline__ u64 home_slot(u64 h, int pbits, int gbits, u64 slice) {
-    /* slices hold fewer than 2^32 slots (the host checks the table capacities): the 32 hash bits
-     * below the partition bits pick the slot with one 32-bit multiply-high */
-    const u32 x = (u32)((h << pbits) >> 32);
-    const u32 in_slice = __umulhi(x, (u32)slice);
-    if (pbits == 0) return in_slice;
-    return (u64)((u32)(h >> (64 - pbits)) >> gbits) * (u32)slice + in_slice;
+/* home slot of a k-mer with hash h in the table slice [off, off+len): len < 2^32 (the host checks
+ * the table capacities), one 32-bit multiply-high on the upper hash bits */
+__device__ __forceinline__ u32 slot_in(u64 h, u32 off, u32 len) { return off + __umulhi((u32)(h >> 32), len); }
+
+/* Minimizers.  An m-mer (m <= 10 bases, 2 bits each) is hashed to 32 bits; the minimizer value of a
+ * k-mer is the SMALLEST hash among its k-m+1 m-mers, a function of the k-mer alone, and the k-mer's
+ * bucket (the finest partitioning) is a second hash of that value: the minimum of ~26 hashes is far
+ * from uniform, its re-hash is. */
+__device__ __forceinline__ u32 mini_hash(u32 x) {
+    u32 h = x * 0x9E3779B1u;
+    h ^= h >> 15;
+    return h * 0x2C1B3C6Du;
+}
+__device__ __forceinline__ u32 mini_bucket(u32 minh) {
+    u32 h = (minh ^ 0x5BD1E995u) * 0x85EBCA77u;
+    h ^= h >> 13;
+    h *= 0xC2B2AE3Du;
+    return h >> (32 - HIST_BITS);
 }
 
 /* bits [2i, 2i+2k) of a record's base words */
@@ -299,25 +323,28 @@ __device__ __forceinline__ u32 kmer_last(u64 lo, u64 hi, int k) {
     return (u32)(bit < 64 ? lo >> bit : hi >> (bit - 64)) & 3u;
 }
 
-/* ------------------------------------------------------------------------------------------ */
-/* tuples: one per N-free window.  word0 = k-mer bits 0..63; word1 = k-mer bits 64.. (hb bits)  */
-/* | flags << hb (FLB bits) | fp << (hb+FLB) | stamp << (hb+FLB+fb)              (narrow, 16 B);   */
-/* when fewer than 4 fingerprint bits would fit the stamp moves to a third word (wide, 24 B)    */
-/* and fb = 32.  fp = fingerprint of the record's whole sequence: two records with different    */
-/* fingerprints hold different reads, which settles hasMultipleUniqueReads without touching the */
-/* reads again (equal fingerprints fall back to the exact comparison).  The gate bit is implied */
-/* by the region the tuple lies in.                                                              */
-/* ------------------------------------------------------------------------------------------ */
-template <bool WIDE>
-__device__ __forceinline__ void tuple_load(const u64 *base, u64 t, u64 &lo, u64 &w1, u64 &w2) {
-    if (WIDE) {
-        const u64 *p = base + t * 3;
-        lo = ld_stream_u64(p); w1 = ld_stream_u64(p + 1); w2 = ld_stream_u64(p + 2);
-    } else {
-        ld_stream_v2(base + t * 2, lo, w1);
-        w2 = 0;
+/* bucket of an arbitrary packed k-mer (table builds and edge lookups; the streaming kernels slide the
+ * minimum along the read instead, see Mini) */
+__device__ __forceinline__ u32 kmer_bucket_of(u64 lo, u64 hi, int span, u32 mmask) {
+    u32 minh = ~0u;
+    for (int j = 0; j < span; j++) {
+        minh = min(minh, mini_hash((u32)lo & mmask));
+        lo = (lo >> 2) | (hi << 62);
+        hi >>= 2;
     }
+    return mini_bucket(minh);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Per-window tuples.  The table passes expand the runs into one tuple per window, in registers; */
+/* windows that need the slow path are parked in shared-memory queues in this form:             */
+/* word0 = k-mer bits 0..63; word1 = k-mer bits 64.. (hb bits) | flags << hb (FLB bits) |       */
+/* fp << (hb+FLB) | stamp << (hb+FLB+fb) (narrow, 16 B); when fewer than 4 fingerprint bits      */
+/* would fit the stamp moves to a third word (wide, 24 B).  fp = fingerprint of the record's    */
+/* whole sequence: two records with different fingerprints hold different reads, which settles  */
+/* hasMultipleUniqueReads without touching the reads again (equal fingerprints fall back to the */
+/* exact comparison).                                                                            */
+/* ------------------------------------------------------------------------------------------ */
 template <bool WIDE>
 __device__ __forceinline__ void tuple_decode(const Part &pt, u64 w1, u64 w2, u64 &hi, u32 &fl, u32 &fp, u64 &stamp) {
     hi = pt.hb ? (w1 & ((1ull << pt.hb) - 1)) : 0ull;
@@ -424,15 +451,11 @@ k_pack(PackArgs a, Geom g) {
 
 /* ------------------------------------------------------------------------------------------ */
 /* Streaming the packed reads (k_count, k_scatter).  A block walks tiles of g.tile_rec records   */
-/* block-stride; the three arrays of a tile are brought into shared memory by TMA bulk copies    */
-/* (double buffered, one elected thread issues, everybody waits on the mbarrier).  Thread t owns */
-/* one SEGMENT of a record: SEG consecutive windows, whose k-mer and gate/N masks it ROLLS (one  */
-/* new base and one new mask bit per window) instead of re-extracting them.                      */
+/* block-stride; the arrays of a tile are brought into shared memory by TMA bulk copies (double  */
+/* buffered, one elected thread issues, everybody waits on the mbarrier).  Thread t owns one     */
+/* SEGMENT of a record: up to SEG_MAX consecutive windows, whose k-mer, gate/N masks and          */
+/* minimizer it ROLLS (one new base and one new mask bit per window) instead of re-extracting.   */
 /* ------------------------------------------------------------------------------------------ */
-constexpr int SEG_COUNT = 16;           /* windows per thread segment in k_count (fewer, larger tiles) */
-/* k_scatter<SG>: SG = 8 (2048-tuple stage, 3 blocks per SM) up to 128 partitions, 16 (4096-tuple stage)
- * beyond, so that a bucket's run in the stage stays >= 8 tuples (one 128-byte bulk store) */
-
 struct BlockTiles {
     u64 *buf;   /* [2][a | b | c | d] */
     u64 *bar;   /* [2] */
@@ -463,7 +486,7 @@ __device__ __forceinline__ BlockTiles tiles_setup(unsigned char *smem, const Geo
     __syncthreads();
     return t;
 }
-/* one thread: start the three bulk copies of `tile` into buffer i */
+/* one thread: start the bulk copies of `tile` into buffer i */
 __device__ __forceinline__ void tiles_issue(const BlockTiles &t, int i, const Geom &g, u64 tile,
                                             const u64 *ga, const u64 *gb, const u64 *gc, const u64 *gd = nullptr) {
     const u32 bytes_a = g.tile_rec * (u32)g.nb * 8u, bytes_m = g.tile_rec * (u32)g.nm * 8u;
@@ -477,12 +500,12 @@ __device__ __forceinline__ void tiles_issue(const BlockTiles &t, int i, const Ge
 
 /* a thread's rolling view of its segment: window i of record `rec`.  start() pulls everything the
  * segment will need out of shared memory into registers (the k-mer of the first window and, for
- * each of the SEG-1 steps, the base and mask bits that enter the window), so that a step is a
- * handful of shifts. */
+ * each of the up to SEG_MAX-1 steps plus one look-ahead, the base and mask bits that enter the
+ * window), so that a step is a handful of shifts. */
 struct Roll {
     u64 lo, hi;     /* k-mer of the current window */
     u64 mv, mg, mh; /* k mask bits: N-free / gate-passing / all phreds >= HIQ (only when started with a hiq array) */
-    u32 nbase;      /* 2-bit codes of the bases i+k, i+k+1, ... (next to enter) */
+    u64 nbase;      /* 2-bit codes of the bases i+k, i+k+1, ... (next to enter) */
     u32 nv, ng, nh; /* their mask bits; bit 0 = position i+k */
     int i;
     bool has_h;
@@ -495,11 +518,11 @@ struct Roll {
         mv = extract_mask(v, g.nm, i0) & g.kones;
         mg = extract_mask(gd, g.nm, i0) & g.kones;
         mh = has_h ? extract_mask(sh + (size_t)rec * g.nm, g.nm, i0) & g.kones : 0ull;
-        /* positions i0+k .. i0+k+15 (at most SEG_COUNT = 16 steps; beyond the read: zero words / zero bits) */
+        /* positions i0+k .. i0+k+31 (at most SEG_MAX-1 steps and one look-ahead; beyond the read: zero words / zero bits) */
         const int j = i0 + g.k;
         u64 nl, nhi;
         extract_kmer(b, g.nb, j < 32 * g.nb ? j : 32 * g.nb - 1, ~0ull, 0ull, nl, nhi);
-        nbase = j < 32 * g.nb ? (u32)nl : 0u;
+        nbase = j < 32 * g.nb ? nl : 0ull;
         const bool in = j < 64 * g.nm;
         nv = in ? (u32)extract_mask(v, g.nm, j) : 0u;
         ng = in ? (u32)extract_mask(gd, g.nm, j) : 0u;
@@ -507,10 +530,10 @@ struct Roll {
     }
     /* is there a window i+1, i.e. does base i+k exist and is it ACGT / what is it */
     __device__ __forceinline__ bool next_valid() const { return nv & 1u; }
-    __device__ __forceinline__ u32 next_base() const { return nbase & 3u; }
+    __device__ __forceinline__ u32 next_base() const { return (u32)nbase & 3u; }
     /* move to window i+1 (caller guarantees i+1 < w, so base i+k exists) */
     __device__ __forceinline__ void step(const Geom &g) {
-        kmer_succ(lo, hi, nbase & 3u, g.k, lo, hi);
+        kmer_succ(lo, hi, (u32)nbase & 3u, g.k, lo, hi);
         mv = (mv >> 1) | ((u64)(nv & 1u) << (g.k - 1));
         mg = (mg >> 1) | ((u64)(ng & 1u) << (g.k - 1));
         if (has_h) mh = (mh >> 1) | ((u64)(nh & 1u) << (g.k - 1));
@@ -521,29 +544,121 @@ struct Roll {
     __device__ __forceinline__ bool gated(const Geom &g) const { return mg == g.kones; }
 };
 
+/* Sliding minimum of the m-mer hashes along a segment (the minimizer value of every window),
+ * branch-uniform: the m-mer positions are cut into blocks of `span`; a window that starts at offset
+ * r of block t covers the suffix [r, span) of block t and the prefix [0, r) of block t+1, so its
+ * minimum is min(suffix-min of t at r, running prefix-min of t+1).  The thread's scratch (span words
+ * of shared memory, stride THREADS) holds block t's suffix minima; slot r-1 is dead once window r is
+ * reached and takes block t+1's hash as it arrives; when block t+1 is complete one backward sweep
+ * turns it into suffix minima.  Every thread of a warp is at the same r, so nothing diverges. */
+struct Mini {
+    u32 *buf;
+    u32 x, pre;
+    int r;
+    __device__ __forceinline__ void sweep(int span) {
+        u32 run = ~0u;
+        for (int j = span - 1; j >= 0; j--) { run = min(run, buf[j * THREADS]); buf[j * THREADS] = run; }
+    }
+    /* first window of the segment: its k-mer holds all m-mers of block 0 */
+    __device__ __forceinline__ u32 start(u64 lo, u64 hi, const Geom &g) {
+        for (int j = 0; j < g.span; j++) {
+            x = (u32)lo & g.mmask;
+            buf[j * THREADS] = mini_hash(x);
+            lo = (lo >> 2) | (hi << 62);
+            hi >>= 2;
+        }
+        sweep(g.span);
+        r = 0; pre = ~0u;
+        return buf[0];
+    }
+    /* next window: base c enters */
+    __device__ __forceinline__ u32 step(u32 c, const Geom &g) {
+        x = (x >> 2) | (c << (2 * (g.m - 1)));
+        const u32 h = mini_hash(x);
+        buf[r * THREADS] = h;          /* offset r of the next block; this slot's suffix minimum is no longer needed */
+        r++;
+        if (r == g.span) { sweep(g.span); r = 0; pre = ~0u; return buf[0]; }
+        pre = min(pre, h);
+        return min(buf[r * THREADS], pre);
+    }
+};
+
+/* Walks one thread segment (windows i0 .. i0+n-1 of record `rec`) and reports its RUNS: maximal
+ * stretches of consecutive N-free windows whose k-mers fall into the same minimizer bucket, cut
+ * at run_max windows and at the segment's end.  on_run(first window, length, bucket, gate bits,
+ * all->=HIQ bits, does the window after the run exist and is it N-free); on_gated(k-mer, bucket)
+ * for every window that passes the quality gate.  The loop runs g.seg times in every thread so
+ * that the warp stays converged for Mini's shared-memory sweeps. */
+template <class OnRun, class OnGated>
+__device__ __forceinline__ void scan_runs(const u64 *sb, const u64 *sg, const u64 *sv, const u64 *sh, u32 rec, int i0, int n,
+                                          const Geom &g, u32 *scratch, OnRun on_run, OnGated on_gated) {
+    Roll r;
+    Mini mn;
+    mn.buf = scratch;
+    int run_len = 0, run_a = 0;
+    u32 run_b = 0, gm = 0, hm = 0, minh = 0;
+    for (int j = 0; j < g.seg; j++) {
+        if (j < n) {
+            if (j == 0) { r.start(sb, sg, sv, rec, i0, g, sh); minh = mn.start(r.lo, r.hi, g); }
+            else { const u32 c = r.next_base(); r.step(g); minh = mn.step(c, g); }
+            const bool v = r.valid(g);
+            const u32 b = mini_bucket(minh);
+            if (run_len && (!v || b != run_b || run_len == g.run_max)) {
+                /* the window after the run is this one: it exists, and it is N-free iff v */
+                on_run(run_a, run_len, run_b, gm, hm, v ? 1u : 0u);
+                run_len = 0;
+            }
+            if (v) {
+                if (!run_len) { run_a = r.i; run_b = b; gm = hm = 0; }
+                const bool gt = r.gated(g);
+                gm |= (u32)gt << run_len;
+                hm |= (u32)(r.mh == g.kones) << run_len;
+                run_len++;
+                if (gt) on_gated(r.lo, r.hi, b);
+            }
+        }
+    }
+    if (run_len) on_run(run_a, run_len, run_b, gm, hm, (r.i + 1 < g.w && r.next_valid()) ? 1u : 0u);
+}
+
 /* ------------------------------------------------------------------------------------------ */
-/* K0 k_count: one streaming pass over the packed reads that sizes everything else:            */
-/*   - exact number of gated / N-free-but-ungated windows per top-8-bit hash bucket (tuple      */
-/*     region sizes for any P <= 256),                                                           */
-/*   - HyperLogLog over the gated k-mers -> pass-1 table capacity, so that the table is neither */
-/*     rehashed (the reference's dense_hash_map doubles, internal/densehashtable.h:631-653) nor */
-/*     grossly over-allocated.                                                                   */
+/* K0 k_count: one streaming pass over the packed reads that sizes everything else, per        */
+/* minimizer bucket:                                                                             */
+/*   - runs, gated windows and N-free windows (exact: the scatter's region sizes),              */
+/*   - a small HyperLogLog of the gated k-mers -> table-1 slice sizes, so that the table is     */
+/*     neither rehashed (the reference's dense_hash_map doubles, internal/densehashtable.h      */
+/*     :631-653) nor grossly over-allocated.                                                     */
+/* hist [3][NBUCKET] u64 (runs | gated | N-free), hll [NBUCKET][BHLL] bytes (4 per u32 word).    */
+/* Runs once per staged read set (its results do not depend on mf / mq).                         */
 /* ------------------------------------------------------------------------------------------ */
 __host__ __device__ inline size_t count_head_bytes() {
-    return ((size_t)(1 << HLL_BITS) + (size_t)WARPS * 2 * (1 << HIST_BITS)) * sizeof(u32);
+    return ((size_t)NBUCKET * BHLL / 4 + (size_t)3 * NBUCKET) * sizeof(u32);
+}
+__host__ __device__ inline size_t scratch_bytes(const Geom &g) { return (size_t)g.span * THREADS * sizeof(u32); }
+/* max of the byte at position idx of a packed byte array */
+__device__ __forceinline__ void byte_max(u32 *words, u32 idx, u32 v, bool global) {
+    u32 *wp = words + (idx >> 2);
+    const u32 sh = (idx & 3u) * 8u;
+    u32 cur = *reinterpret_cast<volatile u32 *>(wp);
+    while (((cur >> sh) & 0xFFu) < v) {
+        const u32 nv = (cur & ~(0xFFu << sh)) | (v << sh);
+        const u32 old = atomicCAS(wp, cur, nv);
+        if (old == cur) break;
+        cur = old;
+    }
 }
 __global__ void __launch_bounds__(THREADS)
 k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *__restrict__ valid,
-        Geom g, u32 *hll, u64 *hist /* [2][256] */) {
+        Geom g, u32 *hll, u64 *hist /* [3][NBUCKET] */) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int M = 1 << HLL_BITS, HB = 1 << HIST_BITS;
+    constexpr int HW = NBUCKET * BHLL / 4;
     u32 *reg = reinterpret_cast<u32 *>(smem);
-    u32 *sh = reg + M;  /* [WARPS][2][HB]: warp-private counters keep shared-memory atomics apart */
-    for (int i = threadIdx.x; i < M + WARPS * 2 * HB; i += THREADS) reg[i] = 0;
-    BlockTiles t = tiles_setup(smem + count_head_bytes(), g, 2);
-    u32 *mine = sh + (threadIdx.x >> 5) * 2 * HB;
-    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG_COUNT;
-    const int n = rec < g.tile_rec ? min(SEG_COUNT, g.w - (int)i0) : 0;
+    u32 *sh = reg + HW;  /* [3][NBUCKET] */
+    for (int i = threadIdx.x; i < HW + 3 * NBUCKET; i += THREADS) reg[i] = 0;
+    u32 *scratch = reinterpret_cast<u32 *>(smem + count_head_bytes()) + threadIdx.x;
+    BlockTiles t = tiles_setup(smem + count_head_bytes() + scratch_bytes(g), g, 2);
+    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * (u32)g.seg;
+    const int n = rec < g.tile_rec ? max(0, min(g.seg, g.w - (int)i0)) : 0;
     const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
     if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, bases, good, valid);
     u64 tile = blockIdx.x;
@@ -552,229 +667,220 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
         if (tile < g.n_tiles) {
             if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, bases, good, valid);
             mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
-            if (n > 0) {
-                Roll r;
-                r.start(t.a(buf), t.b(buf), t.c(buf), rec, (int)i0, g);
-                for (int j = 0; j < n; j++) {
-                    if (j) r.step(g);
-                    if (!r.valid(g)) continue;
-                    const bool gated = r.gated(g);
-                    const u64 h = hash_key(r.lo, r.hi);
-                    atomicAdd(&mine[(gated ? 0 : HB) + (u32)(h >> (64 - HIST_BITS))], 1u);
-                    if (gated) {
-                        /* HLL uses the low hash bits so that it is independent of the partition bits */
-                        const u32 idx = (u32)h & (M - 1);
-                        const u32 rho = (u32)__clzll((long long)((h << 8) | (1ull << 20))) + 1;
-                        if (reg[idx] < rho) atomicMax(&reg[idx], rho);
-                    }
-                }
-            }
+            scan_runs(t.a(buf), t.b(buf), t.c(buf), nullptr, rec, (int)i0, n, g, scratch,
+                [&](int, int len, u32 b, u32 gm, u32, u32) {
+                    atomicAdd(&sh[b], 1u);
+                    if (gm) atomicAdd(&sh[NBUCKET + b], (u32)__popc(gm));
+                    atomicAdd(&sh[2 * NBUCKET + b], (u32)len);
+                },
+                [&](u64 lo, u64 hi, u32 b) {
+                    const u64 h = hash_key(lo, hi);
+                    /* register = low hash bits, rank = leading zeros of the rest (1..58) */
+                    byte_max(reg, b * BHLL + ((u32)h & (BHLL - 1)), (u32)__clzll((long long)(h >> BHLL_BITS)) - (BHLL_BITS - 1), false);
+                });
         }
         __syncthreads();   /* everybody is done with buffer `buf` before it is refilled */
         /* u32 counters: flush long before they can overflow (uniform trip count) */
         if ((it & 0xFFFF) == 0xFFFF) {
-            for (int i = threadIdx.x; i < WARPS * 2 * HB; i += THREADS) { u32 v = sh[i]; if (v) { atomicAdd(&hist[i % (2 * HB)], (u64)v); sh[i] = 0; } }
+            for (int i = threadIdx.x; i < 3 * NBUCKET; i += THREADS) { u32 v = sh[i]; if (v) { atomicAdd(&hist[i], (u64)v); sh[i] = 0; } }
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < M; i += THREADS)
-        if (reg[i]) atomicMax(&hll[i], reg[i]);
-    for (int i = threadIdx.x; i < 2 * HB; i += THREADS) {
-        u64 v = 0;
-        for (int wv = 0; wv < WARPS; wv++) v += sh[wv * 2 * HB + i];
-        if (v) atomicAdd(&hist[i], v);
+    for (int i = threadIdx.x; i < HW; i += THREADS) {
+        const u32 v = reg[i];
+        for (int b = 0; v && b < 4; b++) if ((v >> (8 * b)) & 0xFFu) byte_max(hll, 4u * i + b, (v >> (8 * b)) & 0xFFu, true);
     }
+    for (int i = threadIdx.x; i < 3 * NBUCKET; i += THREADS)
+        if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K1 k_scatter: every N-free window becomes a tuple in its hash partition's region:           */
-/* regions [gated p=0..P-1][ungated p=0..P-1]; cursor[] starts at the region offsets (exclusive */
-/* scan of k_count's histogram).  Per tile a block                                               */
-/*   1. counts its windows per bucket (warp-private shared-memory counters; the value returned  */
-/*      by the atomic is the window's rank among the warp's windows of that bucket),             */
-/*   2. scans the counters into block-local offsets and reserves one run per non-empty bucket   */
-/*      with a single global atomic,                                                             */
-/*   3. re-rolls the windows and writes the tuples into a shared-memory stage in bucket order,   */
-/*   4. copies the stage out: consecutive threads write consecutive tuples of a run, so global  */
-/*      stores are full-sector and coalesced although the destination is a 2P-way scatter.      */
+/* Run records: 32 bytes = one sector.                                                           */
+/*   w0, w1 : the bases first window .. last window + k - 1 (+ the base after them when the      */
+/*            window after the run exists), 2 bits each from bit 0: at most 64 bases            */
+/*   w2     : gate bit of window j at bit j (24) | window-all->=HIQ bit at 24+j (24) |           */
+/*            length-1 at 48 (5) | next-window-exists at 53 | record-start-all->=HIQ at 54 |     */
+/*            fingerprint bits 16..24 at 55 (9)                                                  */
+/*   w3     : stamp of the first window (STAMP_BITS) | bucket at 40 (8) | fingerprint bits 0..15 at 48 */
 /* ------------------------------------------------------------------------------------------ */
+constexpr int RUN_WORDS = 4;
+constexpr int RUN_FP_BITS = 25;
+__device__ __forceinline__ u32 run_len(u64 w2) { return ((u32)(w2 >> 48) & 31u) + 1u; }
+__device__ __forceinline__ u32 run_bucket(u64 w3) { return (u32)(w3 >> STAMP_BITS) & (NBUCKET - 1); }
+__device__ __forceinline__ void ld_run(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    /* streaming (touched once per pass): evict-first so that it does not push the L2-resident table slice out */
+    asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1 k_scatter: every run goes to the region of its hash unit in the tuple buffer of the       */
+/* device that owns the unit (cursor[] starts at this device's share of each region, from the   */
+/* all-gathered k_count histograms).  Per tile a block                                           */
+/*   1. rolls its windows once: run descriptors go to a list in shared memory, units are counted,*/
+/*   2. scans the counters into stage offsets and reserves one range per non-empty unit with a  */
+/*      single global atomic,                                                                    */
+/*   3. builds the run records from the list (balanced over the threads) into a stage ordered   */
+/*      by unit,                                                                                 */
+/*   4. copies the stage out: one TMA bulk store per non-empty unit, straight to the unit's     */
+/*      region on this device or, through peer-mapped memory, on the owner's: the scatter IS    */
+/*      the all-to-all of a sharded build.                                                       */
+/* Runs beyond the list's capacity (a tile with pathologically short runs) are written one by   */
+/* one.  Units of other rounds have no destination and are skipped.                              */
+/* ------------------------------------------------------------------------------------------ */
+constexpr u32 STAGE_RUNS = 1024;
 struct ScatterArgs {
     const u64 *bases, *good, *valid, *hiq;
-    u64 *const *tbase; /* [2 << pbits] tuple buffer of the device that owns the bucket's partition (peer-mapped
-                          when that is another device: the scatter IS the all-to-all of a sharded build) */
-    u64 *cursor;       /* [2 << pbits] next free tuple of this device's share of the bucket's region */
-    const u64 *limit;  /* [2 << pbits] end of that share (overrun check) */
+    u64 *const *tbase; /* [units] tuple buffer of the device that owns the unit (peer-mapped when that is another
+                          device); null: not in this round */
+    u64 *cursor;       /* [units] next free run of this device's share of the unit's region */
+    const u64 *limit;  /* [units] end of that share (overrun check) */
     u64 rec_base;      /* global number of this device's first record */
     Counters *ctr;
 };
 struct ScatterSmem {
-    u32 *wcnt;   /* [WARPS][NBK] counters, then warp offsets inside the bucket's run */
-    u32 *boff;   /* [NBK + 1] start of each bucket's run in the stage */
-    u64 *gbase;  /* [NBK] global tuple index of the run */
-    u32 *fp;     /* [tile_rec] read fingerprints */
-    unsigned short *sbk; /* [THREADS * SG] bucket of a staged tuple */
-    u64 *stage;  /* [THREADS * SG][2 or 3] */
+    u32 *cnt;    /* [NBUCKET] runs of the tile per unit, then the fill cursor of phase 3 */
+    u32 *boff;   /* [NBUCKET + 1] start of each unit's range in the stage */
+    u64 *gbase;  /* [NBUCKET] global run index of the range */
+    u64 **dst;   /* [NBUCKET] copy of tbase */
+    u32 *fp;     /* [tile_rec] read fingerprint | record-start-all->=HIQ << 31 */
+    u32 *n_list; /* runs in the list */
+    u64 *list;   /* [STAGE_RUNS][2] run descriptors */
+    u64 *stage;  /* [STAGE_RUNS][4]; the same memory serves as Mini's scratch while the windows are rolled */
     unsigned char *tiles;
 };
 __host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
-__host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *base, const Geom &g, int nbk, int wide) {
-    const size_t MAX_STAGE = (size_t)THREADS * g.seg;
+__host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *base, const Geom &g) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t at = off; off = align128(off + bytes); return at; };
-    size_t a_wcnt = take((size_t)WARPS * nbk * 4), a_boff = take((size_t)(nbk + 1) * 4), a_gbase = take((size_t)nbk * 8);
-    size_t a_fp = take((size_t)g.tile_rec * 4), a_sbk = take((size_t)MAX_STAGE * 2);
-    size_t a_stage = take((size_t)MAX_STAGE * (wide ? 24 : 16)), a_tiles = take(block_tile_bytes(g, 3));
+    const size_t a_cnt = take((size_t)NBUCKET * 4), a_boff = take((size_t)(NBUCKET + 1) * 4), a_gbase = take((size_t)NBUCKET * 8);
+    const size_t a_dst = take((size_t)NBUCKET * 8), a_fp = take((size_t)g.tile_rec * 4), a_n = take(16);
+    const size_t a_list = take((size_t)STAGE_RUNS * 16);
+    const size_t stage_b = (size_t)STAGE_RUNS * RUN_WORDS * 8, scr_b = scratch_bytes(g);
+    const size_t a_stage = take(stage_b > scr_b ? stage_b : scr_b), a_tiles = take(block_tile_bytes(g, 3));
     if (o) {
-        o->wcnt = reinterpret_cast<u32 *>(base + a_wcnt); o->boff = reinterpret_cast<u32 *>(base + a_boff);
-        o->gbase = reinterpret_cast<u64 *>(base + a_gbase); o->fp = reinterpret_cast<u32 *>(base + a_fp);
-        o->sbk = reinterpret_cast<unsigned short *>(base + a_sbk); o->stage = reinterpret_cast<u64 *>(base + a_stage);
+        o->cnt = reinterpret_cast<u32 *>(base + a_cnt); o->boff = reinterpret_cast<u32 *>(base + a_boff);
+        o->gbase = reinterpret_cast<u64 *>(base + a_gbase); o->dst = reinterpret_cast<u64 **>(base + a_dst);
+        o->fp = reinterpret_cast<u32 *>(base + a_fp); o->n_list = reinterpret_cast<u32 *>(base + a_n);
+        o->list = reinterpret_cast<u64 *>(base + a_list); o->stage = reinterpret_cast<u64 *>(base + a_stage);
         o->tiles = base + a_tiles;
     }
     return off;
 }
+/* run descriptor (phase 1 -> phase 3): d0 = gate bits | HIQ bits << 24 | (len-1) << 48 | next << 53;
+ * d1 = record in tile | first window << 16 | bucket << 24 */
+__device__ __forceinline__ void build_run(u64 d0, u64 d1, const u64 *sb, const u32 *sfp, const Geom &g, u64 rec0,
+                                          u64 &w0, u64 &w1, u64 &w2, u64 &w3) {
+    const u32 rec = (u32)d1 & 0xFFFFu, a = (u32)(d1 >> 16) & 0xFFu, b = (u32)(d1 >> 24) & 0xFFu;
+    extract_kmer(sb + (size_t)rec * g.nb, g.nb, (int)a, ~0ull, ~0ull, w0, w1);
+    const u32 f = sfp[rec], fp = f & ((1u << RUN_FP_BITS) - 1);
+    w2 = d0 | ((u64)(f >> 31) << 54) | ((u64)(fp >> 16) << 55);
+    w3 = ((rec0 + rec) * (u64)g.w + a) | ((u64)b << STAMP_BITS) | ((u64)(fp & 0xFFFFu) << 48);
+}
 
-template <int SG>
 __global__ void __launch_bounds__(THREADS)
 k_scatter(ScatterArgs a, Geom g, Part pt) {
-    constexpr int SEG = SG;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int P = 1 << pt.pbits, NBK = 2 * P;
+    const int NU = NBUCKET >> pt.ushift;
     ScatterSmem sm;
-    scatter_carve(&sm, smem, g, NBK, pt.wide);
+    scatter_carve(&sm, smem, g);
     BlockTiles t = tiles_setup(sm.tiles, g, 3);
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u32 *mine = sm.wcnt + wid * NBK;
-    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * SEG;
-    const int n = rec < g.tile_rec ? min(SEG, g.w - (int)i0) : 0;
-    const u32 fpmask = (u32)((1ull << pt.fb) - 1);
-    const int tw = pt.wide ? 3 : 2;
+    u32 *scratch = reinterpret_cast<u32 *>(sm.stage) + threadIdx.x;
+    const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * (u32)g.seg;
+    const int n = rec < g.tile_rec ? max(0, min(g.seg, g.w - (int)i0)) : 0;
     const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
+    for (int u = threadIdx.x; u < NU; u += THREADS) sm.dst[u] = a.tbase[u];
     if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, a.bases, a.good, a.valid, a.hiq);
     u64 tile = blockIdx.x;
     for (u64 it = 0; it < n_iter; it++, tile += gridDim.x) {
         const int buf = (int)(it & 1);
-        const bool have = tile < g.n_tiles;   /* block-uniform */
-        if (!have) break;
-        for (int i = threadIdx.x; i < WARPS * NBK; i += THREADS) sm.wcnt[i] = 0;
-        if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, a.bases, a.good, a.valid, a.hiq);
+        if (tile >= g.n_tiles) break;   /* block-uniform */
+        for (int i = threadIdx.x; i < NU; i += THREADS) sm.cnt[i] = 0;
+        if (threadIdx.x == 0) {
+            *sm.n_list = 0;
+            if (tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, a.bases, a.good, a.valid, a.hiq);
+        }
         mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
         __syncthreads();
         const u64 *sb = t.a(buf), *sg = t.b(buf), *sv = t.c(buf), *sh = t.d(buf);
-        /* read fingerprints of the tile's records */
+        const u64 rec0 = a.rec_base + tile * g.tile_rec;
+        /* read fingerprints of the tile's records; are the record's first k phreds all >= HIQ?  (the first
+         * occurrence of a k-mer contributes the RECORD's first k qualities to the sums, :337-339) */
         for (u32 r = threadIdx.x; r < g.tile_rec; r += THREADS) {
             u64 h = 0x9E3779B97F4A7C15ull;
             for (int i = 0; i < g.nb; i++) h = hash_key(sb[(size_t)r * g.nb + i], h);
             for (int i = 0; i < g.nm; i++) h = hash_key(sv[(size_t)r * g.nm + i], h);
-            sm.fp[r] = (u32)(h >> 32) & fpmask;
+            const u32 rec_hi = (extract_mask(sh + (size_t)r * g.nm, g.nm, 0) & g.kones) == g.kones ? 1u : 0u;
+            sm.fp[r] = ((u32)(h >> 32) & ((1u << RUN_FP_BITS) - 1)) | (rec_hi << 31);
         }
-        /* 1. bucket and rank of every window of this thread's segment: code = bucket << 16 | rank */
-        u32 code[SEG];
-        {
-            Roll r;
-            if (n > 0) r.start(sb, sg, sv, rec, (int)i0, g);
-#pragma unroll
-            for (int j = 0; j < SEG; j++) {
-                code[j] = NIL32;
-                if (j < n) {
-                    if (j) r.step(g);
-                    if (r.valid(g)) {
-                        const u64 h = hash_key(r.lo, r.hi);
-                        const u32 part = pt.pbits ? (u32)(h >> (64 - pt.pbits)) : 0u;
-                        if (((part >> pt.rshift) & pt.rmask) == pt.round) {   /* this round's share of the hash space */
-                            const u32 bk = part + (r.gated(g) ? 0u : (u32)P);
-                            code[j] = (bk << 16) | atomicAdd(&mine[bk], 1u);
-                        }
-                    }
+        __syncthreads();   /* fingerprints are read by the overflow path of phase 1 */
+        /* 1. roll the windows: run descriptors -> list, per-unit counts */
+        scan_runs(sb, sg, sv, sh, rec, (int)i0, n, g, scratch,
+            [&](int ra, int len, u32 b, u32 gm, u32 hm, u32 nx) {
+                const u32 u = b >> pt.ushift;
+                if (!sm.dst[u]) return;   /* another round's share of the hash space */
+                const u64 d0 = (u64)gm | ((u64)hm << 24) | ((u64)(len - 1) << 48) | ((u64)nx << 53);
+                const u64 d1 = (u64)rec | ((u64)ra << 16) | ((u64)b << 24);
+                const u32 e = atomicAdd(sm.n_list, 1u);
+                if (e < STAGE_RUNS) {
+                    sm.list[2 * e] = d0; sm.list[2 * e + 1] = d1;
+                    atomicAdd(&sm.cnt[u], 1u);
+                } else {   /* list full: this run goes out on its own */
+                    u64 w0, w1, w2, w3;
+                    build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
+                    const u64 at = atomicAdd(&a.cursor[u], 1ull);
+                    if (at < a.limit[u]) st_sector(sm.dst[u] + at * RUN_WORDS, w0, w1, w2, w3);
+                    else atomicExch(&a.ctr->overflow, 4u);
                 }
-            }
-        }
+            },
+            [&](u64, u64, u32) {});
         __syncthreads();
-        /* 2. offsets.  Every bucket: warp counters -> exclusive prefix over the warps, total */
-        for (int b = threadIdx.x; b < NBK; b += THREADS) {
-            u32 run = 0;
-            for (int wv = 0; wv < WARPS; wv++) { u32 c = sm.wcnt[wv * NBK + b]; sm.wcnt[wv * NBK + b] = run; run += c; }
-            sm.boff[b + 1] = run;
+        /* 2. reserve the global ranges; stage offsets = exclusive scan of the counts */
+        for (int u = threadIdx.x; u < NU; u += THREADS) {
+            const u32 c = sm.cnt[u];
             u64 gbs = INF64;
-            if (run) {
-                gbs = atomicAdd(&a.cursor[b], (u64)run);
-                if (gbs + run > a.limit[b]) { atomicExch(&a.ctr->overflow, 4u); gbs = INF64; }
+            if (c) {
+                gbs = atomicAdd(&a.cursor[u], (u64)c);
+                if (gbs + c > a.limit[u]) { atomicExch(&a.ctr->overflow, 4u); gbs = INF64; }
             }
-            sm.gbase[b] = gbs;
+            sm.gbase[u] = gbs;
         }
-        __syncthreads();
-        if (wid == 0) {   /* exclusive scan of the totals by one warp: lane owns NBK/32 consecutive buckets */
-            const int per = (NBK + 31) / 32;
+        if (wid == 0) {   /* one warp: lane owns NU/32 consecutive units */
+            const int per = (NU + 31) / 32;
             u32 sum = 0;
-            for (int j = 0; j < per; j++) { int b = lane * per + j; if (b < NBK) sum += sm.boff[b + 1]; }
+            for (int j = 0; j < per; j++) { int u = lane * per + j; if (u < NU) sum += sm.cnt[u]; }
             u32 incl = sum;
             for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
             u32 run = incl - sum;
             for (int j = 0; j < per; j++) {
-                int b = lane * per + j;
-                if (b < NBK) { u32 c = sm.boff[b + 1]; sm.boff[b + 1] = run + c; run += c; }
+                int u = lane * per + j;
+                if (u < NU) { sm.boff[u] = run; run += sm.cnt[u]; }
             }
-            if (lane == 0) sm.boff[0] = 0;
+            if (lane == 31) sm.boff[NU] = run;
         }
         __syncthreads();
-        /* 3. stage the tuples in bucket order */
-        if (n > 0) {
-            Roll r;
-            r.start(sb, sg, sv, rec, (int)i0, g, sh);
-            const u32 fp = sm.fp[rec];
-            /* are the record's first k phreds all >= HIQ?  (the first occurrence of a k-mer contributes
-             * the RECORD's first k qualities to the sums, :337-339) */
-            const u32 rec_hi = (extract_mask(sh + (size_t)rec * g.nm, g.nm, 0) & g.kones) == g.kones ? 16u : 0u;
-            const u64 stamp0 = (a.rec_base + tile * g.tile_rec + rec) * (u64)g.w;
-#pragma unroll
-            for (int j = 0; j < SEG; j++) {
-                if (j < n) {
-                    if (j) r.step(g);
-                    if (code[j] != NIL32) {
-                        const u32 bk = code[j] >> 16;
-                        const u32 pos = sm.boff[bk] + mine[bk] + (code[j] & 0xFFFFu);
-                        u32 fl = rec_hi | (r.mh == g.kones ? 8u : 0u);
-                        if (r.i + 1 < g.w && r.next_valid()) fl |= 1u | (r.next_base() << 1);
-                        const u64 w1 = r.hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + FLB));
-                        const u64 stamp = stamp0 + (u64)r.i;
-                        u64 *dst = sm.stage + (size_t)pos * tw;
-                        dst[0] = r.lo;
-                        if (pt.wide) { dst[1] = w1; dst[2] = stamp; }
-                        else dst[1] = w1 | (stamp << (pt.hb + FLB + pt.fb));
-                        sm.sbk[pos] = (unsigned short)bk;
-                    }
-                }
-            }
-        }
+        for (int u = threadIdx.x; u < NU; u += THREADS) sm.cnt[u] = 0;   /* now the fill cursors */
         __syncthreads();
-        /* 4. copy out.  16-byte tuples: one TMA bulk store per non-empty bucket, straight from the
-         * stage to the bucket's region (on this device or, through peer-mapped memory, on the
-         * owner's): a run is contiguous on both sides.  24-byte tuples keep the per-tuple stores. */
-        const u32 total = sm.boff[NBK];
-        if (!pt.wide) {
-            fence_proxy_async();     /* the stage was written with ordinary stores */
-            __syncthreads();
-            for (int b = threadIdx.x; b < NBK; b += THREADS) {
-                const u32 run = sm.boff[b + 1] - sm.boff[b];
-                const u64 gbs = sm.gbase[b];
-                if (run && gbs != INF64) tma_store_1d(a.tbase[b] + gbs * 2, sm.stage + (size_t)sm.boff[b] * 2, run * 16u);
-            }
-            tma_store_commit();
-            tma_store_wait_read();   /* the stage may be overwritten by the next tile */
+        /* 3. build the runs into the stage, unit by unit */
+        const u32 n_list = min(*sm.n_list, STAGE_RUNS);
+        for (u32 e = threadIdx.x; e < n_list; e += THREADS) {
+            const u64 d0 = sm.list[2 * e], d1 = sm.list[2 * e + 1];
+            const u32 u = ((u32)(d1 >> 24) & 0xFFu) >> pt.ushift;
+            u64 w0, w1, w2, w3;
+            build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
+            u64 *dst = sm.stage + (size_t)(sm.boff[u] + atomicAdd(&sm.cnt[u], 1u)) * RUN_WORDS;
+            dst[0] = w0; dst[1] = w1; dst[2] = w2; dst[3] = w3;
         }
-        for (u32 e = threadIdx.x; pt.wide && e < total; e += THREADS) {
-            const u32 bk = sm.sbk[e];
-            const u64 gbs = sm.gbase[bk];
-            if (gbs == INF64) continue;
-            const u64 dst = gbs + (e - sm.boff[bk]);
-            const u64 *src = sm.stage + (size_t)e * tw;
-            u64 *out = a.tbase[bk];
-            if (pt.wide) {
-                u64 *p = out + dst * 3;
-                st_stream_u64(p, src[0]); st_stream_u64(p + 1, src[1]); st_stream_u64(p + 2, src[2]);
-            } else {
-                st_stream_v2(out + dst * 2, src[0], src[1]);
-            }
+        fence_proxy_async();     /* the stage was written with ordinary stores */
+        __syncthreads();
+        /* 4. copy out: a range is contiguous on both sides */
+        for (int u = threadIdx.x; u < NU; u += THREADS) {
+            const u32 c = sm.boff[u + 1] - sm.boff[u];
+            const u64 gbs = sm.gbase[u];
+            if (c && gbs != INF64) tma_store_1d(sm.dst[u] + gbs * RUN_WORDS, sm.stage + (size_t)sm.boff[u] * RUN_WORDS, c * (u32)(RUN_WORDS * 8));
         }
+        tma_store_commit();
+        tma_store_wait_read();   /* the stage becomes Mini's scratch again */
         __syncthreads();
     }
 }
@@ -823,7 +929,7 @@ __device__ __forceinline__ bool same_read(const Reads &rd, u64 r1, u64 r2, int n
 /*                   can fail the quality-sum test (every gated quality is >= 20), see k_prune. */
 /* ------------------------------------------------------------------------------------------ */
 struct Pass1Args {
-    const u64 *tuples;
+    const u64 *runs;  /* [pt.n_runs][RUN_WORDS], grouped by hash unit */
     Reads rd;
     Slot1 *table;
     u64 cap;
@@ -875,6 +981,74 @@ struct WarpQueue {
         return qn + __popc(ballot);
     }
 };
+
+/* Expansion of runs into per-window tuples.  A warp takes 32 runs at a time (one per lane, parked
+ * in shared memory), counts the windows this pass looks at (pass 1: the gated ones, pass 2: all) and
+ * deals them out evenly: window t of the chunk belongs to the run l whose inclusive prefix count is
+ * the first one above t (five shuffles), and is that run's (t - exclusive prefix)-th selected window.
+ * Every lane thus holds BATCH independent windows whatever the run lengths are. */
+struct RunFeed {
+    u64 *rw;        /* [32][RUN_WORDS] this warp's chunk */
+    u32 cnt, incl, total;
+    template <bool GATED_ONLY>
+    __device__ __forceinline__ void load(const u64 *runs, u64 ri, u64 n_runs) {
+        const u32 lane = threadIdx.x & 31;
+        u64 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        cnt = 0;
+        if (ri < n_runs) {
+            ld_run(runs + ri * RUN_WORDS, w0, w1, w2, w3);
+            cnt = GATED_ONLY ? (u32)__popc((u32)w2 & 0xFFFFFFu) : run_len(w2);
+        }
+        incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
+        total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncwarp();
+        u64 *p = rw + lane * RUN_WORDS;
+        p[0] = w0; p[1] = w1; p[2] = w2; p[3] = w3;
+        __syncwarp();
+    }
+    /* window t (< total) of the chunk: the run's words and the window's index in the run.  Warp-converged. */
+    template <bool GATED_ONLY>
+    __device__ __forceinline__ void locate(u32 t, u64 &w0, u64 &w1, u64 &w2, u64 &w3, u32 &j) const {
+        u32 l = 0;
+#pragma unroll
+        for (int s = 16; s; s >>= 1) { const u32 v = __shfl_sync(0xFFFFFFFFu, incl, l + s - 1); if (v <= t) l += s; }
+        u32 nth = t - __shfl_sync(0xFFFFFFFFu, incl - cnt, l);
+        const u64 *p = rw + l * RUN_WORDS;
+        w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
+        if (GATED_ONLY) {   /* position of the nth set gate bit */
+            u32 m = (u32)w2 & 0xFFFFFFu;
+            j = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                const u32 c = (u32)__popc(m & ((1u << s) - 1u));
+                if (nth >= c) { nth -= c; m >>= s; j += s; }
+            }
+        } else {
+            j = nth;
+        }
+    }
+};
+/* window j of a run -> its k-mer and its tuple words (the form the slow-path queues hold) */
+template <bool WIDE>
+__device__ __forceinline__ void run_window(const Geom &g, const Part &pt, u64 w0, u64 w1, u64 w2, u64 w3, u32 j,
+                                           u64 &lo, u64 &hi, u64 &t1, u64 &t2, bool &gated, u32 &bucket) {
+    const u32 sh = 2u * j;   /* <= 46 */
+    lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    hi = w1 >> sh;
+    lo &= g.kmask_lo; hi &= g.kmask_hi;
+    const u32 p = j + (u32)g.k;   /* the base after the window: position <= 63 of the run's bases */
+    const u32 c = (u32)((p < 32 ? w0 >> (2 * p) : w1 >> (2 * (p - 32)))) & 3u;
+    const bool has_next = j + 1 < run_len(w2) || ((w2 >> 53) & 1ull);
+    const u32 fl = (has_next ? 1u | (c << 1) : 0u) | ((u32)(w2 >> (24 + j)) & 1u) << 3 | ((u32)(w2 >> 54) & 1u) << 4;
+    const u32 fp = (((u32)(w3 >> 48) & 0xFFFFu) | (((u32)(w2 >> 55) & 0x1FFu) << 16)) & (u32)((1ull << pt.fb) - 1);
+    const u64 stamp = (w3 & ((1ull << STAMP_BITS) - 1)) + j;
+    gated = (w2 >> j) & 1ull;
+    bucket = run_bucket(w3);
+    t1 = hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + FLB));
+    if (WIDE) t2 = stamp;
+    else { t1 |= stamp << (pt.hb + FLB + pt.fb); t2 = 0; }
+}
 
 struct LogCursor { u32 base, used; };   /* warp-uniform: the warp's current chunk of log blocks */
 
@@ -933,30 +1107,31 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
         if (a.nb_ranks) {
             const u32 ballot = __ballot_sync(0xFFFFFFFFu, claimed);
             if (ballot) {
-                const u32 n = __popc(ballot);
-                if (lc.used + n > LOG_CHUNK) {
-                    u32 base = 0;
-                    if (lane == 0) base = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
-                    lc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    lc.used = 0;
+                /* blocks come from the warp's current chunk of LOG_CHUNK; when it runs out the remaining
+                 * claims of this step continue in a new chunk (nothing of a chunk is ever left unused) */
+                const u32 n = __popc(ballot), room = LOG_CHUNK - lc.used, my = __popc(ballot & lt);
+                u32 fresh = 0;
+                if (n > room) {
+                    if (lane == 0) fresh = atomicAdd(&a.ctr->log_used, LOG_CHUNK);
+                    fresh = __shfl_sync(0xFFFFFFFFu, fresh, 0);
                 }
                 if (claimed) {
-                    blk = lc.base + lc.used + __popc(ballot & lt);
+                    blk = my < room ? lc.base + lc.used + my : fresh + (my - room);
                     if (blk < a.log_blocks) slot->head = blk;
                     else { atomicExch(&a.ctr->overflow, 2u); blk = NIL32; slot->head = 0; }
                 }
-                lc.used += n;
+                if (n > room) { lc.base = fresh; lc.used = n - room; }
+                else lc.used += n;
             }
         }
         /* update the slot (:334-352) */
-        if (found && (pt.dbg & 4u)) { have = false; found = false; }
         if (found) {
             const u32 r = (u32)(stamp / (u64)g.w);
             const u64 entry = stamp | ((fl & 8u) ? LOG_A : 0ull) | ((fl & 16u) ? LOG_B : 0ull);
             if (claimed) {
                 /* first arrival: arrival rank 0, nothing to compare with, and nobody else touches the slot
                  * until the first-record word is published: plain stores, no atomics */
-                if (a.nb_ranks && blk != NIL32 && !(pt.dbg & 8u)) a.log[(u64)blk * a.nb_ranks] = entry;
+                if (a.nb_ranks && blk != NIL32) a.log[(u64)blk * a.nb_ranks] = entry;
                 st_cg_u64(reinterpret_cast<u64 *>(&slot->first_rec), (u64)r | ((u64)fp << 32));
             } else {
                 const u32 cw = (u32)q2, cnt = cw & CNT_MASK;       /* arrivals after the claimer seen so far */
@@ -968,7 +1143,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
                 if (!(cw & CNT_MULTI) && first_rec != r &&
                     (first_fp != fp || !same_read(a.rd, first_rec, r, g.nb, g.nm)))
                     atomicOr(&slot->count, CNT_MULTI);
-                if (rank < a.nb_ranks && blk != NIL32 && !(pt.dbg & 8u)) a.log[(u64)blk * a.nb_ranks + rank] = entry;
+                if (rank < a.nb_ranks && blk != NIL32) a.log[(u64)blk * a.nb_ranks + rank] = entry;
             }
             have = false;
         }
@@ -978,6 +1153,21 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
     const u32 left = q.push(0, have, lo, rw1, rw2, idx);
     __syncwarp();
     return left;
+}
+
+/* adds a warp's cached increments of hot k-mers to the table.  The count shares its word with the
+ * SURV / MULTI flags (bits 30, 31): a k-mer that is already far past the cap (the cached adds are
+ * not bounded by the fast path's stale view of the count) gets nothing more, so the count can never
+ * carry into the flags however often a k-mer occurs. */
+__device__ __forceinline__ void hot_flush(Slot1 *table, u32 *hidx, u32 *hcnt) {
+    for (u32 i = threadIdx.x & 31; i < HOTC; i += 32) {
+        const u32 c = hcnt[i];
+        if (c) {
+            u32 *cp = &table[hidx[i]].count;
+            if ((*reinterpret_cast<volatile u32 *>(cp) & CNT_MASK) < (1u << 24)) atomicAdd(cp, c);
+        }
+        hidx[i] = NIL32; hcnt[i] = 0;
+    }
 }
 
 template <bool WIDE>
@@ -990,77 +1180,75 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
     u32 *hidx = reinterpret_cast<u32 *>(smem + WARPS * WarpQueue<WIDE, QCAP1>::bytes()) + (threadIdx.x >> 5) * 2 * HOTC;
     u32 *hcnt = hidx + HOTC;
     for (u32 i = threadIdx.x & 31; i < HOTC; i += 32) { hidx[i] = NIL32; hcnt[i] = 0; }
+    RunFeed feed;
+    feed.rw = reinterpret_cast<u64 *>(smem + WARPS * (WarpQueue<WIDE, QCAP1>::bytes() + 2 * HOTC * sizeof(u32))) + (threadIdx.x >> 5) * 32 * RUN_WORDS;
     __syncwarp();
+    const u32 lane = threadIdx.x & 31;
     u32 since_flush = 0;
     LogCursor lc; lc.base = 0; lc.used = LOG_CHUNK;
     u32 qn = 0, n_slow = 0;   /* warp-uniform */
-    const u64 span = (u64)THREADS * BATCH;
-    const u64 n_blk = (pt.n_gated + span - 1) / span;
-    const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
+    const u64 n_chunk = (pt.n_runs + THREADS - 1) / THREADS;
     static_assert(BATCH == 4, "issue_fence takes four operands");
-    for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
-        const u64 t0 = blk * span + threadIdx.x;
-        u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], k0[BATCH], k1[BATCH], m2[BATCH];
-        u32 idx[BATCH];   /* table capacities stay below 2^32 slots (checked on the host) */
-        /* A1: the batch's tuples (coalesced, streaming), all loads in flight together */
+    for (u64 chunk = blockIdx.x; chunk < n_chunk; chunk += gridDim.x) {
+        feed.load<true>(a.runs, chunk * THREADS + threadIdx.x, pt.n_runs);
+        for (u32 base = 0; base < feed.total; base += 32 * BATCH) {
+            u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], k0[BATCH], k1[BATCH], m2[BATCH], hi[BATCH];
+            u32 idx[BATCH];   /* table capacities stay below 2^32 slots (checked on the host) */
+            /* A1: this lane's windows of the batch -> k-mer, tuple words, home slot */
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const u64 t = t0 + (u64)u * THREADS;
-            lo[u] = w1[u] = 0; if (WIDE) w2[u] = 0;
-            idx[u] = t < pt.n_gated ? 0u : NIL32;
-            if (t < pt.n_gated) tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
-        }
-        /* A2: their home slots, again all in flight together */
-#pragma unroll
-        for (int u = 0; u < BATCH; u++)
-            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.gbits, pt.slice1);
-        issue_fence(idx[0], idx[1], idx[2], idx[3]);
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            k0[u] = k1[u] = m2[u] = 0;
-            if (idx[u] != NIL32) {
-                u64 unused;
-                if (pt.dbg & 16u) ld_sector(a.table + idx[u], k0[u], k1[u], m2[u], unused);
-                else ld_sector_ca(a.table + idx[u], k0[u], k1[u], m2[u], unused);
+            for (int u = 0; u < BATCH; u++) {
+                const u32 t = base + (u32)u * 32u + lane;
+                u64 r0, r1, r2, r3, t2; u32 j, bucket; bool gated;
+                feed.locate<true>(min(t, feed.total - 1), r0, r1, r2, r3, j);
+                run_window<WIDE>(g, pt, r0, r1, r2, r3, j, lo[u], hi[u], w1[u], t2, gated, bucket);
+                if (WIDE) w2[u] = t2;
+                const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (bucket >> pt.ushift)));   /* off1, len1, off2, len2 */
+                idx[u] = t < feed.total ? slot_in(hash_key(lo[u], hi[u]), ut.x, ut.y) : NIL32;
             }
-        }
-        /* B: fast path = the k-mer sits in its home slot, is already known to come from several
-         * reads and has passed the logging ranks: one RED.  Everything else is queued. */
+            issue_fence(idx[0], idx[1], idx[2], idx[3]);
+            /* A2: the home slots, all loads in flight together */
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const bool valid = idx[u] != NIL32;
-            const u32 cw = (u32)m2[u], cnt = cw & CNT_MASK;
-            const bool fast = valid && k0[u] == lo[u] && k1[u] == (w1[u] & hmask) && (cw & CNT_MULTI) && cnt + 1 >= a.nb_ranks;
-            if (fast && cnt + 1 < CNT_CAP && !(pt.dbg & 2u)) {
-                bool cached = false;
-                if (cnt >= pt.hot_t) {
-                    const u32 e = (idx[u] * 0x9E3779B1u) >> (32 - HOTC_BITS);
-                    const u32 old = atomicCAS(&hidx[e], NIL32, idx[u]);
-                    if (old == NIL32 || old == idx[u]) { atomicAdd(&hcnt[e], 1u); cached = true; }
+            for (int u = 0; u < BATCH; u++) {
+                k0[u] = k1[u] = m2[u] = 0;
+                if (idx[u] != NIL32) {
+                    u64 unused;
+                    ld_sector_ca(a.table + idx[u], k0[u], k1[u], m2[u], unused);
                 }
-                if (!cached) atomicAdd(&a.table[idx[u]].count, 1u);
             }
-            qn = q.push(qn, valid && !fast && !(pt.dbg & 1u), lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
-        }
-        if (++since_flush >= pt.hot_flush) {
-            since_flush = 0;
-            __syncwarp();
-            for (u32 i = threadIdx.x & 31; i < HOTC; i += 32) {
-                if (hcnt[i]) atomicAdd(&a.table[hidx[i]].count, hcnt[i]);
-                hidx[i] = NIL32; hcnt[i] = 0;
+            /* B: fast path = the k-mer sits in its home slot, is already known to come from several
+             * reads and has passed the logging ranks: one RED.  Everything else is queued. */
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const bool valid = idx[u] != NIL32;
+                const u32 cw = (u32)m2[u], cnt = cw & CNT_MASK;
+                const bool fast = valid && k0[u] == lo[u] && k1[u] == hi[u] && (cw & CNT_MULTI) && cnt + 1 >= a.nb_ranks;
+                if (fast && cnt + 1 < CNT_CAP) {
+                    bool cached = false;
+                    if (cnt >= pt.hot_t) {
+                        const u32 e = (idx[u] * 0x9E3779B1u) >> (32 - HOTC_BITS);
+                        const u32 old = atomicCAS(&hidx[e], NIL32, idx[u]);
+                        if (old == NIL32 || old == idx[u]) { atomicAdd(&hcnt[e], 1u); cached = true; }
+                    }
+                    if (!cached) atomicAdd(&a.table[idx[u]].count, 1u);
+                }
+                qn = q.push(qn, valid && !fast, lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
             }
-            __syncwarp();
-        }
-        if (qn >= pt.qflush1) {
-            n_slow += qn; qn = pass1_drain<WIDE>(a, g, pt, q, qn, lc, false); n_slow -= qn;
+            if (++since_flush >= pt.hot_flush) {
+                since_flush = 0;
+                __syncwarp();
+                hot_flush(a.table, hidx, hcnt);
+                __syncwarp();
+            }
+            if (qn >= pt.qflush1) {
+                n_slow += qn; qn = pass1_drain<WIDE>(a, g, pt, q, qn, lc, false); n_slow -= qn;
+            }
         }
     }
     __syncwarp();
-    for (u32 i = threadIdx.x & 31; i < HOTC; i += 32)
-        if (hcnt[i]) atomicAdd(&a.table[hidx[i]].count, hcnt[i]);
+    hot_flush(a.table, hidx, hcnt);
     n_slow += qn;
     pass1_drain<WIDE>(a, g, pt, q, qn, lc, true);
-    if ((threadIdx.x & 31) == 0 && n_slow) atomicAdd(&a.ctr->n_slow1, (u64)n_slow);
+    if (lane == 0 && n_slow) atomicAdd(&a.ctr->n_slow1, (u64)n_slow);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1194,19 +1382,27 @@ __device__ __forceinline__ u64 t2_probe_from(const Slot2 *t, u64 cap, u64 idx, u
     }
     return INF64;
 }
-__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, const Part &pt, u64 lo, u64 hi, u64 &q2, u64 &q3) {
-    return t2_probe_from(t, cap, home_slot(hash_key(lo, hi), pt.pbits, pt.gbits, pt.slice2), lo, hi, q2, q3);
+/* home slot of an arbitrary k-mer in table 2: in the slice of its hash unit, or anywhere in a flat (merged) table */
+__device__ __forceinline__ u32 t2_home(const Part &pt, const Geom &g, u64 lo, u64 hi) {
+    const u64 h = hash_key(lo, hi);
+    if (pt.flat) return slot_in(h, 0u, pt.flat_len);
+    const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (kmer_bucket_of(lo, hi, g.span, g.mmask) >> pt.ushift)));
+    return slot_in(h, ut.z, ut.w);
+}
+__device__ __forceinline__ u64 t2_find(const Slot2 *t, u64 cap, const Part &pt, const Geom &g, u64 lo, u64 hi, u64 &q2, u64 &q3) {
+    return t2_probe_from(t, cap, t2_home(pt, g, lo, hi), lo, hi, q2, q3);
 }
 
 __global__ void __launch_bounds__(THREADS)
-k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Part pt, Counters *ctr) {
+k_build_table2(const Slot1 *t1, u64 cap1, Slot2 *t2, u64 cap2, Geom g, Part pt, Counters *ctr) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
     for (; i < cap1; i += stride) {
         u64 q0, q1, q2, q3;
         ld_sector(&t1[i], q0, q1, q2, q3);
         if (q0 == EMPTY64 && q1 == EMPTY64) continue;
         if (!((u32)q2 & CNT_SURV)) continue;
-        const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.gbits, pt.slice2), q0, q1);
+        /* (the slice a table-1 slot lies in says nothing: probing runs past slice ends) */
+        const u64 at = t2_insert(t2, cap2, t2_home(pt, g, q0, q1), q0, q1);
         if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
         /* the gated occurrences are N-free occurrences: seed node->frequency with them */
         const u32 cnt = ((u32)q2 & CNT_MASK) + 1;
@@ -1255,13 +1451,13 @@ k_compact_table2(const Slot2 *t, u64 cap, Slot2 *out, u64 *n_out) {
     }
 }
 __global__ void __launch_bounds__(THREADS)
-k_table2_from_records(const Slot2 *rec, u64 n, Slot2 *t2, u64 cap2, Part pt, Counters *ctr) {
+k_table2_from_records(const Slot2 *rec, u64 n, Slot2 *t2, u64 cap2, Geom g, Part pt, Counters *ctr) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         u64 q0, q1, q2, q3, r0, r1, r2, r3;
         ld_sector(&rec[i], q0, q1, q2, q3);
         ld_sector(reinterpret_cast<const char *>(&rec[i]) + 32, r0, r1, r2, r3);
-        const u64 at = t2_insert(t2, cap2, home_slot(hash_key(q0, q1), pt.pbits, pt.gbits, pt.slice2), q0, q1);
+        const u64 at = t2_insert(t2, cap2, t2_home(pt, g, q0, q1), q0, q1);
         if (at == INF64) { atomicExch(&ctr->overflow, 3u); continue; }
         Slot2 *o = t2 + at;
         o->count = (u32)q2; o->rank = 0; o->first_any = q3;
@@ -1281,7 +1477,7 @@ k_table2_from_records(const Slot2 *rec, u64 n, Slot2 *t2, u64 cap2, Part pt, Cou
 /* the loaded value already dominates, so hot k-mers cost reads only.                           */
 /* ------------------------------------------------------------------------------------------ */
 struct Pass2Args {
-    const u64 *tuples;
+    const u64 *runs;
     Slot2 *table;
     u64 cap;
     Counters *ctr;
@@ -1355,59 +1551,62 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
     WarpQueue<WIDE> q;
     q.setup(smem);
+    RunFeed feed;
+    feed.rw = reinterpret_cast<u64 *>(smem + WARPS * WarpQueue<WIDE>::bytes()) + (threadIdx.x >> 5) * 32 * RUN_WORDS;
     const u32 lane = threadIdx.x & 31;
-    const u64 span = (u64)THREADS * BATCH;
-    const u64 n_blk = (pt.n_valid + span - 1) / span;
-    const u64 hmask = pt.hb ? ((1ull << pt.hb) - 1) : 0ull;
+    const u64 n_chunk = (pt.n_runs + THREADS - 1) / THREADS;
     u32 n_hits = 0, qn = 0, n_slow = 0, n_hits_u = 0;
-    for (u64 blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
-        const u64 t0 = blk * span + threadIdx.x;
-        u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
-        u32 idx[BATCH];
-        /* A1: tuples */
+    for (u64 chunk = blockIdx.x; chunk < n_chunk; chunk += gridDim.x) {
+        feed.load<false>(a.runs, chunk * THREADS + threadIdx.x, pt.n_runs);
+        for (u32 base = 0; base < feed.total; base += 32 * BATCH) {
+            u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], hi[BATCH], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
+            u32 idx[BATCH], ung = 0;
+            /* A1: this lane's windows of the batch */
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const u64 t = t0 + (u64)u * THREADS;
-            lo[u] = w1[u] = 0; if (WIDE) w2[u] = 0;
-            idx[u] = t < pt.n_valid ? 0u : NIL32;
-            if (t < pt.n_valid) tuple_load<WIDE>(a.tuples, t, lo[u], w1[u], w2[WIDE ? u : 0]);
-        }
-        /* A2: the hot sector of the home slot and, speculatively, the out_first word this
-         * window would update; all loads of the batch in flight together */
-#pragma unroll
-        for (int u = 0; u < BATCH; u++)
-            if (idx[u] != NIL32) idx[u] = (u32)home_slot(hash_key(lo[u], w1[u] & hmask), pt.pbits, pt.gbits, pt.slice2);
-        issue_fence(idx[0], idx[1], idx[2], idx[3]);
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            q0[u] = q1[u] = q2[u] = q3[u] = of[u] = 0;
-            if (idx[u] != NIL32) {
-                const u32 fl = (u32)(w1[u] >> pt.hb) & 7u;
-                const Slot2 *s = a.table + idx[u];
-                ld_sector_ca(s, q0[u], q1[u], q2[u], q3[u]);
-                if (fl & 1u) of[u] = ld_ca_u64(&s->out_first[fl >> 1]);
+            for (int u = 0; u < BATCH; u++) {
+                const u32 t = base + (u32)u * 32u + lane;
+                u64 r0, r1, r2, r3, t2; u32 j, bucket; bool gated;
+                feed.locate<false>(min(t, feed.total - 1), r0, r1, r2, r3, j);
+                run_window<WIDE>(g, pt, r0, r1, r2, r3, j, lo[u], hi[u], w1[u], t2, gated, bucket);
+                if (WIDE) w2[u] = t2;
+                if (!gated) ung |= 1u << u;
+                const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (bucket >> pt.ushift)));
+                idx[u] = t < feed.total ? slot_in(hash_key(lo[u], hi[u]), ut.z, ut.w) : NIL32;
             }
-        }
-        /* B: hit at home -> reductions; empty home -> the k-mer did not survive; otherwise queue.
-         * node->frequency counts every N-free occurrence; the gated ones were already counted by
-         * pass 1 (k_build_table2 seeds count with them), so only ungated tuples add to it. */
+            issue_fence(idx[0], idx[1], idx[2], idx[3]);
+            /* A2: the hot sector of the home slot and, speculatively, the out_first word this
+             * window would update; all loads of the batch in flight together */
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const bool valid = idx[u] != NIL32;
-            const bool ungated = t0 + (u64)u * THREADS >= pt.n_gated;
-            u64 hi, stamp; u32 fl, fp;
-            tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], hi, fl, fp, stamp);
-            const bool hit = valid && q0[u] == lo[u] && q1[u] == hi;
-            const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
-            if (hit) {
-                if (!(pt.dbg & 64u)) pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
-                n_hits++;
-                n_hits_u += ungated;
+            for (int u = 0; u < BATCH; u++) {
+                q0[u] = q1[u] = q2[u] = q3[u] = of[u] = 0;
+                if (idx[u] != NIL32) {
+                    const u32 fl = (u32)(w1[u] >> pt.hb) & 7u;
+                    const Slot2 *s = a.table + idx[u];
+                    ld_sector_ca(s, q0[u], q1[u], q2[u], q3[u]);
+                    if (fl & 1u) of[u] = ld_ca_u64(&s->out_first[fl >> 1]);
+                }
             }
-            qn = q.push(qn, valid && !hit && !empty && !(pt.dbg & 32u), lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
-        }
-        if (qn >= pt.qflush2) {
-            n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false, n_hits_u); n_slow -= qn;
+            /* B: hit at home -> reductions; empty home -> the k-mer did not survive; otherwise queue.
+             * node->frequency counts every N-free occurrence; the gated ones were already counted by
+             * pass 1 (k_build_table2 seeds count with them), so only ungated windows add to it. */
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const bool valid = idx[u] != NIL32;
+                const bool ungated = (ung >> u) & 1u;
+                u64 khi, stamp; u32 fl, fp;
+                tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], khi, fl, fp, stamp);
+                const bool hit = valid && q0[u] == lo[u] && q1[u] == hi[u];
+                const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
+                if (hit) {
+                    pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
+                    n_hits++;
+                    n_hits_u += ungated;
+                }
+                qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
+            }
+            if (qn >= pt.qflush2) {
+                n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false, n_hits_u); n_slow -= qn;
+            }
         }
     }
     n_slow += qn;
@@ -1486,7 +1685,7 @@ k_export(ExportArgs a, Geom g, Part pt) {
         if (tf == INF64) continue;
         u64 slo, shi, q2, q3;
         kmer_succ(lo, hi, c, g.k, slo, shi);
-        u64 idx = t2_find(a.table, a.cap, pt, slo, shi, q2, q3);
+        u64 idx = t2_find(a.table, a.cap, pt, g, slo, shi, q2, q3);
         if (idx == INF64) continue;
         tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
     }
@@ -1500,7 +1699,7 @@ k_export(ExportArgs a, Geom g, Part pt) {
     for (u32 c = 0; c < 4; c++) {
         u64 plo, phi, q2, q3;
         kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
-        u64 idx = t2_find(a.table, a.cap, pt, plo, phi, q2, q3);
+        u64 idx = t2_find(a.table, a.cap, pt, g, plo, phi, q2, q3);
         if (idx == INF64) continue;
         u64 tf = a.table[idx].out_first[last];
         if (tf == INF64) continue;

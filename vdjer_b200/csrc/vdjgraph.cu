@@ -142,19 +142,25 @@ enum { BUF_BASES = 0, BUF_VALID, BUF_QUAL, BUF_STRAND, BUF_TUPLES, BUF_GATHER, N
 static_assert(NBUF == VDJGRAPH_SHARD_NBUF, "header and library disagree");
 
 struct Shard {
-    int G = 1, rank = 0, gbits = 0;
+    int G = 1, rank = 0;
     uint64_t rec_base[MAX_DEV + 1] = {};
     uint64_t total_records = 0;
-    std::vector<uint64_t> cnt;                    /* [G][2][P] windows per device, class, partition */
+    /* the plan (identical on every rank: a function of the all-gathered histograms only) */
+    int NU = 1, ushift = HIST_BITS;               /* hash units = minimizer buckets >> ushift */
+    std::vector<uint64_t> runs, gated, valid;     /* [G][NU] per source device and unit */
+    std::vector<double> est;                      /* [NU] distinct gated k-mers (HyperLogLog) */
+    std::vector<int> owner, round_of;             /* [NU] device and round that process the unit */
+    std::vector<UnitTab> utab;                    /* [NU] this device's table slices of the current round */
+    double slot_scale = 1.0;                      /* table-1 slots per estimated k-mer, relative to the default */
+    bool ignore_hint = false;                     /* the caller's table_capacity turned out too small */
     void *peer[MAX_DEV][NBUF] = {};
     bool peers_set = false;
-    uint64_t n_gated_own = 0, n_valid_own = 0;    /* tuples this device receives */
+    uint64_t n_runs_own = 0, n_gated_own = 0;     /* what this device receives in the current round */
     uint64_t n_gated_src = 0, n_valid_src = 0;    /* windows this device produces */
     double est_distinct = 0;
     uint64_t surv_all[MAX_DEV] = {}, surv_off[MAX_DEV + 1] = {};
-    /* rounds: hash super-partitions processed one after the other (tuples of one round in HBM at a time) */
-    int S = 1, sbits = 0, rnd = 0;
-    std::vector<uint64_t> own_gated, own_valid;   /* [S] tuples this device receives in each round */
+    /* rounds: groups of hash units processed one after the other (runs and tables of one round in HBM at a time) */
+    int S = 1, rnd = 0;
     uint64_t surv_done = 0;                       /* survivor records of the finished rounds (in d_rec) */
     float acc[6] = {};                            /* scatter, init1, pass1, prune, table2, pass2 ms summed over the rounds */
     bool merged() const { return G > 1 || S > 1; } /* the finish builds one table over survivor RECORDS */
@@ -166,7 +172,7 @@ struct vdjgraph_ctx {
     int device = 0;
     int sm_count = 0;
     size_t mem_total = 0;
-    Geom g, gc;
+    Geom g;
     uint64_t R_pad = 0;
     bool any_strand1 = false;
     bool staged = false, ran = false, staged_direct = false;
@@ -176,11 +182,12 @@ struct vdjgraph_ctx {
 
     DevBuf d_bad, d_bases, d_good, d_valid, d_hiq, d_qual, d_strand;
     PinBuf h_bad;
-    DevBuf d_t1, d_log, d_t2, d_hll, d_ctr, d_hist, d_cursor, d_tuples;
+    DevBuf d_t1, d_log, d_t2, d_hll, d_ctr, d_hist, d_cursor, d_tuples, d_utab;
     DevBuf d_keys[2], d_vals[2], d_cub;
     DevBuf d_first_pos, d_freq, d_odeg, d_ideg, d_osucc, d_ipred, d_klo, d_khi;
     DevBuf d_pre_klo, d_pre_khi, d_pre_freq, d_pre_n;
-    PinBuf h_ctr, h_hll, h_hist, h_cursor;
+    PinBuf h_ctr, h_hll, h_hist, h_cursor, h_utab;
+    float ms_count = 0;
     Part part;
     PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
@@ -210,16 +217,8 @@ int check_params(const vdjgraph_params *p) {
     return 0;
 }
 
-/* tiling of the packed reads for a streaming kernel whose threads own `seg` windows each */
-void tile_geom(Geom &g, int seg, uint64_t R) {
-    g.seg = seg;
-    g.segs = (g.w + seg - 1) / seg;
-    uint32_t tr = (uint32_t)THREADS / (uint32_t)g.segs;
-    tr &= ~1u;   /* even: TMA bulk copies need 16-byte sizes and addresses */
-    g.tile_rec = tr;
-    g.n_tiles = (R + tr - 1) / tr;
-}
-
+/* Geometry of the packed reads and of the streaming kernels' tiles: a record's w windows are cut
+ * into `segs` thread segments of at most SEG_MAX windows, a block tile holds THREADS / segs records. */
 void make_geom(vdjgraph_ctx *c, uint64_t R) {
     Geom &g = c->g;
     g.L = c->prm.read_length;
@@ -232,11 +231,17 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     g.kmask_lo = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
     g.kmask_hi = bits > 64 ? ((1ull << (bits - 64)) - 1) : 0ull;
     g.kones = (1ull << g.k) - 1;
-    /* c->g tiles for k_scatter, c->gc for k_count; the arrays are padded for both */
-    c->gc = g;
-    tile_geom(c->gc, SEG_COUNT, R);
-    tile_geom(g, 8, R);
-    c->R_pad = std::max(g.n_tiles * g.tile_rec, c->gc.n_tiles * c->gc.tile_rec);
+    g.m = std::min(g.k, MINI_M);
+    g.span = g.k - g.m + 1;
+    g.mmask = (1u << (2 * g.m)) - 1u;
+    g.run_max = std::min(RUN_MAX, 64 - g.k);
+    g.segs = (g.w + SEG_MAX - 1) / SEG_MAX;
+    g.seg = (g.w + g.segs - 1) / g.segs;
+    uint32_t tr = (uint32_t)THREADS / (uint32_t)g.segs;
+    tr &= ~1u;   /* even: TMA bulk copies need 16-byte sizes and addresses */
+    g.tile_rec = tr;
+    g.n_tiles = (R + tr - 1) / tr;
+    c->R_pad = g.n_tiles * g.tile_rec;
 }
 
 int ensure_workers(vdjgraph_ctx *c, int n) {
@@ -360,8 +365,9 @@ int blocks_per_sm(const void *kernel, size_t smem) {
     return std::max(1, n);
 }
 
-double hll_estimate(const uint32_t *reg) {
-    const int M = 1 << HLL_BITS;
+/* HyperLogLog estimate from one bucket's BHLL byte registers */
+double hll_estimate(const uint8_t *reg) {
+    const int M = BHLL;
     double sum = 0;
     int zeros = 0;
     for (int i = 0; i < M; i++) { sum += std::ldexp(1.0, -(int)reg[i]); zeros += reg[i] == 0; }
@@ -427,11 +433,11 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.stream) cudaStreamDestroy(w.stream);
     }
     DevBuf *db[] = { &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
-                     &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
+                     &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_utab, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
     for (DevBuf *b : db) b->release();
-    PinBuf *pb[] = { &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+    PinBuf *pb[] = { &c->h_utab, &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
     for (int i = 0; i < 13; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -451,6 +457,8 @@ extern "C" int vdjgraph_set_params(vdjgraph_ctx *c, const vdjgraph_params *param
     c->ran = false;
     return 0;
 }
+
+namespace { int run_count(vdjgraph_ctx *c); }
 
 /* np / ns count TEXT records.  fwd = 0: the reference's buffers (every read followed by its reverse
  * complement).  fwd = 1: forward reads only; the packed read set is the same as if the reverse
@@ -524,6 +532,9 @@ static int stage_impl(vdjgraph_ctx *c, const char *primary, size_t np, const cha
         h2d = Rt * rec_len;
     }
     CK(cudaStreamSynchronize(c->stream));
+    /* per-bucket window / run counts and cardinality registers of the packed reads: the build's plan
+     * needs nothing else, and they depend on the reads and on k only */
+    if ((rc = run_count(c))) return rc;
     memset(&c->res, 0, sizeof(c->res));
     c->res.ms_stage = (float)(wall_ms() - t0);
     c->res.h2d_bytes = h2d;
@@ -552,7 +563,6 @@ extern "C" int vdjgraph_stage_forward(vdjgraph_ctx *c, const char *primary_reads
 /* ========================================================================================== */
 namespace {
 
-constexpr int HB = 1 << HIST_BITS;
 
 int phase_check(vdjgraph_ctx *c, int want, const char *what) {
     if (!c) return fail(VDJGRAPH_ERR_PARAM, "ctx is NULL");
@@ -561,65 +571,90 @@ int phase_check(vdjgraph_ctx *c, int want, const char *what) {
     return 0;
 }
 
-/* K0: window counts per hash bucket + HyperLogLog of the gated k-mers -> h_hist, h_hll */
+constexpr size_t HIST_WORDS = 3 * NBUCKET;          /* runs | gated windows | N-free windows, per bucket */
+constexpr size_t HLL_BYTES = (size_t)NBUCKET * BHLL;
+static_assert(HIST_WORDS == VDJGRAPH_SHARD_HIST && HLL_BYTES == VDJGRAPH_SHARD_HLL, "header and library disagree");
+
+/* K0, part of staging (its results depend on the reads and on k only): runs / gated / N-free windows
+ * per minimizer bucket + per-bucket HyperLogLog of the gated k-mers -> h_hist, h_hll */
 int run_count(vdjgraph_ctx *c) {
-    const Geom g = c->gc;
+    const Geom g = c->g;
     cudaStream_t s = c->stream;
     int rc;
-    memset(&c->ctr, 0, sizeof(c->ctr));
-    vdjgraph_result &res = c->res;
-    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = res.n_slow1 = res.n_slow2 = res.n_hits_ungated = 0;
-    res.ms_device = res.ms_estimate = res.ms_scatter = res.ms_init1 = res.ms_pass1 = res.ms_prune = 0;
-    res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
-    res.table1_slots = res.table2_slots = 0;
-    res.partitions = 0; res.tuple_bytes = 0;
-    res.kernel_launches = 0;
     if ((rc = c->d_ctr.ensure(sizeof(Counters)))) return rc;
-    if ((rc = c->d_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
-    if ((rc = c->d_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->d_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->d_tbase.ensure(2 * HB * sizeof(void *)))) return rc;
+    if ((rc = c->d_hll.ensure(HLL_BYTES))) return rc;
+    if ((rc = c->d_hist.ensure(HIST_WORDS * sizeof(uint64_t)))) return rc;
+    if ((rc = c->d_cursor.ensure(2 * NBUCKET * sizeof(uint64_t)))) return rc;
+    if ((rc = c->d_tbase.ensure(NBUCKET * sizeof(void *)))) return rc;
+    if ((rc = c->d_utab.ensure(NBUCKET * sizeof(UnitTab)))) return rc;
     if ((rc = c->h_ctr.ensure(sizeof(Counters)))) return rc;
-    if ((rc = c->h_hll.ensure(sizeof(uint32_t) << HLL_BITS))) return rc;
-    if ((rc = c->h_hist.ensure(2 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->h_cursor.ensure(4 * HB * sizeof(uint64_t)))) return rc;
-    if ((rc = c->h_tbase.ensure(2 * HB * sizeof(void *)))) return rc;
+    if ((rc = c->h_hll.ensure(HLL_BYTES))) return rc;
+    if ((rc = c->h_hist.ensure(HIST_WORDS * sizeof(uint64_t)))) return rc;
+    if ((rc = c->h_cursor.ensure(2 * NBUCKET * sizeof(uint64_t)))) return rc;
+    if ((rc = c->h_tbase.ensure(NBUCKET * sizeof(void *)))) return rc;
+    if ((rc = c->h_utab.ensure(NBUCKET * sizeof(UnitTab)))) return rc;
     CK(cudaEventRecord(c->ev[0], s));
-    CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), s));
-    CK(cudaMemsetAsync(c->d_hll.p, 0, sizeof(uint32_t) << HLL_BITS, s));
-    CK(cudaMemsetAsync(c->d_hist.p, 0, 2 * HB * sizeof(uint64_t), s));
+    CK(cudaMemsetAsync(c->d_hll.p, 0, HLL_BYTES, s));
+    CK(cudaMemsetAsync(c->d_hist.p, 0, HIST_WORDS * sizeof(uint64_t), s));
     if (g.R) {
-        const size_t smem_count = count_head_bytes() + block_tile_bytes(g, 2);
+        const size_t smem_count = count_head_bytes() + scratch_bytes(g) + block_tile_bytes(g, 2);
         const int grid_count = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
         k_count<<<grid_count, THREADS, smem_count, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g,
                                                          c->d_hll.as<u32>(), c->d_hist.as<u64>());
-        res.kernel_launches++;
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->ev[1], s));
-    CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, 2 * HB * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, sizeof(uint32_t) << HLL_BITS, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, HIST_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, HLL_BYTES, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    c->sh.phase = 1;
+    cudaEventElapsedTime(&c->ms_count, c->ev[0], c->ev[1]);
     return 0;
 }
 
-/* partitioning, rounds, tuple format, table sizes, this device's tuple buffer.
- * hist_all: [G][2][HB] window counts of every device; hll: registers merged (max) over the devices.
+void reset_run_stats(vdjgraph_ctx *c) {
+    memset(&c->ctr, 0, sizeof(c->ctr));
+    vdjgraph_result &res = c->res;
+    res.n_nodes = 0; res.n_gated = res.n_pre_total = res.n_pre = res.n_hits = res.n_slow1 = res.n_slow2 = res.n_hits_ungated = 0;
+    res.ms_device = res.ms_scatter = res.ms_init1 = res.ms_pass1 = res.ms_prune = 0;
+    res.ms_table2 = res.ms_pass2 = res.ms_export = 0;
+    res.ms_estimate = c->ms_count;
+    res.table1_slots = res.table2_slots = 0;
+    res.partitions = 0; res.tuple_bytes = 0;
+    res.kernel_launches = 0;
+}
+
+/* table-1 slots of hash unit u (all of it, whichever device / round holds it) */
+uint64_t unit_slots1(const Shard &sh, const vdjgraph_params &prm, int u, double load1) {
+    /* 1.15: the per-unit HyperLogLog has a relative error of ~9 % / sqrt(buckets per unit); a slice that
+     * comes out too small only runs at a higher load (probing continues into the next slice) */
+    double slots = sh.est[u] * 1.15 / load1 * sh.slot_scale;
+    if (prm.table_capacity && !sh.ignore_hint) slots = (double)prm.table_capacity * (sh.est[u] + 1.0) / (sh.est_distinct + sh.NU) * sh.slot_scale;
+    return (uint64_t)slots + 64;
+}
+
+/* Partitioning, devices, rounds, table sizes, this device's run buffer.
+ * hist_all: [G][3][NBUCKET] per-bucket counts of every device; hll: registers merged (max) over the devices.
  * Everything here is a function of the all-gathered inputs only, so every rank of a sharded build
- * arrives at the same partitioning and the same number of rounds. */
-int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
+ * arrives at the same plan. */
+int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
     Shard &sh = c->sh;
     const Geom &g = c->g;
     const int G = sh.G;
+    reset_run_stats(c);
+    CK(cudaEventRecord(c->ev[0], c->stream));   /* start of the device time of this build */
+    /* per-bucket estimates of the distinct gated k-mers */
+    double est_b[NBUCKET];
     uint64_t gated_total = 0;
-    for (int d = 0; d < G; d++)
-        for (int i = 0; i < HB; i++) gated_total += hist_all[(size_t)d * 2 * HB + i];
-    sh.est_distinct = std::min<double>(hll_estimate(hll), (double)gated_total);
+    sh.est_distinct = 0;
+    for (int b = 0; b < NBUCKET; b++) {
+        uint64_t gb = 0;
+        for (int d = 0; d < G; d++) gb += hist_all[((size_t)d * 3 + 1) * NBUCKET + b];
+        est_b[b] = gb ? std::min<double>(hll_estimate(hll + (size_t)b * BHLL), (double)gb) : 0.0;
+        sh.est_distinct += est_b[b];
+        gated_total += gb;
+    }
     const double load1 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD1", 0.5)));
-    /* capacity of the whole (all devices, all rounds) pass-1 table */
-    uint64_t cap1 = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(sh.est_distinct * 1.06 / load1) + 1024;
-    cap1 = std::max<uint64_t>(cap1, 1024);
+    const uint64_t cap1_all = c->prm.table_capacity ? c->prm.table_capacity : (uint64_t)(sh.est_distinct * 1.15 / load1) + 1024;
 
     Part pt;
     memset(&pt, 0, sizeof(pt));
@@ -627,120 +662,137 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll) {
     if (c->prm.partitions) {
         while ((1u << pbits0) < c->prm.partitions && pbits0 < HIST_BITS) pbits0++;
     } else {
-        /* table-1 slices of at most SLICE_BYTES so that a slice is L2-resident */
+        /* table-1 slices of about SLICE_BYTES so that the slice being updated is L2-resident */
         const uint64_t slice_bytes = (uint64_t)(env_double("VDJGRAPH_SLICE_MB", (double)(SLICE_BYTES >> 20)) * 1048576.0);
-        while (pbits0 < HIST_BITS && ((cap1 * sizeof(Slot1)) >> pbits0) > slice_bytes) pbits0++;
+        while (pbits0 < HIST_BITS && ((cap1_all * sizeof(Slot1)) >> pbits0) > slice_bytes) pbits0++;
     }
     pt.hb = std::max(0, 2 * g.k - 64);
     const int sbits = bits_for(sh.total_records * (uint64_t)g.w);
-    /* narrow tuples need room for at least 4 read-fingerprint bits beside the stamp */
+    /* narrow queue tuples need room for at least 4 read-fingerprint bits beside the stamp */
     pt.wide = (pt.hb + FLB + 4 + sbits > 64) || (c->prm.flags & VDJGRAPH_FLAG_WIDE_TUPLES) ? 1 : 0;
-    pt.fb = pt.wide ? std::min(32, 64 - pt.hb - FLB) : std::min(32, 64 - pt.hb - FLB - sbits);
+    pt.fb = std::min(RUN_FP_BITS, pt.wide ? 64 - pt.hb - FLB : 64 - pt.hb - FLB - sbits);
     /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
     pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
-    pt.dbg = (u32)env_double("VDJGRAPH_DBG", 0);
     pt.hot_t = (u32)env_double("VDJGRAPH_HOT_T", 1024);
     pt.hot_flush = (u32)std::max(1.0, env_double("VDJGRAPH_HOT_FLUSH", 3));
     pt.qflush1 = (u32)std::min<double>(QFLUSH1, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 8)));
     pt.qdense1 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE1", 0));
     pt.qflush2 = (u32)std::min<double>(QFLUSH, std::max(1.0, env_double("VDJGRAPH_QFLUSH2", 96)));
     pt.qdense2 = (u32)std::min<double>(32, env_double("VDJGRAPH_QDENSE2", QDENSE));
-    const size_t tuple_bytes = pt.wide ? 24 : 16;
 
-    /* Layout for S rounds: partition pp (the top pbits hash bits) belongs to device pp & (G-1), round
-     * (pp >> gbits) & (S-1).  own[cls][d][r] = tuples device d receives in round r. */
-    std::vector<uint64_t> own;
-    auto layout = [&](int rb, int &pbits) {
-        pbits = std::max(pbits0, sh.gbits + rb);   /* every (device, round) owns at least one partition */
-        const int P = 1 << pbits, fold = HB / P, S = 1 << rb;
-        own.assign((size_t)2 * G * S, 0);
-        for (int d = 0; d < G; d++)
-            for (int cls = 0; cls < 2; cls++)
-                for (int b = 0; b < HB; b++) {
-                    const int pp = b / fold;
-                    own[((size_t)cls * G + (pp & (G - 1))) * S + ((pp >> sh.gbits) & (S - 1))] += hist_all[((size_t)d * 2 + cls) * HB + b];
-                }
-    };
-    /* Working set of one device with S rounds, against its memory: packed reads stay resident; tuples, both tables and the log hold one round; survivor records and the
-     * finishing device's merged table, sort and export buffers hold the whole graph (~0.6 of the
-     * distinct k-mers survive on repertoire data; an underestimate only costs an allocation error,
-     * and `rounds` can be set by the caller). */
+    /* Working set of one device with S rounds, against its memory: packed reads stay resident; runs,
+     * both tables and the log hold one round; survivor records and the finishing device's merged
+     * table, sort and export buffers hold the whole graph (~0.6 of the distinct k-mers survive on
+     * repertoire data; an underestimate only costs an allocation error, and `rounds` can be set by
+     * the caller). */
     int mqc = std::min(std::min(c->prm.min_base_quality, 254), QSUM_SAT);
     const int NBq = mqc > 0 ? (mqc + GATE_Q - 1) / GATE_Q : 0;
     uint64_t rec_max = 0;
     for (int d = 0; d < G; d++) rec_max = std::max(rec_max, sh.rec_base[d + 1] - sh.rec_base[d]);
     const double reads_bytes = (double)rec_max * ((double)g.nb * 8 + 3.0 * g.nm * 8 + g.L + 1);
     const double budget = env_double("VDJGRAPH_MEM_BUDGET_MB", 0.9 * (double)c->mem_total / 1048576.0) * 1048576.0;
-    auto working_set = [&](int rb) {
-        const int S = 1 << rb;
-        uint64_t tmax = 0, gmax = 0;
-        for (int d = 0; d < G; d++)
-            for (int r = 0; r < S; r++) {
-                const uint64_t gt = own[((size_t)0 * G + d) * S + r], vt = gt + own[((size_t)1 * G + d) * S + r];
-                tmax = std::max(tmax, vt); gmax = std::max(gmax, gt);
+    sh.slot_scale = 1.0; sh.ignore_hint = false;
+
+    /* Layout for S rounds over NU units: units go to devices, largest first, each to the device with
+     * the fewest N-free windows so far (minimizer buckets are far from equal: a few hold the constant
+     * region's k-mers); a device's units go to its rounds the same way, by runs. */
+    std::vector<uint64_t> tot_runs, tot_gated, tot_valid, load_dev, load_rnd, gated_rnd;
+    std::vector<double> est_rnd;
+    auto layout = [&](int S, int pbits) {
+        const int NU = 1 << pbits, fold = NBUCKET / NU;
+        sh.NU = NU; sh.ushift = HIST_BITS - pbits; sh.S = S;
+        sh.runs.assign((size_t)G * NU, 0); sh.gated.assign((size_t)G * NU, 0); sh.valid.assign((size_t)G * NU, 0);
+        sh.est.assign(NU, 0.0);
+        tot_runs.assign(NU, 0); tot_gated.assign(NU, 0); tot_valid.assign(NU, 0);
+        for (int b = 0; b < NBUCKET; b++) {
+            const int u = b / fold;
+            sh.est[u] += est_b[b];
+            for (int d = 0; d < G; d++) {
+                const uint64_t *h = hist_all + (size_t)d * HIST_WORDS;
+                sh.runs[(size_t)d * NU + u] += h[b]; sh.gated[(size_t)d * NU + u] += h[NBUCKET + b]; sh.valid[(size_t)d * NU + u] += h[2 * NBUCKET + b];
+                tot_runs[u] += h[b]; tot_gated[u] += h[NBUCKET + b]; tot_valid[u] += h[2 * NBUCKET + b];
             }
-        const double cap1_dev = (double)cap1 / ((double)G * S) + 1024;
-        const double nodes = 0.6 * sh.est_distinct;
-        return reads_bytes + (double)tmax * tuple_bytes + cap1_dev * sizeof(Slot1)
-             + std::min((double)gmax, cap1_dev) * NBq * 8.0
-             + nodes / ((double)G * S) * 4.0 * sizeof(Slot2)
-             + (G * S > 1 ? nodes * (sizeof(Slot2) / (double)G + 3.0 * sizeof(Slot2)) : 0.0) + nodes * 70.0;
+        }
+        std::vector<int> order(NU);
+        for (int u = 0; u < NU; u++) order[u] = u;
+        sh.owner.assign(NU, 0); sh.round_of.assign(NU, 0);
+        if (G > 1) {
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tot_valid[x] > tot_valid[y]; });
+            load_dev.assign(G, 0);
+            for (int u : order) {
+                int best = 0;
+                for (int d = 1; d < G; d++) if (load_dev[d] < load_dev[best]) best = d;
+                sh.owner[u] = best;
+                load_dev[best] += tot_valid[u] + 1;   /* + 1: empty units spread out too */
+            }
+        }
+        load_rnd.assign((size_t)G * S, 0); gated_rnd.assign((size_t)G * S, 0); est_rnd.assign((size_t)G * S, 0.0);
+        for (int u = 0; u < NU; u++) order[u] = u;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tot_runs[x] > tot_runs[y]; });
+        for (int u : order) {
+            const int d = sh.owner[u];
+            int best = 0;
+            for (int r = 1; r < S; r++) if (load_rnd[(size_t)d * S + r] < load_rnd[(size_t)d * S + best]) best = r;
+            sh.round_of[u] = best;
+            load_rnd[(size_t)d * S + best] += tot_runs[u] + 1;
+            gated_rnd[(size_t)d * S + best] += tot_gated[u];
+            est_rnd[(size_t)d * S + best] += (double)unit_slots1(sh, c->prm, u, load1);
+        }
     };
-    int rb = 0, pbits = 0;
-    const int rb_max = HIST_BITS - sh.gbits;
+    auto working_set = [&]() {
+        double worst = 0;
+        const double nodes = 0.6 * sh.est_distinct;
+        for (size_t i = 0; i < load_rnd.size(); i++) {
+            const double cap1_dev = est_rnd[i];
+            const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + cap1_dev * sizeof(Slot1)
+                            + std::min((double)gated_rnd[i], cap1_dev) * NBq * 8.0
+                            + nodes / ((double)G * sh.S) * 4.0 * sizeof(Slot2)
+                            + (G * sh.S > 1 ? nodes * (sizeof(Slot2) / (double)G + 3.0 * sizeof(Slot2)) : 0.0) + nodes * 70.0;
+            worst = std::max(worst, ws);
+        }
+        return worst;
+    };
+    int gb = 0;
+    while ((1 << gb) < G) gb++;
+    int rb = 0;
+    const int rb_max = HIST_BITS - gb;
     if (c->prm.rounds) {
         while ((1u << rb) < c->prm.rounds) rb++;
-        if (rb > rb_max) return fail(VDJGRAPH_ERR_PARAM, "rounds %u x %d devices exceed %d partitions", c->prm.rounds, G, HB);
-        layout(rb, pbits);
+        if (rb > rb_max) return fail(VDJGRAPH_ERR_PARAM, "rounds %u x %d devices exceed %d hash units", c->prm.rounds, G, NBUCKET);
+        layout(1 << rb, std::max(pbits0, gb + rb));   /* every (device, round) can own at least one unit */
     } else {
         for (;; rb++) {
-            layout(rb, pbits);
-            if (working_set(rb) <= budget || rb == rb_max) break;
+            layout(1 << rb, std::max(pbits0, gb + rb));
+            if (working_set() <= budget || rb == rb_max) break;
         }
     }
-    sh.S = 1 << rb; sh.sbits = rb; sh.rnd = 0; sh.surv_done = 0;
+    sh.rnd = 0; sh.surv_done = 0;
     memset(sh.acc, 0, sizeof(sh.acc));
-    const int S = sh.S;
-    pt.pbits = pbits;
-    pt.gbits = sh.gbits + sh.sbits;
-    pt.rshift = (u32)sh.gbits; pt.rmask = (u32)(S - 1); pt.round = 0;
-
-    /* fold the 256-bucket histograms to P partitions: cnt[d][cls][p] */
-    const int P = 1 << pbits, fold = HB / P;
-    sh.cnt.assign((size_t)G * 2 * P, 0);
-    for (int d = 0; d < G; d++)
-        for (int cls = 0; cls < 2; cls++)
-            for (int pp = 0; pp < P; pp++) {
-                uint64_t n = 0;
-                for (int j = 0; j < fold; j++) n += hist_all[((size_t)d * 2 + cls) * HB + pp * fold + j];
-                sh.cnt[((size_t)d * 2 + cls) * P + pp] = n;
-            }
-    /* what this device receives in every round (its partitions, from every device) and what it produces */
-    sh.own_gated.assign(S, 0); sh.own_valid.assign(S, 0);
-    uint64_t valid_max = 0;
-    for (int r = 0; r < S; r++) {
-        sh.own_gated[r] = own[((size_t)0 * G + sh.rank) * S + r];
-        sh.own_valid[r] = sh.own_gated[r] + own[((size_t)1 * G + sh.rank) * S + r];
-        valid_max = std::max(valid_max, sh.own_valid[r]);
-    }
-    sh.n_gated_src = sh.n_valid_src = 0;
-    for (int cls = 0; cls < 2; cls++)
-        for (int pp = 0; pp < P; pp++) {
-            const uint64_t mine = sh.cnt[((size_t)sh.rank * 2 + cls) * P + pp];
-            sh.n_valid_src += mine; if (cls == 0) sh.n_gated_src += mine;
-        }
-    sh.n_gated_own = sh.own_gated[0];
-    sh.n_valid_own = sh.own_valid[0];
-    pt.n_gated = sh.n_gated_own;
-    pt.n_valid = sh.n_valid_own;
+    pt.ushift = sh.ushift;
+    pt.ut = c->d_utab.as<UnitTab>();
     c->part = pt;
-    c->cap1 = std::max<uint64_t>(1024, (cap1 >> (sh.gbits + sh.sbits)) + 1024);
+
+    /* what this device produces, and the largest round it receives */
+    sh.n_gated_src = sh.n_valid_src = 0;
+    for (int u = 0; u < sh.NU; u++) { sh.n_gated_src += sh.gated[(size_t)sh.rank * sh.NU + u]; sh.n_valid_src += sh.valid[(size_t)sh.rank * sh.NU + u]; }
+    uint64_t runs_max = 0;
+    for (int r = 0; r < sh.S; r++) {
+        uint64_t n = 0;
+        for (int u = 0; u < sh.NU; u++) if (sh.owner[u] == sh.rank && sh.round_of[u] == r) n += tot_runs[u];
+        runs_max = std::max(runs_max, n);
+    }
     int rc;
-    if ((rc = c->d_tuples.ensure(std::max<size_t>(16, valid_max * tuple_bytes)))) return rc;
-    c->res.partitions = (uint32_t)P;
-    c->res.tuple_bytes = (uint32_t)tuple_bytes;
-    c->res.rounds = (uint32_t)S;
+    if ((rc = c->d_tuples.ensure(std::max<size_t>(32, runs_max * RUN_WORDS * 8)))) return rc;
+    c->res.partitions = (uint32_t)sh.NU;
+    c->res.tuple_bytes = (uint32_t)(pt.wide ? 24 : 16);
+    c->res.rounds = (uint32_t)sh.S;
     c->res.n_gated = sh.n_gated_src;
+    uint64_t all_runs = 0, all_valid = 0;
+    for (int u = 0; u < sh.NU; u++) { all_runs += tot_runs[u]; all_valid += tot_valid[u]; }
+    c->res.n_runs = 0;
+    for (int u = 0; u < sh.NU; u++) c->res.n_runs += sh.runs[(size_t)sh.rank * sh.NU + u];
+    c->res.run_bytes = (uint32_t)(RUN_WORDS * 8);
+    (void)all_runs; (void)all_valid; (void)gated_total;
     sh.peers_set = false;
     sh.phase = 2;
     return 0;
@@ -756,67 +808,63 @@ void set_self_peers(vdjgraph_ctx *c) {
     c->sh.peers_set = true;
 }
 
-/* K1: scatter this device's windows into the tuple buffers of the partitions' owners */
+/* K1: scatter this device's runs into the buffers of the units' owners */
 int run_scatter(vdjgraph_ctx *c) {
     Shard &sh = c->sh;
     if (!sh.peers_set) return fail(VDJGRAPH_ERR_STATE, "peer buffers not set");
-    c->part.round = (u32)sh.rnd;
-    c->part.n_gated = sh.n_gated_own = sh.own_gated[sh.rnd];
-    c->part.n_valid = sh.n_valid_own = sh.own_valid[sh.rnd];
-    const Part pt = c->part;
-    /* 8-window segments up to 128 partitions, 16-window segments (k_count's tiling) beyond */
-    /* Over 4 or 8 devices most runs are bulk stores into a peer's memory: the larger tiles make them
-     * twice as long (256 B instead of 128 B at 128 partitions), which NVLink rewards (4 GPUs: scatter
-     * 9.2 -> 7.6 ms).  VDJGRAPH_SCATTER_SEG16 = 0 / 1 overrides. */
-    const bool seg16 = (2 << pt.pbits) > 256 || env_double("VDJGRAPH_SCATTER_SEG16", sh.G >= 4 ? 1 : 0) != 0;
-    const Geom g = seg16 ? c->gc : c->g;
+    const Geom g = c->g;
     cudaStream_t s = c->stream;
-    const int G = sh.G, P = 1 << pt.pbits, PL = P >> pt.gbits;
-    /* region start of (cls, local partition) of THIS ROUND in every owner's buffer, then this device's
-     * share of it; the buckets of other rounds get no destination (the kernel skips their windows) */
-    uint64_t *cur = c->h_cursor.as<uint64_t>(), *lim = cur + 2 * HB;
+    const int G = sh.G, NU = sh.NU;
+    /* Region of unit u of THIS ROUND in its owner's buffer (units in unit order, each holding the runs
+     * of device 0, 1, ... in that order), then this device's share of it; the units of other rounds
+     * get no destination (the kernel skips their runs). */
+    uint64_t *cur = c->h_cursor.as<uint64_t>(), *lim = cur + NBUCKET;
     void **tb = c->h_tbase.as<void *>();
-    for (int b = 0; b < 2 * HB; b++) { cur[b] = 0; lim[b] = 0; tb[b] = nullptr; }
-    for (int o = 0; o < G; o++) {
-        uint64_t off = 0;
-        for (int cls = 0; cls < 2; cls++)
-            for (int lp = 0; lp < PL; lp++) {
-                const int pp = (lp << pt.gbits) | (sh.rnd << sh.gbits) | o;
-                uint64_t before = 0, total = 0;
-                for (int d = 0; d < G; d++) {
-                    const uint64_t n = sh.cnt[((size_t)d * 2 + cls) * P + pp];
-                    if (d < sh.rank) before += n;
-                    total += n;
-                }
-                const int b = cls * P + pp;
-                cur[b] = off + before;
-                lim[b] = cur[b] + sh.cnt[((size_t)sh.rank * 2 + cls) * P + pp];
-                tb[b] = sh.peer[o][BUF_TUPLES];
-                if (!tb[b] && lim[b] > cur[b]) return fail(VDJGRAPH_ERR_STATE, "no tuple buffer for device %d", o);
-                off += total;
-            }
+    uint64_t off[MAX_DEV] = {};
+    sh.n_runs_own = sh.n_gated_own = 0;
+    for (int u = 0; u < NBUCKET; u++) { cur[u] = 0; lim[u] = 0; tb[u] = nullptr; }
+    for (int u = 0; u < NU; u++) {
+        if (sh.round_of[u] != sh.rnd) continue;
+        const int o = sh.owner[u];
+        uint64_t before = 0, total = 0, gated = 0;
+        for (int d = 0; d < G; d++) {
+            const uint64_t n = sh.runs[(size_t)d * NU + u];
+            if (d < sh.rank) before += n;
+            total += n;
+            gated += sh.gated[(size_t)d * NU + u];
+        }
+        cur[u] = off[o] + before;
+        lim[u] = cur[u] + sh.runs[(size_t)sh.rank * NU + u];
+        tb[u] = sh.peer[o][BUF_TUPLES];
+        if (!tb[u]) {
+            if (lim[u] > cur[u]) return fail(VDJGRAPH_ERR_STATE, "no run buffer for device %d", o);
+            tb[u] = sh.peer[sh.rank][BUF_TUPLES];   /* nothing goes there; the kernel only needs "this round" */
+        }
+        off[o] += total;
+        if (o == sh.rank) { sh.n_runs_own += total; sh.n_gated_own += gated; }
     }
-    CK(cudaMemcpyAsync(c->d_cursor.p, cur, 4 * HB * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->d_tbase.p, tb, 2 * HB * sizeof(void *), cudaMemcpyHostToDevice, s));
+    c->part.n_runs = sh.n_runs_own;
+    const Part pt = c->part;
+    CK(cudaMemcpyAsync(c->d_cursor.p, cur, 2 * NBUCKET * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_tbase.p, tb, NBUCKET * sizeof(void *), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), s));
     CK(cudaEventRecord(c->ev[10], s));
     if (g.R) {
         ScatterArgs as;
         as.bases = c->d_bases.as<u64>(); as.good = c->d_good.as<u64>(); as.valid = c->d_valid.as<u64>();
         as.hiq = c->d_hiq.as<u64>();
         as.tbase = c->d_tbase.as<u64 *>();
-        as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + 2 * HB;
+        as.cursor = c->d_cursor.as<u64>(); as.limit = c->d_cursor.as<u64>() + NBUCKET;
         as.rec_base = sh.rec_base[sh.rank];
         as.ctr = c->d_ctr.as<Counters>();
-        const size_t smem_scatter = scatter_carve(nullptr, nullptr, g, 2 * P, pt.wide);
-        const void *fn = seg16 ? (const void *)k_scatter<16> : (const void *)k_scatter<8>;
-        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm(fn, smem_scatter));
-        if (seg16) k_scatter<16><<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
-        else k_scatter<8><<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
+        const size_t smem_scatter = scatter_carve(nullptr, nullptr, g);
+        const int grid_scatter = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_scatter, smem_scatter));
+        k_scatter<<<grid_scatter, THREADS, smem_scatter, s>>>(as, g, pt);
         c->res.kernel_launches++;
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->ev[11], s));
-    if (G > 1) CK(cudaStreamSynchronize(s));   /* the peers' tuples are complete once every device got here */
+    if (G > 1) CK(cudaStreamSynchronize(s));   /* the peers' runs are complete once every device got here */
     sh.phase = 3;
     return 0;
 }
@@ -837,7 +885,7 @@ Reads make_reads(vdjgraph_ctx *c) {
     return rd;
 }
 
-/* K2..K4 on this device's partitions: pass 1, prune, survivor table, pass 2 */
+/* K2..K4 on this device's hash units of the current round: pass 1, prune, survivor table, pass 2 */
 int run_passes(vdjgraph_ctx *c) {
     Shard &sh = c->sh;
     const Geom g = c->g;
@@ -847,10 +895,10 @@ int run_passes(vdjgraph_ctx *c) {
     vdjgraph_result &res = c->res;
     Counters *d_ctr = c->d_ctr.as<Counters>();
     Counters *h_ctr = c->h_ctr.as<Counters>();
-    const int PL = (1 << pt.pbits) >> pt.gbits;
-    const uint64_t n_gated = pt.n_gated, n_valid = pt.n_valid;
+    const uint64_t n_runs = pt.n_runs, n_gated = sh.n_gated_own;
     const Reads rd = make_reads(c);
     const int grid_flat = c->sm_count * 8;
+    const double load1 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD1", 0.5)));
 
     /* pruning constants: T = min(mq, 214) after the <=254 clamp (:1514-1516, :356-360);
      * NB = ceil(T/20) = largest count whose quality sums can still fail */
@@ -858,39 +906,50 @@ int run_passes(vdjgraph_ctx *c) {
     int T = std::min(mq, QSUM_SAT);
     int NB = T > 0 ? (T + GATE_Q - 1) / GATE_Q : 0;
 
-    const uint64_t span = (uint64_t)THREADS * BATCH;
-    const size_t smem_q1 = WARPS * ((pt.wide ? WarpQueue<true, QCAP1>::bytes() : WarpQueue<false, QCAP1>::bytes()) + 2 * HOTC * sizeof(u32));
-    const size_t smem_q = WARPS * (pt.wide ? WarpQueue<true>::bytes() : WarpQueue<false>::bytes());
-    const int grid_p1 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_gated + span - 1) / span,
+    const size_t feed_bytes = (size_t)WARPS * 32 * RUN_WORDS * 8;
+    const size_t smem_q1 = WARPS * ((pt.wide ? WarpQueue<true, QCAP1>::bytes() : WarpQueue<false, QCAP1>::bytes()) + 2 * HOTC * sizeof(u32)) + feed_bytes;
+    const size_t smem_q = WARPS * (pt.wide ? WarpQueue<true>::bytes() : WarpQueue<false>::bytes()) + feed_bytes;
+    const uint64_t n_chunk = (n_runs + THREADS - 1) / THREADS;
+    const int grid_p1 = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_chunk,
                                                 (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, smem_q1)));
-    const int grid_p2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_valid + span - 1) / span,
+    const int grid_p2 = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_chunk,
                                                 (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, smem_q)));
+    UnitTab *ut = c->h_utab.as<UnitTab>();
+    sh.utab.assign(sh.NU, UnitTab{0, 0, 0, 0});
 
-    /* ---- K2 + K3: pass 1 and prune (retried with a larger table if it overflows) ---- */
-    uint64_t cap1 = c->cap1;
+    /* ---- K2 + K3: pass 1 and prune (retried with a larger table / log if they overflow) ---- */
+    uint64_t cap1 = 0;
+    double log_scale = 1.0;
     for (int attempt = 0;; attempt++) {
         if (attempt > 6) return fail(VDJGRAPH_ERR_INTERNAL, "pass-1 table kept overflowing (capacity %llu)", (unsigned long long)cap1);
-        pt.slice1 = (cap1 + PL - 1) / PL;
-        cap1 = pt.slice1 * (uint64_t)PL;
+        /* table-1 slices of this device's units of this round, in unit order */
+        cap1 = 0;
+        for (int u = 0; u < sh.NU; u++) {
+            if (sh.owner[u] != sh.rank || sh.round_of[u] != sh.rnd) continue;
+            const uint64_t len = unit_slots1(sh, c->prm, u, load1);
+            if (cap1 + len > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "pass-1 table would need more than 2^32 slots");
+            sh.utab[u].off1 = (u32)cap1; sh.utab[u].len1 = (u32)len;
+            cap1 += len;
+        }
+        cap1 = std::max<uint64_t>(cap1, 64);
         /* log: one block of NB stamps per distinct k-mer (<= table slots, <= gated windows), plus
          * one partially used chunk of blocks per warp */
         uint64_t warps = (uint64_t)grid_p1 * WARPS;
-        uint64_t log_cap = std::min<uint64_t>(n_gated, cap1) + warps * LOG_CHUNK + LOG_CHUNK;
+        uint64_t log_cap = (uint64_t)((double)std::min<uint64_t>(n_gated, cap1) * log_scale) + warps * LOG_CHUNK + LOG_CHUNK;
         if (NB == 0) log_cap = 1;
         if (log_cap > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "occurrence log would need %llu blocks", (unsigned long long)log_cap);
-        if (cap1 > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "pass-1 table would need %llu slots", (unsigned long long)cap1);
         if ((rc = c->d_t1.ensure(cap1 * sizeof(Slot1)))) return rc;
         if ((rc = c->d_log.ensure(log_cap * (uint64_t)std::max(NB, 1) * sizeof(uint64_t)))) return rc;
         c->cap1 = cap1; c->log_cap = (uint32_t)log_cap;
+        memcpy(ut, sh.utab.data(), sh.NU * sizeof(UnitTab));
+        CK(cudaMemcpyAsync(c->d_utab.p, ut, sh.NU * sizeof(UnitTab), cudaMemcpyHostToDevice, s));
 
-        Counters zero;
-        memset(&zero, 0, sizeof(zero));
-        CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));
+        if (attempt) CK(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), s));   /* first attempt: zeroed before the scatter */
         CK(cudaEventRecord(c->ev[9], s));
         k_init_table1<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1);
         CK(cudaEventRecord(c->ev[2], s));
         Pass1Args a1;
-        a1.tuples = c->d_tuples.as<u64>();
+        a1.runs = c->d_tuples.as<u64>();
         a1.rd = rd;
         a1.table = c->d_t1.as<Slot1>(); a1.cap = cap1;
         a1.log = c->d_log.as<u64>(); a1.log_blocks = (uint32_t)log_cap; a1.nb_ranks = (uint32_t)NB;
@@ -907,32 +966,51 @@ int run_passes(vdjgraph_ctx *c) {
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        if (h_ctr->overflow == 4) return fail(VDJGRAPH_ERR_INTERNAL, "tuple region overrun in k_scatter");
-        if (h_ctr->overflow) { cap1 *= 2; continue; }
-        if (h_ctr->internal && !pt.dbg) return fail(VDJGRAPH_ERR_INTERNAL, "occurrence log inconsistent (code %u)", h_ctr->internal);
+        if (h_ctr->overflow == 4) return fail(VDJGRAPH_ERR_INTERNAL, "run region overrun in k_scatter");
+        if (h_ctr->overflow == 2) { log_scale *= 2.0; continue; }   /* the occurrence log ran out of blocks */
+        if (h_ctr->overflow) {   /* table full or a probe chain past MAX_PROBE: a too small hint is dropped, else more room */
+            if (c->prm.table_capacity && !sh.ignore_hint) sh.ignore_hint = true;
+            else sh.slot_scale *= 2.0;
+            continue;
+        }
+        if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "occurrence log inconsistent (code %u)", h_ctr->internal);
         break;
     }
     const uint64_t n_surv = h_ctr->n_surv;
-    res.n_slow1 += h_ctr->n_slow1;          /* sums over the rounds (zeroed by run_count) */
+    res.n_slow1 += h_ctr->n_slow1;          /* sums over the rounds (zeroed by run_plan) */
     res.n_pre_total += h_ctr->n_distinct;
     res.n_pre += n_surv;
     if (res.n_pre_total > REF_MAX_NODES)
         return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu distinct gated k-mers exceed MAX_NODES (assembler2_vdj.c:73)", (unsigned long long)res.n_pre_total);
 
     /* ---- survivor table + pass 2 ---- */
+    /* table-2 slices: the survivors are spread over the units like the distinct k-mers (no per-unit
+     * survivor count exists; at the default load of 0.25 a unit with twice the average survival
+     * rate runs at 0.5) */
     const double load2 = std::min(0.9, std::max(0.05, env_double("VDJGRAPH_LOAD2", 0.25)));
-    pt.slice2 = (std::max<uint64_t>(1024, (uint64_t)((double)n_surv / load2) + 64) + PL - 1) / PL;
-    const uint64_t cap2 = pt.slice2 * (uint64_t)PL;
-    if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
+    uint64_t cap2 = 0;
+    {
+        double est_own = 0;
+        for (int u = 0; u < sh.NU; u++) if (sh.owner[u] == sh.rank && sh.round_of[u] == sh.rnd) est_own += sh.est[u] + 1.0;
+        for (int u = 0; u < sh.NU; u++) {
+            if (sh.owner[u] != sh.rank || sh.round_of[u] != sh.rnd) continue;
+            const uint64_t len = (uint64_t)((double)n_surv / load2 * (sh.est[u] + 1.0) / est_own) + 64;
+            if (cap2 + len > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "survivor table too large");
+            sh.utab[u].off2 = (u32)cap2; sh.utab[u].len2 = (u32)len;
+            cap2 += len;
+        }
+        cap2 = std::max<uint64_t>(cap2, 64);
+    }
     if ((rc = c->d_t2.ensure(cap2 * sizeof(Slot2)))) return rc;
     c->cap2 = cap2;
-    c->part = pt;
+    memcpy(ut, sh.utab.data(), sh.NU * sizeof(UnitTab));
+    CK(cudaMemcpyAsync(c->d_utab.p, ut, sh.NU * sizeof(UnitTab), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(c->ev[5], s));
     k_init_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t2.as<Slot2>(), cap2);
-    k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, pt, d_ctr);
+    k_build_table2<<<grid_flat, THREADS, 0, s>>>(c->d_t1.as<Slot1>(), cap1, c->d_t2.as<Slot2>(), cap2, g, pt, d_ctr);
     CK(cudaEventRecord(c->ev[6], s));
     Pass2Args a2;
-    a2.tuples = c->d_tuples.as<u64>();
+    a2.runs = c->d_tuples.as<u64>();
     a2.table = c->d_t2.as<Slot2>(); a2.cap = cap2; a2.ctr = d_ctr;
     if (pt.wide) k_pass2<true><<<grid_p2, THREADS, smem_q, s>>>(a2, g, pt);
     else k_pass2<false><<<grid_p2, THREADS, smem_q, s>>>(a2, g, pt);
@@ -994,16 +1072,14 @@ int run_finish(vdjgraph_ctx *c) {
         const Slot2 *records = sh.G > 1 ? c->d_gather.as<Slot2>() : c->d_rec.as<Slot2>();
         n_surv = sh.G > 1 ? sh.surv_off[sh.G] : sh.surv_done;
         /* merged table: its own partitioning (locality does not matter here), no device split */
-        pt.gbits = 0;
-        pt.pbits = 0;
-        pt.slice2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
-        cap2 = pt.slice2;
+        cap2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
         if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "merged survivor table too large");
+        pt.flat = 1; pt.flat_len = (u32)cap2;
         if ((rc = c->d_t2m.ensure(cap2 * sizeof(Slot2)))) return rc;
         table = c->d_t2m.as<Slot2>();
         CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
         k_init_table2<<<grid_flat, THREADS, 0, s>>>(table, cap2);
-        k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(records, n_surv, table, cap2, pt, d_ctr);
+        k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(records, n_surv, table, cap2, g, pt, d_ctr);
         res.kernel_launches += 2;
     }
     const size_t na = std::max<uint64_t>(n_surv, 1);
@@ -1040,7 +1116,7 @@ int run_finish(vdjgraph_ctx *c) {
     CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (h_ctr->overflow) return fail(VDJGRAPH_ERR_INTERNAL, "survivor table overflow (code %u)", h_ctr->overflow);
-    if (h_ctr->internal && !pt.dbg) return fail(VDJGRAPH_ERR_INTERNAL, "export invariant violated (code %u)", h_ctr->internal);
+    if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "export invariant violated (code %u)", h_ctr->internal);
     if (n_surv && h_ctr->n_nodes != n_surv)
         return fail(VDJGRAPH_ERR_INTERNAL, "collected %llu nodes, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
     c->ctr = *h_ctr;
@@ -1052,8 +1128,7 @@ int run_finish(vdjgraph_ctx *c) {
     } else {
         res.n_pre = n_surv;
     }
-    /* per-kernel times of this device's share */
-    cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
+    /* per-kernel times of this device's share (k_count ran with the staging: ms_estimate) */
     if (sh.merged()) {
         res.ms_scatter = sh.acc[0]; res.ms_init1 = sh.acc[1]; res.ms_pass1 = sh.acc[2];
         res.ms_prune = sh.acc[3]; res.ms_table2 = sh.acc[4]; res.ms_pass2 = sh.acc[5];
@@ -1067,7 +1142,7 @@ int run_finish(vdjgraph_ctx *c) {
     }
     cudaEventElapsedTime(&res.ms_export, c->ev[12], c->ev[8]);
     if (sh.G == 1) cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
-    else res.ms_device = res.ms_estimate + res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
+    else res.ms_device = res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
     sh.phase = 7;
     c->ran = true;
     return 0;
@@ -1076,11 +1151,10 @@ int run_finish(vdjgraph_ctx *c) {
 void fill_times_nonfinisher(vdjgraph_ctx *c) {
     vdjgraph_result &res = c->res;
     const Shard &sh = c->sh;
-    cudaEventElapsedTime(&res.ms_estimate, c->ev[0], c->ev[1]);
     res.ms_scatter = sh.acc[0]; res.ms_init1 = sh.acc[1]; res.ms_pass1 = sh.acc[2];
     res.ms_prune = sh.acc[3]; res.ms_table2 = sh.acc[4]; res.ms_pass2 = sh.acc[5];
     res.ms_export = 0;
-    res.ms_device = res.ms_estimate + res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2;
+    res.ms_device = res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2;
 }
 
 } // namespace
@@ -1091,11 +1165,9 @@ extern "C" int vdjgraph_run(vdjgraph_ctx *c) {
     if (c->sh.G != 1) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_run on a sharded context; use the vdjgraph_shard_* phases");
     CK(cudaSetDevice(c->device));
     c->ran = false;
-    make_geom(c, c->g.R);
     int rc;
-    if ((rc = run_count(c))) return rc;
-    if (c->g.R == 0) { c->ran = true; return 0; }
-    if ((rc = run_plan(c, c->h_hist.as<uint64_t>(), c->h_hll.as<uint32_t>()))) return rc;
+    if (c->g.R == 0) { reset_run_stats(c); c->ran = true; return 0; }
+    if ((rc = run_plan(c, c->h_hist.as<uint64_t>(), c->h_hll.as<uint8_t>()))) return rc;
     set_self_peers(c);
     for (int r = 0; r < c->sh.S; r++) {
         c->sh.rnd = r;
@@ -1127,8 +1199,6 @@ static int shard_stage_impl(vdjgraph_ctx *c, const char *primary, size_t np, con
     if (rc) return rc;
     Shard &sh = c->sh;
     sh.G = (int)G; sh.rank = (int)info->rank;
-    sh.gbits = 0;
-    while ((1u << sh.gbits) < G) sh.gbits++;
     sh.total_records = info->total_records;
     memset(sh.rec_base, 0, sizeof(sh.rec_base));
     sh.rec_base[sh.rank] = info->record_base;   /* the others arrive with vdjgraph_shard_plan */
@@ -1147,21 +1217,20 @@ extern "C" int vdjgraph_shard_stage_forward(vdjgraph_ctx *c, const char *primary
     return shard_stage_impl(c, primary_reads, np, secondary_reads, ns, info, 1);
 }
 
-extern "C" int vdjgraph_shard_count(vdjgraph_ctx *c, uint64_t *hist, uint32_t *hll) {
+/* the per-bucket counts and HyperLogLog registers of this rank's staged records (k_count ran with the staging) */
+extern "C" int vdjgraph_shard_count(vdjgraph_ctx *c, uint64_t *hist, uint8_t *hll) {
     if (c && c->staged && c->sh.phase >= 6) c->sh.phase = 0;   /* another build of the same staged records */
     int rc = phase_check(c, 0, "vdjgraph_shard_count");
     if (rc) return rc;
     if (!hist || !hll) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
-    CK(cudaSetDevice(c->device));
     c->ran = false;
-    make_geom(c, c->g.R);
-    if ((rc = run_count(c))) return rc;
-    memcpy(hist, c->h_hist.p, 2 * HB * sizeof(uint64_t));
-    memcpy(hll, c->h_hll.p, sizeof(uint32_t) << HLL_BITS);
+    memcpy(hist, c->h_hist.p, HIST_WORDS * sizeof(uint64_t));
+    memcpy(hll, c->h_hll.p, HLL_BYTES);
+    c->sh.phase = 1;
     return 0;
 }
 
-extern "C" int vdjgraph_shard_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint32_t *hll_merged,
+extern "C" int vdjgraph_shard_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll_merged,
                                    const uint64_t *record_counts) {
     int rc = phase_check(c, 1, "vdjgraph_shard_plan");
     if (rc) return rc;

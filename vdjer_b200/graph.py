@@ -50,6 +50,7 @@ class _Result(C.Structure):
         ("table1_slots", C.c_uint64), ("table2_slots", C.c_uint64),
         ("partitions", C.c_uint32), ("tuple_bytes", C.c_uint32), ("rounds", C.c_uint32), ("reserved", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("n_runs", C.c_uint64), ("run_bytes", C.c_uint32), ("reserved2", C.c_uint32),
     ]
 
 
@@ -73,7 +74,7 @@ EXPORTS = [
     "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
 ]
 
-SHARD_NBUF, SHARD_HIST, SHARD_HLL = 6, 512, 4096
+SHARD_NBUF, SHARD_HIST, SHARD_HLL = 6, 768, 32768   # buffers; uint64 counts; uint8 registers
 BUF_GATHER = 5
 
 
@@ -342,13 +343,13 @@ class GraphBuilder:
 
     def shard_count(self):
         hist = np.zeros(SHARD_HIST, np.uint64)
-        hll = np.zeros(SHARD_HLL, np.uint32)
+        hll = np.zeros(SHARD_HLL, np.uint8)
         self._check(self._lib.vdjgraph_shard_count(self._ctx, hist.ctypes.data, hll.ctypes.data))
         return hist, hll
 
     def shard_plan(self, hist_all: np.ndarray, hll_merged: np.ndarray, record_counts: np.ndarray):
         h = np.ascontiguousarray(hist_all, np.uint64)
-        m = np.ascontiguousarray(hll_merged, np.uint32)
+        m = np.ascontiguousarray(hll_merged, np.uint8)
         r = np.ascontiguousarray(record_counts, np.uint64)
         self._check(self._lib.vdjgraph_shard_plan(self._ctx, h.ctypes.data, m.ctypes.data, r.ctypes.data))
 
@@ -402,7 +403,7 @@ class GraphBuilder:
     def _stats(r: _Result) -> dict:
         return {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
                 for k, _ in _Result._fields_
-                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple", "rounds"))}
+                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple", "rounds", "run_bytes"))}
 
     def _graph(self, r: _Result, copy: bool = True) -> Graph:
         n = int(r.n_nodes)

@@ -30,7 +30,7 @@ RECORD_BYTES = lambda L: 2 * L + 1  # noqa: E731
 def plan_inputs(hists: list[np.ndarray], hlls: list[np.ndarray], counts: list[int]):
     """What every rank hands to vdjgraph_shard_plan, from the all-gathered per-rank pieces."""
     hist_all = np.stack([np.asarray(h, np.uint64) for h in hists])
-    hll = np.maximum.reduce([np.asarray(h, np.uint32) for h in hlls])
+    hll = np.maximum.reduce([np.asarray(h, np.uint8) for h in hlls])   # byte registers: element-wise max
     return hist_all, hll, np.asarray(counts, np.uint64)
 
 
@@ -217,9 +217,9 @@ class DistributedBuilder:
 
         hist, hll = b.shard_count()
         mark()
-        pieces = self._gather(np.concatenate([hist.view(np.uint32), hll]))     # one exchange for both
+        pieces = self._gather(np.concatenate([hist.view(np.uint8), hll]))     # one exchange for both
         mark()
-        n_h = hist.size * 2
+        n_h = hist.size * 8
         hist_all, hll_m, cnt = plan_inputs([x[:n_h].copy().view(np.uint64) for x in pieces], [x[n_h:] for x in pieces], self.counts)
         b.shard_plan(hist_all, hll_m, cnt)
         mark()
