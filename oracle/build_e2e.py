@@ -91,7 +91,6 @@ def patched_sources(tmp: str, gpu: bool) -> list[str]:
                 text = sub_once(text, block,
                                 "#ifdef VDJER_WITH_VDJGRAPH\n"
                                 "\t\tif (vdjgraph_assemble_block(input, unaligned_input, nodes, pool) != 0)\n\t\t\texit(-1);\n"
-                                "\t\tprint_status(\"POST_BUILD_GRAPH2\");\n"
                                 "\t\troot_nodes = identify_root_nodes(nodes);\n"
                                 "#else\n\\1#endif\n\\2", "assemble() block")
         else:

@@ -64,6 +64,12 @@ constexpr int NBUCKET = 1 << HIST_BITS;
 constexpr int BHLL_BITS = 7;     /* HyperLogLog registers (bytes) per bucket: sigma ~ 9 % per bucket, < 1 % over all */
 constexpr int BHLL = 1 << BHLL_BITS;
 constexpr int BATCH = 4;         /* independent table probes a thread keeps in flight */
+#ifndef PASS1_MIN_BLOCKS
+#define PASS1_MIN_BLOCKS 4
+#endif
+#ifndef PASS2_MIN_BLOCKS
+#define PASS2_MIN_BLOCKS 3
+#endif
 constexpr int MINI_M = 10;       /* minimizer length in bases (m = min(k, MINI_M)) */
 constexpr int RUN_MAX = 24;      /* windows per run: two 24-bit flag fields share one word of the run record */
 constexpr int SEG_MAX = 32;      /* windows per thread segment of the streaming kernels (a run never crosses a segment) */
@@ -88,7 +94,9 @@ static_assert(sizeof(Slot1) == 32, "Slot1 must be one sector");
 struct __align__(64) Slot2 {
     u64 klo, khi;
     u32 count;        /* N-free occurrences -> node->frequency */
-    u32 rank;         /* creation rank (node id - 1), filled by k_assign_rank */
+    u32 rank;         /* creation rank (node id - 1), filled by k_assign_rank.  During pass 2: four bytes, byte c =
+                         an upper bound of out_first[c] >> cshift (255 = nothing yet), lowered AFTER out_first[c]: a
+                         window whose coarse stamp is above it cannot lower out_first[c] and skips that sector */
     u64 first_any;    /* min stamp over occurrences -> node->kmer, node id order */
     u64 out_first[4]; /* min stamp of an occurrence followed by base c -> toNodes order */
 };
@@ -107,6 +115,7 @@ struct Geom {
     int m, span;        /* minimizer length min(k, MINI_M); m-mers per window: k - m + 1 */
     u32 mmask;          /* 2m ones */
     int run_max;        /* windows per run: min(RUN_MAX, 64 - k), so that a run's bases fit 128 bits */
+    u32 stage_runs;     /* runs a k_scatter block stages per tile (expected count + margin; the rest go out one by one) */
 };
 
 /* The tables of one device as seen by the kernels: hash unit u (= minimizer bucket >> ushift; a unit
@@ -126,6 +135,7 @@ struct Part {
     u32 flat;           /* 1: one slice [0, flat_len) for every k-mer (the merged table of a sharded / multi-round
                            finish): no minimizer is computed */
     u32 flat_len;
+    u32 cshift;         /* coarse stamp = min(254, stamp >> cshift) */
     u64 n_runs;         /* runs in this device's buffer (this round) */
     const UnitTab *ut;  /* [NBUCKET >> ushift], device memory */
 };
@@ -267,9 +277,18 @@ __device__ __forceinline__ u64 hash_key(u64 lo, u64 hi) {
     h ^= h >> 32;
     return h;
 }
-/* home slot of a k-mer with hash h in the table slice [off, off+len): len < 2^32 (the host checks
- * the table capacities), one 32-bit multiply-high on the upper hash bits */
-__device__ __forceinline__ u32 slot_in(u64 h, u32 off, u32 len) { return off + __umulhi((u32)(h >> 32), len); }
+/* 32-bit hash of a packed k-mer for the table slots (hash_key's three 64-bit multiplies are the
+ * most expensive thing the fast paths of the table passes would do per window) */
+__device__ __forceinline__ u32 hash_slot(u64 lo, u64 hi) {
+    u32 x = (u32)lo * 0x9E3779B1u ^ (u32)(lo >> 32) * 0x85EBCA77u ^ (u32)hi * 0xC2B2AE3Du ^ (u32)(hi >> 32) * 0x27D4EB2Fu;
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12; x *= 0x297A2D39u;
+    x ^= x >> 15;
+    return x;
+}
+/* home slot of a k-mer with slot hash h in the table slice [off, off+len): len < 2^32 (the host
+ * checks the table capacities), one 32-bit multiply-high */
+__device__ __forceinline__ u32 slot_in(u32 h, u32 off, u32 len) { return off + __umulhi(h, len); }
 
 /* Minimizers.  An m-mer (m <= 10 bases, 2 bits each) is hashed to 32 bits; the minimizer value of a
  * k-mer is the SMALLEST hash among its k-m+1 m-mers, a function of the k-mer alone, and the k-mer's
@@ -498,51 +517,55 @@ __device__ __forceinline__ void tiles_issue(const BlockTiles &t, int i, const Ge
     if (gd) tma_load_1d(dst + t.off_d, gd + tile * g.tile_rec * (u64)g.nm, bytes_m, &t.bar[i]);
 }
 
-/* a thread's rolling view of its segment: window i of record `rec`.  start() pulls everything the
- * segment will need out of shared memory into registers (the k-mer of the first window and, for
- * each of the up to SEG_MAX-1 steps plus one look-ahead, the base and mask bits that enter the
- * window), so that a step is a handful of shifts. */
-struct Roll {
-    u64 lo, hi;     /* k-mer of the current window */
-    u64 mv, mg, mh; /* k mask bits: N-free / gate-passing / all phreds >= HIQ (only when started with a hiq array) */
-    u64 nbase;      /* 2-bit codes of the bases i+k, i+k+1, ... (next to enter) */
-    u32 nv, ng, nh; /* their mask bits; bit 0 = position i+k */
-    int i;
-    bool has_h;
-    __device__ __forceinline__ void start(const u64 *sb, const u64 *sg, const u64 *sv, u32 rec, int i0, const Geom &g,
-                                          const u64 *sh = nullptr) {
-        const u64 *b = sb + (size_t)rec * g.nb, *gd = sg + (size_t)rec * g.nm, *v = sv + (size_t)rec * g.nm;
-        i = i0;
-        has_h = sh != nullptr;
-        extract_kmer(b, g.nb, i0, g.kmask_lo, g.kmask_hi, lo, hi);
-        mv = extract_mask(v, g.nm, i0) & g.kones;
-        mg = extract_mask(gd, g.nm, i0) & g.kones;
-        mh = has_h ? extract_mask(sh + (size_t)rec * g.nm, g.nm, i0) & g.kones : 0ull;
-        /* positions i0+k .. i0+k+31 (at most SEG_MAX-1 steps and one look-ahead; beyond the read: zero words / zero bits) */
-        const int j = i0 + g.k;
-        u64 nl, nhi;
-        extract_kmer(b, g.nb, j < 32 * g.nb ? j : 32 * g.nb - 1, ~0ull, 0ull, nl, nhi);
-        nbase = j < 32 * g.nb ? nl : 0ull;
-        const bool in = j < 64 * g.nm;
-        nv = in ? (u32)extract_mask(v, g.nm, j) : 0u;
-        ng = in ? (u32)extract_mask(gd, g.nm, j) : 0u;
-        nh = in && has_h ? (u32)extract_mask(sh + (size_t)rec * g.nm, g.nm, j) : 0u;
+/* 128 bits of a bit array (nw words) starting at bit `bit0`; bits beyond the array read as zero */
+__device__ __forceinline__ void extract_bits128(const u64 *m, int nw, int bit0, u64 &lo, u64 &hi) {
+    const int wi = bit0 >> 6, sh = bit0 & 63;
+    const u64 w0 = wi < nw ? m[wi] : 0ull;
+    const u64 w1 = wi + 1 < nw ? m[wi + 1] : 0ull;
+    const u64 w2 = wi + 2 < nw ? m[wi + 2] : 0ull;
+    if (sh) { lo = (w0 >> sh) | (w1 << (64 - sh)); hi = (w1 >> sh) | (w2 << (64 - sh)); }
+    else { lo = w0; hi = w1; }
+}
+__device__ __forceinline__ void shr128(u64 &lo, u64 &hi, int s) {   /* 0 <= s < 128 */
+    if (s >= 64) { lo = hi >> (s - 64); hi = 0ull; }
+    else if (s) { lo = (lo >> s) | (hi << (64 - s)); hi >>= s; }
+}
+/* Erosion by k: bit i of the result = bits i .. i+k-1 of (lo,hi) are all ones, i.e. "the window that
+ * starts at i passes" for a per-base mask.  Built from erosions by powers of two (E_{a+b}[i] =
+ * E_a[i] & E_b[i+a]): ~2 log2 k shift-and steps for ALL windows of a segment at once, instead of one
+ * rolling mask per window.  Only the low word of the result is used (<= SEG_MAX + 1 windows). */
+__device__ __forceinline__ u64 erode128(u64 lo, u64 hi, int k) {
+    u64 pl = lo, ph = hi, al = ~0ull, ah = ~0ull;
+    int alen = 0;
+    for (int plen = 1; plen <= k; plen <<= 1) {
+        if (k & plen) {
+            u64 tl = pl, th = ph;
+            shr128(tl, th, alen);
+            al &= tl; ah &= th;
+            alen += plen;
+        }
+        u64 tl = pl, th = ph;
+        shr128(tl, th, plen);
+        pl &= tl; ph &= th;
     }
-    /* is there a window i+1, i.e. does base i+k exist and is it ACGT / what is it */
-    __device__ __forceinline__ bool next_valid() const { return nv & 1u; }
-    __device__ __forceinline__ u32 next_base() const { return (u32)nbase & 3u; }
-    /* move to window i+1 (caller guarantees i+1 < w, so base i+k exists) */
-    __device__ __forceinline__ void step(const Geom &g) {
-        kmer_succ(lo, hi, (u32)nbase & 3u, g.k, lo, hi);
-        mv = (mv >> 1) | ((u64)(nv & 1u) << (g.k - 1));
-        mg = (mg >> 1) | ((u64)(ng & 1u) << (g.k - 1));
-        if (has_h) mh = (mh >> 1) | ((u64)(nh & 1u) << (g.k - 1));
-        nbase >>= 2; nv >>= 1; ng >>= 1; nh >>= 1;
-        i++;
+    return al;
+}
+/* the same when windows + k - 1 <= 64 bits are looked at (shifts below 64 only: k <= 50) */
+__device__ __forceinline__ u64 erode64(u64 m, int k) {
+    u64 p = m, a = ~0ull;
+    int alen = 0;
+    for (int plen = 1; plen <= k; plen <<= 1) {
+        if (k & plen) { a &= p >> alen; alen += plen; }
+        p &= p >> plen;
     }
-    __device__ __forceinline__ bool valid(const Geom &g) const { return mv == g.kones; }
-    __device__ __forceinline__ bool gated(const Geom &g) const { return mg == g.kones; }
-};
+    return a;
+}
+/* bit j of the result: the window that starts at bit i0+j of the per-base mask m (nw words) passes */
+__device__ __forceinline__ u64 window_mask(const u64 *m, int nw, int i0, const Geom &g) {
+    u64 lo, hi;
+    extract_bits128(m, nw, i0, lo, hi);
+    return g.seg + g.k <= 64 ? erode64(lo, g.k) : erode128(lo, hi, g.k);
+}
 
 /* Sliding minimum of the m-mer hashes along a segment (the minimizer value of every window),
  * branch-uniform: the m-mer positions are cut into blocks of `span`; a window that starts at offset
@@ -583,42 +606,80 @@ struct Mini {
     }
 };
 
-/* Walks one thread segment (windows i0 .. i0+n-1 of record `rec`) and reports its RUNS: maximal
+/* Walks one thread segment (windows i0 .. i0+n-1 of record `rec`) and finds its RUNS: maximal
  * stretches of consecutive N-free windows whose k-mers fall into the same minimizer bucket, cut
- * at run_max windows and at the segment's end.  on_run(first window, length, bucket, gate bits,
- * all->=HIQ bits, does the window after the run exist and is it N-free); on_gated(k-mer, bucket)
- * for every window that passes the quality gate.  The loop runs g.seg times in every thread so
- * that the warp stays converged for Mini's shared-memory sweeps. */
-template <class OnRun, class OnGated>
-__device__ __forceinline__ void scan_runs(const u64 *sb, const u64 *sg, const u64 *sv, const u64 *sh, u32 rec, int i0, int n,
-                                          const Geom &g, u32 *scratch, OnRun on_run, OnGated on_gated) {
-    Roll r;
+ * at run_max windows and at the segment's end.
+ * Which windows are N-free / gated / all >= HIQ comes from one erosion of the per-base masks per
+ * segment; the window loop rolls only the m-mer and its sliding minimum and notes where a run
+ * starts (bit j of `starts`) and with which bucket (sbk[ordinal * THREADS], a byte array in shared
+ * memory).  It runs g.seg times in every thread, so the warp stays converged for Mini's sweeps.
+ * KMERS: also roll the k-mer itself and call on_gated(k-mer, bucket) for every window that passes
+ * the quality gate (k_count's cardinality registers; the scatter needs m-mers only). */
+struct SegRuns {
+    u64 V, G, H;     /* bit j: window i0+j is N-free / passes the quality gate / has all phreds >= HIQ; V also has bit n */
+    u32 starts;      /* bit j: a run starts at window i0+j */
+    u32 left;        /* starts not yet taken by next() */
+    u32 ord;         /* ordinal of the next run */
+    /* the next run: first window (relative to i0), length; false when there is none */
+    __device__ __forceinline__ bool next(int n, int &s, int &len) {
+        if (!left) return false;
+        s = __ffs((int)left) - 1;
+        left &= left - 1;
+        /* it ends before the next start, the next window that is not N-free, or the segment's end */
+        const u64 stop = ((((u64)starts | ~V) >> s) >> 1) | (1ull << (n - s - 1));
+        len = __ffsll((long long)stop);
+        ord++;
+        return true;
+    }
+    /* does the window after run (s, len) exist, and is it N-free? */
+    __device__ __forceinline__ u32 has_next(int s, int len) const { return (u32)(V >> (s + len)) & 1u; }
+};
+template <bool KMERS, class OnGated>
+__device__ __forceinline__ SegRuns scan_runs(const u64 *sb, const u64 *sg, const u64 *sv, const u64 *sh, u32 rec, int i0, int n,
+                                             const Geom &g, u32 *scratch, u8 *sbk, OnGated on_gated) {
     Mini mn;
     mn.buf = scratch;
-    int run_len = 0, run_a = 0;
-    u32 run_b = 0, gm = 0, hm = 0, minh = 0;
+    SegRuns sr;
+    sr.V = sr.G = sr.H = 0; sr.starts = 0; sr.ord = 0;
+    u64 lo = 0, hi = 0, nbase = 0;
+    if (n > 0) {
+        sr.V = window_mask(sv + (size_t)rec * g.nm, g.nm, i0, g);
+        sr.G = window_mask(sg + (size_t)rec * g.nm, g.nm, i0, g);
+        if (sh) sr.H = window_mask(sh + (size_t)rec * g.nm, g.nm, i0, g);
+        const u64 *b = sb + (size_t)rec * g.nb;
+        extract_kmer(b, g.nb, i0, g.kmask_lo, g.kmask_hi, lo, hi);
+        /* the bases that enter the window: positions i0+k .. i0+k+31 */
+        const int j = i0 + g.k;
+        u64 nl = 0, nh;
+        if (j < 32 * g.nb) extract_kmer(b, g.nb, j, ~0ull, 0ull, nl, nh);
+        nbase = nl;
+    }
+    u32 run_len = 0, run_b = 0, minh = 0, n_starts = 0;
     for (int j = 0; j < g.seg; j++) {
         if (j < n) {
-            if (j == 0) { r.start(sb, sg, sv, rec, i0, g, sh); minh = mn.start(r.lo, r.hi, g); }
-            else { const u32 c = r.next_base(); r.step(g); minh = mn.step(c, g); }
-            const bool v = r.valid(g);
+            if (j == 0) minh = mn.start(lo, hi, g);
+            else {
+                const u32 c = (u32)nbase & 3u;
+                nbase >>= 2;
+                minh = mn.step(c, g);
+                if (KMERS) kmer_succ(lo, hi, c, g.k, lo, hi);
+            }
+            const bool v = (sr.V >> j) & 1ull;
             const u32 b = mini_bucket(minh);
-            if (run_len && (!v || b != run_b || run_len == g.run_max)) {
-                /* the window after the run is this one: it exists, and it is N-free iff v */
-                on_run(run_a, run_len, run_b, gm, hm, v ? 1u : 0u);
+            const bool fresh = v && (run_len == 0 || b != run_b || run_len == (u32)g.run_max);
+            if (fresh) {
+                sbk[n_starts * THREADS] = (u8)b;
+                n_starts++;
+                sr.starts |= 1u << j;
+                run_b = b;
                 run_len = 0;
             }
-            if (v) {
-                if (!run_len) { run_a = r.i; run_b = b; gm = hm = 0; }
-                const bool gt = r.gated(g);
-                gm |= (u32)gt << run_len;
-                hm |= (u32)(r.mh == g.kones) << run_len;
-                run_len++;
-                if (gt) on_gated(r.lo, r.hi, b);
-            }
+            run_len = v ? run_len + 1 : 0;
+            if (KMERS && ((sr.G >> j) & 1ull)) on_gated(lo, hi, b);
         }
     }
-    if (run_len) on_run(run_a, run_len, run_b, gm, hm, (r.i + 1 < g.w && r.next_valid()) ? 1u : 0u);
+    sr.left = sr.starts;
+    return sr;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -631,10 +692,12 @@ __device__ __forceinline__ void scan_runs(const u64 *sb, const u64 *sg, const u6
 /* hist [3][NBUCKET] u64 (runs | gated | N-free), hll [NBUCKET][BHLL] bytes (4 per u32 word).    */
 /* Runs once per staged read set (its results do not depend on mf / mq).                         */
 /* ------------------------------------------------------------------------------------------ */
+__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t count_head_bytes() {
     return ((size_t)NBUCKET * BHLL / 4 + (size_t)3 * NBUCKET) * sizeof(u32);
 }
 __host__ __device__ inline size_t scratch_bytes(const Geom &g) { return (size_t)g.span * THREADS * sizeof(u32); }
+__host__ __device__ inline size_t sbk_bytes(const Geom &g) { return align128((size_t)g.seg * THREADS); }
 /* max of the byte at position idx of a packed byte array */
 __device__ __forceinline__ void byte_max(u32 *words, u32 idx, u32 v, bool global) {
     u32 *wp = words + (idx >> 2);
@@ -649,35 +712,38 @@ __device__ __forceinline__ void byte_max(u32 *words, u32 idx, u32 v, bool global
 }
 __global__ void __launch_bounds__(THREADS)
 k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *__restrict__ valid,
-        Geom g, u32 *hll, u64 *hist /* [3][NBUCKET] */) {
+        Geom g, u64 tile0, u64 tile1 /* tiles [tile0, tile1): one staging chunk, or everything */, u32 *hll, u64 *hist /* [3][NBUCKET] */) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int HW = NBUCKET * BHLL / 4;
     u32 *reg = reinterpret_cast<u32 *>(smem);
     u32 *sh = reg + HW;  /* [3][NBUCKET] */
     for (int i = threadIdx.x; i < HW + 3 * NBUCKET; i += THREADS) reg[i] = 0;
     u32 *scratch = reinterpret_cast<u32 *>(smem + count_head_bytes()) + threadIdx.x;
-    BlockTiles t = tiles_setup(smem + count_head_bytes() + scratch_bytes(g), g, 2);
+    u8 *sbk = smem + count_head_bytes() + scratch_bytes(g) + threadIdx.x;   /* [g.seg][THREADS] run buckets */
+    BlockTiles t = tiles_setup(smem + count_head_bytes() + scratch_bytes(g) + sbk_bytes(g), g, 2);
     const u32 rec = threadIdx.x / (u32)g.segs, i0 = (threadIdx.x % (u32)g.segs) * (u32)g.seg;
     const int n = rec < g.tile_rec ? max(0, min(g.seg, g.w - (int)i0)) : 0;
-    const u64 n_iter = (g.n_tiles + gridDim.x - 1) / gridDim.x;
-    if (threadIdx.x == 0 && blockIdx.x < g.n_tiles) tiles_issue(t, 0, g, blockIdx.x, bases, good, valid);
-    u64 tile = blockIdx.x;
+    const u64 n_iter = (tile1 - tile0 + gridDim.x - 1) / gridDim.x;
+    if (threadIdx.x == 0 && tile0 + blockIdx.x < tile1) tiles_issue(t, 0, g, tile0 + blockIdx.x, bases, good, valid);
+    u64 tile = tile0 + blockIdx.x;
     for (u64 it = 0; it < n_iter; it++, tile += gridDim.x) {
         const int buf = (int)(it & 1);
-        if (tile < g.n_tiles) {
-            if (threadIdx.x == 0 && tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, bases, good, valid);
+        if (tile < tile1) {
+            if (threadIdx.x == 0 && tile + gridDim.x < tile1) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, bases, good, valid);
             mbar_wait(&t.bar[buf], (u32)(it >> 1) & 1);
-            scan_runs(t.a(buf), t.b(buf), t.c(buf), nullptr, rec, (int)i0, n, g, scratch,
-                [&](int, int len, u32 b, u32 gm, u32, u32) {
-                    atomicAdd(&sh[b], 1u);
-                    if (gm) atomicAdd(&sh[NBUCKET + b], (u32)__popc(gm));
-                    atomicAdd(&sh[2 * NBUCKET + b], (u32)len);
-                },
+            SegRuns sr = scan_runs<true>(t.a(buf), t.b(buf), t.c(buf), nullptr, rec, (int)i0, n, g, scratch, sbk,
                 [&](u64 lo, u64 hi, u32 b) {
                     const u64 h = hash_key(lo, hi);
                     /* register = low hash bits, rank = leading zeros of the rest (1..58) */
                     byte_max(reg, b * BHLL + ((u32)h & (BHLL - 1)), (u32)__clzll((long long)(h >> BHLL_BITS)) - (BHLL_BITS - 1), false);
                 });
+            int rs, len;
+            while (sr.next(n, rs, len)) {
+                const u32 b = sbk[(sr.ord - 1) * THREADS], gm = (u32)(sr.G >> rs) & ((1u << len) - 1u);
+                atomicAdd(&sh[b], 1u);
+                if (gm) atomicAdd(&sh[NBUCKET + b], (u32)__popc(gm));
+                atomicAdd(&sh[2 * NBUCKET + b], (u32)len);
+            }
         }
         __syncthreads();   /* everybody is done with buffer `buf` before it is refilled */
         /* u32 counters: flush long before they can overflow (uniform trip count) */
@@ -727,7 +793,6 @@ __device__ __forceinline__ void ld_run(const u64 *p, u64 &a, u64 &b, u64 &c, u64
 /* Runs beyond the list's capacity (a tile with pathologically short runs) are written one by   */
 /* one.  Units of other rounds have no destination and are skipped.                              */
 /* ------------------------------------------------------------------------------------------ */
-constexpr u32 STAGE_RUNS = 1024;
 struct ScatterArgs {
     const u64 *bases, *good, *valid, *hiq;
     u64 *const *tbase; /* [units] tuple buffer of the device that owns the unit (peer-mapped when that is another
@@ -738,29 +803,31 @@ struct ScatterArgs {
     Counters *ctr;
 };
 struct ScatterSmem {
-    u32 *cnt;    /* [NBUCKET] runs of the tile per unit, then the fill cursor of phase 3 */
+    u32 *cnt;    /* [NBUCKET] runs of the tile per unit */
+    u32 *fill;   /* [NBUCKET] fill cursor of phase 3 */
     u32 *boff;   /* [NBUCKET + 1] start of each unit's range in the stage */
     u64 *gbase;  /* [NBUCKET] global run index of the range */
     u64 **dst;   /* [NBUCKET] copy of tbase */
     u32 *fp;     /* [tile_rec] read fingerprint | record-start-all->=HIQ << 31 */
     u32 *n_list; /* runs in the list */
-    u64 *list;   /* [STAGE_RUNS][2] run descriptors */
-    u64 *stage;  /* [STAGE_RUNS][4]; the same memory serves as Mini's scratch while the windows are rolled */
+    u8 *sbk;     /* [g.seg][THREADS] buckets of a thread's runs, in order */
+    u64 *list;   /* [g.stage_runs][2] run descriptors */
+    u64 *stage;  /* [g.stage_runs][4]; the same memory serves as Mini's scratch while the windows are rolled */
     unsigned char *tiles;
 };
-__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *base, const Geom &g) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t at = off; off = align128(off + bytes); return at; };
-    const size_t a_cnt = take((size_t)NBUCKET * 4), a_boff = take((size_t)(NBUCKET + 1) * 4), a_gbase = take((size_t)NBUCKET * 8);
+    const size_t a_cnt = take((size_t)NBUCKET * 4), a_fill = take((size_t)NBUCKET * 4), a_boff = take((size_t)(NBUCKET + 1) * 4), a_gbase = take((size_t)NBUCKET * 8);
     const size_t a_dst = take((size_t)NBUCKET * 8), a_fp = take((size_t)g.tile_rec * 4), a_n = take(16);
-    const size_t a_list = take((size_t)STAGE_RUNS * 16);
-    const size_t stage_b = (size_t)STAGE_RUNS * RUN_WORDS * 8, scr_b = scratch_bytes(g);
+    const size_t a_list = take((size_t)g.stage_runs * 16), a_sbk = take(sbk_bytes(g));
+    const size_t stage_b = (size_t)g.stage_runs * RUN_WORDS * 8, scr_b = scratch_bytes(g);
     const size_t a_stage = take(stage_b > scr_b ? stage_b : scr_b), a_tiles = take(block_tile_bytes(g, 3));
     if (o) {
-        o->cnt = reinterpret_cast<u32 *>(base + a_cnt); o->boff = reinterpret_cast<u32 *>(base + a_boff);
+        o->cnt = reinterpret_cast<u32 *>(base + a_cnt); o->fill = reinterpret_cast<u32 *>(base + a_fill); o->boff = reinterpret_cast<u32 *>(base + a_boff);
         o->gbase = reinterpret_cast<u64 *>(base + a_gbase); o->dst = reinterpret_cast<u64 **>(base + a_dst);
         o->fp = reinterpret_cast<u32 *>(base + a_fp); o->n_list = reinterpret_cast<u32 *>(base + a_n);
+        o->sbk = base + a_sbk;
         o->list = reinterpret_cast<u64 *>(base + a_list); o->stage = reinterpret_cast<u64 *>(base + a_stage);
         o->tiles = base + a_tiles;
     }
@@ -795,7 +862,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
     for (u64 it = 0; it < n_iter; it++, tile += gridDim.x) {
         const int buf = (int)(it & 1);
         if (tile >= g.n_tiles) break;   /* block-uniform */
-        for (int i = threadIdx.x; i < NU; i += THREADS) sm.cnt[i] = 0;
+        for (int i = threadIdx.x; i < NU; i += THREADS) { sm.cnt[i] = 0; sm.fill[i] = 0; }
         if (threadIdx.x == 0) {
             *sm.n_list = 0;
             if (tile + gridDim.x < g.n_tiles) tiles_issue(t, buf ^ 1, g, tile + gridDim.x, a.bases, a.good, a.valid, a.hiq);
@@ -814,26 +881,39 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             sm.fp[r] = ((u32)(h >> 32) & ((1u << RUN_FP_BITS) - 1)) | (rec_hi << 31);
         }
         __syncthreads();   /* fingerprints are read by the overflow path of phase 1 */
-        /* 1. roll the windows: run descriptors -> list, per-unit counts */
-        scan_runs(sb, sg, sv, sh, rec, (int)i0, n, g, scratch,
-            [&](int ra, int len, u32 b, u32 gm, u32 hm, u32 nx) {
-                const u32 u = b >> pt.ushift;
-                if (!sm.dst[u]) return;   /* another round's share of the hash space */
-                const u64 d0 = (u64)gm | ((u64)hm << 24) | ((u64)(len - 1) << 48) | ((u64)nx << 53);
-                const u64 d1 = (u64)rec | ((u64)ra << 16) | ((u64)b << 24);
-                const u32 e = atomicAdd(sm.n_list, 1u);
-                if (e < STAGE_RUNS) {
-                    sm.list[2 * e] = d0; sm.list[2 * e + 1] = d1;
-                    atomicAdd(&sm.cnt[u], 1u);
-                } else {   /* list full: this run goes out on its own */
-                    u64 w0, w1, w2, w3;
-                    build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
-                    const u64 at = atomicAdd(&a.cursor[u], 1ull);
-                    if (at < a.limit[u]) st_sector(sm.dst[u] + at * RUN_WORDS, w0, w1, w2, w3);
-                    else atomicExch(&a.ctr->overflow, 4u);
+        /* 1. roll the windows, then (warp-converged) run descriptors -> list, per-unit counts */
+        {
+            SegRuns sr = scan_runs<false>(sb, sg, sv, sh, rec, (int)i0, n, g, scratch, sm.sbk + threadIdx.x, [](u64, u64, u32) {});
+            for (;;) {
+                int rs = 0, len = 1;
+                const bool has = sr.next(n, rs, len);
+                if (!__ballot_sync(0xFFFFFFFFu, has)) break;
+                const u32 b = has ? sm.sbk[(sr.ord - 1) * THREADS + threadIdx.x] : 0u, u = b >> pt.ushift;
+                const bool ship = has && sm.dst[u];   /* no destination: another round's share of the hash space */
+                const u32 ball = __ballot_sync(0xFFFFFFFFu, ship);
+                if (!ball) continue;
+                u32 e0 = 0;
+                if (lane == 0) e0 = atomicAdd(sm.n_list, (u32)__popc(ball));
+                e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+                if (ship) {
+                    const u32 lm = (1u << len) - 1u;
+                    const u64 d0 = (u64)((u32)(sr.G >> rs) & lm) | ((u64)((u32)(sr.H >> rs) & lm) << 24) | ((u64)(len - 1) << 48) |
+                                   ((u64)sr.has_next(rs, len) << 53);
+                    const u64 d1 = (u64)rec | ((u64)(i0 + rs) << 16) | ((u64)b << 24);
+                    const u32 e = e0 + (u32)__popc(ball & ((1u << lane) - 1u));
+                    if (e < g.stage_runs) {
+                        sm.list[2 * e] = d0; sm.list[2 * e + 1] = d1;
+                        atomicAdd(&sm.cnt[u], 1u);
+                    } else {   /* list full: this run goes out on its own */
+                        u64 w0, w1, w2, w3;
+                        build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
+                        const u64 at = atomicAdd(&a.cursor[u], 1ull);
+                        if (at < a.limit[u]) st_sector(sm.dst[u] + at * RUN_WORDS, w0, w1, w2, w3);
+                        else atomicExch(&a.ctr->overflow, 4u);
+                    }
                 }
-            },
-            [&](u64, u64, u32) {});
+            }
+        }
         __syncthreads();
         /* 2. reserve the global ranges; stage offsets = exclusive scan of the counts */
         for (int u = threadIdx.x; u < NU; u += THREADS) {
@@ -859,16 +939,14 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             if (lane == 31) sm.boff[NU] = run;
         }
         __syncthreads();
-        for (int u = threadIdx.x; u < NU; u += THREADS) sm.cnt[u] = 0;   /* now the fill cursors */
-        __syncthreads();
         /* 3. build the runs into the stage, unit by unit */
-        const u32 n_list = min(*sm.n_list, STAGE_RUNS);
+        const u32 n_list = min(*sm.n_list, g.stage_runs);
         for (u32 e = threadIdx.x; e < n_list; e += THREADS) {
             const u64 d0 = sm.list[2 * e], d1 = sm.list[2 * e + 1];
             const u32 u = ((u32)(d1 >> 24) & 0xFFu) >> pt.ushift;
             u64 w0, w1, w2, w3;
             build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
-            u64 *dst = sm.stage + (size_t)(sm.boff[u] + atomicAdd(&sm.cnt[u], 1u)) * RUN_WORDS;
+            u64 *dst = sm.stage + (size_t)(sm.boff[u] + atomicAdd(&sm.fill[u], 1u)) * RUN_WORDS;
             dst[0] = w0; dst[1] = w1; dst[2] = w2; dst[3] = w3;
         }
         fence_proxy_async();     /* the stage was written with ordinary stores */
@@ -969,6 +1047,20 @@ struct WarpQueue {
         idx = reinterpret_cast<u32 *>(w1 + (WIDE ? 2 : 1) * QC);
     }
     __host__ __device__ static constexpr size_t bytes() { return (size_t)QC * (WIDE ? 28 : 20); }
+    /* the same, the tuple words being built (by the deferred lanes only) by make(t1, t2) */
+    template <class Make>
+    __device__ __forceinline__ u32 push_lazy(u32 qn, bool defer, u64 l, u32 i, Make make) {
+        const u32 lane = threadIdx.x & 31;
+        const u32 ballot = __ballot_sync(0xFFFFFFFFu, defer);
+        if (defer) {
+            const u32 pos = qn + __popc(ballot & ((1u << lane) - 1));
+            u64 a, b;
+            make(a, b);
+            lo[pos] = l; w1[pos] = a; idx[pos] = i;
+            if (WIDE) w2[pos] = b;
+        }
+        return qn + __popc(ballot);
+    }
     /* warp-converged push of the lanes with `defer` set; returns the new count */
     __device__ __forceinline__ u32 push(u32 qn, bool defer, u64 l, u64 a, u64 b, u32 i) {
         const u32 lane = threadIdx.x & 31;
@@ -984,12 +1076,26 @@ struct WarpQueue {
 
 /* Expansion of runs into per-window tuples.  A warp takes 32 runs at a time (one per lane, parked
  * in shared memory), counts the windows this pass looks at (pass 1: the gated ones, pass 2: all) and
- * deals them out evenly: window t of the chunk belongs to the run l whose inclusive prefix count is
- * the first one above t (five shuffles), and is that run's (t - exclusive prefix)-th selected window.
- * Every lane thus holds BATCH independent windows whatever the run lengths are. */
+ * deals them out evenly: every lane takes BATCH CONSECUTIVE windows of the chunk's window sequence.
+ * The first one is located by a search over the runs' prefix counts (five shuffles); from there a
+ * cursor walks the selected windows of the run and steps into the next run when it is used up, so
+ * that everything that is per run (stamp, fingerprint, table slice) is decoded once per run, not
+ * per window.  Every lane holds BATCH independent windows whatever the run lengths are. */
+struct RunCursor {
+    u64 w0, w1, w2;     /* the run's bases and flag word */
+    u64 stamp0;         /* stamp of its window 0 */
+    u32 off, len;       /* table slice of its hash unit */
+    u32 l;              /* run index in the chunk */
+    u32 j;              /* current window */
+    u32 rem;            /* selected windows above j, shifted down by j+1 */
+};
 struct RunFeed {
     u64 *rw;        /* [32][RUN_WORDS] this warp's chunk */
     u32 cnt, incl, total;
+    template <bool GATED_ONLY>
+    __device__ __forceinline__ static u32 selected(u64 w2) {
+        return GATED_ONLY ? (u32)w2 & 0xFFFFFFu : (1u << run_len(w2)) - 1u;   /* run_len <= 24 */
+    }
     template <bool GATED_ONLY>
     __device__ __forceinline__ void load(const u64 *runs, u64 ri, u64 n_runs) {
         const u32 lane = threadIdx.x & 31;
@@ -997,54 +1103,88 @@ struct RunFeed {
         cnt = 0;
         if (ri < n_runs) {
             ld_run(runs + ri * RUN_WORDS, w0, w1, w2, w3);
-            cnt = GATED_ONLY ? (u32)__popc((u32)w2 & 0xFFFFFFu) : run_len(w2);
+            cnt = (u32)__popc(selected<GATED_ONLY>(w2));
         }
         incl = cnt;
         for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
         total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         __syncwarp();
         u64 *p = rw + lane * RUN_WORDS;
-        p[0] = w0; p[1] = w1; p[2] = w2; p[3] = w3;
+        p[0] = w0; p[1] = w1; p[2] = ri < n_runs ? w2 : 0ull; p[3] = w3;
         __syncwarp();
     }
-    /* window t (< total) of the chunk: the run's words and the window's index in the run.  Warp-converged. */
-    template <bool GATED_ONLY>
-    __device__ __forceinline__ void locate(u32 t, u64 &w0, u64 &w1, u64 &w2, u64 &w3, u32 &j) const {
+    /* decode run c.l; TAB2: the slice of table 2, else of table 1 */
+    template <bool TAB2>
+    __device__ __forceinline__ void open(RunCursor &c, const Part &pt) const {
+        const u64 *p = rw + c.l * RUN_WORDS;
+        c.w0 = p[0]; c.w1 = p[1]; c.w2 = p[2];
+        const u64 w3 = p[3];
+        c.stamp0 = w3 & ((1ull << STAMP_BITS) - 1);
+        const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (run_bucket(w3) >> pt.ushift)));   /* off1, len1, off2, len2 */
+        c.off = TAB2 ? ut.z : ut.x;
+        c.len = TAB2 ? ut.w : ut.y;
+    }
+    /* position the cursor on window t (< total) of the chunk.  Warp-converged (shuffles). */
+    template <bool GATED_ONLY, bool TAB2>
+    __device__ __forceinline__ void seek(u32 t, RunCursor &c, const Part &pt) const {
         u32 l = 0;
 #pragma unroll
         for (int s = 16; s; s >>= 1) { const u32 v = __shfl_sync(0xFFFFFFFFu, incl, l + s - 1); if (v <= t) l += s; }
         u32 nth = t - __shfl_sync(0xFFFFFFFFu, incl - cnt, l);
-        const u64 *p = rw + l * RUN_WORDS;
-        w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
-        if (GATED_ONLY) {   /* position of the nth set gate bit */
-            u32 m = (u32)w2 & 0xFFFFFFu;
-            j = 0;
+        c.l = l;
+        open<TAB2>(c, pt);
+        u32 m = selected<GATED_ONLY>(c.w2), j = 0;
+        if (GATED_ONLY) {   /* position of the nth set bit */
 #pragma unroll
             for (int s = 16; s; s >>= 1) {
-                const u32 c = (u32)__popc(m & ((1u << s) - 1u));
-                if (nth >= c) { nth -= c; m >>= s; j += s; }
+                const u32 k = (u32)__popc(m & ((1u << s) - 1u));
+                if (nth >= k) { nth -= k; m >>= s; j += s; }
             }
+            m >>= 1;
         } else {
             j = nth;
+            m >>= j + 1;
         }
+        c.j = j; c.rem = m;
+    }
+    /* the fingerprint carried by run l (fb bits) */
+    __device__ __forceinline__ u32 fingerprint(u32 l, const Part &pt) const {
+        const u64 *p = rw + l * RUN_WORDS;
+        return (((u32)(p[3] >> 48) & 0xFFFFu) | (((u32)(p[2] >> 55) & 0x1FFu) << 16)) & (u32)((1ull << pt.fb) - 1);
+    }
+    /* the next selected window of the chunk (the caller knows there is one) */
+    template <bool GATED_ONLY, bool TAB2>
+    __device__ __forceinline__ void next(RunCursor &c, const Part &pt) const {
+        if (c.rem) {
+            const u32 s = (u32)__ffs((int)c.rem);
+            c.j += s; c.rem >>= s;
+            return;
+        }
+        u32 m = 0;
+        while (!m && c.l < 31) { c.l++; m = selected<GATED_ONLY>(rw[c.l * RUN_WORDS + 2]); }
+        open<TAB2>(c, pt);
+        const u32 s = m ? (u32)__ffs((int)m) : 1u;
+        c.j = s - 1; c.rem = m >> s;
     }
 };
-/* window j of a run -> its k-mer and its tuple words (the form the slow-path queues hold) */
-template <bool WIDE>
-__device__ __forceinline__ void run_window(const Geom &g, const Part &pt, u64 w0, u64 w1, u64 w2, u64 w3, u32 j,
-                                           u64 &lo, u64 &hi, u64 &t1, u64 &t2, bool &gated, u32 &bucket) {
-    const u32 sh = 2u * j;   /* <= 46 */
-    lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
-    hi = w1 >> sh;
+/* the cursor's window -> its k-mer and home slot: all the fast path of pass 1 needs */
+__device__ __forceinline__ void run_kmer(const Geom &g, const RunCursor &c, u64 &lo, u64 &hi, u32 &idx) {
+    const u32 sh = 2u * c.j;   /* <= 46 */
+    lo = sh ? (c.w0 >> sh) | (c.w1 << (64 - sh)) : c.w0;
+    hi = c.w1 >> sh;
     lo &= g.kmask_lo; hi &= g.kmask_hi;
+    idx = slot_in(hash_slot(lo, hi), c.off, c.len);
+}
+/* flag bits of window j of a run (FLB bits: has-next, next base, window all >= HIQ, record start all >= HIQ) */
+__device__ __forceinline__ u32 run_flags(const Geom &g, u64 w0, u64 w1, u64 w2, u32 j) {
     const u32 p = j + (u32)g.k;   /* the base after the window: position <= 63 of the run's bases */
-    const u32 c = (u32)((p < 32 ? w0 >> (2 * p) : w1 >> (2 * (p - 32)))) & 3u;
+    const u32 nb = (u32)((p < 32 ? w0 >> (2 * p) : w1 >> (2 * (p - 32)))) & 3u;
     const bool has_next = j + 1 < run_len(w2) || ((w2 >> 53) & 1ull);
-    const u32 fl = (has_next ? 1u | (c << 1) : 0u) | ((u32)(w2 >> (24 + j)) & 1u) << 3 | ((u32)(w2 >> 54) & 1u) << 4;
-    const u32 fp = (((u32)(w3 >> 48) & 0xFFFFu) | (((u32)(w2 >> 55) & 0x1FFu) << 16)) & (u32)((1ull << pt.fb) - 1);
-    const u64 stamp = (w3 & ((1ull << STAMP_BITS) - 1)) + j;
-    gated = (w2 >> j) & 1ull;
-    bucket = run_bucket(w3);
+    return (has_next ? 1u | (nb << 1) : 0u) | ((u32)(w2 >> (24 + j)) & 1u) << 3 | ((u32)(w2 >> 54) & 1u) << 4;
+}
+/* tuple words (the form the slow-path queues hold) of a window with these flags, fingerprint and stamp */
+template <bool WIDE>
+__device__ __forceinline__ void pack_tuple(const Part &pt, u64 hi, u32 fl, u32 fp, u64 stamp, u64 &t1, u64 &t2) {
     t1 = hi | ((u64)fl << pt.hb) | ((u64)fp << (pt.hb + FLB));
     if (WIDE) t2 = stamp;
     else { t1 |= stamp << (pt.hb + FLB + pt.fb); t2 = 0; }
@@ -1171,7 +1311,7 @@ __device__ __forceinline__ void hot_flush(Slot1 *table, u32 *hidx, u32 *hcnt) {
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, PASS1_MIN_BLOCKS)
 k_pass1(Pass1Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
     WarpQueue<WIDE, QCAP1> q;
@@ -1192,18 +1332,23 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
     for (u64 chunk = blockIdx.x; chunk < n_chunk; chunk += gridDim.x) {
         feed.load<true>(a.runs, chunk * THREADS + threadIdx.x, pt.n_runs);
         for (u32 base = 0; base < feed.total; base += 32 * BATCH) {
-            u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], k0[BATCH], k1[BATCH], m2[BATCH], hi[BATCH];
+            u64 lo[BATCH], k0[BATCH], k1[BATCH], m2[BATCH], hi[BATCH];
             u32 idx[BATCH];   /* table capacities stay below 2^32 slots (checked on the host) */
-            /* A1: this lane's windows of the batch -> k-mer, tuple words, home slot */
+            u32 ref[BATCH];   /* run in the chunk | window in the run << 8 */
+            /* A1: this lane's BATCH consecutive windows of the chunk -> k-mer, home slot */
+            {
+                const u32 t0 = base + lane * BATCH;
+                RunCursor cur;
+                feed.seek<true, false>(min(t0, feed.total - 1), cur, pt);
 #pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                const u32 t = base + (u32)u * 32u + lane;
-                u64 r0, r1, r2, r3, t2; u32 j, bucket; bool gated;
-                feed.locate<true>(min(t, feed.total - 1), r0, r1, r2, r3, j);
-                run_window<WIDE>(g, pt, r0, r1, r2, r3, j, lo[u], hi[u], w1[u], t2, gated, bucket);
-                if (WIDE) w2[u] = t2;
-                const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (bucket >> pt.ushift)));   /* off1, len1, off2, len2 */
-                idx[u] = t < feed.total ? slot_in(hash_key(lo[u], hi[u]), ut.x, ut.y) : NIL32;
+                for (int u = 0; u < BATCH; u++) {
+                    lo[u] = hi[u] = 0; idx[u] = NIL32; ref[u] = 0;
+                    if (t0 + u < feed.total) {
+                        if (u) feed.next<true, false>(cur, pt);
+                        run_kmer(g, cur, lo[u], hi[u], idx[u]);
+                        ref[u] = cur.l | (cur.j << 8);
+                    }
+                }
             }
             issue_fence(idx[0], idx[1], idx[2], idx[3]);
             /* A2: the home slots, all loads in flight together */
@@ -1216,7 +1361,8 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
                 }
             }
             /* B: fast path = the k-mer sits in its home slot, is already known to come from several
-             * reads and has passed the logging ranks: one RED.  Everything else is queued. */
+             * reads and has passed the logging ranks: one RED.  Everything else is queued, with its
+             * flags, fingerprint and stamp (only now read from the run). */
 #pragma unroll
             for (int u = 0; u < BATCH; u++) {
                 const bool valid = idx[u] != NIL32;
@@ -1231,7 +1377,12 @@ k_pass1(Pass1Args a, Geom g, Part pt) {
                     }
                     if (!cached) atomicAdd(&a.table[idx[u]].count, 1u);
                 }
-                qn = q.push(qn, valid && !fast, lo[u], w1[u], w2[WIDE ? u : 0], idx[u]);
+                qn = q.push_lazy(qn, valid && !fast, lo[u], idx[u], [&](u64 &t1, u64 &t2) {
+                    const u32 l = ref[u] & 0xFFu, j = ref[u] >> 8;
+                    const u64 *p = feed.rw + l * RUN_WORDS;
+                    pack_tuple<WIDE>(pt, hi[u], run_flags(g, p[0], p[1], p[2], j), feed.fingerprint(l, pt),
+                                     (p[3] & ((1ull << STAMP_BITS) - 1)) + j, t1, t2);
+                });
             }
             if (++since_flush >= pt.hot_flush) {
                 since_flush = 0;
@@ -1384,7 +1535,7 @@ __device__ __forceinline__ u64 t2_probe_from(const Slot2 *t, u64 cap, u64 idx, u
 }
 /* home slot of an arbitrary k-mer in table 2: in the slice of its hash unit, or anywhere in a flat (merged) table */
 __device__ __forceinline__ u32 t2_home(const Part &pt, const Geom &g, u64 lo, u64 hi) {
-    const u64 h = hash_key(lo, hi);
+    const u32 h = hash_slot(lo, hi);
     if (pt.flat) return slot_in(h, 0u, pt.flat_len);
     const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (kmer_bucket_of(lo, hi, g.span, g.mmask) >> pt.ushift)));
     return slot_in(h, ut.z, ut.w);
@@ -1483,11 +1634,25 @@ struct Pass2Args {
     Counters *ctr;
 };
 
-/* reductions of one pass-2 hit; c2/c3/o are the loaded count word, first_any and out_first[c] */
-__device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2, u64 c3, u64 o, bool has_next, u32 c, u64 stamp) {
+__device__ __forceinline__ u32 coarse_stamp(u64 stamp, u32 cshift) { return (u32)min((u64)254, stamp >> cshift); }
+/* can a window with this stamp, followed by base c, still lower out_first[c]?  c2 = the slot's count | coarse word */
+__device__ __forceinline__ bool edge_open(u64 c2, u32 c, u32 coarse) { return coarse <= ((u32)(c2 >> (32 + 8 * c)) & 0xFFu); }
+/* reductions of one pass-2 hit; c2/c3/o are the loaded count word, first_any and out_first[c]
+ * (o is only looked at when edge_open) */
+__device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2, u64 c3, u64 o, bool edge, u32 c, u64 stamp, u32 coarse) {
     if (count_it && (u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
     if (stamp < c3) atomicMin(&slot->first_any, stamp);
-    if (has_next && stamp < o) atomicMin(&slot->out_first[c], stamp);
+    if (edge && stamp < o) {
+        atomicMin(&slot->out_first[c], stamp);
+        /* then (never before) lower the coarse bound in the hot sector */
+        const u32 sh = 8 * c;
+        u32 cur = *reinterpret_cast<volatile u32 *>(&slot->rank);
+        while (((cur >> sh) & 0xFFu) > coarse) {
+            const u32 old = atomicCAS(&slot->rank, cur, (cur & ~(0xFFu << sh)) | (coarse << sh));
+            if (old == cur) break;
+            cur = old;
+        }
+    }
 }
 
 /* slow path of pass 2: tuples whose home slot holds a different k-mer; queue entries carry the
@@ -1525,11 +1690,11 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, W
             u64 q0, q1, q2, q3;
             ld_sector(slot, q0, q1, q2, q3);
             if (q0 == lo && q1 == hi) {
-                const bool has_next = fl & 1u;
-                const u32 c = (fl >> 1) & 3u;
+                const u32 c = (fl >> 1) & 3u, coarse = coarse_stamp(stamp, pt.cshift);
+                const bool edge = (fl & 1u) && edge_open(q2, c, coarse);
                 u64 o = 0;
-                if (has_next) o = ld_cg_u64(&slot->out_first[c]);
-                pass2_update(slot, count_it, q2, q3, o, has_next, c, stamp);
+                if (edge) o = ld_cg_u64(&slot->out_first[c]);
+                pass2_update(slot, count_it, q2, q3, o, edge, c, stamp, coarse);
                 n_hits++;
                 n_hits_u += count_it;
                 have = false;
@@ -1546,7 +1711,7 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, W
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, PASS2_MIN_BLOCKS)
 k_pass2(Pass2Args a, Geom g, Part pt) {
     extern __shared__ __align__(128) unsigned char smem[];
     WarpQueue<WIDE> q;
@@ -1559,31 +1724,41 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
     for (u64 chunk = blockIdx.x; chunk < n_chunk; chunk += gridDim.x) {
         feed.load<false>(a.runs, chunk * THREADS + threadIdx.x, pt.n_runs);
         for (u32 base = 0; base < feed.total; base += 32 * BATCH) {
-            u64 lo[BATCH], w1[BATCH], w2[WIDE ? BATCH : 1], hi[BATCH], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
-            u32 idx[BATCH], ung = 0;
-            /* A1: this lane's windows of the batch */
+            u64 lo[BATCH], hi[BATCH], stamp[BATCH], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
+            u32 idx[BATCH], fl[BATCH];   /* fl: the window's FLB flag bits | gated << FLB */
+            /* A1: this lane's BATCH consecutive windows of the chunk */
+            {
+                const u32 t0 = base + lane * BATCH;
+                RunCursor cur;
+                feed.seek<false, true>(min(t0, feed.total - 1), cur, pt);
 #pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                const u32 t = base + (u32)u * 32u + lane;
-                u64 r0, r1, r2, r3, t2; u32 j, bucket; bool gated;
-                feed.locate<false>(min(t, feed.total - 1), r0, r1, r2, r3, j);
-                run_window<WIDE>(g, pt, r0, r1, r2, r3, j, lo[u], hi[u], w1[u], t2, gated, bucket);
-                if (WIDE) w2[u] = t2;
-                if (!gated) ung |= 1u << u;
-                const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (bucket >> pt.ushift)));
-                idx[u] = t < feed.total ? slot_in(hash_key(lo[u], hi[u]), ut.z, ut.w) : NIL32;
+                for (int u = 0; u < BATCH; u++) {
+                    lo[u] = hi[u] = stamp[u] = 0; idx[u] = NIL32; fl[u] = 0;
+                    if (t0 + u < feed.total) {
+                        if (u) feed.next<false, true>(cur, pt);
+                        run_kmer(g, cur, lo[u], hi[u], idx[u]);
+                        fl[u] = run_flags(g, cur.w0, cur.w1, cur.w2, cur.j) | ((u32)(cur.w2 >> cur.j) & 1u) << FLB;
+                        stamp[u] = cur.stamp0 + cur.j;
+                    }
+                }
             }
             issue_fence(idx[0], idx[1], idx[2], idx[3]);
-            /* A2: the hot sector of the home slot and, speculatively, the out_first word this
-             * window would update; all loads of the batch in flight together */
+            /* A2: the hot sector of the home slot, all loads of the batch in flight together */
 #pragma unroll
             for (int u = 0; u < BATCH; u++) {
-                q0[u] = q1[u] = q2[u] = q3[u] = of[u] = 0;
-                if (idx[u] != NIL32) {
-                    const u32 fl = (u32)(w1[u] >> pt.hb) & 7u;
-                    const Slot2 *s = a.table + idx[u];
-                    ld_sector_ca(s, q0[u], q1[u], q2[u], q3[u]);
-                    if (fl & 1u) of[u] = ld_ca_u64(&s->out_first[fl >> 1]);
+                q0[u] = q1[u] = q2[u] = q3[u] = 0;
+                if (idx[u] != NIL32) ld_sector_ca(a.table + idx[u], q0[u], q1[u], q2[u], q3[u]);
+            }
+            /* A3: the out_first word a hit would update -- only when the coarse bound in the hot sector says
+             * this window can still lower it (the first occurrences of an edge; later ones cost one sector) */
+            u32 edges = 0;
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                of[u] = 0;
+                if (idx[u] != NIL32 && q0[u] == lo[u] && q1[u] == hi[u] && (fl[u] & 1u) &&
+                    edge_open(q2[u], (fl[u] >> 1) & 3u, coarse_stamp(stamp[u], pt.cshift))) {
+                    edges |= 1u << u;
+                    of[u] = ld_ca_u64(&a.table[idx[u]].out_first[(fl[u] >> 1) & 3u]);
                 }
             }
             /* B: hit at home -> reductions; empty home -> the k-mer did not survive; otherwise queue.
@@ -1592,17 +1767,18 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
 #pragma unroll
             for (int u = 0; u < BATCH; u++) {
                 const bool valid = idx[u] != NIL32;
-                const bool ungated = (ung >> u) & 1u;
-                u64 khi, stamp; u32 fl, fp;
-                tuple_decode<WIDE>(pt, w1[u], w2[WIDE ? u : 0], khi, fl, fp, stamp);
+                const bool ungated = !((fl[u] >> FLB) & 1u);
                 const bool hit = valid && q0[u] == lo[u] && q1[u] == hi[u];
                 const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
                 if (hit) {
-                    pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], fl & 1u, (fl >> 1) & 3u, stamp);
+                    pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], (edges >> u) & 1u, (fl[u] >> 1) & 3u, stamp[u],
+                                 coarse_stamp(stamp[u], pt.cshift));
                     n_hits++;
                     n_hits_u += ungated;
                 }
-                qn = q.push(qn, valid && !hit && !empty, lo[u], w1[u], w2[WIDE ? u : 0], idx[u] | (ungated ? 0x80000000u : 0u));
+                qn = q.push_lazy(qn, valid && !hit && !empty, lo[u], idx[u] | (ungated ? 0x80000000u : 0u), [&](u64 &t1, u64 &t2) {
+                    pack_tuple<WIDE>(pt, hi[u], fl[u] & ((1u << FLB) - 1), 0u, stamp[u], t1, t2);
+                });
             }
             if (qn >= pt.qflush2) {
                 n_slow += qn; n_hits += pass2_drain<WIDE>(a, pt, q, qn, false, n_hits_u); n_slow -= qn;

@@ -188,6 +188,8 @@ struct vdjgraph_ctx {
     DevBuf d_pre_klo, d_pre_khi, d_pre_freq, d_pre_n;
     PinBuf h_ctr, h_hll, h_hist, h_cursor, h_utab;
     float ms_count = 0;
+    size_t count_smem = 0;
+    int count_bps = 1;
     Part part;
     PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
@@ -241,6 +243,10 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     tr &= ~1u;   /* even: TMA bulk copies need 16-byte sizes and addresses */
     g.tile_rec = tr;
     g.n_tiles = (R + tr - 1) / tr;
+    /* runs a tile is expected to hold: one per segment plus one per minimizer change (every (span+1)/2
+     * windows on random sequence), with a third on top; tiles with more spill to single stores */
+    const double expect = (double)tr * g.segs + (double)tr * g.w * 2.0 / (g.span + 1);
+    g.stage_runs = (uint32_t)std::min<double>(2048.0, std::max(256.0, std::ceil(expect * 1.35 / 128.0) * 128.0));
     c->R_pad = g.n_tiles * g.tile_rec;
 }
 
@@ -259,6 +265,14 @@ int ensure_workers(vdjgraph_ctx *c, int n) {
 /* Staging = raw text to the device + k_pack there.  The host only moves bytes: worker threads
  * copy chunks of the caller's (pageable) buffers into their page-locked buffers and queue the
  * H2D copy and the chunk's k_pack launch on their own stream, double buffered. */
+/* text records per staging chunk: a multiple of the streaming kernels' tile, so that a chunk's packed
+ * records are whole tiles and k_count can run on them right behind k_pack */
+uint64_t chunk_records(const vdjgraph_ctx *c, uint32_t base) {
+    const uint64_t tr = c->g.tile_rec;
+    return std::max<uint64_t>(tr, (base / tr) * tr);
+}
+int count_chunk(vdjgraph_ctx *c, cudaStream_t s, uint64_t rec_lo, uint64_t rec_hi, bool last);
+
 struct StageShared {
     vdjgraph_ctx *c;
     const char *primary, *secondary;
@@ -274,12 +288,13 @@ void stage_worker(StageShared *s, int wi) {
     const Geom &g = c->g;
     if (cudaSetDevice(c->device) != cudaSuccess) { s->status = VDJGRAPH_ERR_CUDA; return; }
     const size_t rec_len = (size_t)2 * g.L + 1;
-    const uint64_t n_chunks = (s->R + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    const uint64_t CH = chunk_records(c, STAGE_CHUNK);
+    const uint64_t n_chunks = (s->R + CH - 1) / CH;
     int b = 0;
     for (;;) {
         uint64_t ch = s->next_chunk.fetch_add(1);
         if (ch >= n_chunks || s->status.load() != 0) break;
-        const uint64_t r_lo = ch * STAGE_CHUNK, r_hi = std::min<uint64_t>(s->R, r_lo + STAGE_CHUNK);
+        const uint64_t r_lo = ch * CH, r_hi = std::min<uint64_t>(s->R, r_lo + CH);
         const uint64_t n = r_hi - r_lo;
         if (w.busy[b]) { cudaEventSynchronize(w.ev[b]); w.busy[b] = false; }
         char *pin = w.buf[b].as<char>();
@@ -300,6 +315,7 @@ void stage_worker(StageShared *s, int wi) {
             const int grid = (int)std::min<uint64_t>((n + WARPS - 1) / WARPS, (uint64_t)c->sm_count * 8);
             k_pack<<<grid, THREADS, 0, w.stream>>>(pa, g);
             e = cudaGetLastError();
+            if (e == cudaSuccess && count_chunk(c, w.stream, r_lo << s->fwd, r_hi << s->fwd, r_hi == s->R)) e = cudaErrorUnknown;
         }
         if (e == cudaSuccess) e = cudaEventRecord(w.ev[b], w.stream);
         if (e != cudaSuccess) { s->status = VDJGRAPH_ERR_CUDA; break; }
@@ -333,11 +349,12 @@ int stage_direct(vdjgraph_ctx *c, const char *primary, uint64_t np, const char *
     int rc;
     if ((rc = ensure_workers(c, DIRECT_STREAMS))) return rc;
     for (int i = 0; i < DIRECT_STREAMS; i++)
-        if ((rc = c->workers[i].dbuf[0].ensure((size_t)DIRECT_CHUNK * rec_len))) return rc;
-    const uint64_t n_chunks = (R + DIRECT_CHUNK - 1) / DIRECT_CHUNK;
+        if ((rc = c->workers[i].dbuf[0].ensure((size_t)chunk_records(c, DIRECT_CHUNK) * rec_len))) return rc;
+    const uint64_t CH = chunk_records(c, DIRECT_CHUNK);
+    const uint64_t n_chunks = (R + CH - 1) / CH;
     for (uint64_t ch = 0; ch < n_chunks; ch++) {
         StageWorker &w = c->workers[ch % DIRECT_STREAMS];
-        const uint64_t r_lo = ch * DIRECT_CHUNK, r_hi = std::min<uint64_t>(R, r_lo + DIRECT_CHUNK), n = r_hi - r_lo;
+        const uint64_t r_lo = ch * CH, r_hi = std::min<uint64_t>(R, r_lo + CH), n = r_hi - r_lo;
         unsigned char *dst = w.dbuf[0].as<unsigned char>();   /* stream order: its previous k_pack has read it */
         const uint64_t np_part = r_lo < np ? std::min<uint64_t>(r_hi, np) - r_lo : 0;
         if (np_part) CK(cudaMemcpyAsync(dst, primary + r_lo * rec_len, np_part * rec_len, cudaMemcpyHostToDevice, w.stream));
@@ -353,16 +370,26 @@ int stage_direct(vdjgraph_ctx *c, const char *primary, uint64_t np, const char *
         const int grid = (int)std::min<uint64_t>((n + WARPS - 1) / WARPS, (uint64_t)c->sm_count * 8);
         k_pack<<<grid, THREADS, 0, w.stream>>>(pa, g);
         CK(cudaGetLastError());
+        if ((rc = count_chunk(c, w.stream, r_lo << fwd, r_hi << fwd, r_hi == R))) return rc;
     }
     for (int i = 0; i < DIRECT_STREAMS; i++) CK(cudaStreamSynchronize(c->workers[i].stream));
     return 0;
 }
 
-int blocks_per_sm(const void *kernel, size_t smem) {
+/* resident blocks per SM of a persistent kernel; `cap` > 0 limits them and shrinks the shared-memory
+ * carve-out to what that many blocks need, so that the rest of the SM's 256 KB stays L1 (the table
+ * passes live on L1 hits of the hot k-mers' slots) */
+int blocks_per_sm(const void *kernel, size_t smem, int cap = 0) {
     int n = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, THREADS, smem);
-    return std::max(1, n);
+    n = std::max(1, n);
+    if (cap > 0) {
+        n = std::min(n, cap);
+        const double need = (double)n * (double)(smem + 1024) / (228.0 * 1024.0) * 100.0;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min(100.0, std::ceil(need)));
+    }
+    return n;
 }
 
 /* HyperLogLog estimate from one bucket's BHLL byte registers */
@@ -458,7 +485,7 @@ extern "C" int vdjgraph_set_params(vdjgraph_ctx *c, const vdjgraph_params *param
     return 0;
 }
 
-namespace { int run_count(vdjgraph_ctx *c); }
+namespace { int count_begin(vdjgraph_ctx *c); int count_end(vdjgraph_ctx *c); }
 
 /* np / ns count TEXT records.  fwd = 0: the reference's buffers (every read followed by its reverse
  * complement).  fwd = 1: forward reads only; the packed read set is the same as if the reverse
@@ -490,26 +517,28 @@ static int stage_impl(vdjgraph_ctx *c, const char *primary, size_t np, const cha
     }
     uint64_t h2d = 0;
     c->any_strand1 = false;
+    if ((rc = count_begin(c))) return rc;
     if (R) {
         const size_t rec_len = (size_t)2 * g.L + 1;
         if ((rc = c->d_bad.ensure(3 * sizeof(uint64_t))) || (rc = c->h_bad.ensure(3 * sizeof(uint64_t)))) return rc;
         uint64_t *hb = c->h_bad.as<uint64_t>();
         hb[0] = hb[1] = ~0ull; hb[2] = 0;
         CK(cudaMemcpyAsync(c->d_bad.p, hb, 3 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));   /* padding memsets and the flags are in place before the workers start */
+        CK(cudaStreamSynchronize(c->stream));   /* padding memsets, flags and zeroed counters are in place before the workers start */
         const bool direct = is_page_locked(primary, np * rec_len) && is_page_locked(secondary, ns * rec_len);
         if (direct) {
             if ((rc = stage_direct(c, primary, np, secondary, Rt, fwd))) return rc;
         } else {
-        const uint64_t n_chunks = (Rt + STAGE_CHUNK - 1) / STAGE_CHUNK;
+        const uint64_t CH = chunk_records(c, STAGE_CHUNK);
+        const uint64_t n_chunks = (Rt + CH - 1) / CH;
         int nt = c->prm.host_threads > 0 ? c->prm.host_threads : (int)std::min(16u, std::thread::hardware_concurrency());
         nt = std::max(1, std::min<int>(nt, 64));
         nt = (int)std::min<uint64_t>((uint64_t)nt, n_chunks);
         if ((rc = ensure_workers(c, nt))) return rc;
         for (int i = 0; i < nt; i++)
             for (int b = 0; b < 2; b++)
-                if ((rc = c->workers[i].buf[b].ensure((size_t)STAGE_CHUNK * rec_len)) ||
-                    (rc = c->workers[i].dbuf[b].ensure((size_t)STAGE_CHUNK * rec_len))) return rc;
+                if ((rc = c->workers[i].buf[b].ensure((size_t)CH * rec_len)) ||
+                    (rc = c->workers[i].dbuf[b].ensure((size_t)CH * rec_len))) return rc;
         StageShared sh;
         sh.c = c; sh.primary = primary; sh.secondary = secondary; sh.np = np; sh.R = Rt; sh.fwd = fwd;
         std::vector<std::thread> th;
@@ -532,9 +561,9 @@ static int stage_impl(vdjgraph_ctx *c, const char *primary, size_t np, const cha
         h2d = Rt * rec_len;
     }
     CK(cudaStreamSynchronize(c->stream));
-    /* per-bucket window / run counts and cardinality registers of the packed reads: the build's plan
-     * needs nothing else, and they depend on the reads and on k only */
-    if ((rc = run_count(c))) return rc;
+    /* per-bucket window / run counts and cardinality registers of the packed reads (k_count ran chunk
+     * by chunk behind the packing): the build's plan needs nothing else */
+    if ((rc = count_end(c))) return rc;
     memset(&c->res, 0, sizeof(c->res));
     c->res.ms_stage = (float)(wall_ms() - t0);
     c->res.h2d_bytes = h2d;
@@ -576,9 +605,11 @@ constexpr size_t HLL_BYTES = (size_t)NBUCKET * BHLL;
 static_assert(HIST_WORDS == VDJGRAPH_SHARD_HIST && HLL_BYTES == VDJGRAPH_SHARD_HLL, "header and library disagree");
 
 /* K0, part of staging (its results depend on the reads and on k only): runs / gated / N-free windows
- * per minimizer bucket + per-bucket HyperLogLog of the gated k-mers -> h_hist, h_hll */
-int run_count(vdjgraph_ctx *c) {
-    const Geom g = c->g;
+ * per minimizer bucket + per-bucket HyperLogLog of the gated k-mers.  count_begin zeroes the device
+ * accumulators, count_chunk queues k_count on the whole tiles of one staging chunk behind the chunk's
+ * k_pack (same stream; a fraction of the SMs: it hides behind the next chunk's copy), count_end
+ * brings the totals to the host: h_hist, h_hll. */
+int count_begin(vdjgraph_ctx *c) {
     cudaStream_t s = c->stream;
     int rc;
     if ((rc = c->d_ctr.ensure(sizeof(Counters)))) return rc;
@@ -593,21 +624,30 @@ int run_count(vdjgraph_ctx *c) {
     if ((rc = c->h_cursor.ensure(2 * NBUCKET * sizeof(uint64_t)))) return rc;
     if ((rc = c->h_tbase.ensure(NBUCKET * sizeof(void *)))) return rc;
     if ((rc = c->h_utab.ensure(NBUCKET * sizeof(UnitTab)))) return rc;
-    CK(cudaEventRecord(c->ev[0], s));
     CK(cudaMemsetAsync(c->d_hll.p, 0, HLL_BYTES, s));
     CK(cudaMemsetAsync(c->d_hist.p, 0, HIST_WORDS * sizeof(uint64_t), s));
-    if (g.R) {
-        const size_t smem_count = count_head_bytes() + scratch_bytes(g) + block_tile_bytes(g, 2);
-        const int grid_count = (int)std::min<uint64_t>(g.n_tiles, (uint64_t)c->sm_count * blocks_per_sm((const void *)k_count, smem_count));
-        k_count<<<grid_count, THREADS, smem_count, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g,
-                                                         c->d_hll.as<u32>(), c->d_hist.as<u64>());
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(c->ev[1], s));
+    c->count_smem = count_head_bytes() + scratch_bytes(c->g) + sbk_bytes(c->g) + block_tile_bytes(c->g, 2);
+    c->count_bps = blocks_per_sm((const void *)k_count, c->count_smem);
+    return 0;
+}
+/* packed records [rec_lo, rec_hi) have just been packed on stream s; rec_lo is a tile boundary, and so
+ * is rec_hi unless this is the last chunk (then the zeroed padding records complete the last tile) */
+int count_chunk(vdjgraph_ctx *c, cudaStream_t s, uint64_t rec_lo, uint64_t rec_hi, bool last) {
+    const Geom &g = c->g;
+    const uint64_t tile0 = rec_lo / g.tile_rec, tile1 = last ? g.n_tiles : rec_hi / g.tile_rec;
+    if (tile1 <= tile0) return 0;
+    /* a quarter of the machine per chunk: several chunks are in flight on their streams */
+    const int grid = (int)std::min<uint64_t>(tile1 - tile0, std::max(1, c->sm_count * c->count_bps / 4));
+    k_count<<<grid, THREADS, c->count_smem, s>>>(c->d_bases.as<u64>(), c->d_good.as<u64>(), c->d_valid.as<u64>(), g, tile0, tile1,
+                                                  c->d_hll.as<u32>(), c->d_hist.as<u64>());
+    CK(cudaGetLastError());
+    return 0;
+}
+int count_end(vdjgraph_ctx *c) {
+    cudaStream_t s = c->stream;
     CK(cudaMemcpyAsync(c->h_hist.p, c->d_hist.p, HIST_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c->h_hll.p, c->d_hll.p, HLL_BYTES, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    cudaEventElapsedTime(&c->ms_count, c->ev[0], c->ev[1]);
     return 0;
 }
 
@@ -673,6 +713,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
     pt.fb = std::min(RUN_FP_BITS, pt.wide ? 64 - pt.hb - FLB : 64 - pt.hb - FLB - sbits);
     /* test hook: fewer fingerprint bits force the exact read comparison on (almost) every k-mer */
     pt.fb = std::max(0, std::min(pt.fb, (int)env_double("VDJGRAPH_FP_BITS", 32.0)));
+    pt.cshift = (u32)std::max(0, sbits - 8);
     pt.hot_t = (u32)env_double("VDJGRAPH_HOT_T", 1024);
     pt.hot_flush = (u32)std::max(1.0, env_double("VDJGRAPH_HOT_FLUSH", 3));
     pt.qflush1 = (u32)std::min<double>(QFLUSH1, std::max(1.0, env_double("VDJGRAPH_QFLUSH1", 8)));
@@ -911,9 +952,9 @@ int run_passes(vdjgraph_ctx *c) {
     const size_t smem_q = WARPS * (pt.wide ? WarpQueue<true>::bytes() : WarpQueue<false>::bytes()) + feed_bytes;
     const uint64_t n_chunk = (n_runs + THREADS - 1) / THREADS;
     const int grid_p1 = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_chunk,
-                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, smem_q1)));
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass1<true> : (const void *)k_pass1<false>, smem_q1, (int)env_double("VDJGRAPH_P1_BLOCKS", 0))));
     const int grid_p2 = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_chunk,
-                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, smem_q)));
+                                                (uint64_t)c->sm_count * blocks_per_sm(pt.wide ? (const void *)k_pass2<true> : (const void *)k_pass2<false>, smem_q, (int)env_double("VDJGRAPH_P2_BLOCKS", PASS2_MIN_BLOCKS))));
     UnitTab *ut = c->h_utab.as<UnitTab>();
     sh.utab.assign(sh.NU, UnitTab{0, 0, 0, 0});
 

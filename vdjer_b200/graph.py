@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libvdjgraph.so")
+    # VDJGRAPH_LIB: another build of the same library (tuning experiments, profiles/variants.sh)
+    return os.environ.get("VDJGRAPH_LIB") or os.path.join(_HERE, "libvdjgraph.so")
 
 
 class VdjGraphError(RuntimeError):

@@ -140,6 +140,10 @@ class _Peers:
         self.cache = {}
 
 
+class ShardAborted(RuntimeError):
+    """Another rank of the sharded build failed; this rank stopped with it."""
+
+
 class DistributedBuilder:
     """One rank of the sharded build (one process per GPU).  `dist`: torch.distributed (initialised);
     `group`: process group for the small host exchanges (default group if None); `device`: where
@@ -155,33 +159,53 @@ class DistributedBuilder:
         self.G = dist.get_world_size(group) if group is not None else dist.get_world_size()
         self.rank = dist.get_rank(group) if group is not None else dist.get_rank()
         self.counts = None
+        self._err = None
         self.peers = _Peers()
         self.table = [[0] * SHARD_NBUF for _ in range(self.G)]
 
+    def _try(self, fn, *args, default=None):
+        """A library phase of this rank.  When it fails the exception is parked, the rank keeps taking
+        part in the collectives with placeholder data, and the next collective makes EVERY rank raise:
+        no rank is left waiting in a barrier for one that has gone."""
+        if self._err is not None:
+            return default
+        try:
+            return fn(*args)
+        except Exception as e:   # noqa: BLE001
+            self._err = e
+            return default
+
     def _gather(self, arr: np.ndarray) -> np.ndarray:
-        """all-gather a small fixed-shape array: result [G, *arr.shape]."""
+        """all-gather a small fixed-shape array: result [G, *arr.shape].  Every exchange also carries
+        each rank's failure flag (see _try)."""
         import torch
         a = np.ascontiguousarray(arr)
-        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy())
+        payload = np.concatenate([a.view(np.uint8).reshape(-1), np.array([1 if self._err is not None else 0], np.uint8)])
+        t = torch.from_numpy(payload)
         if self.device is not None:
             t = t.to(self.device)
         out = [torch.empty_like(t) for _ in range(self.G)]
         kw = {"group": self.group} if self.group is not None else {}
         self.dist.all_gather(out, t, **kw)
         flat = torch.stack(out).cpu().numpy()
-        return flat.view(a.dtype).reshape((self.G,) + a.shape)
+        bad = [r for r in range(self.G) if flat[r, -1]]
+        if bad:
+            err, self._err = self._err, None
+            if err is not None:
+                raise err
+            raise ShardAborted(f"sharded build aborted: rank(s) {bad} failed")
+        return np.ascontiguousarray(flat[:, :-1]).view(a.dtype).reshape((self.G,) + a.shape)
 
     def _barrier(self):
-        kw = {"group": self.group} if self.group is not None else {}
-        self.dist.barrier(**kw)
+        self._gather(np.zeros(0, np.uint8))
 
     def _exchange(self, only):
         """all-gather the IPC handles of this rank's buffers in `only`; map the peers'."""
-        ptrs, _ = self.b.shard_buffers()
+        ptrs, _ = self._try(self.b.shard_buffers, default=([0] * SHARD_NBUF, None))
         mine = np.zeros((SHARD_NBUF, 64), np.uint8)
         have = np.zeros(SHARD_NBUF, np.uint8)
         for i in only:
-            h = self.peers.export(ptrs[i])
+            h = self._try(self.peers.export, ptrs[i], default=b"")
             if h:
                 mine[i] = np.frombuffer(h, np.uint8)
                 have[i] = 1
@@ -190,8 +214,8 @@ class DistributedBuilder:
             if r != self.rank:
                 hs, hv = handles[r][:SHARD_NBUF * 64].reshape(SHARD_NBUF, 64), handles[r][SHARD_NBUF * 64:]
                 for i in only:
-                    self.table[r][i] = self.peers.map(r, i, hs[i].tobytes() if hv[i] else b"")
-        self.b.shard_set_peers(self.table)
+                    self.table[r][i] = self._try(self.peers.map, r, i, hs[i].tobytes() if hv[i] else b"", default=0)
+        self._try(self.b.shard_set_peers, self.table)
 
     def stage(self, primary, secondary=b"", forward: bool = False):
         """forward: this rank's buffers hold forward reads only (every rank alike)."""
@@ -199,9 +223,9 @@ class DistributedBuilder:
         self.counts = [int(x) for x in self._gather(np.array([n_local], np.int64))[:, 0]]
         base = int(sum(self.counts[:self.rank]))
         if forward:
-            self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)), forward=True)
+            self._try(lambda: self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)), forward=True))
         else:
-            self.b.shard_stage(primary, secondary, self.G, self.rank, base, int(sum(self.counts)))
+            self._try(self.b.shard_stage, primary, secondary, self.G, self.rank, base, int(sum(self.counts)))
 
     def run(self):
         """count -> plan -> scatter (= the all-to-all) -> passes -> gather -> finish on the staged
@@ -215,41 +239,46 @@ class DistributedBuilder:
         def mark():
             t.append(time.perf_counter())
 
-        hist, hll = b.shard_count()
+        from .graph import SHARD_HIST, SHARD_HLL
+        hist, hll = self._try(b.shard_count, default=(np.zeros(SHARD_HIST, np.uint64), np.zeros(SHARD_HLL, np.uint8)))
         mark()
         pieces = self._gather(np.concatenate([hist.view(np.uint8), hll]))     # one exchange for both
         mark()
         n_h = hist.size * 8
         hist_all, hll_m, cnt = plan_inputs([x[:n_h].copy().view(np.uint64) for x in pieces], [x[n_h:] for x in pieces], self.counts)
-        b.shard_plan(hist_all, hll_m, cnt)
+        self._try(b.shard_plan, hist_all, hll_m, cnt)
         mark()
         self._exchange([i for i in range(SHARD_NBUF) if i != BUF_GATHER])
         self._barrier()                     # every peer buffer exists and is mapped everywhere
-        b.shard_release_retired()
+        self._try(b.shard_release_retired)
         mark()
         t_sc = t_pa = 0.0
-        for rnd in range(b.shard_rounds()):
+        n_rounds = self._try(b.shard_rounds, default=0)
+        n_rounds = int(self._gather(np.array([n_rounds], np.int64)).max())   # a failed rank still walks the rounds
+        n_surv = 0
+        for rnd in range(n_rounds):
             if rnd:
-                self._barrier()             # the owners have consumed the previous round's tuples
+                self._barrier()             # the owners have consumed the previous round's runs
             t0 = time.perf_counter()
-            b.shard_scatter()
-            self._barrier()                 # every rank's tuples of this round have arrived
+            self._try(b.shard_scatter)
+            self._barrier()                 # every rank's runs of this round have arrived
             t1 = time.perf_counter()
-            n_surv = b.shard_passes()
+            n_surv = self._try(b.shard_passes, default=0)
             t_sc += t1 - t0
             t_pa += time.perf_counter() - t1
         t.append(t[-1] + t_sc)
         t.append(t[-1] + t_pa)
         surv = [int(x) for x in self._gather(np.array([n_surv], np.int64))[:, 0]]
-        b.shard_gather_plan(surv)
+        self._try(b.shard_gather_plan, surv)
         self._exchange([BUF_GATHER])
         mark()
-        b.shard_send()
+        self._try(b.shard_send)
         self._barrier()                     # rank 0 holds every survivor record
         mark()
-        b.shard_release_retired()
+        self._try(b.shard_release_retired)
         if self.rank == 0:
-            b.shard_finish()
+            self._try(b.shard_finish)
+        self._barrier()                     # nobody returns before the finish is known to have worked
         mark()
         names = ["count", "x_hist", "plan", "x_peers", "scatter+barrier", "passes", "x_surv", "send+barrier", "finish"]
         self.phase_ms = {n: (t[i + 1] - t[i]) * 1e3 for i, n in enumerate(names)}
