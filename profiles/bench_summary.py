@@ -12,8 +12,8 @@ for line in sys.stdin:
         continue
     print(f"value {d['value'] / 1e9:.2f} G windows/s  ms/step {d['ms_per_step']:.2f}  e2e {d['e2e']['value'] / 1e9:.2f} G/s "
           f"({d['e2e']['ms_per_step']:.1f} ms: stage {d['e2e']['ms_stage']:.1f} dev {d['e2e']['ms_device']:.1f} fetch {d['e2e']['ms_fetch']:.1f})")
-    if "e2e_forward_reads" in d:
-        f = d["e2e_forward_reads"]
+    if "e2e_text_records" in d:
+        f = d["e2e_text_records"]
         print(f"e2e from forward reads only {f['value'] / 1e9:.2f} G/s ({f['ms_per_step']:.1f} ms: stage {f['ms_stage']:.1f} dev {f['ms_device']:.1f} fetch {f['ms_fetch']:.1f})")
     print("kernel_ms", {k: round(v, 3) for k, v in d["kernel_ms"].items()})
     print("roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), "(survey formula", round(d["roofline"].get("survey_formula", {}).get("frac", -1), 3), ") path", round(d["roofline_path"]["frac"], 3),
@@ -24,6 +24,11 @@ for line in sys.stdin:
     if "roofline_atomic" in d:
         ra = d["roofline_atomic"]
         print("atomic roof: pass1", round(ra["k_pass1"]["frac"], 3), "pass2", round(ra["k_pass2"]["frac"], 3))
+    if "parity_check" in d:
+        print("parity_check", d["parity_check"])
+    if "digest_check" in d:
+        print("digest_check", d["digest_check"])
+    print("runs", c.get("runs"), "windows/run", c.get("windows_per_run"), "run bytes/window", c.get("run_bytes_per_window"))
     if "shard_phase_ms_rank0" in d:
         print("shard phases (rank 0, wall ms)", d["shard_phase_ms_rank0"])
     if "cpu_baseline" in d:

@@ -1822,11 +1822,22 @@ __global__ void k_assign_rank(Slot2 *t, const u32 *vals, u64 n) {
     if (i < n) t[vals[i]].rank = (u32)i;
 }
 
+/* one node on its way out: written by k_export at the node's creation rank (two full sectors),
+ * turned into the result's structure-of-arrays by k_unpack_nodes */
+struct __align__(32) NodeOut {
+    u64 first_pos;
+    u32 succ[4];
+    u32 freq_deg;     /* frequency | out_deg << 16 | in_deg << 24 */
+    u32 pad;
+    u32 pred[4];
+    u64 klo, khi;
+};
+static_assert(sizeof(NodeOut) == 64, "NodeOut must be two sectors");
+
 struct ExportArgs {
     const Slot2 *table;
     u64 cap;
-    const u64 *keys;   /* sorted first_any */
-    const u32 *vals;   /* slot of rank i */
+    NodeOut *out;      /* [n] by creation rank */
     u64 n;
     u64 *first_pos;
     u16 *frequency;
@@ -1843,47 +1854,91 @@ __device__ __forceinline__ void sort_desc4(u64 (&t)[4], u32 (&v)[4], int n) {
         }
 }
 
+/* Walks the survivor table in SLOT order, not in creation order: the successors and predecessors of
+ * a k-mer almost always share its minimizer, hence its hash unit, hence its table slice, so that the
+ * <= 8 lookups per node hit the slice that is L2-resident anyway (in creation order they were ~8
+ * DRAM-random probes per node, 60 % of the finish of a sharded build). */
 __global__ void __launch_bounds__(THREADS)
 k_export(ExportArgs a, Geom g, Part pt) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < a.cap; i += stride) {
+        u64 lo, hi, c2, c3;
+        ld_sector(&a.table[i], lo, hi, c2, c3);
+        if (lo == EMPTY64 && hi == EMPTY64) continue;
+        u64 of[4];
+        ld_sector(reinterpret_cast<const char *>(&a.table[i]) + 32, of[0], of[1], of[2], of[3]);
+        const u32 cnt = (u32)c2, rank = (u32)(c2 >> 32);
+        NodeOut o;
+        o.first_pos = c3; o.pad = 0; o.klo = lo; o.khi = hi;
+        u64 tt[4]; u32 vv[4];
+        /* toNodes: successors K[1:]+c that survived, newest first-seen at the head (:223-229) */
+        int n = 0;
+        for (u32 c = 0; c < 4; c++) {
+            if (of[c] == INF64) continue;
+            u64 slo, shi, q2, q3;
+            kmer_succ(lo, hi, c, g.k, slo, shi);
+            u64 idx = t2_find(a.table, a.cap, pt, g, slo, shi, q2, q3);
+            if (idx == INF64) continue;
+            tt[n] = of[c]; vv[n] = (u32)(q2 >> 32); n++;
+        }
+        sort_desc4(tt, vv, n);
+        u32 fd = (cnt > CNT_CAP ? CNT_CAP : cnt) | ((u32)n << 16);
+        for (int e = 0; e < 4; e++) o.succ[e] = e < n ? vv[e] : NIL32;
+        /* fromNodes: predecessors c+K[:-1] that survived and were seen followed by K's last base;
+         * the edge P->K was first linked at P.out_first[last(K)] + 1 (:231-236) */
+        n = 0;
+        const u32 last = kmer_last(lo, hi, g.k);
+        for (u32 c = 0; c < 4; c++) {
+            u64 plo, phi, q2, q3;
+            kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
+            u64 idx = t2_find(a.table, a.cap, pt, g, plo, phi, q2, q3);
+            if (idx == INF64) continue;
+            u64 tf = ld_cg_u64(&a.table[idx].out_first[last]);
+            if (tf == INF64) continue;
+            tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+        }
+        sort_desc4(tt, vv, n);
+        fd |= (u32)n << 24;
+        o.freq_deg = fd;
+        for (int e = 0; e < 4; e++) o.pred[e] = e < n ? vv[e] : NIL32;
+        const u64 *w = reinterpret_cast<const u64 *>(&o);
+        st_sector(&a.out[rank], w[0], w[1], w[2], w[3]);
+        st_sector(reinterpret_cast<char *>(&a.out[rank]) + 32, w[4], w[5], w[6], w[7]);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_unpack_nodes(ExportArgs a) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const Slot2 *s = a.table + a.vals[i];
-    const u64 lo = s->klo, hi = s->khi;
-    u32 cnt = s->count;
-    a.first_pos[i] = a.keys[i];
-    a.frequency[i] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);
-    if (a.kmer_lo) { a.kmer_lo[i] = lo; a.kmer_hi[i] = hi; }
-    u64 tt[4]; u32 vv[4];
-    /* toNodes: successors K[1:]+c that survived, newest first-seen at the head (:223-229) */
-    int n = 0;
-    for (u32 c = 0; c < 4; c++) {
-        u64 tf = s->out_first[c];
-        if (tf == INF64) continue;
-        u64 slo, shi, q2, q3;
-        kmer_succ(lo, hi, c, g.k, slo, shi);
-        u64 idx = t2_find(a.table, a.cap, pt, g, slo, shi, q2, q3);
-        if (idx == INF64) continue;
-        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+    u64 w[8];
+    ld_sector(&a.out[i], w[0], w[1], w[2], w[3]);
+    ld_sector(reinterpret_cast<const char *>(&a.out[i]) + 32, w[4], w[5], w[6], w[7]);
+    const u32 fd = (u32)w[3];
+    a.first_pos[i] = w[0];
+    a.frequency[i] = (u16)(fd & 0xFFFFu);
+    a.out_deg[i] = (u8)((fd >> 16) & 0xFFu);
+    a.in_deg[i] = (u8)(fd >> 24);
+    reinterpret_cast<ulonglong2 *>(a.out_succ)[i] = make_ulonglong2(w[1], w[2]);
+    reinterpret_cast<ulonglong2 *>(a.in_pred)[i] = make_ulonglong2(w[4], w[5]);
+    if (a.kmer_lo) { a.kmer_lo[i] = w[6]; a.kmer_hi[i] = w[7]; }
+}
+
+/* survivors per minimizer bucket among the records of a sharded / multi-round finish: sizes the slices
+ * of the merged table */
+__global__ void __launch_bounds__(THREADS)
+k_unit_count(const Slot2 *rec, u64 n, Geom g, u32 *hist /* [NBUCKET] */) {
+    __shared__ u32 sh[NBUCKET];
+    for (int i = threadIdx.x; i < NBUCKET; i += THREADS) sh[i] = 0;
+    __syncthreads();
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 lo, hi;
+        ld_cg_v2(&rec[i], lo, hi);
+        atomicAdd(&sh[kmer_bucket_of(lo, hi, g.span, g.mmask)], 1u);
     }
-    sort_desc4(tt, vv, n);
-    a.out_deg[i] = (u8)n;
-    for (int e = 0; e < 4; e++) a.out_succ[i * 4 + e] = e < n ? vv[e] : NIL32;
-    /* fromNodes: predecessors c+K[:-1] that survived and were seen followed by K's last base;
-     * the edge P->K was first linked at P.out_first[last(K)] + 1 (:231-236) */
-    n = 0;
-    const u32 last = kmer_last(lo, hi, g.k);
-    for (u32 c = 0; c < 4; c++) {
-        u64 plo, phi, q2, q3;
-        kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
-        u64 idx = t2_find(a.table, a.cap, pt, g, plo, phi, q2, q3);
-        if (idx == INF64) continue;
-        u64 tf = a.table[idx].out_first[last];
-        if (tf == INF64) continue;
-        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
-    }
-    sort_desc4(tt, vv, n);
-    a.in_deg[i] = (u8)n;
-    for (int e = 0; e < 4; e++) a.in_pred[i * 4 + e] = e < n ? vv[e] : NIL32;
+    __syncthreads();
+    for (int i = threadIdx.x; i < NBUCKET; i += THREADS) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
 /* pruned pass-1 table for parity checks */
