@@ -1822,6 +1822,39 @@ __global__ void k_assign_rank(Slot2 *t, const u32 *vals, u64 n) {
     if (i < n) t[vals[i]].rank = (u32)i;
 }
 
+/* The minimizer values of a k-mer's four successors and four predecessors from ONE scan of its
+ * m-mers: a successor K[1:]+c keeps K's m-mers but the first and gains one at the end, a
+ * predecessor c+K[:-1] keeps all but the last and gains one at the front. */
+struct NeighbourMini {
+    u32 tail, head;      /* min hash over K's m-mer positions >= 1 / <= span-2 (~0 when there is none) */
+    u32 x_first, x_last; /* K's first and last m-mer */
+    __device__ __forceinline__ void scan(u64 lo, u64 hi, const Geom &g) {
+        tail = head = ~0u;
+        x_first = (u32)lo & g.mmask;
+        for (int j = 0; j < g.span; j++) {
+            x_last = (u32)lo & g.mmask;
+            const u32 h = mini_hash(x_last);
+            if (j > 0) tail = min(tail, h);
+            if (j < g.span - 1) head = min(head, h);
+            lo = (lo >> 2) | (hi << 62);
+            hi >>= 2;
+        }
+    }
+    __device__ __forceinline__ u32 succ_bucket(u32 c, const Geom &g) const {
+        return mini_bucket(min(tail, mini_hash((x_last >> 2) | (c << (2 * (g.m - 1))))));
+    }
+    __device__ __forceinline__ u32 pred_bucket(u32 c, const Geom &g) const {
+        return mini_bucket(min(head, mini_hash(((x_first << 2) | c) & g.mmask)));
+    }
+};
+/* home slot in table 2 of a k-mer whose bucket is known */
+__device__ __forceinline__ u32 t2_home_in(const Part &pt, u32 bucket, u64 lo, u64 hi) {
+    const u32 h = hash_slot(lo, hi);
+    if (pt.flat) return slot_in(h, 0u, pt.flat_len);
+    const uint4 ut = __ldg(reinterpret_cast<const uint4 *>(pt.ut + (bucket >> pt.ushift)));
+    return slot_in(h, ut.z, ut.w);
+}
+
 /* one node on its way out: written by k_export at the node's creation rank (two full sectors),
  * turned into the result's structure-of-arrays by k_unpack_nodes */
 struct __align__(32) NodeOut {
@@ -1838,6 +1871,7 @@ struct ExportArgs {
     const Slot2 *table;
     u64 cap;
     NodeOut *out;      /* [n] by creation rank */
+    const u32 *slots;  /* [n] the occupied slots in (roughly) slot order: k_collect's list before it was sorted */
     u64 n;
     u64 *first_pos;
     u16 *frequency;
@@ -1854,30 +1888,33 @@ __device__ __forceinline__ void sort_desc4(u64 (&t)[4], u32 (&v)[4], int n) {
         }
 }
 
-/* Walks the survivor table in SLOT order, not in creation order: the successors and predecessors of
- * a k-mer almost always share its minimizer, hence its hash unit, hence its table slice, so that the
+/* Walks the survivors in SLOT order, not in creation order: the successors and predecessors of a
+ * k-mer almost always share its minimizer, hence its hash unit, hence its table slice, so that the
  * <= 8 lookups per node hit the slice that is L2-resident anyway (in creation order they were ~8
- * DRAM-random probes per node, 60 % of the finish of a sharded build). */
+ * DRAM-random probes per node, 60 % of the finish of a sharded build).  One thread per node (the
+ * dense slot list of k_collect), so that warps are full. */
 __global__ void __launch_bounds__(THREADS)
 k_export(ExportArgs a, Geom g, Part pt) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
-    for (; i < a.cap; i += stride) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; t < a.n; t += stride) {
+        const u64 i = a.slots[t];
         u64 lo, hi, c2, c3;
         ld_sector(&a.table[i], lo, hi, c2, c3);
-        if (lo == EMPTY64 && hi == EMPTY64) continue;
         u64 of[4];
         ld_sector(reinterpret_cast<const char *>(&a.table[i]) + 32, of[0], of[1], of[2], of[3]);
         const u32 cnt = (u32)c2, rank = (u32)(c2 >> 32);
         NodeOut o;
         o.first_pos = c3; o.pad = 0; o.klo = lo; o.khi = hi;
         u64 tt[4]; u32 vv[4];
+        NeighbourMini nm;
+        nm.scan(lo, hi, g);
         /* toNodes: successors K[1:]+c that survived, newest first-seen at the head (:223-229) */
         int n = 0;
         for (u32 c = 0; c < 4; c++) {
             if (of[c] == INF64) continue;
             u64 slo, shi, q2, q3;
             kmer_succ(lo, hi, c, g.k, slo, shi);
-            u64 idx = t2_find(a.table, a.cap, pt, g, slo, shi, q2, q3);
+            u64 idx = t2_probe_from(a.table, a.cap, t2_home_in(pt, nm.succ_bucket(c, g), slo, shi), slo, shi, q2, q3);
             if (idx == INF64) continue;
             tt[n] = of[c]; vv[n] = (u32)(q2 >> 32); n++;
         }
@@ -1891,7 +1928,7 @@ k_export(ExportArgs a, Geom g, Part pt) {
         for (u32 c = 0; c < 4; c++) {
             u64 plo, phi, q2, q3;
             kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
-            u64 idx = t2_find(a.table, a.cap, pt, g, plo, phi, q2, q3);
+            u64 idx = t2_probe_from(a.table, a.cap, t2_home_in(pt, nm.pred_bucket(c, g), plo, phi), plo, phi, q2, q3);
             if (idx == INF64) continue;
             u64 tf = ld_cg_u64(&a.table[idx].out_first[last]);
             if (tf == INF64) continue;

@@ -1160,12 +1160,12 @@ int run_finish(vdjgraph_ctx *c) {
         const int gb = (int)((n_surv + THREADS - 1) / THREADS);
         k_assign_rank<<<gb, THREADS, 0, s>>>(table, c->d_vals[1].as<u32>(), n_surv);
         ExportArgs ae;
-        ae.table = table; ae.cap = cap2; ae.out = c->d_nodes.as<NodeOut>();
+        ae.table = table; ae.cap = cap2; ae.out = c->d_nodes.as<NodeOut>(); ae.slots = c->d_vals[0].as<u32>();
         ae.n = n_surv; ae.first_pos = c->d_first_pos.as<u64>(); ae.frequency = c->d_freq.as<u16>();
         ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
         ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
         ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
-        k_export<<<grid_flat, THREADS, 0, s>>>(ae, g, pt);
+        k_export<<<(int)std::min<uint64_t>(gb, (uint64_t)grid_flat), THREADS, 0, s>>>(ae, g, pt);
         k_unpack_nodes<<<gb, THREADS, 0, s>>>(ae);
         res.kernel_launches += 4;
     }
