@@ -48,7 +48,11 @@ constexpr u32 CNT_CAP = 32765;   /* MAX_FREQUENCY-1, :66, :262, :345 */
 constexpr int GATE_Q = 20;       /* MIN_BASE_QUALITY, :76 */
 constexpr int HIQ = 30;          /* "high quality": windows whose phreds are all >= HIQ let prune bound the quality
                                     sums without reading quality rows (k_prune) */
-constexpr int FLB = 5;           /* window flag bits: has-next, next base (2), window all >= HIQ, record start all >= HIQ */
+constexpr int FLB = 6;           /* window flag bits: has-next, next base (2), then pass 1: window all >= HIQ, record start
+                                    all >= HIQ; pass 2: has-previous, previous base (2) */
+constexpr u32 CNT2_MASK = 0x00FFFFFFu; /* Slot2::count: N-free occurrences; bits 24..27: in-mask (base c preceded the k-mer
+                                          in some read): the export probes only the predecessors that can exist */
+constexpr int CNT2_IN = 24;
 constexpr u64 LOG_A = 1ull << 62, LOG_B = 1ull << 63;   /* those two flags in a log entry, above the stamp */
 constexpr int QSUM_SAT = 214;    /* MAX_QUAL_SUM-41, :356 */
 constexpr int MAX_LOG_RANKS = 11;/* ceil(214/20) */
@@ -766,11 +770,12 @@ k_count(const u64 *__restrict__ bases, const u64 *__restrict__ good, const u64 *
 /*            window after the run exists), 2 bits each from bit 0: at most 64 bases            */
 /*   w2     : gate bit of window j at bit j (24) | window-all->=HIQ bit at 24+j (24) |           */
 /*            length-1 at 48 (5) | next-window-exists at 53 | record-start-all->=HIQ at 54 |     */
-/*            fingerprint bits 16..24 at 55 (9)                                                  */
+/*            previous-window-exists at 55 | the base before the run at 56 (2) |                 */
+/*            fingerprint bits 16..21 at 58 (6)                                                  */
 /*   w3     : stamp of the first window (STAMP_BITS) | bucket at 40 (8) | fingerprint bits 0..15 at 48 */
 /* ------------------------------------------------------------------------------------------ */
 constexpr int RUN_WORDS = 4;
-constexpr int RUN_FP_BITS = 25;
+constexpr int RUN_FP_BITS = 22;
 __device__ __forceinline__ u32 run_len(u64 w2) { return ((u32)(w2 >> 48) & 31u) + 1u; }
 __device__ __forceinline__ u32 run_bucket(u64 w3) { return (u32)(w3 >> STAMP_BITS) & (NBUCKET - 1); }
 __device__ __forceinline__ void ld_run(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
@@ -835,12 +840,15 @@ __host__ __device__ inline size_t scatter_carve(ScatterSmem *o, unsigned char *b
 }
 /* run descriptor (phase 1 -> phase 3): d0 = gate bits | HIQ bits << 24 | (len-1) << 48 | next << 53;
  * d1 = record in tile | first window << 16 | bucket << 24 */
-__device__ __forceinline__ void build_run(u64 d0, u64 d1, const u64 *sb, const u32 *sfp, const Geom &g, u64 rec0,
+__device__ __forceinline__ void build_run(u64 d0, u64 d1, const u64 *sb, const u64 *sv, const u32 *sfp, const Geom &g, u64 rec0,
                                           u64 &w0, u64 &w1, u64 &w2, u64 &w3) {
     const u32 rec = (u32)d1 & 0xFFFFu, a = (u32)(d1 >> 16) & 0xFFu, b = (u32)(d1 >> 24) & 0xFFu;
     extract_kmer(sb + (size_t)rec * g.nb, g.nb, (int)a, ~0ull, ~0ull, w0, w1);
     const u32 f = sfp[rec], fp = f & ((1u << RUN_FP_BITS) - 1);
-    w2 = d0 | ((u64)(f >> 31) << 54) | ((u64)(fp >> 16) << 55);
+    /* the window before the run's first one exists and is N-free iff the base before it is ACGT */
+    u64 prev = 0;
+    if (a > 0 && bit_at(sv + (size_t)rec * g.nm, (int)a - 1)) prev = 1ull | ((u64)base_at(sb + (size_t)rec * g.nb, (int)a - 1) << 1);
+    w2 = d0 | ((u64)(f >> 31) << 54) | (prev << 55) | ((u64)(fp >> 16) << 58);
     w3 = ((rec0 + rec) * (u64)g.w + a) | ((u64)b << STAMP_BITS) | ((u64)(fp & 0xFFFFu) << 48);
 }
 
@@ -906,7 +914,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
                         atomicAdd(&sm.cnt[u], 1u);
                     } else {   /* list full: this run goes out on its own */
                         u64 w0, w1, w2, w3;
-                        build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
+                        build_run(d0, d1, sb, sv, sm.fp, g, rec0, w0, w1, w2, w3);
                         const u64 at = atomicAdd(&a.cursor[u], 1ull);
                         if (at < a.limit[u]) st_sector(sm.dst[u] + at * RUN_WORDS, w0, w1, w2, w3);
                         else atomicExch(&a.ctr->overflow, 4u);
@@ -945,7 +953,7 @@ k_scatter(ScatterArgs a, Geom g, Part pt) {
             const u64 d0 = sm.list[2 * e], d1 = sm.list[2 * e + 1];
             const u32 u = ((u32)(d1 >> 24) & 0xFFu) >> pt.ushift;
             u64 w0, w1, w2, w3;
-            build_run(d0, d1, sb, sm.fp, g, rec0, w0, w1, w2, w3);
+            build_run(d0, d1, sb, sv, sm.fp, g, rec0, w0, w1, w2, w3);
             u64 *dst = sm.stage + (size_t)(sm.boff[u] + atomicAdd(&sm.fill[u], 1u)) * RUN_WORDS;
             dst[0] = w0; dst[1] = w1; dst[2] = w2; dst[3] = w3;
         }
@@ -1150,7 +1158,7 @@ struct RunFeed {
     /* the fingerprint carried by run l (fb bits) */
     __device__ __forceinline__ u32 fingerprint(u32 l, const Part &pt) const {
         const u64 *p = rw + l * RUN_WORDS;
-        return (((u32)(p[3] >> 48) & 0xFFFFu) | (((u32)(p[2] >> 55) & 0x1FFu) << 16)) & (u32)((1ull << pt.fb) - 1);
+        return (((u32)(p[3] >> 48) & 0xFFFFu) | (((u32)(p[2] >> 58) & 0x3Fu) << 16)) & (u32)((1ull << pt.fb) - 1);
     }
     /* the next selected window of the chunk (the caller knows there is one) */
     template <bool GATED_ONLY, bool TAB2>
@@ -1181,6 +1189,15 @@ __device__ __forceinline__ u32 run_flags(const Geom &g, u64 w0, u64 w1, u64 w2, 
     const u32 nb = (u32)((p < 32 ? w0 >> (2 * p) : w1 >> (2 * (p - 32)))) & 3u;
     const bool has_next = j + 1 < run_len(w2) || ((w2 >> 53) & 1ull);
     return (has_next ? 1u | (nb << 1) : 0u) | ((u32)(w2 >> (24 + j)) & 1u) << 3 | ((u32)(w2 >> 54) & 1u) << 4;
+}
+/* the same for pass 2: has-next, next base, has-previous, previous base */
+__device__ __forceinline__ u32 run_flags2(const Geom &g, u64 w0, u64 w1, u64 w2, u32 j) {
+    const u32 p = j + (u32)g.k;
+    const u32 nb = (u32)((p < 32 ? w0 >> (2 * p) : w1 >> (2 * (p - 32)))) & 3u;
+    const bool has_next = j + 1 < run_len(w2) || ((w2 >> 53) & 1ull);
+    /* window j > 0 follows window j-1 of the same run; window 0 follows the base noted in the run, if any */
+    const u32 prev = j ? 1u | (((u32)(w0 >> (2 * (j - 1))) & 3u) << 1) : (u32)(w2 >> 55) & 7u;
+    return (has_next ? 1u | (nb << 1) : 0u) | prev << 3;
 }
 /* tuple words (the form the slow-path queues hold) of a window with these flags, fingerprint and stamp */
 template <bool WIDE>
@@ -1639,8 +1656,11 @@ __device__ __forceinline__ u32 coarse_stamp(u64 stamp, u32 cshift) { return (u32
 __device__ __forceinline__ bool edge_open(u64 c2, u32 c, u32 coarse) { return coarse <= ((u32)(c2 >> (32 + 8 * c)) & 0xFFu); }
 /* reductions of one pass-2 hit; c2/c3/o are the loaded count word, first_any and out_first[c]
  * (o is only looked at when edge_open) */
-__device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2, u64 c3, u64 o, bool edge, u32 c, u64 stamp, u32 coarse) {
-    if (count_it && (u32)c2 < CNT_CAP) atomicAdd(&slot->count, 1u);
+__device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2, u64 c3, u64 o, bool edge, u32 c, u64 stamp, u32 coarse, u32 fl) {
+    if (count_it && ((u32)c2 & CNT2_MASK) < CNT_CAP) atomicAdd(&slot->count, 1u);
+    /* in-mask: this k-mer was seen preceded by base (fl >> 4) & 3 */
+    const u32 in_bit = ((fl >> 3) & 1u) << (CNT2_IN + ((fl >> 4) & 3u));
+    if (in_bit & ~(u32)c2) atomicOr(&slot->count, in_bit);
     if (stamp < c3) atomicMin(&slot->first_any, stamp);
     if (edge && stamp < o) {
         atomicMin(&slot->out_first[c], stamp);
@@ -1694,7 +1714,7 @@ __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, W
                 const bool edge = (fl & 1u) && edge_open(q2, c, coarse);
                 u64 o = 0;
                 if (edge) o = ld_cg_u64(&slot->out_first[c]);
-                pass2_update(slot, count_it, q2, q3, o, edge, c, stamp, coarse);
+                pass2_update(slot, count_it, q2, q3, o, edge, c, stamp, coarse, fl);
                 n_hits++;
                 n_hits_u += count_it;
                 have = false;
@@ -1737,7 +1757,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
                     if (t0 + u < feed.total) {
                         if (u) feed.next<false, true>(cur, pt);
                         run_kmer(g, cur, lo[u], hi[u], idx[u]);
-                        fl[u] = run_flags(g, cur.w0, cur.w1, cur.w2, cur.j) | ((u32)(cur.w2 >> cur.j) & 1u) << FLB;
+                        fl[u] = run_flags2(g, cur.w0, cur.w1, cur.w2, cur.j) | ((u32)(cur.w2 >> cur.j) & 1u) << FLB;
                         stamp[u] = cur.stamp0 + cur.j;
                     }
                 }
@@ -1772,7 +1792,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
                 const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
                 if (hit) {
                     pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], (edges >> u) & 1u, (fl[u] >> 1) & 3u, stamp[u],
-                                 coarse_stamp(stamp[u], pt.cshift));
+                                 coarse_stamp(stamp[u], pt.cshift), fl[u]);
                     n_hits++;
                     n_hits_u += ungated;
                 }
@@ -1855,23 +1875,11 @@ __device__ __forceinline__ u32 t2_home_in(const Part &pt, u32 bucket, u64 lo, u6
     return slot_in(h, ut.z, ut.w);
 }
 
-/* one node on its way out: written by k_export at the node's creation rank (two full sectors),
- * turned into the result's structure-of-arrays by k_unpack_nodes */
-struct __align__(32) NodeOut {
-    u64 first_pos;
-    u32 succ[4];
-    u32 freq_deg;     /* frequency | out_deg << 16 | in_deg << 24 */
-    u32 pad;
-    u32 pred[4];
-    u64 klo, khi;
-};
-static_assert(sizeof(NodeOut) == 64, "NodeOut must be two sectors");
-
 struct ExportArgs {
     const Slot2 *table;
     u64 cap;
-    NodeOut *out;      /* [n] by creation rank */
-    const u32 *slots;  /* [n] the occupied slots in (roughly) slot order: k_collect's list before it was sorted */
+    const u64 *keys;   /* sorted first_any */
+    const u32 *vals;   /* slot of rank i */
     u64 n;
     u64 *first_pos;
     u16 *frequency;
@@ -1888,94 +1896,55 @@ __device__ __forceinline__ void sort_desc4(u64 (&t)[4], u32 (&v)[4], int n) {
         }
 }
 
-/* Walks the survivors in SLOT order, not in creation order: the successors and predecessors of a
- * k-mer almost always share its minimizer, hence its hash unit, hence its table slice, so that the
- * <= 8 lookups per node hit the slice that is L2-resident anyway (in creation order they were ~8
- * DRAM-random probes per node, 60 % of the finish of a sharded build).  One thread per node (the
- * dense slot list of k_collect), so that warps are full. */
+/* one thread per node, in creation order (coalesced result rows).  Measured and rejected: walking
+ * the table in slot order with a bucket-sliced merged table, to keep the <= 8 neighbour lookups of
+ * a node inside one L2-resident slice (its neighbours mostly share its minimizer): the scattered
+ * 64-byte result records and the denser slices cost more than the locality gave (finish at 8 GPUs
+ * 7.7 -> 13.8 ms, configs[4] at full size 140 -> 245 ms). */
 __global__ void __launch_bounds__(THREADS)
 k_export(ExportArgs a, Geom g, Part pt) {
-    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
-    for (; t < a.n; t += stride) {
-        const u64 i = a.slots[t];
-        u64 lo, hi, c2, c3;
-        ld_sector(&a.table[i], lo, hi, c2, c3);
-        u64 of[4];
-        ld_sector(reinterpret_cast<const char *>(&a.table[i]) + 32, of[0], of[1], of[2], of[3]);
-        const u32 cnt = (u32)c2, rank = (u32)(c2 >> 32);
-        NodeOut o;
-        o.first_pos = c3; o.pad = 0; o.klo = lo; o.khi = hi;
-        u64 tt[4]; u32 vv[4];
-        NeighbourMini nm;
-        nm.scan(lo, hi, g);
-        /* toNodes: successors K[1:]+c that survived, newest first-seen at the head (:223-229) */
-        int n = 0;
-        for (u32 c = 0; c < 4; c++) {
-            if (of[c] == INF64) continue;
-            u64 slo, shi, q2, q3;
-            kmer_succ(lo, hi, c, g.k, slo, shi);
-            u64 idx = t2_probe_from(a.table, a.cap, t2_home_in(pt, nm.succ_bucket(c, g), slo, shi), slo, shi, q2, q3);
-            if (idx == INF64) continue;
-            tt[n] = of[c]; vv[n] = (u32)(q2 >> 32); n++;
-        }
-        sort_desc4(tt, vv, n);
-        u32 fd = (cnt > CNT_CAP ? CNT_CAP : cnt) | ((u32)n << 16);
-        for (int e = 0; e < 4; e++) o.succ[e] = e < n ? vv[e] : NIL32;
-        /* fromNodes: predecessors c+K[:-1] that survived and were seen followed by K's last base;
-         * the edge P->K was first linked at P.out_first[last(K)] + 1 (:231-236) */
-        n = 0;
-        const u32 last = kmer_last(lo, hi, g.k);
-        for (u32 c = 0; c < 4; c++) {
-            u64 plo, phi, q2, q3;
-            kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
-            u64 idx = t2_probe_from(a.table, a.cap, t2_home_in(pt, nm.pred_bucket(c, g), plo, phi), plo, phi, q2, q3);
-            if (idx == INF64) continue;
-            u64 tf = ld_cg_u64(&a.table[idx].out_first[last]);
-            if (tf == INF64) continue;
-            tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
-        }
-        sort_desc4(tt, vv, n);
-        fd |= (u32)n << 24;
-        o.freq_deg = fd;
-        for (int e = 0; e < 4; e++) o.pred[e] = e < n ? vv[e] : NIL32;
-        const u64 *w = reinterpret_cast<const u64 *>(&o);
-        st_sector(&a.out[rank], w[0], w[1], w[2], w[3]);
-        st_sector(reinterpret_cast<char *>(&a.out[rank]) + 32, w[4], w[5], w[6], w[7]);
-    }
-}
-
-__global__ void __launch_bounds__(THREADS)
-k_unpack_nodes(ExportArgs a) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    u64 w[8];
-    ld_sector(&a.out[i], w[0], w[1], w[2], w[3]);
-    ld_sector(reinterpret_cast<const char *>(&a.out[i]) + 32, w[4], w[5], w[6], w[7]);
-    const u32 fd = (u32)w[3];
-    a.first_pos[i] = w[0];
-    a.frequency[i] = (u16)(fd & 0xFFFFu);
-    a.out_deg[i] = (u8)((fd >> 16) & 0xFFu);
-    a.in_deg[i] = (u8)(fd >> 24);
-    reinterpret_cast<ulonglong2 *>(a.out_succ)[i] = make_ulonglong2(w[1], w[2]);
-    reinterpret_cast<ulonglong2 *>(a.in_pred)[i] = make_ulonglong2(w[4], w[5]);
-    if (a.kmer_lo) { a.kmer_lo[i] = w[6]; a.kmer_hi[i] = w[7]; }
-}
-
-/* survivors per minimizer bucket among the records of a sharded / multi-round finish: sizes the slices
- * of the merged table */
-__global__ void __launch_bounds__(THREADS)
-k_unit_count(const Slot2 *rec, u64 n, Geom g, u32 *hist /* [NBUCKET] */) {
-    __shared__ u32 sh[NBUCKET];
-    for (int i = threadIdx.x; i < NBUCKET; i += THREADS) sh[i] = 0;
-    __syncthreads();
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        u64 lo, hi;
-        ld_cg_v2(&rec[i], lo, hi);
-        atomicAdd(&sh[kmer_bucket_of(lo, hi, g.span, g.mmask)], 1u);
+    const Slot2 *s = a.table + a.vals[i];
+    const u64 lo = s->klo, hi = s->khi;
+    const u32 cw = s->count, cnt = cw & CNT2_MASK, in_mask = (cw >> CNT2_IN) & 15u;
+    a.first_pos[i] = a.keys[i];
+    a.frequency[i] = (u16)(cnt > CNT_CAP ? CNT_CAP : cnt);
+    if (a.kmer_lo) { a.kmer_lo[i] = lo; a.kmer_hi[i] = hi; }
+    u64 tt[4]; u32 vv[4];
+    NeighbourMini nm;
+    if (!pt.flat) nm.scan(lo, hi, g);     /* the buckets of all eight neighbours from one scan of the k-mer */
+    /* toNodes: successors K[1:]+c that survived, newest first-seen at the head (:223-229) */
+    int n = 0;
+    for (u32 c = 0; c < 4; c++) {
+        u64 tf = s->out_first[c];
+        if (tf == INF64) continue;
+        u64 slo, shi, q2, q3;
+        kmer_succ(lo, hi, c, g.k, slo, shi);
+        u64 idx = t2_probe_from(a.table, a.cap, t2_home_in(pt, pt.flat ? 0u : nm.succ_bucket(c, g), slo, shi), slo, shi, q2, q3);
+        if (idx == INF64) continue;
+        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NBUCKET; i += THREADS) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    sort_desc4(tt, vv, n);
+    a.out_deg[i] = (u8)n;
+    for (int e = 0; e < 4; e++) a.out_succ[i * 4 + e] = e < n ? vv[e] : NIL32;
+    /* fromNodes: predecessors c+K[:-1] that survived and were seen followed by K's last base;
+     * the edge P->K was first linked at P.out_first[last(K)] + 1 (:231-236) */
+    n = 0;
+    const u32 last = kmer_last(lo, hi, g.k);
+    for (u32 c = 0; c < 4; c++) {
+        if (!((in_mask >> c) & 1u)) continue;   /* never seen after base c: c+K[:-1] -> K was never linked */
+        u64 plo, phi, q2, q3;
+        kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
+        u64 idx = t2_probe_from(a.table, a.cap, t2_home_in(pt, pt.flat ? 0u : nm.pred_bucket(c, g), plo, phi), plo, phi, q2, q3);
+        if (idx == INF64) continue;
+        u64 tf = a.table[idx].out_first[last];
+        if (tf == INF64) continue;
+        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+    }
+    sort_desc4(tt, vv, n);
+    a.in_deg[i] = (u8)n;
+    for (int e = 0; e < 4; e++) a.in_pred[i * 4 + e] = e < n ? vv[e] : NIL32;
 }
 
 /* pruned pass-1 table for parity checks */

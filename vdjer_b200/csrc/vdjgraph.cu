@@ -194,8 +194,7 @@ struct vdjgraph_ctx {
     PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
 
-    DevBuf d_tbase, d_rec, d_gather, d_t2m, d_nodes, d_uhist;
-    PinBuf h_uhist;
+    DevBuf d_tbase, d_rec, d_gather, d_t2m;
     PinBuf h_tbase;
     Shard sh;
 
@@ -460,12 +459,12 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_nodes, &c->d_uhist, &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_utab, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
     for (DevBuf *b : db) b->release();
-    PinBuf *pb[] = { &c->h_uhist, &c->h_utab, &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+    PinBuf *pb[] = { &c->h_utab, &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
     for (int i = 0; i < 13; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -1113,35 +1112,20 @@ int run_finish(vdjgraph_ctx *c) {
         /* all survivor records: gathered from every device, or this device's own rounds */
         const Slot2 *records = sh.G > 1 ? c->d_gather.as<Slot2>() : c->d_rec.as<Slot2>();
         n_surv = sh.G > 1 ? sh.surv_off[sh.G] : sh.surv_done;
-        /* merged table: one slice per minimizer bucket, sized from the records (no device split any
-         * more); the records arrive grouped by unit, and a k-mer's neighbours mostly share its bucket,
-         * so both the inserts and the edge lookups of the export stay inside L2-resident slices */
-        if ((rc = c->d_uhist.ensure(NBUCKET * sizeof(u32))) || (rc = c->h_uhist.ensure(NBUCKET * sizeof(u32)))) return rc;
-        CK(cudaMemsetAsync(c->d_uhist.p, 0, NBUCKET * sizeof(u32), s));
-        if (n_surv) k_unit_count<<<grid_flat, THREADS, 0, s>>>(records, n_surv, g, c->d_uhist.as<u32>());
-        CK(cudaMemcpyAsync(c->h_uhist.p, c->d_uhist.p, NBUCKET * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        UnitTab *ut = c->h_utab.as<UnitTab>();
-        cap2 = 0;
-        for (int b = 0; b < NBUCKET; b++) {
-            const uint64_t len = (uint64_t)c->h_uhist.as<u32>()[b] * 2 + 64;
-            ut[b] = UnitTab{0, 0, (u32)cap2, (u32)len};
-            cap2 += len;
-        }
+        /* merged table: one flat slice (the finish looks k-mers up by slot hash alone), no device split */
+        cap2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
         if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "merged survivor table too large");
-        CK(cudaMemcpyAsync(c->d_utab.p, ut, NBUCKET * sizeof(UnitTab), cudaMemcpyHostToDevice, s));
-        pt.flat = 0; pt.ushift = 0;
+        pt.flat = 1; pt.flat_len = (u32)cap2;
         if ((rc = c->d_t2m.ensure(cap2 * sizeof(Slot2)))) return rc;
         table = c->d_t2m.as<Slot2>();
         CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
         k_init_table2<<<grid_flat, THREADS, 0, s>>>(table, cap2);
         k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(records, n_surv, table, cap2, g, pt, d_ctr);
-        res.kernel_launches += 3;
+        res.kernel_launches += 2;
     }
     const size_t na = std::max<uint64_t>(n_surv, 1);
     if ((rc = c->d_keys[0].ensure(na * 8)) || (rc = c->d_keys[1].ensure(na * 8)) ||
         (rc = c->d_vals[0].ensure(na * 4)) || (rc = c->d_vals[1].ensure(na * 4)) ||
-        (rc = c->d_nodes.ensure(na * sizeof(NodeOut))) ||
         (rc = c->d_first_pos.ensure(na * 8)) || (rc = c->d_freq.ensure(na * 2)) ||
         (rc = c->d_odeg.ensure(na)) || (rc = c->d_ideg.ensure(na)) ||
         (rc = c->d_osucc.ensure(na * 16)) || (rc = c->d_ipred.ensure(na * 16)))
@@ -1160,14 +1144,13 @@ int run_finish(vdjgraph_ctx *c) {
         const int gb = (int)((n_surv + THREADS - 1) / THREADS);
         k_assign_rank<<<gb, THREADS, 0, s>>>(table, c->d_vals[1].as<u32>(), n_surv);
         ExportArgs ae;
-        ae.table = table; ae.cap = cap2; ae.out = c->d_nodes.as<NodeOut>(); ae.slots = c->d_vals[0].as<u32>();
+        ae.table = table; ae.cap = cap2; ae.keys = c->d_keys[1].as<u64>(); ae.vals = c->d_vals[1].as<u32>();
         ae.n = n_surv; ae.first_pos = c->d_first_pos.as<u64>(); ae.frequency = c->d_freq.as<u16>();
         ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
         ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
         ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
-        k_export<<<(int)std::min<uint64_t>(gb, (uint64_t)grid_flat), THREADS, 0, s>>>(ae, g, pt);
-        k_unpack_nodes<<<gb, THREADS, 0, s>>>(ae);
-        res.kernel_launches += 4;
+        k_export<<<gb, THREADS, 0, s>>>(ae, g, pt);
+        res.kernel_launches += 3;
     }
     CK(cudaEventRecord(c->ev[8], s));
     CK(cudaGetLastError());
