@@ -160,6 +160,7 @@ class DistributedBuilder:
         self.rank = dist.get_rank(group) if group is not None else dist.get_rank()
         self.counts = None
         self._err = None
+        self._gather_mapped = False
         self.peers = _Peers()
         self.table = [[0] * SHARD_NBUF for _ in range(self.G)]
 
@@ -199,8 +200,8 @@ class DistributedBuilder:
     def _barrier(self):
         self._gather(np.zeros(0, np.uint8))
 
-    def _exchange(self, only):
-        """all-gather the IPC handles of this rank's buffers in `only`; map the peers'."""
+    def _handles(self, only) -> np.ndarray:
+        """IPC handles of this rank's buffers in `only`: [NBUF*64 handle bytes | NBUF present flags]."""
         ptrs, _ = self._try(self.b.shard_buffers, default=([0] * SHARD_NBUF, None))
         mine = np.zeros((SHARD_NBUF, 64), np.uint8)
         have = np.zeros(SHARD_NBUF, np.uint8)
@@ -209,13 +210,21 @@ class DistributedBuilder:
             if h:
                 mine[i] = np.frombuffer(h, np.uint8)
                 have[i] = 1
-        handles = self._gather(np.concatenate([mine.reshape(-1), have]))
+        return np.concatenate([mine.reshape(-1), have])
+
+    def _install(self, handles, only):
+        """map the peers' buffers in `only` from their all-gathered handles and hand the table to the library
+        (a mapping is kept as long as its handle does not change, see _Peers)"""
         for r in range(self.G):
             if r != self.rank:
                 hs, hv = handles[r][:SHARD_NBUF * 64].reshape(SHARD_NBUF, 64), handles[r][SHARD_NBUF * 64:]
                 for i in only:
                     self.table[r][i] = self._try(self.peers.map, r, i, hs[i].tobytes() if hv[i] else b"", default=0)
         self._try(self.b.shard_set_peers, self.table)
+
+    def _exchange(self, only):
+        """all-gather the IPC handles of this rank's buffers in `only`; map the peers'."""
+        self._install(self._gather(self._handles(only)), only)
 
     def stage(self, primary, secondary=b"", forward: bool = False):
         """forward: this rank's buffers hold forward reads only (every rank alike)."""
@@ -240,21 +249,33 @@ class DistributedBuilder:
             t.append(time.perf_counter())
 
         from .graph import SHARD_HIST, SHARD_HLL
+        NH = SHARD_NBUF * 65
+        data = [i for i in range(SHARD_NBUF) if i != BUF_GATHER]
         hist, hll = self._try(b.shard_count, default=(np.zeros(SHARD_HIST, np.uint64), np.zeros(SHARD_HLL, np.uint8)))
+        before, _ = self._try(b.shard_buffers, default=([0] * SHARD_NBUF, None))
         mark()
-        pieces = self._gather(np.concatenate([hist.view(np.uint8), hll]))     # one exchange for both
+        # one exchange: histograms, cardinality registers and the handles of the buffers as they are now
+        pieces = self._gather(np.concatenate([hist.view(np.uint8), hll, self._handles(data)]))
         mark()
         n_h = hist.size * 8
-        hist_all, hll_m, cnt = plan_inputs([x[:n_h].copy().view(np.uint64) for x in pieces], [x[n_h:] for x in pieces], self.counts)
+        hist_all, hll_m, cnt = plan_inputs([x[:n_h].copy().view(np.uint64) for x in pieces], [x[n_h:-NH] for x in pieces], self.counts)
         self._try(b.shard_plan, hist_all, hll_m, cnt)
         mark()
-        self._exchange([i for i in range(SHARD_NBUF) if i != BUF_GATHER])
-        self._barrier()                     # every peer buffer exists and is mapped everywhere
+        # the plan may have grown this rank's run buffer: only then are handles exchanged again.  This
+        # gather is also the barrier "every peer buffer exists" and carries the number of rounds.
+        after, sizes = self._try(b.shard_buffers, default=([0] * SHARD_NBUF, [0] * SHARD_NBUF))
+        grown = any(before[i] != after[i] for i in data)
+        n_rounds = self._try(b.shard_rounds, default=0)
+        flags = self._gather(np.array([1 if grown else 0, n_rounds], np.int64))
+        n_rounds = int(flags[:, 1].max())   # a failed rank still walks the rounds
+        if flags[:, 0].any():
+            self._exchange(data)
+            self._barrier()                 # ... and is mapped everywhere
+        else:
+            self._install([x[-NH:] for x in pieces], data)
         self._try(b.shard_release_retired)
         mark()
         t_sc = t_pa = 0.0
-        n_rounds = self._try(b.shard_rounds, default=0)
-        n_rounds = int(self._gather(np.array([n_rounds], np.int64)).max())   # a failed rank still walks the rounds
         n_surv = 0
         for rnd in range(n_rounds):
             if rnd:
@@ -268,9 +289,16 @@ class DistributedBuilder:
             t_pa += time.perf_counter() - t1
         t.append(t[-1] + t_sc)
         t.append(t[-1] + t_pa)
-        surv = [int(x) for x in self._gather(np.array([n_surv], np.int64))[:, 0]]
+        # survivor counts, and how much the finishing rank's gather buffer holds: every rank can tell
+        # whether rank 0 has to grow it (only then is its handle exchanged again)
+        got = self._gather(np.array([n_surv, sizes[BUF_GATHER] if sizes else 0, 1 if self._gather_mapped else 0], np.int64))
+        surv = [int(x) for x in got[:, 0]]
         self._try(b.shard_gather_plan, surv)
-        self._exchange([BUF_GATHER])
+        if max(sum(surv), 1) * 64 > int(got[0, 1]) or not got[:, 2].all():
+            self._exchange([BUF_GATHER])
+            self._gather_mapped = True
+        else:
+            self._try(self.b.shard_set_peers, self.table)
         mark()
         self._try(b.shard_send)
         self._barrier()                     # rank 0 holds every survivor record
