@@ -119,6 +119,7 @@ struct Geom {
     int m, span;        /* minimizer length min(k, MINI_M); m-mers per window: k - m + 1 */
     u32 mmask;          /* 2m ones */
     int run_max;        /* windows per run: min(RUN_MAX, 64 - k), so that a run's bases fit 128 bits */
+    u64 w_magic;        /* ceil(2^64 / w): stamp / w = umul64hi(stamp, w_magic) for stamps < 2^STAMP_BITS (w = 1: see make_geom) */
     u32 stage_runs;     /* runs a k_scatter block stages per tile (expected count + margin; the rest go out one by one) */
 };
 
@@ -1100,6 +1101,7 @@ struct RunCursor {
 struct RunFeed {
     u64 *rw;        /* [32][RUN_WORDS] this warp's chunk */
     u32 cnt, incl, total;
+    u32 live;       /* bit l: run l of the chunk has windows this pass looks at */
     template <bool GATED_ONLY>
     __device__ __forceinline__ static u32 selected(u64 w2) {
         return GATED_ONLY ? (u32)w2 & 0xFFFFFFu : (1u << run_len(w2)) - 1u;   /* run_len <= 24 */
@@ -1116,6 +1118,7 @@ struct RunFeed {
         incl = cnt;
         for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
         total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        live = __ballot_sync(0xFFFFFFFFu, cnt != 0);
         __syncwarp();
         u64 *p = rw + lane * RUN_WORDS;
         p[0] = w0; p[1] = w1; p[2] = ri < n_runs ? w2 : 0ull; p[3] = w3;
@@ -1168,9 +1171,11 @@ struct RunFeed {
             c.j += s; c.rem >>= s;
             return;
         }
-        u32 m = 0;
-        while (!m && c.l < 31) { c.l++; m = selected<GATED_ONLY>(rw[c.l * RUN_WORDS + 2]); }
+        /* the next run that has any (the caller knows there is one) */
+        const u32 ahead = c.l < 31 ? live >> (c.l + 1) : 0u;
+        c.l += ahead ? (u32)__ffs((int)ahead) : 0u;
         open<TAB2>(c, pt);
+        const u32 m = selected<GATED_ONLY>(c.w2);
         const u32 s = m ? (u32)__ffs((int)m) : 1u;
         c.j = s - 1; c.rem = m >> s;
     }
@@ -1283,7 +1288,7 @@ __device__ __forceinline__ u32 pass1_drain(const Pass1Args &a, const Geom &g, co
         }
         /* update the slot (:334-352) */
         if (found) {
-            const u32 r = (u32)(stamp / (u64)g.w);
+            const u32 r = g.w_magic ? (u32)__umul64hi(stamp, g.w_magic) : (u32)stamp;   /* stamp / w, exact for stamps below 2^40 */
             const u64 entry = stamp | ((fl & 8u) ? LOG_A : 0ull) | ((fl & 16u) ? LOG_B : 0ull);
             if (claimed) {
                 /* first arrival: arrival rank 0, nothing to compare with, and nobody else touches the slot
@@ -1745,7 +1750,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
         feed.load<false>(a.runs, chunk * THREADS + threadIdx.x, pt.n_runs);
         for (u32 base = 0; base < feed.total; base += 32 * BATCH) {
             u64 lo[BATCH], hi[BATCH], stamp[BATCH], q0[BATCH], q1[BATCH], q2[BATCH], q3[BATCH], of[BATCH];
-            u32 idx[BATCH], fl[BATCH];   /* fl: the window's FLB flag bits | gated << FLB */
+            u32 idx[BATCH], fl[BATCH];   /* fl: the window's FLB flag bits | gated << FLB | coarse stamp << 8 */
             /* A1: this lane's BATCH consecutive windows of the chunk */
             {
                 const u32 t0 = base + lane * BATCH;
@@ -1759,6 +1764,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
                         run_kmer(g, cur, lo[u], hi[u], idx[u]);
                         fl[u] = run_flags2(g, cur.w0, cur.w1, cur.w2, cur.j) | ((u32)(cur.w2 >> cur.j) & 1u) << FLB;
                         stamp[u] = cur.stamp0 + cur.j;
+                        fl[u] |= coarse_stamp(stamp[u], pt.cshift) << 8;
                     }
                 }
             }
@@ -1776,7 +1782,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
             for (int u = 0; u < BATCH; u++) {
                 of[u] = 0;
                 if (idx[u] != NIL32 && q0[u] == lo[u] && q1[u] == hi[u] && (fl[u] & 1u) &&
-                    edge_open(q2[u], (fl[u] >> 1) & 3u, coarse_stamp(stamp[u], pt.cshift))) {
+                    edge_open(q2[u], (fl[u] >> 1) & 3u, (fl[u] >> 8) & 0xFFu)) {
                     edges |= 1u << u;
                     of[u] = ld_ca_u64(&a.table[idx[u]].out_first[(fl[u] >> 1) & 3u]);
                 }
@@ -1792,7 +1798,7 @@ k_pass2(Pass2Args a, Geom g, Part pt) {
                 const bool empty = q0[u] == EMPTY64 && q1[u] == EMPTY64;
                 if (hit) {
                     pass2_update(a.table + idx[u], ungated, q2[u], q3[u], of[u], (edges >> u) & 1u, (fl[u] >> 1) & 3u, stamp[u],
-                                 coarse_stamp(stamp[u], pt.cshift), fl[u]);
+                                 (fl[u] >> 8) & 0xFFu, fl[u]);
                     n_hits++;
                     n_hits_u += ungated;
                 }

@@ -237,6 +237,8 @@ void make_geom(vdjgraph_ctx *c, uint64_t R) {
     g.span = g.k - g.m + 1;
     g.mmask = (1u << (2 * g.m)) - 1u;
     g.run_max = std::min(RUN_MAX, 64 - g.k);
+    /* ceil(2^64 / w); for w = 1 the quotient 2^64 does not fit: 2^64 - 1 gives stamp - 1 for stamp > 0, so w = 1 keeps the plain division (see k_pass1) */
+    g.w_magic = g.w > 1 ? (~0ull / (uint64_t)g.w) + 1 : 0;
     g.segs = (g.w + SEG_MAX - 1) / SEG_MAX;
     g.seg = (g.w + g.segs - 1) / g.segs;
     uint32_t tr = (uint32_t)THREADS / (uint32_t)g.segs;
