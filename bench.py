@@ -196,15 +196,7 @@ def cpu_baseline(wl: dict, sample_pairs: int, extras: bool = False):
                                         "sample": f"first {max(1, sample_pairs // 4)} pairs, compiled -g without -O like the reference's Makefile:8 ({tg:.1f} s)"}
         except Exception as e:   # the -g library is optional
             out["reference_flags_g"] = {"unavailable": str(e)[:100]}
-        # what the reference-side glue pays after vdjgraph_build returns: node pool, sparsehash `nodes`
-        # map in the reference's insertion order, edge lists (glue/vdjgraph_glue.inc), per node
-        if loader.have_glue():
-            try:
-                ms = min(loader.glue_rebuild_ms(primary, secondary, wl["read_length"], wl["k"], r) for _ in range(2))
-                out["glue_rebuild"] = {"ms_sample": ms, "nodes_sample": r["n_nodes"], "us_per_node": ms * 1e3 / max(1, r["n_nodes"]),
-                                       "note": "vdjgraph_rebuild_nodes on the sample's graph; scales with the node count"}
-            except Exception as e:
-                out["glue_rebuild"] = {"unavailable": str(e)[:100]}
+    out["_primary"], out["_secondary"] = primary, secondary
     return out
 
 
@@ -286,6 +278,52 @@ def shard_parity_check(torch, dist, db, local_rank: int, rank: int, world: int):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if float(ok[0]) == 0:
         raise SystemExit("bench: the sharded graph differs from the single-GPU graph")
+    return out
+
+
+def glue_cost(args, wl, cb, device, primary, secondary, fwd_in, n_nodes):
+    """What the reference-side glue (glue/vdjgraph_glue.inc) costs after the library call, per node, on
+    the CPU-baseline sample: (a) `nodes` bulk-loaded from the map layout the library exports
+    (VDJGRAPH_FLAG_HASHMAP_LAYOUT, computed on the device), (b) the inserts replayed on one thread as in
+    round 1; and what the layout costs the library call on the full workload.  Part of the cpu_baseline
+    leg (it drives the reference's own containers through oracle/_ref/libvdjglue.so)."""
+    from oracle import loader
+    if not loader.have_glue():
+        return None
+    from vdjer_b200 import GraphBuilder, PinnedRecords, forward_reads
+    L, k, mf, mq = wl["read_length"], wl["k"], wl["mf"], wl["mq"]
+    out = {}
+    try:
+        with GraphBuilder(L, k, mf, mq, device=device, hashmap_layout=True) as gl:
+            if fwd_in:
+                fp, fs = primary, secondary
+            else:
+                fp, fs = forward_reads(primary, L), forward_reads(secondary, L)
+            pin = None if args.pageable else PinnedRecords(fp, fs)
+            gl.build_forward(fp, fs, copy=False)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                g = gl.build_forward(fp, fs, copy=False)
+            out["e2e_ms_with_layout"] = (time.perf_counter() - t0) / args.steps * 1e3
+            out["ms_hashmap_layout"] = g.stats["ms_hashmap"]
+            out["hm_buckets"] = g.stats["hm_buckets"]
+            if pin is not None:
+                pin.close()
+            gs = gl.build(cb["_primary"], cb["_secondary"])
+        bulk = min(loader.glue_rebuild_ms(cb["_primary"], cb["_secondary"], L, k, gs) for _ in range(2))
+        os.environ["VDJGRAPH_GLUE_REPLAY"] = "1"
+        try:
+            replay = min(loader.glue_rebuild_ms(cb["_primary"], cb["_secondary"], L, k, gs) for _ in range(2))
+        finally:
+            del os.environ["VDJGRAPH_GLUE_REPLAY"]
+        out.update({"nodes_sample": gs.n_nodes, "ms_sample": bulk, "us_per_node": bulk * 1e3 / max(1, gs.n_nodes),
+                    "ms_sample_replayed_inserts": replay, "us_per_node_replayed_inserts": replay * 1e3 / max(1, gs.n_nodes),
+                    "ms_at_this_graph": bulk * 1e3 / max(1, gs.n_nodes) * n_nodes * 1e-3,
+                    "note": "vdjgraph_rebuild_nodes on the sample's graph (scales with the node count): node pool, `nodes` map "
+                            "bulk-loaded through sparsehash's unserialize from the exported layout, edge lists; "
+                            "`replayed_inserts` = the round-1 way (one insert per node on one thread)"})
+    except Exception as e:   # noqa: BLE001
+        out["unavailable"] = str(e)[:200]
     return out
 
 
@@ -557,11 +595,14 @@ def main():
         if not args.no_cpu_baseline:
             cb = cpu_baseline(wl, args.cpu_sample_pairs, extras=True)
             line["cpu_baseline"] = {k2: v for k2, v in cb.items() if not k2.startswith("_")}
-            gr = line["cpu_baseline"].get("glue_rebuild")
-            if gr and "us_per_node" in gr:
-                # the drop-in cost as V'DJer sees it: the library call plus the reference-side rebuild of ITS structures
-                gr["ms_at_this_graph"] = gr["us_per_node"] * stats["n_nodes"] * 1e-3
-                line["e2e"]["ms_with_glue_rebuild"] = ms_e2e + gr["ms_at_this_graph"]
+            if not sharded:
+                gr = glue_cost(args, wl, cb, local_rank, primary, secondary, fwd_in, stats["n_nodes"])
+                if gr:
+                    # the drop-in cost as V'DJer sees it: the library call (with the layout of the reference's
+                    # `nodes` map computed on the device) plus the reference-side rebuild of ITS structures
+                    line["cpu_baseline"]["glue_rebuild"] = gr
+                    if "ms_at_this_graph" in gr:
+                        line["e2e"]["ms_with_glue_rebuild"] = gr["e2e_ms_with_layout"] + gr["ms_at_this_graph"]
         print(json.dumps(line), flush=True)
     if world > 1:
         db.close()

@@ -67,6 +67,11 @@ typedef struct vdjgraph_params {
 
 #define VDJGRAPH_FLAG_EXPORT_KEYS 1u /* also export the packed k-mer of every node (kmer_lo/kmer_hi) */
 #define VDJGRAPH_FLAG_WIDE_TUPLES 2u /* force the 24-byte tuple format (normally chosen when k and the input size need it) */
+#define VDJGRAPH_FLAG_HASHMAP_LAYOUT 4u /* also export the layout of the reference's `nodes` map (hm_buckets, hm_slots): which
+                                           bucket of dense_hash_map<const char*, node*, my_hash, eqstr> every node occupies after
+                                           build_graph2's inserts (:305), so that the glue can load the map in one pass instead of
+                                           replaying the inserts.  Computed on the device (MurmurHash64A, sparsehash's probing and
+                                           doubling); see glue/vdjgraph_glue.inc */
 
 /*
  * The graph the reference holds after build_graph2 (:1408), as structure-of-arrays indexed by
@@ -117,6 +122,10 @@ typedef struct vdjgraph_result {
     uint64_t n_runs;                     /* run records ("super-k-mers") this device shipped: stretches of consecutive
                                             N-free windows that share a minimizer bucket, one 32-byte record each */
     uint32_t run_bytes, reserved2;       /* bytes per run record */
+    /* VDJGRAPH_FLAG_HASHMAP_LAYOUT: the reference's `nodes` map after the block, bucket by bucket */
+    uint64_t hm_buckets;                 /* its bucket count (0 without the flag) */
+    const uint32_t *hm_slots;            /* [hm_buckets] node in the bucket (creation rank), 0xFFFFFFFF = empty bucket */
+    float ms_hashmap, reserved3;         /* device time of the layout, inside ms_device */
 } vdjgraph_result;
 
 /* Pruned pass-1 table (debug/parity export; unordered): what pre_nodes holds after :1393. */

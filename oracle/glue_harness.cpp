@@ -109,3 +109,50 @@ extern "C" double vdjglue_rebuild_ms(const char *primary, const char *secondary,
     if (rc) return (double)rc;
     return (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
 }
+
+/* The iteration order of the reference's `nodes` map after its own build_graph2 (node creation ranks,
+ * i.e. id - 1, in dense_hash_map bucket order) and the bucket count: what the library's
+ * hashmap-layout export (vdjgraph_result.hm_order) must reproduce.  Returns the node count or < 0. */
+extern "C" long vdjglue_iteration_order(const char *primary, const char *secondary, int L, int k, int mf, int mq,
+                                        const char *scratch_dir, uint32_t *out_ids, long cap, uint64_t *n_buckets) {
+    set_default_params(&p);
+    p.kmer = k;
+    p.min_node_freq = mf;
+    p.min_base_quality = mq > MAX_QUAL_SUM - 1 ? MAX_QUAL_SUM - 1 : mq;
+    if (!g_vjf_ready) {
+        std::string v = std::string(scratch_dir) + "/empty_v_index";
+        std::string j = std::string(scratch_dir) + "/empty_j_index";
+        FILE *f = fopen(v.c_str(), "w"); if (!f) return -3; fclose(f);
+        f = fopen(j.c_str(), "w"); if (!f) return -3; fclose(f);
+        vjf_init((char *)v.c_str(), (char *)j.c_str(), 4, 10, 90, 'W', 486, 162);
+        g_vjf_ready = true;
+    }
+    read_length = L;
+    kmer_size = k;
+    node_id = 1;
+    struct_pool pool;
+    memset(&pool, 0, sizeof(pool));
+    node_map_t *nodes = new node_map_t();
+    nodes->set_empty_key(NULL);
+    pre_map_t pre_nodes;
+    pre_nodes.set_empty_key(NULL);
+    char *deleted_key = (char *)calloc(k, 1);
+    pre_nodes.set_deleted_key(deleted_key);
+    build_pre_graph(primary, pre_nodes);
+    build_pre_graph(secondary, pre_nodes);
+    prune_pre_graph(pre_nodes);
+    pool.nodes = (struct node *)calloc(pre_nodes.size() + 1, sizeof(struct node));
+    pool.idx = 0;
+    pool.size = pre_nodes.size() + 3;
+    build_graph2(primary, nodes, &pool, 1, pre_nodes);
+    build_graph2(secondary, nodes, &pool, 0, pre_nodes);
+    free(deleted_key);
+    long n = 0;
+    for (node_map_t::const_iterator it = nodes->begin(); it != nodes->end(); ++it) {
+        if (n < cap) out_ids[n] = (uint32_t)(it->second->id - 1);
+        n++;
+    }
+    if (n_buckets) *n_buckets = (uint64_t)nodes->bucket_count();
+    delete nodes;
+    return n;
+}

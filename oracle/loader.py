@@ -127,12 +127,35 @@ def have_glue() -> bool:
     return os.path.exists(GLUE_LIB)
 
 
+def _result_from(graph):
+    """(struct, keep-alive list): a vdjgraph_result over the arrays of a Graph / oracle dict; `hm_slots`
+    (the layout of the reference's `nodes` map) is passed on when the graph has it."""
+    from vdjer_b200.graph import _Result   # struct layout of include/vdjgraph.h
+    def get(n):
+        return graph.get(n) if isinstance(graph, dict) else getattr(graph, n, None)
+    r = _Result()
+    r.n_nodes = len(get("first_pos"))
+    keep = []
+    for name, dt in [("first_pos", np.uint64), ("frequency", np.uint16), ("out_deg", np.uint8),
+                     ("in_deg", np.uint8), ("out_succ", np.uint32), ("in_pred", np.uint32)]:
+        a = np.ascontiguousarray(get(name), dtype=dt)
+        keep.append(a)
+        setattr(r, name, a.ctypes.data_as(type(getattr(r, name))))
+    hm = get("hm_slots")
+    if hm is not None:
+        a = np.ascontiguousarray(hm, dtype=np.uint32)
+        keep.append(a)
+        r.hm_slots = a.ctypes.data_as(type(r.hm_slots))
+        r.hm_buckets = a.size
+    keep.append(r)
+    return r, keep
+
+
 def glue_dot(primary, secondary, read_length: int, k: int, mf: int, mq: int, dot_path: str,
              graph=None, scratch_dir: str | None = None):
     """Write the reference's vdjer.dot for these records.  graph=None: built by the reference's own
     functions; otherwise an object/dict with first_pos, frequency, out_deg, in_deg, out_succ,
     in_pred (the vdjgraph_result arrays), rebuilt through the glue.  Returns (n_nodes, n_roots)."""
-    from vdjer_b200.graph import _Result   # struct layout of include/vdjgraph.h
     p, s = _cbuf(primary), _cbuf(secondary)
     lib = C.CDLL(GLUE_LIB)
     lib.vdjglue_dot.restype = C.c_long
@@ -140,15 +163,7 @@ def glue_dot(primary, secondary, read_length: int, k: int, mf: int, mq: int, dot
                                 C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
     res_ptr, keep = None, []
     if graph is not None:
-        get = (lambda n: graph[n]) if isinstance(graph, dict) else (lambda n: getattr(graph, n))
-        r = _Result()
-        r.n_nodes = len(get("first_pos"))
-        for name, dt in [("first_pos", np.uint64), ("frequency", np.uint16), ("out_deg", np.uint8),
-                         ("in_deg", np.uint8), ("out_succ", np.uint32), ("in_pred", np.uint32)]:
-            a = np.ascontiguousarray(get(name), dtype=dt)
-            keep.append(a)
-            setattr(r, name, a.ctypes.data_as(type(getattr(r, name))))
-        keep.append(r)
+        r, keep = _result_from(graph)
         res_ptr = C.addressof(r)
     n_roots = C.c_long(0)
     scratch = scratch_dir or os.path.join(HERE, "_ref")
@@ -162,22 +177,32 @@ def glue_dot(primary, secondary, read_length: int, k: int, mf: int, mq: int, dot
 def glue_rebuild_ms(primary, secondary, read_length: int, k: int, graph, scratch_dir: str | None = None) -> float:
     """Wall time (ms) of glue/vdjgraph_glue.inc's vdjgraph_rebuild_nodes on these result arrays:
     what the reference-side glue costs after vdjgraph_build has returned."""
-    from vdjer_b200.graph import _Result
     p, s = _cbuf(primary), _cbuf(secondary)
     lib = C.CDLL(GLUE_LIB)
     lib.vdjglue_rebuild_ms.restype = C.c_double
     lib.vdjglue_rebuild_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p]
-    get = (lambda n: graph[n]) if isinstance(graph, dict) else (lambda n: getattr(graph, n))
-    r = _Result()
-    r.n_nodes = len(get("first_pos"))
-    keep = []
-    for name, dt in [("first_pos", np.uint64), ("frequency", np.uint16), ("out_deg", np.uint8),
-                     ("in_deg", np.uint8), ("out_succ", np.uint32), ("in_pred", np.uint32)]:
-        a = np.ascontiguousarray(get(name), dtype=dt)
-        keep.append(a)
-        setattr(r, name, a.ctypes.data_as(type(getattr(r, name))))
+    r, keep = _result_from(graph)
     scratch = scratch_dir or os.path.join(HERE, "_ref")
     ms = lib.vdjglue_rebuild_ms(p.ctypes.data, s.ctypes.data, read_length, k, scratch.encode(), C.addressof(r))
     if ms < 0:
         raise RuntimeError(f"vdjglue_rebuild_ms failed with {ms}")
     return float(ms)
+
+
+def reference_iteration_order(primary, secondary, read_length: int, k: int, mf: int, mq: int, n_nodes: int,
+                              scratch_dir: str | None = None):
+    """(ids, bucket_count): node creation ranks in the iteration order of the reference's own `nodes`
+    dense_hash_map after build_graph2, and its bucket count."""
+    p, s = _cbuf(primary), _cbuf(secondary)
+    lib = C.CDLL(GLUE_LIB)
+    lib.vdjglue_iteration_order.restype = C.c_long
+    lib.vdjglue_iteration_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                            C.c_void_p, C.c_long, C.POINTER(C.c_uint64)]
+    out = np.zeros(max(n_nodes, 1), np.uint32)
+    nb = C.c_uint64(0)
+    scratch = scratch_dir or os.path.join(HERE, "_ref")
+    n = lib.vdjglue_iteration_order(p.ctypes.data, s.ctypes.data, read_length, k, mf, mq, scratch.encode(),
+                                    out.ctypes.data, n_nodes, C.byref(nb))
+    if n != n_nodes:
+        raise RuntimeError(f"vdjglue_iteration_order returned {n}, expected {n_nodes}")
+    return out[:n_nodes], int(nb.value)

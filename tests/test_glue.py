@@ -41,13 +41,35 @@ def test_vdjer_dot_identical_from_oracle_arrays(tmp_path, built, name):
 
 
 @needs_glue
+@pytest.mark.parametrize("name", ["igh_default_k35", "permissive_k25", "pooled_2x100_k35", "k16", "hand_edges"])
+def test_vdjer_dot_identical_with_bulk_loaded_map(tmp_path, built, name):
+    """The glue's fast path: `nodes` loaded in one pass (sparsehash unserialize) from the bucket layout --
+    here the sequential model's (tests/hashmap_model.py), on the GPU the library's -- instead of replaying
+    the inserts.  Same vdjer.dot, i.e. same iteration order, ids, edges and condensed sequences."""
+    from tests import hashmap_model
+    from tests.util import kmer_codes_at
+    import numpy as np
+
+    def with_layout(p, s, c):
+        g = loader.build(p, s, c["L"], c["k"], c["mf"], c["mq"], kind="port")
+        slots, _ = hashmap_model.layout(kmer_codes_at(p, s, c["L"], c["k"], g["first_pos"]))
+        g["hm_slots"] = np.where(slots < 0, 0xFFFFFFFF, slots).astype(np.uint32)
+        return g
+
+    want, got, ref_dot, glue_dot = _dots(tmp_path, name, with_layout)
+    assert got == want, f"{name}: (nodes, roots) {got} != {want}"
+    assert glue_dot == ref_dot, f"{name}: vdjer.dot differs"
+
+
+@needs_glue
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout", [False, True])
 @pytest.mark.parametrize("name", DOT_CASES)
-def test_vdjer_dot_identical_from_cuda_graph(tmp_path, built, name):
+def test_vdjer_dot_identical_from_cuda_graph(tmp_path, built, name, layout):
     from vdjer_b200 import GraphBuilder
 
     def cuda(p, s, c):
-        with GraphBuilder(c["L"], c["k"], c["mf"], c["mq"]) as gb:
+        with GraphBuilder(c["L"], c["k"], c["mf"], c["mq"], hashmap_layout=layout) as gb:
             return gb.build(p, s)
 
     want, got, ref_dot, glue_dot = _dots(tmp_path, name, cuda)

@@ -1953,6 +1953,99 @@ k_export(ExportArgs a, Geom g, Part pt) {
     for (int e = 0; e < 4; e++) a.in_pred[i * 4 + e] = e < n ? vv[e] : NIL32;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Layout of the reference's `nodes` map (first half).  Everything downstream of   */
+/* the block iterates dense_hash_map<const char*, node*, my_hash, eqstr> (:599, :659, :1139), so */
+/* vdjer.dot, the ROOT_INIT lines and the root list depend on the BUCKET every node lands in:   */
+/* MurmurHash64A of the k ASCII characters (hash_utils.c:5-46, seed 97), divided by 8 because    */
+/* the key is a pointer (sparsehash hashtable-common.h:352-361), first-come-first-served         */
+/* triangular probing (densehashtable.h:119), the table doubling whenever an insert would fill   */
+/* more than half of it, each time by re-inserting the old table in BUCKET order (:631-653).     */
+/* The glue used to replay those inserts on one host thread (0.25 us per node, 80 % of its      */
+/* cost).  Here every doubling stage is laid out in parallel: first-come-first-served open       */
+/* addressing is the unique stable assignment in which every bucket prefers the element that is  */
+/* earlier in the insertion sequence, so elements simply keep proposing (atomicMin of their      */
+/* sequence key) to the next bucket of their probe sequence until nobody is displaced any more.  */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ u64 murmur64a_kmer(u64 lo, u64 hi, int k) {
+    const u64 m = 0xc6a4a7935bd1e995ull;
+    const int r = 47;
+    u64 h = 97ull ^ ((u64)k * m);
+    int done = 0;
+    for (; done + 8 <= k; done += 8) {   /* eight characters = one little-endian word */
+        u64 w = 0;
+        for (int j = 0; j < 8; j++) {
+            const u32 c = (u32)lo & 3u;
+            w |= (u64)(c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : 'T') << (8 * j);
+            lo = (lo >> 2) | (hi << 62);
+            hi >>= 2;
+        }
+        w *= m; w ^= w >> r; w *= m;
+        h ^= w; h *= m;
+    }
+    if (done < k) {
+        u64 w = 0;
+        for (int j = 0; done + j < k; j++) {
+            const u32 c = (u32)lo & 3u;
+            w |= (u64)(c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : 'T') << (8 * j);
+            lo = (lo >> 2) | (hi << 62);
+            hi >>= 2;
+        }
+        h ^= w; h *= m;
+    }
+    h ^= h >> r; h *= m; h ^= h >> r;
+    return h;
+}
+/* the hash as the container uses it, per node in creation order */
+__global__ void __launch_bounds__(THREADS)
+k_hm_hash(const u64 *klo, const u64 *khi, u64 n, int k, u64 *hash) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hash[i] = murmur64a_kmer(klo[i], khi[i], k) >> 3;
+}
+struct HmStage {
+    const u64 *hash;     /* [n] */
+    u64 *owner;          /* [buckets] sequence key << 32 | element; all ones = empty */
+    u32 *probe;          /* [n] collisions so far in this stage */
+    u32 *prev_bucket;    /* [n] bucket in the previous stage's table */
+    u32 *changed;
+    u32 n_old, n_all;    /* elements re-inserted from the previous table / elements of this stage */
+    u32 prev_buckets;    /* size of the previous table: keys of the newly inserted elements start there */
+    u32 mask;
+};
+__device__ __forceinline__ u32 hm_bucket(const HmStage &a, u32 e) {
+    const u64 p = a.probe[e];
+    return (u32)(a.hash[e] + p * (p + 1) / 2) & a.mask;
+}
+__device__ __forceinline__ u64 hm_key(const HmStage &a, u32 e) {
+    /* the old table's elements come first, in its bucket order; then the new ones in creation order */
+    const u32 key = e < a.n_old ? a.prev_bucket[e] : a.prev_buckets + (e - a.n_old);
+    return ((u64)key << 32) | e;
+}
+/* one round: an element that does not (or no longer) own its bucket moves on; everybody (re)proposes */
+__global__ void __launch_bounds__(THREADS)
+k_hm_round(HmStage a, int first) {
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_all) return;
+    if (first) a.probe[e] = 0;
+    else if ((u32)ld_cg_u64(&a.owner[hm_bucket(a, e)]) != e) {
+        a.probe[e]++;
+        *a.changed = 1u;
+    }
+    atomicMin(&a.owner[hm_bucket(a, e)], hm_key(a, e));
+}
+/* after the last round: remember the buckets for the next stage */
+__global__ void __launch_bounds__(THREADS)
+k_hm_settle(HmStage a) {
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < a.n_all) a.prev_bucket[e] = hm_bucket(a, e);
+}
+/* the final table as the glue reads it: node per bucket, NIL32 = empty */
+__global__ void __launch_bounds__(THREADS)
+k_hm_slots(const u64 *owner, u64 buckets, u32 *slots) {
+    const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < buckets) slots[b] = owner[b] == ~0ull ? NIL32 : (u32)owner[b];
+}
+
 /* pruned pass-1 table for parity checks */
 __global__ void __launch_bounds__(THREADS)
 k_export_pre(const Slot1 *t, u64 cap, u64 *klo, u64 *khi, u16 *freq, u64 *n_out) {

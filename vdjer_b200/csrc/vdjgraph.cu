@@ -195,6 +195,9 @@ struct vdjgraph_ctx {
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
 
     DevBuf d_tbase, d_rec, d_gather, d_t2m;
+    DevBuf d_hm_hash, d_hm_probe, d_hm_prev, d_hm_owner, d_hm_slots, d_hm_flag;
+    PinBuf h_hm_slots, h_hm_flag;
+    cudaEvent_t ev_hm[2] = {};
     PinBuf h_tbase;
     Shard sh;
 
@@ -445,6 +448,7 @@ extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out
     memset(&c->ctr, 0, sizeof(c->ctr));
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 13 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev_hm[i]);
     if (e != cudaSuccess) { delete c; return fail(VDJGRAPH_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return 0;
@@ -461,15 +465,16 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_hm_hash, &c->d_hm_probe, &c->d_hm_prev, &c->d_hm_owner, &c->d_hm_slots, &c->d_hm_flag, &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_utab, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
     for (DevBuf *b : db) b->release();
-    PinBuf *pb[] = { &c->h_utab, &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
+    PinBuf *pb[] = { &c->h_hm_slots, &c->h_hm_flag, &c->h_utab, &c->h_tbase, &c->h_bad, &c->h_ctr, &c->h_hll, &c->h_hist, &c->h_cursor, &c->h_first_pos, &c->h_freq, &c->h_odeg, &c->h_ideg, &c->h_osucc,
                      &c->h_ipred, &c->h_klo, &c->h_khi, &c->h_pre_klo, &c->h_pre_khi, &c->h_pre_freq, &c->h_pre_n };
     for (PinBuf *b : pb) b->release();
     for (int i = 0; i < 13; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; i++) if (c->ev_hm[i]) cudaEventDestroy(c->ev_hm[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1094,6 +1099,58 @@ int run_passes(vdjgraph_ctx *c) {
     return 0;
 }
 
+/* VDJGRAPH_FLAG_HASHMAP_LAYOUT: the bucket of every node in the reference's `nodes` map (kernels.cuh,
+ * k_hm_*).  One stage per table size 32, 64, ...: the stage's elements are the old table's, in its
+ * bucket order, then the nodes created while the table had this size; rounds of propose / move-on
+ * until a batch of rounds changes nothing. */
+int run_hashmap_layout(vdjgraph_ctx *c, uint64_t n) {
+    cudaStream_t s = c->stream;
+    int rc;
+    vdjgraph_result &res = c->res;
+    CK(cudaEventRecord(c->ev_hm[0], s));
+    uint64_t final_buckets = 32;
+    while (n > final_buckets / 2) final_buckets *= 2;
+    if (final_buckets > (1ull << 32)) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "hash-map layout for %llu nodes", (unsigned long long)n);
+    const size_t na = std::max<uint64_t>(n, 1);
+    if ((rc = c->d_hm_hash.ensure(na * 8)) || (rc = c->d_hm_probe.ensure(na * 4)) || (rc = c->d_hm_prev.ensure(na * 4)) ||
+        (rc = c->d_hm_owner.ensure(final_buckets * 8)) || (rc = c->d_hm_slots.ensure(final_buckets * 4)) ||
+        (rc = c->d_hm_flag.ensure(16)) || (rc = c->h_hm_flag.ensure(16)))
+        return rc;
+    const int gb = (int)((na + THREADS - 1) / THREADS);
+    if (n) k_hm_hash<<<gb, THREADS, 0, s>>>(c->d_klo.as<u64>(), c->d_khi.as<u64>(), n, c->g.k, c->d_hm_hash.as<u64>());
+    HmStage st;
+    st.hash = c->d_hm_hash.as<u64>(); st.owner = c->d_hm_owner.as<u64>(); st.probe = c->d_hm_probe.as<u32>();
+    st.prev_bucket = c->d_hm_prev.as<u32>(); st.changed = c->d_hm_flag.as<u32>();
+    uint64_t T = 32, n_prev = 0, prev_T = 0;
+    u32 *h_flag = c->h_hm_flag.as<u32>();
+    for (;;) {
+        const uint64_t n_t = std::min<uint64_t>(n, T / 2);
+        st.n_old = (u32)n_prev; st.n_all = (u32)n_t; st.prev_buckets = (u32)prev_T; st.mask = (u32)(T - 1);
+        CK(cudaMemsetAsync(st.owner, 0xFF, T * 8, s));
+        const int g_t = (int)std::max<uint64_t>(1, (n_t + THREADS - 1) / THREADS);
+        if (n_t) {
+            k_hm_round<<<g_t, THREADS, 0, s>>>(st, 1);
+            for (int batch = 0;; batch++) {
+                if (batch > 4096) return fail(VDJGRAPH_ERR_INTERNAL, "hash-map layout did not settle");
+                CK(cudaMemsetAsync(st.changed, 0, 4, s));
+                for (int r = 0; r < 4; r++) k_hm_round<<<g_t, THREADS, 0, s>>>(st, 0);
+                res.kernel_launches += 4;
+                CK(cudaMemcpyAsync(h_flag, st.changed, 4, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (!*h_flag) break;
+            }
+            k_hm_settle<<<g_t, THREADS, 0, s>>>(st);
+        }
+        if (n_t == n) break;
+        prev_T = T; n_prev = n_t; T *= 2;
+    }
+    k_hm_slots<<<(int)((T + THREADS - 1) / THREADS), THREADS, 0, s>>>(st.owner, T, c->d_hm_slots.as<u32>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_hm[1], s));
+    res.hm_buckets = T;
+    return 0;
+}
+
 /* K5: creation ranks and edge lists.  One device: straight from its survivor table.  Sharded: the
  * finishing device first builds one table over the survivor records gathered from all devices. */
 int run_finish(vdjgraph_ctx *c) {
@@ -1132,7 +1189,8 @@ int run_finish(vdjgraph_ctx *c) {
         (rc = c->d_odeg.ensure(na)) || (rc = c->d_ideg.ensure(na)) ||
         (rc = c->d_osucc.ensure(na * 16)) || (rc = c->d_ipred.ensure(na * 16)))
         return rc;
-    const bool want_keys = c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS;
+    const bool want_layout = c->prm.flags & VDJGRAPH_FLAG_HASHMAP_LAYOUT;
+    const bool want_keys = (c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS) || want_layout;   /* the layout hashes the nodes' k-mers */
     if (want_keys && ((rc = c->d_klo.ensure(na * 8)) || (rc = c->d_khi.ensure(na * 8)))) return rc;
     const int end_bit = bits_for(sh.total_records * (uint64_t)g.w);
     size_t cub_bytes = 0;
@@ -1154,6 +1212,8 @@ int run_finish(vdjgraph_ctx *c) {
         k_export<<<gb, THREADS, 0, s>>>(ae, g, pt);
         res.kernel_launches += 3;
     }
+    res.hm_buckets = 0; res.ms_hashmap = 0;
+    if (want_layout && (rc = run_hashmap_layout(c, n_surv))) return rc;
     CK(cudaEventRecord(c->ev[8], s));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -1164,6 +1224,7 @@ int run_finish(vdjgraph_ctx *c) {
         return fail(VDJGRAPH_ERR_INTERNAL, "collected %llu nodes, expected %llu", (unsigned long long)h_ctr->n_nodes, (unsigned long long)n_surv);
     c->ctr = *h_ctr;
     res.n_nodes = n_surv;
+    if (res.hm_buckets) cudaEventElapsedTime(&res.ms_hashmap, c->ev_hm[0], c->ev_hm[1]);
     if (!sh.merged()) {
         res.n_hits = h_ctr->n_hits;
         res.n_slow2 = h_ctr->n_slow2;
@@ -1472,7 +1533,15 @@ extern "C" int vdjgraph_fetch(vdjgraph_ctx *c, vdjgraph_result *out) {
         }
         CK(cudaStreamSynchronize(s));
     }
+    if (c->res.hm_buckets) {   /* the layout exists even for an empty graph: 32 empty buckets */
+        cudaStream_t s = c->stream;
+        if ((rc = c->h_hm_slots.ensure(c->res.hm_buckets * 4))) return rc;
+        CK(cudaMemcpyAsync(c->h_hm_slots.p, c->d_hm_slots.p, c->res.hm_buckets * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        bytes += c->res.hm_buckets * 4;
+    }
     vdjgraph_result &r = c->res;
+    r.hm_slots = c->res.hm_buckets ? c->h_hm_slots.as<uint32_t>() : nullptr;
     r.first_pos = c->h_first_pos.as<uint64_t>();
     r.frequency = c->h_freq.as<uint16_t>();
     r.out_deg = c->h_odeg.as<uint8_t>();
@@ -1492,7 +1561,7 @@ extern "C" int vdjgraph_stats(vdjgraph_ctx *c, vdjgraph_result *out) {
     if (!c->ran && c->sh.phase < 6) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_stats before vdjgraph_run");
     *out = c->res;
     out->first_pos = nullptr; out->frequency = nullptr; out->out_deg = out->in_deg = nullptr;
-    out->out_succ = out->in_pred = nullptr; out->kmer_lo = out->kmer_hi = nullptr;
+    out->out_succ = out->in_pred = nullptr; out->kmer_lo = out->kmer_hi = nullptr; out->hm_slots = nullptr;
     return 0;
 }
 

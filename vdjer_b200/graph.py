@@ -52,6 +52,7 @@ class _Result(C.Structure):
         ("partitions", C.c_uint32), ("tuple_bytes", C.c_uint32), ("rounds", C.c_uint32), ("reserved", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("n_runs", C.c_uint64), ("run_bytes", C.c_uint32), ("reserved2", C.c_uint32),
+        ("hm_buckets", C.c_uint64), ("hm_slots", C.POINTER(C.c_uint32)), ("ms_hashmap", C.c_float), ("reserved3", C.c_float),
     ]
 
 
@@ -62,6 +63,7 @@ class _PreTable(C.Structure):
 
 FLAG_EXPORT_KEYS = 1
 FLAG_WIDE_TUPLES = 2
+FLAG_HASHMAP_LAYOUT = 4
 
 EXPORTS = [
     "vdjgraph_version", "vdjgraph_last_error", "vdjgraph_create", "vdjgraph_destroy",
@@ -212,6 +214,7 @@ class Graph:
     kmer_lo: np.ndarray | None
     kmer_hi: np.ndarray | None
     stats: dict = field(default_factory=dict)
+    hm_slots: np.ndarray | None = None   # u32 [hm_buckets]: node per bucket of the reference's `nodes` map (hashmap_layout=True)
 
 
 @dataclass
@@ -237,11 +240,12 @@ class GraphBuilder:
 
     def __init__(self, read_length: int, k: int = 35, mf: int = 3, mq: int = 90, device: int = -1,
                  host_threads: int = 0, table_capacity: int = 0, export_keys: bool = False,
-                 partitions: int = 0, wide_tuples: bool = False, rounds: int = 0):
+                 partitions: int = 0, wide_tuples: bool = False, rounds: int = 0, hashmap_layout: bool = False):
         self._lib = load_library()
         self._ctx = C.c_void_p()
         self._p = _Params(read_length, k, mf, mq, device, host_threads, table_capacity,
-                          (FLAG_EXPORT_KEYS if export_keys else 0) | (FLAG_WIDE_TUPLES if wide_tuples else 0),
+                          (FLAG_EXPORT_KEYS if export_keys else 0) | (FLAG_WIDE_TUPLES if wide_tuples else 0) |
+                          (FLAG_HASHMAP_LAYOUT if hashmap_layout else 0),
                           partitions, rounds, 0)
         self._check(self._lib.vdjgraph_create(C.byref(self._p), C.byref(self._ctx)))
         self._keep = None
@@ -404,7 +408,7 @@ class GraphBuilder:
     def _stats(r: _Result) -> dict:
         return {k: (float(getattr(r, k)) if k.startswith("ms_") else int(getattr(r, k)))
                 for k, _ in _Result._fields_
-                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple", "rounds", "run_bytes"))}
+                if k.startswith(("n_", "ms_", "table", "h2d", "d2h", "kernel", "partitions", "tuple", "rounds", "run_bytes", "hm_buckets"))}
 
     def _graph(self, r: _Result, copy: bool = True) -> Graph:
         n = int(r.n_nodes)
@@ -414,4 +418,5 @@ class GraphBuilder:
             _np_from(r.out_deg, n, np.uint8, 1, copy), _np_from(r.in_deg, n, np.uint8, 1, copy),
             _np_from(r.out_succ, n, np.uint32, 4, copy), _np_from(r.in_pred, n, np.uint32, 4, copy),
             _np_from(r.kmer_lo, n, np.uint64, 1, copy) if r.kmer_lo else None,
-            _np_from(r.kmer_hi, n, np.uint64, 1, copy) if r.kmer_hi else None, stats)
+            _np_from(r.kmer_hi, n, np.uint64, 1, copy) if r.kmer_hi else None, stats,
+            _np_from(r.hm_slots, int(r.hm_buckets), np.uint32, 1, copy) if r.hm_slots else None)
