@@ -310,18 +310,31 @@ def glue_cost(args, wl, cb, device, primary, secondary, fwd_in, n_nodes):
             if pin is not None:
                 pin.close()
             gs = gl.build(cb["_primary"], cb["_secondary"])
-        bulk = min(loader.glue_rebuild_ms(cb["_primary"], cb["_secondary"], L, k, gs) for _ in range(2))
-        os.environ["VDJGRAPH_GLUE_REPLAY"] = "1"
-        try:
-            replay = min(loader.glue_rebuild_ms(cb["_primary"], cb["_secondary"], L, k, gs) for _ in range(2))
-        finally:
-            del os.environ["VDJGRAPH_GLUE_REPLAY"]
-        out.update({"nodes_sample": gs.n_nodes, "ms_sample": bulk, "us_per_node": bulk * 1e3 / max(1, gs.n_nodes),
-                    "ms_sample_replayed_inserts": replay, "us_per_node_replayed_inserts": replay * 1e3 / max(1, gs.n_nodes),
-                    "ms_at_this_graph": bulk * 1e3 / max(1, gs.n_nodes) * n_nodes * 1e-3,
+        # the glue spreads its work over --t threads (VDJGRAPH_GLUE_THREADS overrides); BASELINE runs the
+        # reference with --t = host cores, the glue uses at most 16
+        nt = min(16, os.cpu_count() or 1)
+
+        def timed(threads: int, replay: bool) -> float:
+            os.environ["VDJGRAPH_GLUE_THREADS"] = str(threads)
+            if replay:
+                os.environ["VDJGRAPH_GLUE_REPLAY"] = "1"
+            try:
+                return min(loader.glue_rebuild_ms(cb["_primary"], cb["_secondary"], L, k, gs) for _ in range(2))
+            finally:
+                os.environ.pop("VDJGRAPH_GLUE_THREADS", None)
+                os.environ.pop("VDJGRAPH_GLUE_REPLAY", None)
+
+        bulk, replay, bulk1, replay1 = timed(nt, False), timed(nt, True), timed(1, False), timed(1, True)
+        per = 1e3 / max(1, gs.n_nodes)
+        out.update({"nodes_sample": gs.n_nodes, "threads": nt, "ms_sample": bulk, "us_per_node": bulk * per,
+                    "us_per_node_replayed_inserts": replay * per,
+                    "us_per_node_one_thread": bulk1 * per, "us_per_node_replayed_inserts_one_thread": replay1 * per,
+                    "ms_at_this_graph": bulk * per * n_nodes * 1e-3,
+                    "ms_at_this_graph_replayed_inserts": replay * per * n_nodes * 1e-3,
                     "note": "vdjgraph_rebuild_nodes on the sample's graph (scales with the node count): node pool, `nodes` map "
-                            "bulk-loaded through sparsehash's unserialize from the exported layout, edge lists; "
-                            "`replayed_inserts` = the round-1 way (one insert per node on one thread)"})
+                            "bulk-loaded through sparsehash's unserialize from the exported layout, edge lists, on `threads` "
+                            "threads (--t); `replayed_inserts` = the round-1 way (one sparsehash insert per node on one thread "
+                            "while the others build flags and lists)"})
     except Exception as e:   # noqa: BLE001
         out["unavailable"] = str(e)[:200]
     return out
