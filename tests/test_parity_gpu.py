@@ -38,6 +38,11 @@ def test_matches_reference_golden(built, name):
     (36, 50, 25, 1, 20, 40000, 200),      # heavy branching
     (37, 150, 41, 3, 90, 10000, 300),
     (38, 255, 50, 3, 90, 4000, 100),      # longest read the reference stores
+    (39, 20, 3, 2, 40, 500, 5),           # k below the minimizer length: the k-mer is its own minimizer
+    (40, 30, 1, 2, 40, 300, 5),           # k = 1: four possible nodes
+    (41, 64, 10, 3, 90, 800, 20),         # k = m: one m-mer per window
+    (42, 64, 11, 3, 90, 800, 20),         # k = m + 1: two
+    (43, 40, 9, 2, 60, 800, 20),
 ])
 def test_matches_oracle_seeded(built, seed, L, k, mf, mq, pairs, clones):
     primary, secondary = synth.generate(n_pairs=pairs, read_length=L, seed=seed, n_clones=clones, threads=4)

@@ -139,6 +139,42 @@ def test_two_rank_rounds_over_gloo(tmp_path):
     assert l0[gp][1] == [30, 33] and l1[gp][1] == [30, 33]
 
 
+def _failing_worker(rank, world, port, out_dir, where):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard._Peers.export = lambda self, ptr: str(ptr).encode().ljust(64, b" ") if ptr else b""
+    shard._Peers.map = lambda self, r, i, h: int(h) + 5 if h else 0
+    shard._Peers.close = lambda self: None
+    b = FakeBuilder(rank, 100 + 20 * rank)
+    if rank == 1:   # this rank's library phase fails (e.g. VDJGRAPH_ERR_NOMEM in vdjgraph_shard_plan)
+        def boom(*a, **k):
+            raise MemoryError("rank 1 ran out of memory")
+        setattr(b, where, boom)
+    outcome = "finished"
+    db = shard.DistributedBuilder(b, dist)
+    try:
+        db.build(None, None)
+    except shard.ShardAborted as e:
+        outcome = "aborted: " + str(e)
+    except MemoryError as e:
+        outcome = "own error: " + str(e)
+    open(os.path.join(out_dir, f"outcome{rank}.txt"), "w").write(outcome)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("where", ["shard_plan", "shard_passes", "shard_send"])
+def test_a_failing_rank_aborts_every_rank(tmp_path, where):
+    """a rank that raises half-way through run() must not leave the others waiting in a
+    barrier.  The failing rank re-raises its own error, the other one raises ShardAborted; both return."""
+    world, port = 2, 33500 + os.getpid() % 2000 + {"shard_plan": 0, "shard_passes": 1, "shard_send": 2}[where]
+    mp.spawn(_failing_worker, args=(world, port, str(tmp_path), where), nprocs=world, join=True)
+    o0 = open(tmp_path / "outcome0.txt").read()
+    o1 = open(tmp_path / "outcome1.txt").read()
+    assert o0.startswith("aborted") and "[1]" in o0, o0
+    assert o1.startswith("own error"), o1
+
+
 def test_shard_ranges_and_split():
     assert shard.shard_ranges(10, 4) == [(0, 4), (4, 8), (8, 10), (10, 10)]
     for total, G in [(0, 2), (7, 8), (1000, 8), (1001, 4)]:
