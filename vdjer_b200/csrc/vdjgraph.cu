@@ -793,7 +793,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
         for (size_t i = 0; i < load_rnd.size(); i++) {
             const double cap1_dev = est_rnd[i];
             const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + cap1_dev * sizeof(Slot1)
-                            + std::min((double)gated_rnd[i], cap1_dev) * NBq * 8.0
+                            + std::min((double)gated_rnd[i], cap1_dev * load1 / 1.15 * 1.3) * NBq * 8.0
                             + nodes / ((double)G * sh.S) * 4.0 * sizeof(Slot2)
                             + (G * sh.S > 1 ? nodes * (sizeof(Slot2) / (double)G + 3.0 * sizeof(Slot2)) : 0.0) + nodes * 70.0;
             worst = std::max(worst, ws);
@@ -983,7 +983,11 @@ int run_passes(vdjgraph_ctx *c) {
         /* log: one block of NB stamps per distinct k-mer (<= table slots, <= gated windows), plus
          * one partially used chunk of blocks per warp */
         uint64_t warps = (uint64_t)grid_p1 * WARPS;
-        uint64_t log_cap = (uint64_t)((double)std::min<uint64_t>(n_gated, cap1) * log_scale) + warps * LOG_CHUNK + LOG_CHUNK;
+        /* (distinct k-mers, estimated: 1.3x the HyperLogLog figure of this device's units; an overrun doubles it) */
+        double est_own = 0;
+        for (int u = 0; u < sh.NU; u++) if (sh.owner[u] == sh.rank && sh.round_of[u] == sh.rnd) est_own += sh.est[u];
+        const uint64_t distinct_cap = std::min<uint64_t>(std::min<uint64_t>(n_gated, cap1), (uint64_t)(est_own * 1.3) + 4096);
+        uint64_t log_cap = (uint64_t)((double)distinct_cap * log_scale) + warps * LOG_CHUNK + LOG_CHUNK;
         if (NB == 0) log_cap = 1;
         if (log_cap > 0xFFFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "occurrence log would need %llu blocks", (unsigned long long)log_cap);
         if ((rc = c->d_t1.ensure(cap1 * sizeof(Slot1)))) return rc;
