@@ -104,3 +104,16 @@ def test_rounds_parameter_errors(built):
         with pytest.raises(VdjGraphError) as e:
             gb.pre_table()
         assert e.value.code == -7
+
+
+def test_large_graph_finish_frees_the_dead_tables(built, monkeypatch):
+    """A merged finish of a large graph gives the last round's tables back before it allocates its own
+    buffers (configs[4] at full size needs that to fit one round); the threshold is lowered here so
+    that a small build takes that path, twice on the same context."""
+    L, k, mf, mq = 50, 35, 3, 90
+    primary, secondary = synth.generate(n_pairs=30000, read_length=L, seed=306, n_clones=500, threads=4)
+    want = loader.build(primary, secondary, L, k, mf, mq, kind="port")
+    monkeypatch.setenv("VDJGRAPH_FREE_TABLES_MB", "0")
+    with GraphBuilder(L, k, mf, mq, rounds=2) as gb:
+        assert_graph_equal(gb.build(primary, secondary), want, "first build")
+        assert_graph_equal(gb.build(primary, secondary), want, "second build (tables re-allocated)")

@@ -132,6 +132,8 @@ struct StageWorker {
 };
 
 constexpr uint32_t STAGE_CHUNK = 32768; /* records per staging chunk (3.3 MB of text at L=50) */
+constexpr double MERGED_SLOTS_PER_NODE = 2.0;   /* slots of the merged survivor table per node (load 0.5) */
+constexpr uint64_t FREE_TABLES_ABOVE = 4ull << 30; /* a merged finish that needs more than this frees the last round's tables first */
 constexpr uint64_t REF_MAX_NODES = 900000000ull; /* MAX_NODES, assembler2_vdj.c:73 */
 constexpr uint64_t SLICE_BYTES = 12ull << 20;   /* table-1 bytes one hash unit addresses: L2-resident (12 MB measured better than 24 and 6) */
 
@@ -789,13 +791,20 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
     };
     auto working_set = [&]() {
         double worst = 0;
-        const double nodes = 0.6 * sh.est_distinct;
+        /* survivors / distinct gated k-mers: 0.19 .. 0.42 on the BASELINE workloads */
+        const double nodes = 0.45 * sh.est_distinct;
+        const bool merged = G * sh.S > 1;
         for (size_t i = 0; i < load_rnd.size(); i++) {
             const double cap1_dev = est_rnd[i];
-            const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + cap1_dev * sizeof(Slot1)
-                            + std::min((double)gated_rnd[i], cap1_dev * load1 / 1.15 * 1.3) * NBq * 8.0
-                            + nodes / ((double)G * sh.S) * 4.0 * sizeof(Slot2)
-                            + (G * sh.S > 1 ? nodes * (sizeof(Slot2) / (double)G + 3.0 * sizeof(Slot2)) : 0.0) + nodes * 70.0;
+            const double tables = cap1_dev * sizeof(Slot1)
+                                + std::min((double)gated_rnd[i], cap1_dev * load1 / 1.15 * 1.3) * NBq * 8.0
+                                + nodes / ((double)G * sh.S) * 4.0 * sizeof(Slot2);
+            /* the finish (on the finishing device): gathered records, merged table, sort buffers, result.  A
+             * merged finish runs when the tables of the last round are no longer needed (run_finish frees
+             * them first when the graph is large) */
+            const double finish = merged ? nodes * (sizeof(Slot2) + MERGED_SLOTS_PER_NODE * sizeof(Slot2) + 70.0) : nodes * 70.0;
+            const double records = merged ? nodes * sizeof(Slot2) / (double)G : 0.0;
+            const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + records + (merged ? std::max(tables, finish) : tables + finish);
             worst = std::max(worst, ws);
         }
         return worst;
@@ -1176,7 +1185,14 @@ int run_finish(vdjgraph_ctx *c) {
         const Slot2 *records = sh.G > 1 ? c->d_gather.as<Slot2>() : c->d_rec.as<Slot2>();
         n_surv = sh.G > 1 ? sh.surv_off[sh.G] : sh.surv_done;
         /* merged table: one flat slice (the finish looks k-mers up by slot hash alone), no device split */
-        cap2 = std::max<uint64_t>(1024, n_surv * 2 + 64);
+        cap2 = std::max<uint64_t>(1024, (uint64_t)((double)n_surv * MERGED_SLOTS_PER_NODE) + 64);
+        /* a large graph: the tables and the log of the last round are dead (the survivors are records
+         * now); give their memory back before the finish takes its own (they are re-allocated by the
+         * next build, which costs little beside a build of this size) */
+        if ((double)(cap2 * sizeof(Slot2)) > env_double("VDJGRAPH_FREE_TABLES_MB", (double)(FREE_TABLES_ABOVE >> 20)) * 1048576.0) {
+            CK(cudaStreamSynchronize(s));
+            c->d_t1.release(); c->d_log.release(); c->d_t2.release();
+        }
         if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "merged survivor table too large");
         pt.flat = 1; pt.flat_len = (u32)cap2;
         if ((rc = c->d_t2m.ensure(cap2 * sizeof(Slot2)))) return rc;
