@@ -133,7 +133,6 @@ struct StageWorker {
 
 constexpr uint32_t STAGE_CHUNK = 32768; /* records per staging chunk (3.3 MB of text at L=50) */
 constexpr double MERGED_SLOTS_PER_NODE = 2.0;   /* slots of the merged survivor table per node (load 0.5) */
-constexpr uint64_t FREE_TABLES_ABOVE = 4ull << 30; /* a merged finish that needs more than this frees the last round's tables first */
 constexpr uint64_t REF_MAX_NODES = 900000000ull; /* MAX_NODES, assembler2_vdj.c:73 */
 constexpr uint64_t SLICE_BYTES = 12ull << 20;   /* table-1 bytes one hash unit addresses: L2-resident (12 MB measured better than 24 and 6) */
 
@@ -789,6 +788,7 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
             est_rnd[(size_t)d * S + best] += (double)unit_slots1(sh, c->prm, u, load1);
         }
     };
+    const bool free_tables = env_double("VDJGRAPH_FREE_TABLES_MB", -1.0) >= 0;
     auto working_set = [&]() {
         double worst = 0;
         /* survivors / distinct gated k-mers: 0.19 .. 0.42 on the BASELINE workloads */
@@ -800,11 +800,11 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
                                 + std::min((double)gated_rnd[i], cap1_dev * load1 / 1.15 * 1.3) * NBq * 8.0
                                 + nodes / ((double)G * sh.S) * 4.0 * sizeof(Slot2);
             /* the finish (on the finishing device): gathered records, merged table, sort buffers, result.  A
-             * merged finish runs when the tables of the last round are no longer needed (run_finish frees
-             * them first when the graph is large) */
+             * merged finish runs when the tables of the last round are no longer needed; with
+             * VDJGRAPH_FREE_TABLES_MB set, run_finish frees them first (see there) */
             const double finish = merged ? nodes * (sizeof(Slot2) + MERGED_SLOTS_PER_NODE * sizeof(Slot2) + 70.0) : nodes * 70.0;
             const double records = merged ? nodes * sizeof(Slot2) / (double)G : 0.0;
-            const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + records + (merged ? std::max(tables, finish) : tables + finish);
+            const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + records + (merged && free_tables ? std::max(tables, finish) : tables + finish);
             worst = std::max(worst, ws);
         }
         return worst;
@@ -1186,14 +1186,16 @@ int run_finish(vdjgraph_ctx *c) {
         n_surv = sh.G > 1 ? sh.surv_off[sh.G] : sh.surv_done;
         /* merged table: one flat slice (the finish looks k-mers up by slot hash alone), no device split */
         cap2 = std::max<uint64_t>(1024, (uint64_t)((double)n_surv * MERGED_SLOTS_PER_NODE) + 64);
-        /* a large graph: the tables and the log of the last round are dead (the survivors are records
-         * now); give their memory back before the finish takes its own (they are re-allocated by the
-         * next build, which costs little beside a build of this size) */
-        if ((double)(cap2 * sizeof(Slot2)) > env_double("VDJGRAPH_FREE_TABLES_MB", (double)(FREE_TABLES_ABOVE >> 20)) * 1048576.0) {
+        /* VDJGRAPH_FREE_TABLES_MB = m: when the merged table exceeds m MB, the tables and the log of the last
+         * round (dead: the survivors are records now) are freed before the finish takes its own memory, and
+         * the plan counts on that.  Off by default: measured on configs[4] at full size on 8 GPUs it lets the
+         * build run in one round (scatter 166 -> 104 ms) but re-allocating 19 GB per build costs as much
+         * (passes 339 -> 424, finish 103 -> 175 ms); it pays for a single build that would otherwise not fit. */
+        const double free_mb = env_double("VDJGRAPH_FREE_TABLES_MB", -1.0);
+        if (free_mb >= 0 && (double)(cap2 * sizeof(Slot2)) > free_mb * 1048576.0) {
             CK(cudaStreamSynchronize(s));
             c->d_t1.release(); c->d_log.release(); c->d_t2.release();
         }
-        if (cap2 > 0x7FFFFFF0ull) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "merged survivor table too large");
         pt.flat = 1; pt.flat_len = (u32)cap2;
         if ((rc = c->d_t2m.ensure(cap2 * sizeof(Slot2)))) return rc;
         table = c->d_t2m.as<Slot2>();
