@@ -18,8 +18,8 @@ synthetic read set.  Unit: windows (k-mer positions) per second, W = records * (
 
 --impl reference times that CPU path alone with the same metric/config.
 N > 1 (torchrun): ONE graph over the reads of all ranks (weak scaling: every rank contributes the
-N=1 workload generated with a rank-specific seed).  k-mers are hash-sharded, the scatter kernel
-writes each tuple into the owning GPU's buffer through peer-mapped memory, survivors are gathered
+N=1 workload, its own pairs of the same repertoire).  k-mers are hash-sharded by minimizer, the scatter
+kernel writes each run into the owning GPU's buffer through peer-mapped memory, survivors are gathered
 on rank 0 which ranks the nodes and builds the edge lists (DESIGN.md "Multi-GPU").  All ranks draw
 disjoint reads from the SAME clone library (one pooled repertoire sequenced N times deeper).
 """
@@ -382,7 +382,7 @@ def main():
                     help="generate forward reads only (half the host memory: configs[4] at full size) and run everything, "
                          "`e2e` included, through vdjgraph_*_forward; the doubled text is never materialised")
     ap.add_argument("--no-forward", action="store_true", help="skip the forward-reads-only end-to-end measurement")
-    ap.add_argument("--rounds", type=int, default=0, help="hash super-partition rounds (0 = auto: 1 unless the tuples exceed HBM)")
+    ap.add_argument("--rounds", type=int, default=0, help="rounds over groups of hash units (0 = auto: 1 unless the working set exceeds HBM)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -435,7 +435,7 @@ def main():
     gb = GraphBuilder(L, k, mf, mq, device=local_rank, host_threads=host_threads, rounds=args.rounds)
     sharded = world > 1
     if sharded:
-        # one graph over the reads of all ranks: k-mers hash-sharded, tuples exchanged by the scatter
+        # one graph over the reads of all ranks: k-mers hash-sharded by minimizer, runs exchanged by the scatter
         # kernel through peer-mapped memory, survivors gathered on rank 0 (vdjer_b200/shard.py)
         from vdjer_b200 import shard
         db = shard.DistributedBuilder(gb, dist, device=f"cuda:{local_rank}")   # small exchanges ride NCCL
@@ -556,8 +556,8 @@ def main():
             "config": {"workload": args.workload, "read_length": L, "k": k, "mf": mf, "mq": mq,
                        "pairs_per_gpu": wl["n_pairs"], "records_per_gpu": stats["n_records"], "windows_per_gpu": W,
                        "l2_policy": "inputs_larger_than_L2 (packed reads + tables >> 126 MB, tables re-initialised every step)",
-                       "parallelism": (f"one graph over {world} GPUs: k-mers hash-sharded (partition p -> GPU p mod {world}), "
-                                       "scatter kernel writes tuples into the owner's peer-mapped buffer, survivors gathered on rank 0; "
+                       "parallelism": (f"one graph over {world} GPUs: k-mers hash-sharded by minimizer (hash units dealt to GPUs by measured load), "
+                                       "scatter kernel writes runs into the owner's peer-mapped buffer, survivors gathered on rank 0; "
                                        "step timed between barriers") if sharded else "1 GPU",
                        "distinct_gated_kmers": int(sums["n_pre_total"]) if sharded else stats["n_pre_total"],
                        "nodes": stats["n_nodes"],

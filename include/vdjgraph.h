@@ -56,17 +56,20 @@ typedef struct vdjgraph_params {
     int32_t host_threads;     /* staging threads (pageable text -> pinned chunks -> H2D; packing runs on the device); 0 = auto */
     uint64_t table_capacity;  /* pass-1 table slots; 0 = auto (cardinality estimate on device) */
     uint32_t flags;           /* VDJGRAPH_FLAG_* */
-    uint32_t partitions;      /* hash partitions (power of two <= 256); 0 = auto (table slice ~24 MB, L2-resident) */
-    uint32_t rounds;          /* hash super-partitions processed one after the other (power of two, rounds * devices
-                                 <= 256): the tuple buffer and both tables hold 1/rounds of the hash space at a time
-                                 and the packed reads are streamed once per round -- for inputs whose tuples do not
-                                 fit HBM (BASELINE configs[4]).  0 = auto: the smallest count whose working set fits
-                                 the device (1 for everything up to configs[3]).  Results do not depend on it */
+    uint32_t partitions;      /* hash units (power of two <= 256: groups of the 256 minimizer buckets, each with its own
+                                 slice of the tables); 0 = auto (table slice ~12 MB, L2-resident) */
+    uint32_t rounds;          /* groups of hash units processed one after the other (power of two, rounds * devices
+                                 <= 256): the run buffer and both tables hold one group at a time and the packed
+                                 reads are streamed once per round -- for inputs whose working set does not fit HBM
+                                 (BASELINE configs[4] on the finishing rank).  0 = auto: the smallest count whose
+                                 working set fits the device (1 for everything up to configs[3] and for configs[4]'s
+                                 per-GPU share).  Results do not depend on it */
     uint32_t reserved;        /* 0 */
 } vdjgraph_params;
 
 #define VDJGRAPH_FLAG_EXPORT_KEYS 1u /* also export the packed k-mer of every node (kmer_lo/kmer_hi) */
-#define VDJGRAPH_FLAG_WIDE_TUPLES 2u /* force the 24-byte tuple format (normally chosen when k and the input size need it) */
+#define VDJGRAPH_FLAG_WIDE_TUPLES 2u /* force the 24-byte form of the per-window tuples the slow-path queues hold (normally chosen when k
+                                        and the input size need it) */
 #define VDJGRAPH_FLAG_HASHMAP_LAYOUT 4u /* also export the layout of the reference's `nodes` map (hm_buckets, hm_slots): which
                                            bucket of dense_hash_map<const char*, node*, my_hash, eqstr> every node occupies after
                                            build_graph2's inserts (:305), so that the glue can load the map in one pass instead of
@@ -102,7 +105,7 @@ typedef struct vdjgraph_result {
     uint64_t n_pre_total;      /* "Pre Num nodes": distinct gated k-mers */
     uint64_t n_pre;            /* "pre nodes after pruning" (= n_nodes) */
     uint64_t n_hits;           /* pass-2 windows whose k-mer survived (uncapped) */
-    uint64_t n_slow1, n_slow2; /* diagnostics: tuples that took the slow (queued) path of pass 1 / pass 2 */
+    uint64_t n_slow1, n_slow2; /* diagnostics: windows that took the slow (queued) path of pass 1 / pass 2 */
     uint64_t n_hits_ungated;   /* pass-2 hits among the windows that failed the quality gate (only those add to node->frequency in pass 2) */
 
     /* timings of the last build, milliseconds */
@@ -115,7 +118,7 @@ typedef struct vdjgraph_result {
     float ms_estimate, ms_scatter, ms_init1, ms_pass1, ms_prune, ms_table2, ms_pass2, ms_export;
     float ms_fetch;            /* D2H of the result (wall clock) */
     uint64_t table1_slots, table2_slots; /* capacities used */
-    uint32_t partitions, tuple_bytes;    /* hash partitions and tuple size used */
+    uint32_t partitions, tuple_bytes;    /* hash units used; bytes of a queued per-window tuple (16 or 24) */
     uint32_t rounds, reserved;           /* super-partition rounds used */
     uint64_t h2d_bytes, d2h_bytes;       /* bytes moved by stage / fetch */
     uint64_t kernel_launches;            /* our kernels launched by the last run (CUB's sort passes not counted) */
@@ -199,10 +202,11 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
 
 /*
  * Sharded build over G = 1, 2, 4 or 8 devices: records are split into contiguous
- * ranges, k-mers are owner-computed (hash partition p belongs to device p mod G).  The caller
+ * ranges, k-mers are owner-computed (every hash unit belongs to one device; units are dealt to devices
+ * largest-first from the all-gathered window counts, identically on every rank).  The caller
  * runs one context per device (one process per GPU, or several contexts in one process) and
  * drives the phases below on all of them, exchanging three small host messages in between.  The
- * bulk exchange is done by the scatter kernel itself, which writes every tuple into the owner's
+ * bulk exchange is done by the scatter kernel itself, which writes every run into the owner's
  * buffer through peer-mapped memory (NVLink); survivors are gathered once, on rank 0, which ranks
  * the nodes and builds the edge lists.  Results are identical to the one-device build.
  *
@@ -213,14 +217,14 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
  *   all ranks : vdjgraph_shard_set_peers ; BARRIER ; vdjgraph_shard_release_retired ; vdjgraph_shard_scatter ; BARRIER
  *   all ranks : vdjgraph_shard_passes                                             -> survivor count
  *   (more than one round, vdjgraph_shard_rounds() > 1: BARRIER ; vdjgraph_shard_scatter ; BARRIER ;
- *    vdjgraph_shard_passes again, once per further round: the scatter of round r+1 overwrites the tuple
+ *    vdjgraph_shard_passes again, once per further round: the scatter of round r+1 overwrites the run
  *    buffers that the owners' passes of round r read)
  *   exchange  : all-gather the survivor counts
  *   all ranks : vdjgraph_shard_gather_plan ; rank 0's GATHER pointer to everybody ; set_peers
  *   all ranks : vdjgraph_shard_send ; BARRIER
  *   rank 0    : vdjgraph_shard_finish -> vdjgraph_fetch
  */
-#define VDJGRAPH_SHARD_NBUF 6       /* bases, valid, qual, strand, tuples, gather */
+#define VDJGRAPH_SHARD_NBUF 6       /* bases, valid, qual, strand, runs, gather */
 #define VDJGRAPH_SHARD_HIST 768     /* uint64 per rank: [runs | gated windows | N-free windows][256 minimizer buckets] */
 #define VDJGRAPH_SHARD_HLL 32768    /* bytes: 128 HyperLogLog registers per minimizer bucket */
 

@@ -133,7 +133,7 @@ struct Part {
     int ushift;         /* unit = bucket >> ushift; NBUCKET >> ushift units */
     int hb;             /* bits of the k-mer above 64: max(0, 2k-64) */
     int wide;           /* 1: 24-byte queue tuples (stamp in a third word) */
-    int fb;             /* read-fingerprint bits carried by a tuple (<= 25; fewer only via the test hook) */
+    int fb;             /* read-fingerprint bits carried by a tuple (<= RUN_FP_BITS; fewer only via the test hook) */
     u32 hot_t, hot_flush; /* pass 1: fast-path increments of k-mers whose count is already >= hot_t are summed in a
                              small per-warp shared-memory cache and added to the table every hot_flush batches */
     u32 qflush1, qdense1, qflush2, qdense2; /* slow-path queue policy of pass 1 / pass 2 (<= QFLUSH, see WarpQueue) */
@@ -785,7 +785,7 @@ __device__ __forceinline__ void ld_run(const u64 *p, u64 &a, u64 &b, u64 &c, u64
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K1 k_scatter: every run goes to the region of its hash unit in the tuple buffer of the       */
+/* K1 k_scatter: every run goes to the region of its hash unit in the run buffer of the         */
 /* device that owns the unit (cursor[] starts at this device's share of each region, from the   */
 /* all-gathered k_count histograms).  Per tile a block                                           */
 /*   1. rolls its windows once: run descriptors go to a list in shared memory, units are counted,*/
@@ -801,7 +801,7 @@ __device__ __forceinline__ void ld_run(const u64 *p, u64 &a, u64 &b, u64 &c, u64
 /* ------------------------------------------------------------------------------------------ */
 struct ScatterArgs {
     const u64 *bases, *good, *valid, *hiq;
-    u64 *const *tbase; /* [units] tuple buffer of the device that owns the unit (peer-mapped when that is another
+    u64 *const *tbase; /* [units] run buffer of the device that owns the unit (peer-mapped when that is another
                           device); null: not in this round */
     u64 *cursor;       /* [units] next free run of this device's share of the unit's region */
     const u64 *limit;  /* [units] end of that share (overrun check) */
@@ -1006,7 +1006,7 @@ __device__ __forceinline__ bool same_read(const Reads &rd, u64 r1, u64 r2, int n
 
 /* ------------------------------------------------------------------------------------------ */
 /* K2 k_pass1: pass 1 = build_pre_graph / add_to_table (:322-409) as commutative reductions    */
-/* over the GATED tuples, walked in partition order so that the table slice being updated is    */
+/* over the GATED windows of the runs, walked unit by unit so that the table slice being updated is */
 /* L2-resident:                                                                                  */
 /*   count        -> pre_node.frequency (:334, :345-347)                                        */
 /*   CNT_MULTI    -> hasMultipleUniqueReads (:349-352): some occurrence's record differs from   */
@@ -1646,7 +1646,7 @@ k_table2_from_records(const Slot2 *rec, u64 n, Slot2 *t2, u64 cap2, Geom g, Part
 /*   out_first[c] -> first time the edge K -> K[1:]+c can have been linked (:311-313); ordering */
 /*                   these reproduces the head-insertion order of toNodes (:223-229) and, read  */
 /*                   from the predecessor's side, of fromNodes (:231-236).                      */
-/* All tuples (gated region, then ungated region) in partition order; atomics are skipped when  */
+/* All windows of all runs, unit by unit; atomics are skipped when                                */
 /* the loaded value already dominates, so hot k-mers cost reads only.                           */
 /* ------------------------------------------------------------------------------------------ */
 struct Pass2Args {
@@ -1681,7 +1681,7 @@ __device__ __forceinline__ void pass2_update(Slot2 *slot, bool count_it, u64 c2,
 }
 
 /* slow path of pass 2: tuples whose home slot holds a different k-mer; queue entries carry the
- * tuple, its home slot and (top bit of idx) whether the tuple is from the ungated region */
+ * tuple, its home slot and (top bit of idx) whether the window failed the quality gate */
 template <bool WIDE>
 __device__ __forceinline__ u32 pass2_drain(const Pass2Args &a, const Part &pt, WarpQueue<WIDE> &q, u32 &qn, bool final, u32 &n_hits_u) {
     const u32 lane = threadIdx.x & 31, lt = (1u << lane) - 1;

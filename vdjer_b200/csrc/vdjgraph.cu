@@ -596,7 +596,7 @@ extern "C" int vdjgraph_stage_forward(vdjgraph_ctx *c, const char *primary_reads
 /* devices (one process per GPU, or G contexts in one process): the caller interleaves them with */
 /* three tiny host exchanges (window histograms, peer pointers, survivor counts); the only bulk  */
 /* data movement between devices is done by the kernels themselves through peer-mapped memory:  */
-/* k_scatter writes each tuple straight into the buffer of the device that owns its partition.  */
+/* k_scatter writes each run straight into the buffer of the device that owns its hash unit.     */
 /* ========================================================================================== */
 namespace {
 

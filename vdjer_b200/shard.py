@@ -1,10 +1,12 @@
 """Sharded graph build over G = 1, 2, 4 or 8 B200s (phases in include/vdjgraph.h).
 
 Records are split into contiguous ranges (rank order = record order), k-mers are owner-computed:
-hash partition p belongs to rank p mod G.  This module is only the host plumbing between the
-library's phases: three small all-gathers (window histograms + record counts + HyperLogLog
-registers, device pointers, survivor counts) and three barriers.  The bulk exchange is inside the
-kernels: k_scatter writes every tuple straight into the owner's buffer through peer-mapped memory
+every hash unit (a group of minimizer buckets) belongs to one rank, chosen by the library from the
+all-gathered window counts.  This module is only the host plumbing between the library's phases:
+six small collectives per build (histograms + HyperLogLog registers + IPC handles in one all-gather,
+a flag gather that doubles as a barrier, one barrier per round, survivor counts, two barriers around
+the send and the finish).  The bulk exchange is inside the kernels: k_scatter writes every run (a
+stretch of consecutive windows, 32 bytes) straight into the owner's buffer through peer-mapped memory
 (NVLink / NVSwitch), the exact read comparison and the quality rows of border k-mers are peer
 loads, and the survivors travel to rank 0 as one device-to-device copy per rank.
 
