@@ -436,7 +436,8 @@ def main():
     sharded = world > 1
     if sharded:
         # one graph over the reads of all ranks: k-mers hash-sharded by minimizer, runs exchanged by the scatter
-        # kernel through peer-mapped memory, survivors gathered on rank 0 (vdjer_b200/shard.py)
+        # kernel through peer-mapped memory, every rank finishes its own survivors and stores the node rows into
+        # rank 0's result buffer (vdjer_b200/shard.py)
         from vdjer_b200 import shard
         db = shard.DistributedBuilder(gb, dist, device=f"cuda:{local_rank}")   # small exchanges ride NCCL
         stage, run = (lambda: db.stage(primary, secondary, forward=fwd_in)), db.run
@@ -557,7 +558,8 @@ def main():
                        "pairs_per_gpu": wl["n_pairs"], "records_per_gpu": stats["n_records"], "windows_per_gpu": W,
                        "l2_policy": "inputs_larger_than_L2 (packed reads + tables >> 126 MB, tables re-initialised every step)",
                        "parallelism": (f"one graph over {world} GPUs: k-mers hash-sharded by minimizer (hash units dealt to GPUs by measured load), "
-                                       "scatter kernel writes runs into the owner's peer-mapped buffer, survivors gathered on rank 0; "
+                                       "scatter kernel writes runs into the owner's peer-mapped buffer, every GPU ranks and links its own survivors "
+                                       "(peer loads for neighbours owned elsewhere, device-side barriers) and stores the node rows into rank 0's result buffer; "
                                        "step timed between barriers") if sharded else "1 GPU",
                        "distinct_gated_kmers": int(sums["n_pre_total"]) if sharded else stats["n_pre_total"],
                        "nodes": stats["n_nodes"],

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VDJGRAPH_ABI_VERSION 4
+#define VDJGRAPH_ABI_VERSION 5
 
 typedef enum vdjgraph_status {
     VDJGRAPH_OK = 0,
@@ -207,8 +207,14 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
  * runs one context per device (one process per GPU, or several contexts in one process) and
  * drives the phases below on all of them, exchanging three small host messages in between.  The
  * bulk exchange is done by the scatter kernel itself, which writes every run into the owner's
- * buffer through peer-mapped memory (NVLink); survivors are gathered once, on rank 0, which ranks
- * the nodes and builds the edge lists.  Results are identical to the one-device build.
+ * buffer through peer-mapped memory (NVLink).  The finish is distributed as well: every device
+ * ranks and links ITS survivors (three steps; a neighbour k-mer is looked up in the table of the
+ * device that owns it, a peer load) and stores the finished node rows into rank 0's result buffer
+ * (peer stores); between the steps the devices meet at a barrier kept in peer memory
+ * (device_barrier = 1: the three steps are queued back to back, no host round trip) or on the
+ * host (device_barrier = 0: every step returns with its stream synchronised and the caller holds
+ * a barrier of its own before the next; needed when several ranks share one process and thread).
+ * Results are identical to the one-device build.
  *
  *   all ranks : vdjgraph_shard_stage -> vdjgraph_shard_count                      -> hist, hll
  *   exchange  : all-gather hist and record counts, element-wise max of hll
@@ -220,11 +226,12 @@ int vdjgraph_fetch(vdjgraph_ctx *ctx, vdjgraph_result *out);
  *    vdjgraph_shard_passes again, once per further round: the scatter of round r+1 overwrites the run
  *    buffers that the owners' passes of round r read)
  *   exchange  : all-gather the survivor counts
- *   all ranks : vdjgraph_shard_gather_plan ; rank 0's GATHER pointer to everybody ; set_peers
- *   all ranks : vdjgraph_shard_send ; BARRIER
- *   rank 0    : vdjgraph_shard_finish -> vdjgraph_fetch
+ *   all ranks : vdjgraph_shard_gather_plan ; everybody's GATHER pointer to everybody (only when one
+ *               had to grow: vdjgraph_shard_finish_bytes tells) ; set_peers ; BARRIER
+ *   all ranks : vdjgraph_shard_finish_step 0, 1, 2  (device_barrier = 0: BARRIER after each)
+ *   all ranks : vdjgraph_shard_finish ; BARRIER ; rank 0: vdjgraph_fetch
  */
-#define VDJGRAPH_SHARD_NBUF 6       /* bases, valid, qual, strand, runs, gather */
+#define VDJGRAPH_SHARD_NBUF 6       /* bases, valid, qual, strand, runs, gather (= the finish's exchange buffer) */
 #define VDJGRAPH_SHARD_HIST 768     /* uint64 per rank: [runs | gated windows | N-free windows][256 minimizer buckets] */
 #define VDJGRAPH_SHARD_HLL 32768    /* bytes: 128 HyperLogLog registers per minimizer bucket */
 
@@ -252,7 +259,12 @@ int vdjgraph_shard_set_peers(vdjgraph_ctx *ctx, void *const *ptrs /*[n_ranks][NB
 int vdjgraph_shard_scatter(vdjgraph_ctx *ctx);
 int vdjgraph_shard_passes(vdjgraph_ctx *ctx, uint64_t *n_survivors /* of this rank, all rounds so far */);
 int vdjgraph_shard_gather_plan(vdjgraph_ctx *ctx, const uint64_t *survivors_all /*[n_ranks]*/);
-int vdjgraph_shard_send(vdjgraph_ctx *ctx);
+/* bytes of rank `rank`'s GATHER buffer that vdjgraph_shard_gather_plan will ask for (a pure function of the
+ * survivor counts: every rank can tell which buffers have to grow, i.e. which handles travel again) */
+int vdjgraph_shard_finish_bytes(const uint64_t *survivors_all /*[n_ranks]*/, uint32_t n_ranks, uint32_t rank, size_t *bytes);
+/* step 0: own survivor table + sorted stamps; 1: creation ranks; 2: edge lists, node rows to rank 0 */
+int vdjgraph_shard_finish_step(vdjgraph_ctx *ctx, int step, int device_barrier);
+/* every rank: waits for its stream, checks its counters; rank 0 also unpacks the rows into the result */
 int vdjgraph_shard_finish(vdjgraph_ctx *ctx);
 /* Peers may keep their mappings across builds.  A buffer that had to grow is replaced, not freed;
  * call this after a barrier that follows vdjgraph_shard_set_peers to free the replaced ones. */

@@ -24,7 +24,7 @@ def test_header_symbols_exported(built):
     assert set(names) == set(graph.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vdjgraph.h but not exported"
-    assert lib.vdjgraph_version() == 4
+    assert lib.vdjgraph_version() == 5
 
 
 def test_struct_layouts_match_header(built):

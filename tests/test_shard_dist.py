@@ -1,8 +1,8 @@
 """CPU, world_size 2 over gloo: the host plumbing of the sharded build (vdjer_b200/shard.py).
 No GPU here, so the library's phases are played by a recording stand-in; what is checked is what
 the plumbing is responsible for: every rank hands the SAME merged inputs to the plan phase, record
-bases follow rank order, peer tables are complete and exclude nobody, the gather pointer of rank 0
-reaches everybody, phases run in the documented order and nobody deadlocks.
+bases follow rank order, peer tables are complete and exclude nobody, every rank's exchange buffer
+reaches every peer, phases run in the documented order and nobody deadlocks.
 The device side of the same flow is covered on a GPU by tests/test_shard_gpu.py."""
 import os
 import sys
@@ -65,11 +65,13 @@ class FakeBuilder:
 
     def shard_gather_plan(self, surv):
         self.log.append(("gather_plan", list(surv)))
-        if self.rank == 0:
-            self.gather = 777
+        self.gather = 777 + 100 * self.rank
 
-    def shard_send(self):
-        self.log.append(("send",))
+    def shard_finish_bytes(self, surv, rank):
+        return 64 * sum(surv) + 8 * surv[rank]
+
+    def shard_finish_step(self, step, device_barrier):
+        self.log.append(("step", step, device_barrier))
 
     def shard_finish(self):
         self.log.append(("finish",))
@@ -101,8 +103,11 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     logs = [np.load(tmp_path / f"log{r}.npy", allow_pickle=True) for r in range(world)]
     (l0, g0), (l1, g1) = logs
     assert g0 == "graph" and g1 is None
-    order = ["stage", "count", "plan", "peers", "release", "scatter", "passes", "gather_plan", "peers", "send", "release"]
-    assert [e[0] for e in l0] == order + ["finish"] and [e[0] for e in l1] == order
+    order = ["stage", "count", "plan", "peers", "release", "scatter", "passes", "gather_plan", "peers", "step", "step", "step",
+             "finish", "release"]
+    assert [e[0] for e in l0] == order and [e[0] for e in l1] == order
+    # the three steps of the finish, in order, meeting in peer memory (the default)
+    assert [e[1:] for e in l0 if e[0] == "step"] == [(0, True), (1, True), (2, True)]
     # record bases follow rank order; totals agree
     assert l0[0] == ("stage", 2, 0, 0, 220) and l1[0] == ("stage", 2, 1, 100, 220)
     # both ranks plan from identical merged inputs
@@ -120,9 +125,9 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     assert t0[0] == [0] * SHARD_NBUF and t1[1] == [0] * SHARD_NBUF
     assert t0[1][:BUF_GATHER] == [2000 + i + 5 for i in range(BUF_GATHER)]
     assert t1[0][:BUF_GATHER] == [1000 + i + 5 for i in range(BUF_GATHER)]
-    # survivor counts all-gathered; rank 0's gather buffer reaches rank 1
+    # survivor counts all-gathered; each rank's exchange buffer reaches the other
     assert l0[7][1] == [10, 11] and l1[7][1] == [10, 11]
-    assert l1[8][1][0][BUF_GATHER] == 777 + 5 and l0[8][1][1][BUF_GATHER] == 0
+    assert l1[8][1][0][BUF_GATHER] == 777 + 5 and l0[8][1][1][BUF_GATHER] == 877 + 5
 
 
 @pytest.mark.timeout(120)
@@ -133,8 +138,8 @@ def test_two_rank_rounds_over_gloo(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path), 3), nprocs=world, join=True)
     logs = [np.load(tmp_path / f"log{r}.npy", allow_pickle=True) for r in range(world)]
     (l0, _), (l1, _) = logs
-    order = ["stage", "count", "plan", "peers", "release"] + ["scatter", "passes"] * 3 + ["gather_plan", "peers", "send", "release"]
-    assert [e[0] for e in l0] == order + ["finish"] and [e[0] for e in l1] == order
+    order = ["stage", "count", "plan", "peers", "release"] + ["scatter", "passes"] * 3 + ["gather_plan", "peers"] + ["step"] * 3 + ["finish", "release"]
+    assert [e[0] for e in l0] == order and [e[0] for e in l1] == order
     gp = order.index("gather_plan")
     assert l0[gp][1] == [30, 33] and l1[gp][1] == [30, 33]
 
@@ -163,11 +168,11 @@ def _failing_worker(rank, world, port, out_dir, where):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("where", ["shard_plan", "shard_passes", "shard_send"])
+@pytest.mark.parametrize("where", ["shard_plan", "shard_passes", "shard_finish_step"])
 def test_a_failing_rank_aborts_every_rank(tmp_path, where):
     """a rank that raises half-way through run() must not leave the others waiting in a
     barrier.  The failing rank re-raises its own error, the other one raises ShardAborted; both return."""
-    world, port = 2, 33500 + os.getpid() % 2000 + {"shard_plan": 0, "shard_passes": 1, "shard_send": 2}[where]
+    world, port = 2, 33500 + os.getpid() % 2000 + {"shard_plan": 0, "shard_passes": 1, "shard_finish_step": 2}[where]
     mp.spawn(_failing_worker, args=(world, port, str(tmp_path), where), nprocs=world, join=True)
     o0 = open(tmp_path / "outcome0.txt").read()
     o1 = open(tmp_path / "outcome1.txt").read()

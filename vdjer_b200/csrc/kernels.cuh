@@ -1954,6 +1954,163 @@ k_export(ExportArgs a, Geom g, Part pt) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* K5 on several devices: every device finishes ITS survivors (the k-mers of the hash units it   */
+/* owns) and only the finished node rows travel.  Per device r, with n_r survivors of n in all:   */
+/*   F1  flat table over its own survivor records, (first_any, slot) sorted by first_any          */
+/*   F2  creation rank of a node = its position in the merge of all devices' sorted stamps:       */
+/*       own position + sum over the peers of lower_bound(peer's stamps, stamp)  (stamps are      */
+/*       window numbers: no two nodes share one); written into the table slot for the peers       */
+/*   F3  edge lists: a neighbour is looked up in the table of the device that owns its minimizer  */
+/*       bucket (a peer load over NVLink for about one neighbour in eight: consecutive k-mers     */
+/*       mostly share their minimizer), the finished 64-byte row is stored at its creation rank   */
+/*       in the finishing device's row buffer (peer stores), which unpacks the rows into the      */
+/*       result arrays.                                                                           */
+/* Between the steps the devices meet at k_peer_barrier (flags in peer memory), not on the host.  */
+/* ------------------------------------------------------------------------------------------ */
+struct __align__(32) NodeRow {
+    u64 first_pos;
+    u16 frequency; u8 out_deg, in_deg; u32 pad;
+    u32 out_succ[4];
+    u32 in_pred[4];
+    u64 kmer_lo, kmer_hi;
+};
+static_assert(sizeof(NodeRow) == 64, "NodeRow must be two sectors");
+
+struct PeerTables {
+    const Slot2 *table[MAX_DEV];   /* every device's flat survivor table (own: local pointer) */
+    u32 len[MAX_DEV];
+    const u8 *owner;               /* [hash units] owning device */
+    u32 ushift;
+};
+struct KeySegs {
+    u64 off[MAX_DEV + 1];          /* device d's sorted stamps are all_keys[off[d] .. off[d+1]) */
+};
+
+__device__ __forceinline__ u64 lower_bound_u64(const u64 *a, u64 n, u64 key) {
+    u64 lo = 0;
+    while (n) {
+        const u64 half = n >> 1;
+        const bool right = ld_ca_u64(a + lo + half) < key;
+        lo = right ? lo + half + 1 : lo;
+        n = right ? n - half - 1 : half;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_global_rank(const u64 *all_keys, const __grid_constant__ KeySegs ks, int G, int self, Slot2 *table, const u32 *vals, u32 *gid, const Counters *ctr) {
+    if (ctr->internal) return;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 n = ks.off[self + 1] - ks.off[self];
+    if (i >= n) return;
+    const u64 key = all_keys[ks.off[self] + i];
+    u64 r = i;
+    for (int d = 0; d < G; d++)
+        if (d != self) r += lower_bound_u64(all_keys + ks.off[d], ks.off[d + 1] - ks.off[d], key);
+    gid[i] = (u32)r;
+    table[vals[i]].rank = (u32)r;
+}
+
+struct ExportDistArgs {
+    const u64 *keys;   /* this device's sorted first_any */
+    const u32 *vals;   /* slot (own table) of its i-th node */
+    const u32 *gid;    /* creation rank of its i-th node */
+    u64 n;
+    NodeRow *rows;     /* the finishing device's row buffer, indexed by creation rank */
+    int self;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_export_dist(ExportDistArgs a, const __grid_constant__ PeerTables pt, Geom g, const Counters *ctr) {
+    if (ctr->internal) return;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Slot2 *s = pt.table[a.self] + a.vals[i];
+    const u64 lo = s->klo, hi = s->khi;
+    const u32 cw = s->count, cnt = cw & CNT2_MASK, in_mask = (cw >> CNT2_IN) & 15u;
+    u64 tt[4]; u32 vv[4];
+    NeighbourMini nm;
+    nm.scan(lo, hi, g);
+    u32 succ[4], pred[4];
+    int n = 0;
+    for (u32 c = 0; c < 4; c++) {
+        const u64 tf = s->out_first[c];
+        if (tf == INF64) continue;
+        u64 slo, shi, q2, q3;
+        kmer_succ(lo, hi, c, g.k, slo, shi);
+        const u32 d = __ldg(pt.owner + (nm.succ_bucket(c, g) >> pt.ushift));
+        const u64 idx = t2_probe_from(pt.table[d], pt.len[d], slot_in(hash_slot(slo, shi), 0u, pt.len[d]), slo, shi, q2, q3);
+        if (idx == INF64) continue;
+        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+    }
+    sort_desc4(tt, vv, n);
+    const int n_out = n;
+    for (int e = 0; e < 4; e++) succ[e] = e < n ? vv[e] : NIL32;
+    n = 0;
+    const u32 last = kmer_last(lo, hi, g.k);
+    for (u32 c = 0; c < 4; c++) {
+        if (!((in_mask >> c) & 1u)) continue;
+        u64 plo, phi, q2, q3;
+        kmer_pred(lo, hi, c, g.kmask_lo, g.kmask_hi, plo, phi);
+        const u32 d = __ldg(pt.owner + (nm.pred_bucket(c, g) >> pt.ushift));
+        const u64 idx = t2_probe_from(pt.table[d], pt.len[d], slot_in(hash_slot(plo, phi), 0u, pt.len[d]), plo, phi, q2, q3);
+        if (idx == INF64) continue;
+        const u64 tf = ld_cg_u64(&pt.table[d][idx].out_first[last]);
+        if (tf == INF64) continue;
+        tt[n] = tf; vv[n] = (u32)(q2 >> 32); n++;
+    }
+    sort_desc4(tt, vv, n);
+    for (int e = 0; e < 4; e++) pred[e] = e < n ? vv[e] : NIL32;
+    NodeRow *row = a.rows + a.gid[i];
+    const u64 w1 = (u64)(u16)(cnt > CNT_CAP ? CNT_CAP : cnt) | ((u64)(u8)n_out << 16) | ((u64)(u8)n << 24);
+    st_sector(row, a.keys[i], w1, (u64)succ[0] | ((u64)succ[1] << 32), (u64)succ[2] | ((u64)succ[3] << 32));
+    st_sector(reinterpret_cast<char *>(row) + 32, (u64)pred[0] | ((u64)pred[1] << 32), (u64)pred[2] | ((u64)pred[3] << 32), lo, hi);
+}
+
+/* the finishing device: rows (creation order) -> the result arrays */
+__global__ void __launch_bounds__(THREADS)
+k_unpack_rows(const NodeRow *rows, u64 n, ExportArgs a) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 q0, q1, q2, q3, r0, r1, r2, r3;
+    ld_sector(rows + i, q0, q1, q2, q3);
+    ld_sector(reinterpret_cast<const char *>(rows + i) + 32, r0, r1, r2, r3);
+    a.first_pos[i] = q0;
+    a.frequency[i] = (u16)q1;
+    a.out_deg[i] = (u8)(q1 >> 16);
+    a.in_deg[i] = (u8)(q1 >> 24);
+    reinterpret_cast<uint4 *>(a.out_succ)[i] = make_uint4((u32)q2, (u32)(q2 >> 32), (u32)q3, (u32)(q3 >> 32));
+    reinterpret_cast<uint4 *>(a.in_pred)[i] = make_uint4((u32)r0, (u32)(r0 >> 32), (u32)r1, (u32)(r1 >> 32));
+    if (a.kmer_lo) { a.kmer_lo[i] = r2; a.kmer_hi[i] = r3; }
+}
+
+/* Barrier between the devices of a sharded finish, on the device: every device owns a block of
+ * MAX_DEV flag words that its peers can store to (peer-mapped); arriving = storing this barrier's
+ * sequence number into my word of everybody's block (after a system-wide fence: the preceding
+ * kernels' peer stores are ordered before it), leaving = all words of my own block have reached it.
+ * One warp; the rest of the stream waits behind this kernel.  A peer that never arrives (its process
+ * died) is given up on after `patience_ns`: the build fails with an error instead of hanging. */
+struct PeerFlags { u64 *flags[MAX_DEV]; };
+__global__ void k_peer_barrier(const __grid_constant__ PeerFlags pf, int G, int self, u64 seq, u64 patience_ns, Counters *ctr) {
+    const int t = threadIdx.x;
+    if (t >= G) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(pf.flags[t] + self), "l"(seq) : "memory");
+    const u64 *mine = pf.flags[self] + t;
+    u64 t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        u64 v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= seq) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > patience_ns) { atomicExch(&ctr->internal, 9u); break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Layout of the reference's `nodes` map (first half).  Everything downstream of   */
 /* the block iterates dense_hash_map<const char*, node*, my_hash, eqstr> (:599, :659, :1139), so */
 /* vdjer.dot, the ROOT_INIT lines and the root list depend on the BUCKET every node lands in:   */

@@ -164,8 +164,11 @@ struct Shard {
     int S = 1, rnd = 0;
     uint64_t surv_done = 0;                       /* survivor records of the finished rounds (in d_rec) */
     float acc[6] = {};                            /* scatter, init1, pass1, prune, table2, pass2 ms summed over the rounds */
-    bool merged() const { return G > 1 || S > 1; } /* the finish builds one table over survivor RECORDS */
-    int phase = 0;  /* 0 staged, 1 counted, 2 planned, 3 scattered, 4 passes done, 5 gather planned, 6 sent, 7 finished */
+    bool merged() const { return G > 1 || S > 1; } /* the finish builds a table over survivor RECORDS */
+    uint64_t bar_seq = 0;                         /* device barriers of this build so far (k_peer_barrier) */
+    /* 0 staged, 1 counted, 2 planned, 3 scattered, 4 passes done, 5 finish planned, 6 / 7 / 8 finish step 1 / 2 / 3
+     * queued or done, 9 finished */
+    int phase = 0;
 };
 
 struct vdjgraph_ctx {
@@ -195,7 +198,7 @@ struct vdjgraph_ctx {
     PinBuf h_first_pos, h_freq, h_odeg, h_ideg, h_osucc, h_ipred, h_klo, h_khi;
     PinBuf h_pre_klo, h_pre_khi, h_pre_freq, h_pre_n;
 
-    DevBuf d_tbase, d_rec, d_gather, d_t2m;
+    DevBuf d_tbase, d_rec, d_gather, d_t2m, d_gid, d_owner;
     DevBuf d_hm_hash, d_hm_probe, d_hm_prev, d_hm_owner, d_hm_slots, d_hm_flag;
     PinBuf h_hm_slots, h_hm_flag;
     cudaEvent_t ev_hm[2] = {};
@@ -466,7 +469,7 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
         if (w.ev[1]) cudaEventDestroy(w.ev[1]);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
-    DevBuf *db[] = { &c->d_hm_hash, &c->d_hm_probe, &c->d_hm_prev, &c->d_hm_owner, &c->d_hm_slots, &c->d_hm_flag, &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
+    DevBuf *db[] = { &c->d_hm_hash, &c->d_hm_probe, &c->d_hm_prev, &c->d_hm_owner, &c->d_hm_slots, &c->d_hm_flag, &c->d_hiq, &c->d_tbase, &c->d_rec, &c->d_gather, &c->d_t2m, &c->d_gid, &c->d_owner, &c->d_bad, &c->d_bases, &c->d_good, &c->d_valid, &c->d_qual, &c->d_strand, &c->d_t1, &c->d_log, &c->d_t2,
                      &c->d_hll, &c->d_ctr, &c->d_hist, &c->d_cursor, &c->d_tuples, &c->d_utab, &c->d_keys[0], &c->d_keys[1], &c->d_vals[0], &c->d_vals[1], &c->d_cub,
                      &c->d_first_pos, &c->d_freq, &c->d_odeg, &c->d_ideg, &c->d_osucc, &c->d_ipred, &c->d_klo,
                      &c->d_khi, &c->d_pre_klo, &c->d_pre_khi, &c->d_pre_freq, &c->d_pre_n };
@@ -1164,8 +1167,8 @@ int run_hashmap_layout(vdjgraph_ctx *c, uint64_t n) {
     return 0;
 }
 
-/* K5: creation ranks and edge lists.  One device: straight from its survivor table.  Sharded: the
- * finishing device first builds one table over the survivor records gathered from all devices. */
+/* K5: creation ranks and edge lists on ONE device: straight from its survivor table, or (several rounds) from
+ * one table over the survivor records of all rounds.  Several devices: finish_step / finish_end below. */
 int run_finish(vdjgraph_ctx *c) {
     Shard &sh = c->sh;
     const Geom g = c->g;
@@ -1181,16 +1184,15 @@ int run_finish(vdjgraph_ctx *c) {
     Slot2 *table = c->d_t2.as<Slot2>();
     CK(cudaEventRecord(c->ev[12], s));
     if (sh.merged()) {
-        /* all survivor records: gathered from every device, or this device's own rounds */
-        const Slot2 *records = sh.G > 1 ? c->d_gather.as<Slot2>() : c->d_rec.as<Slot2>();
-        n_surv = sh.G > 1 ? sh.surv_off[sh.G] : sh.surv_done;
-        /* merged table: one flat slice (the finish looks k-mers up by slot hash alone), no device split */
+        /* several rounds on one device: the survivor records of all rounds */
+        const Slot2 *records = c->d_rec.as<Slot2>();
+        n_surv = sh.surv_done;
+        /* merged table: one flat slice (the finish looks k-mers up by slot hash alone) */
         cap2 = std::max<uint64_t>(1024, (uint64_t)((double)n_surv * MERGED_SLOTS_PER_NODE) + 64);
         /* VDJGRAPH_FREE_TABLES_MB = m: when the merged table exceeds m MB, the tables and the log of the last
          * round (dead: the survivors are records now) are freed before the finish takes its own memory, and
-         * the plan counts on that.  Off by default: measured on configs[4] at full size on 8 GPUs it lets the
-         * build run in one round (scatter 166 -> 104 ms) but re-allocating 19 GB per build costs as much
-         * (passes 339 -> 424, finish 103 -> 175 ms); it pays for a single build that would otherwise not fit. */
+         * the plan counts on that.  Off by default: re-allocating them for the next build costs as much as the
+         * saved round; it pays for a single build that would otherwise not fit. */
         const double free_mb = env_double("VDJGRAPH_FREE_TABLES_MB", -1.0);
         if (free_mb >= 0 && (double)(cap2 * sizeof(Slot2)) > free_mb * 1048576.0) {
             CK(cudaStreamSynchronize(s));
@@ -1267,20 +1269,196 @@ int run_finish(vdjgraph_ctx *c) {
         cudaEventElapsedTime(&res.ms_pass2, c->ev[6], c->ev[7]);
     }
     cudaEventElapsedTime(&res.ms_export, c->ev[12], c->ev[8]);
-    if (sh.G == 1) cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
-    else res.ms_device = res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
-    sh.phase = 7;
+    cudaEventElapsedTime(&res.ms_device, c->ev[0], c->ev[8]);
+    sh.phase = 9;
     c->ran = true;
     return 0;
 }
 
-void fill_times_nonfinisher(vdjgraph_ctx *c) {
+/* The finish of a build over several devices (kernels.cuh, "K5 on several devices").  Every device's exchange
+ * buffer (BUF_GATHER, mapped by its peers) holds: 256 bytes of barrier flags | the sorted stamps of ALL devices
+ * (its own segment is sorted into place, the peers' are copied in) | its flat survivor table | on the finishing
+ * device, the node rows of the whole graph.  Every offset follows from the all-gathered survivor counts. */
+struct FinishLayout { size_t keys_off, table_off, rows_off, bytes; uint64_t n_total, cap; };
+FinishLayout finish_layout(const uint64_t *surv, int G, int rank) {
+    FinishLayout f;
+    f.n_total = 0;
+    for (int d = 0; d < G; d++) f.n_total += surv[d];
+    const uint64_t na = std::max<uint64_t>(f.n_total, 1);
+    f.keys_off = 256;
+    f.table_off = (f.keys_off + na * 8 + 255) & ~(size_t)255;
+    f.cap = std::max<uint64_t>(1024, (uint64_t)((double)surv[rank] * MERGED_SLOTS_PER_NODE) + 64);
+    f.rows_off = f.table_off + f.cap * sizeof(Slot2);
+    f.bytes = f.rows_off + (rank == 0 ? na * sizeof(NodeRow) : 0);
+    return f;
+}
+
+int finish_plan(vdjgraph_ctx *c) {
+    Shard &sh = c->sh;
+    int rc;
+    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank);
+    if (f.n_total >= NIL32) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu nodes", (unsigned long long)f.n_total);
+    /* everything the finish needs is allocated here: its steps are queued without a host synchronisation in
+     * between (an allocation would be one) */
+    void *before = c->d_gather.p;
+    if ((rc = c->d_gather.ensure(f.bytes))) return rc;
+    if (c->d_gather.p != before) CK(cudaMemset(c->d_gather.p, 0, 256));   /* fresh barrier flags */
+    const size_t nr = std::max<uint64_t>(sh.surv_all[sh.rank], 1);
+    if ((rc = c->d_keys[0].ensure(nr * 8)) || (rc = c->d_vals[0].ensure(nr * 4)) || (rc = c->d_vals[1].ensure(nr * 4)) ||
+        (rc = c->d_gid.ensure(nr * 4)) || (rc = c->d_owner.ensure(NBUCKET)))
+        return rc;
+    size_t cub_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_keys[0].as<u64>(), c->d_keys[0].as<u64>(), c->d_vals[0].as<u32>(),
+                                       c->d_vals[1].as<u32>(), (int64_t)nr, 0, 64, c->stream));
+    if ((rc = c->d_cub.ensure(std::max<size_t>(cub_bytes, 16)))) return rc;
+    std::vector<u8> owner(NBUCKET, 0);
+    for (int u = 0; u < sh.NU; u++) owner[u] = (u8)sh.owner[u];
+    CK(cudaMemcpy(c->d_owner.p, owner.data(), NBUCKET, cudaMemcpyHostToDevice));
+    if (sh.rank == 0) {
+        const size_t na = std::max<uint64_t>(f.n_total, 1);
+        if ((rc = c->d_first_pos.ensure(na * 8)) || (rc = c->d_freq.ensure(na * 2)) || (rc = c->d_odeg.ensure(na)) ||
+            (rc = c->d_ideg.ensure(na)) || (rc = c->d_osucc.ensure(na * 16)) || (rc = c->d_ipred.ensure(na * 16)))
+            return rc;
+        if ((c->prm.flags & (VDJGRAPH_FLAG_EXPORT_KEYS | VDJGRAPH_FLAG_HASHMAP_LAYOUT)) &&
+            ((rc = c->d_klo.ensure(na * 8)) || (rc = c->d_khi.ensure(na * 8))))
+            return rc;
+    }
+    return 0;
+}
+
+/* one of the three steps (see kernels.cuh); then the devices meet: on the device (device_barrier: the next step
+ * can be queued at once) or on the host (the stream is synchronised; the caller holds a barrier of its own) */
+int finish_step(vdjgraph_ctx *c, int step, bool device_barrier) {
+    Shard &sh = c->sh;
+    const Geom g = c->g;
+    cudaStream_t s = c->stream;
     vdjgraph_result &res = c->res;
-    const Shard &sh = c->sh;
+    Counters *d_ctr = c->d_ctr.as<Counters>();
+    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank);
+    char *arena = c->d_gather.as<char>();
+    const uint64_t n_r = sh.surv_all[sh.rank];
+    Slot2 *table = reinterpret_cast<Slot2 *>(arena + f.table_off);
+    u64 *all_keys = reinterpret_cast<u64 *>(arena + f.keys_off);
+    const int grid_flat = c->sm_count * 8;
+    const int gb = (int)std::max<uint64_t>(1, (n_r + THREADS - 1) / THREADS);
+    for (int d = 0; d < sh.G; d++)
+        if (!sh.peer[d][BUF_GATHER]) return fail(VDJGRAPH_ERR_STATE, "device %d's exchange buffer is not set", d);
+    if (step == 0) {
+        CK(cudaEventRecord(c->ev[12], s));
+        Part pt = c->part;
+        pt.flat = 1; pt.flat_len = (u32)f.cap;
+        CK(cudaMemsetAsync(&d_ctr->n_nodes, 0, sizeof(u64), s));
+        k_init_table2<<<grid_flat, THREADS, 0, s>>>(table, f.cap);
+        res.kernel_launches++;
+        if (n_r) {
+            k_table2_from_records<<<grid_flat, THREADS, 0, s>>>(c->d_rec.as<Slot2>(), n_r, table, f.cap, g, pt, d_ctr);
+            k_collect<<<grid_flat, THREADS, 0, s>>>(table, f.cap, c->d_keys[0].as<u64>(), c->d_vals[0].as<u32>(), d_ctr);
+            size_t cub_bytes = c->d_cub.cap;
+            CK(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_keys[0].as<u64>(), all_keys + sh.surv_off[sh.rank],
+                                               c->d_vals[0].as<u32>(), c->d_vals[1].as<u32>(), (int64_t)n_r, 0,
+                                               bits_for(sh.total_records * (uint64_t)g.w), s));
+            res.kernel_launches += 2;
+        }
+    } else if (step == 1) {
+        KeySegs ks;
+        for (int d = 0; d <= sh.G; d++) ks.off[d] = sh.surv_off[d];
+        for (int d = 0; d < sh.G; d++)
+            if (d != sh.rank && sh.surv_all[d])
+                CK(cudaMemcpyAsync(all_keys + sh.surv_off[d], (const char *)sh.peer[d][BUF_GATHER] + f.keys_off + sh.surv_off[d] * 8,
+                                   sh.surv_all[d] * 8, cudaMemcpyDefault, s));
+        if (n_r) {
+            k_global_rank<<<gb, THREADS, 0, s>>>(all_keys, ks, sh.G, sh.rank, table, c->d_vals[1].as<u32>(), c->d_gid.as<u32>(), d_ctr);
+            res.kernel_launches++;
+        }
+    } else {
+        if (n_r) {
+            PeerTables pt;
+            for (int d = 0; d < MAX_DEV; d++) { pt.table[d] = nullptr; pt.len[d] = 1; }
+            for (int d = 0; d < sh.G; d++) {
+                const FinishLayout fd = finish_layout(sh.surv_all, sh.G, d);
+                pt.table[d] = reinterpret_cast<const Slot2 *>((const char *)sh.peer[d][BUF_GATHER] + fd.table_off);
+                pt.len[d] = (u32)fd.cap;
+            }
+            pt.owner = c->d_owner.as<u8>();
+            pt.ushift = (u32)sh.ushift;
+            const FinishLayout f0 = finish_layout(sh.surv_all, sh.G, 0);
+            ExportDistArgs a;
+            a.keys = all_keys + sh.surv_off[sh.rank]; a.vals = c->d_vals[1].as<u32>(); a.gid = c->d_gid.as<u32>();
+            a.n = n_r; a.self = sh.rank;
+            a.rows = reinterpret_cast<NodeRow *>((char *)sh.peer[0][BUF_GATHER] + f0.rows_off);
+            k_export_dist<<<gb, THREADS, 0, s>>>(a, pt, g, d_ctr);
+            res.kernel_launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    if (device_barrier) {
+        PeerFlags pf;
+        for (int d = 0; d < MAX_DEV; d++) pf.flags[d] = reinterpret_cast<u64 *>(sh.peer[d < sh.G ? d : sh.rank][BUF_GATHER]);
+        const double patience_s = env_double("VDJGRAPH_BARRIER_PATIENCE_S", 20.0);
+        k_peer_barrier<<<1, 32, 0, s>>>(pf, sh.G, sh.rank, ++sh.bar_seq, (u64)(patience_s * 1e9), d_ctr);
+        res.kernel_launches++;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaStreamSynchronize(s));
+    }
+    sh.phase = 6 + step;
+    return 0;
+}
+
+/* after the third step (and the barrier behind it): the finishing device unpacks the rows; every device checks
+ * its counters */
+int finish_end(vdjgraph_ctx *c) {
+    Shard &sh = c->sh;
+    cudaStream_t s = c->stream;
+    vdjgraph_result &res = c->res;
+    Counters *d_ctr = c->d_ctr.as<Counters>();
+    Counters *h_ctr = c->h_ctr.as<Counters>();
+    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank);
+    int rc;
+    res.hm_buckets = 0; res.ms_hashmap = 0;
+    if (sh.rank == 0) {
+        const bool want_layout = c->prm.flags & VDJGRAPH_FLAG_HASHMAP_LAYOUT;
+        const bool want_keys = (c->prm.flags & VDJGRAPH_FLAG_EXPORT_KEYS) || want_layout;
+        if (f.n_total) {
+            ExportArgs ae;
+            ae.table = nullptr; ae.cap = 0; ae.keys = nullptr; ae.vals = nullptr; ae.n = f.n_total;
+            ae.first_pos = c->d_first_pos.as<u64>(); ae.frequency = c->d_freq.as<u16>();
+            ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
+            ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
+            ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
+            k_unpack_rows<<<(int)((f.n_total + THREADS - 1) / THREADS), THREADS, 0, s>>>(
+                reinterpret_cast<const NodeRow *>(c->d_gather.as<char>() + f.rows_off), f.n_total, ae);
+            res.kernel_launches++;
+            CK(cudaGetLastError());
+        }
+        if (want_layout) {
+            /* a peer that never arrived must not send the layout into a loop over garbage keys */
+            CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "sharded finish failed (code %u)", h_ctr->internal);
+            if ((rc = run_hashmap_layout(c, f.n_total))) return rc;
+        }
+    }
+    CK(cudaEventRecord(c->ev[8], s));
+    CK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_ctr->overflow) return fail(VDJGRAPH_ERR_INTERNAL, "survivor table overflow (code %u)", h_ctr->overflow);
+    if (h_ctr->internal == 9) return fail(VDJGRAPH_ERR_INTERNAL, "a peer device did not reach the barrier of the sharded finish");
+    if (h_ctr->internal) return fail(VDJGRAPH_ERR_INTERNAL, "export invariant violated (code %u)", h_ctr->internal);
+    if (sh.surv_all[sh.rank] && h_ctr->n_nodes != sh.surv_all[sh.rank])
+        return fail(VDJGRAPH_ERR_INTERNAL, "collected %llu nodes, expected %llu", (unsigned long long)h_ctr->n_nodes,
+                    (unsigned long long)sh.surv_all[sh.rank]);
+    c->ctr = *h_ctr;
+    if (res.hm_buckets) cudaEventElapsedTime(&res.ms_hashmap, c->ev_hm[0], c->ev_hm[1]);
     res.ms_scatter = sh.acc[0]; res.ms_init1 = sh.acc[1]; res.ms_pass1 = sh.acc[2];
     res.ms_prune = sh.acc[3]; res.ms_table2 = sh.acc[4]; res.ms_pass2 = sh.acc[5];
-    res.ms_export = 0;
-    res.ms_device = res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2;
+    cudaEventElapsedTime(&res.ms_export, c->ev[12], c->ev[8]);
+    res.ms_device = res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
+    res.n_nodes = sh.rank == 0 ? f.n_total : 0;
+    if (sh.rank == 0) res.n_pre = f.n_total;   /* (the other ranks keep their own survivor count) */
+    sh.phase = 9;
+    c->ran = sh.rank == 0;
+    return 0;
 }
 
 } // namespace
@@ -1345,7 +1523,7 @@ extern "C" int vdjgraph_shard_stage_forward(vdjgraph_ctx *c, const char *primary
 
 /* the per-bucket counts and HyperLogLog registers of this rank's staged records (k_count ran with the staging) */
 extern "C" int vdjgraph_shard_count(vdjgraph_ctx *c, uint64_t *hist, uint8_t *hll) {
-    if (c && c->staged && c->sh.phase >= 6) c->sh.phase = 0;   /* another build of the same staged records */
+    if (c && c->staged && c->sh.phase == 9) c->sh.phase = 0;   /* another build of the same staged records */
     int rc = phase_check(c, 0, "vdjgraph_shard_count");
     if (rc) return rc;
     if (!hist || !hll) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
@@ -1368,7 +1546,12 @@ extern "C" int vdjgraph_shard_plan(vdjgraph_ctx *c, const uint64_t *hist_all, co
     sh.rec_base[sh.G] = base;
     if (base != sh.total_records || record_counts[sh.rank] != c->g.R)
         return fail(VDJGRAPH_ERR_PARAM, "record counts do not add up to total_records / this rank's staged records");
-    return run_plan(c, hist_all, hll_merged);
+    if ((rc = run_plan(c, hist_all, hll_merged))) return rc;
+    /* the barrier flags of the finish start every build at zero (the peers' stores of this build come after
+     * several host exchanges; those of the last build arrived before its final one) */
+    sh.bar_seq = 0;
+    if (sh.G > 1 && c->d_gather.p) CK(cudaMemset(c->d_gather.p, 0, 256));
+    return 0;
 }
 
 extern "C" int vdjgraph_shard_buffers(vdjgraph_ctx *c, void **ptrs, size_t *bytes) {
@@ -1421,38 +1604,36 @@ extern "C" int vdjgraph_shard_gather_plan(vdjgraph_ctx *c, const uint64_t *survi
         return fail(VDJGRAPH_ERR_STATE, "vdjgraph_shard_gather_plan after round %d of %d", c->sh.rnd + 1, c->sh.S);
     CK(cudaSetDevice(c->device));
     Shard &sh = c->sh;
+    if (survivors_all[sh.rank] != sh.surv_done)
+        return fail(VDJGRAPH_ERR_PARAM, "survivors_all[%d] is not this rank's survivor count", sh.rank);
     uint64_t off = 0;
     for (int d = 0; d < sh.G; d++) { sh.surv_all[d] = survivors_all[d]; sh.surv_off[d] = off; off += survivors_all[d]; }
     sh.surv_off[sh.G] = off;
-    if (sh.rank == 0 && sh.G > 1 && (rc = c->d_gather.ensure(std::max<uint64_t>(off, 1) * sizeof(Slot2)))) return rc;
+    if (sh.G > 1 && (rc = finish_plan(c))) return rc;
     sh.phase = 5;
     return 0;
 }
 
-extern "C" int vdjgraph_shard_send(vdjgraph_ctx *c) {
-    int rc = phase_check(c, 5, "vdjgraph_shard_send");
-    if (rc) return rc;
-    CK(cudaSetDevice(c->device));
-    Shard &sh = c->sh;
-    if (sh.G > 1) {
-        Slot2 *dst = (Slot2 *)sh.peer[0][BUF_GATHER];
-        if (!dst) return fail(VDJGRAPH_ERR_STATE, "the finishing device's gather buffer is not set");
-        const uint64_t n = sh.surv_all[sh.rank];
-        /* peer-mapped destination: a plain device-to-device copy over NVLink */
-        if (n) CK(cudaMemcpyAsync(dst + sh.surv_off[sh.rank], c->d_rec.p, n * sizeof(Slot2), cudaMemcpyDefault, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (sh.rank != 0) fill_times_nonfinisher(c);
-    }
-    sh.phase = 6;
+extern "C" int vdjgraph_shard_finish_bytes(const uint64_t *survivors_all, uint32_t n_ranks, uint32_t rank, size_t *bytes) {
+    if (!survivors_all || !bytes || n_ranks < 1 || n_ranks > MAX_DEV || rank >= n_ranks) return fail(VDJGRAPH_ERR_PARAM, "bad argument");
+    *bytes = n_ranks > 1 ? finish_layout(survivors_all, (int)n_ranks, (int)rank).bytes : 0;
     return 0;
 }
 
-extern "C" int vdjgraph_shard_finish(vdjgraph_ctx *c) {
-    int rc = phase_check(c, 6, "vdjgraph_shard_finish");
+extern "C" int vdjgraph_shard_finish_step(vdjgraph_ctx *c, int step, int device_barrier) {
+    if (step < 0 || step > 2) return fail(VDJGRAPH_ERR_PARAM, "finish step %d", step);
+    int rc = phase_check(c, 5 + step, "vdjgraph_shard_finish_step");
     if (rc) return rc;
-    if (c->sh.rank != 0) return fail(VDJGRAPH_ERR_STATE, "only rank 0 finishes");
     CK(cudaSetDevice(c->device));
-    return run_finish(c);
+    if (c->sh.G == 1) { c->sh.phase = 6 + step; return 0; }   /* one device: everything happens in vdjgraph_shard_finish */
+    return finish_step(c, step, device_barrier != 0);
+}
+
+extern "C" int vdjgraph_shard_finish(vdjgraph_ctx *c) {
+    int rc = phase_check(c, 8, "vdjgraph_shard_finish");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    return c->sh.G == 1 ? run_finish(c) : finish_end(c);
 }
 
 /* Frees allocations that were replaced by larger ones while peers could still have them mapped.
@@ -1580,7 +1761,7 @@ extern "C" int vdjgraph_fetch(vdjgraph_ctx *c, vdjgraph_result *out) {
 
 extern "C" int vdjgraph_stats(vdjgraph_ctx *c, vdjgraph_result *out) {
     if (!c || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
-    if (!c->ran && c->sh.phase < 6) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_stats before vdjgraph_run");
+    if (!c->ran && c->sh.phase < 9) return fail(VDJGRAPH_ERR_STATE, "vdjgraph_stats before vdjgraph_run");
     *out = c->res;
     out->first_pos = nullptr; out->frequency = nullptr; out->out_deg = out->in_deg = nullptr;
     out->out_succ = out->in_pred = nullptr; out->kmer_lo = out->kmer_hi = nullptr; out->hm_slots = nullptr;

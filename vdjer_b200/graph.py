@@ -73,7 +73,7 @@ EXPORTS = [
     "vdjgraph_host_alloc", "vdjgraph_host_free", "vdjgraph_host_register", "vdjgraph_host_unregister",
     "vdjgraph_shard_stage", "vdjgraph_shard_stage_forward", "vdjgraph_shard_count", "vdjgraph_shard_plan", "vdjgraph_shard_rounds", "vdjgraph_shard_buffers",
     "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
-    "vdjgraph_shard_send", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
+    "vdjgraph_shard_finish_bytes", "vdjgraph_shard_finish_step", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
     "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
 ]
 
@@ -125,7 +125,8 @@ def load_library():
     lib.vdjgraph_shard_scatter.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_passes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.vdjgraph_shard_gather_plan.argtypes = [C.c_void_p, C.c_void_p]
-    lib.vdjgraph_shard_send.argtypes = [C.c_void_p]
+    lib.vdjgraph_shard_finish_bytes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]
+    lib.vdjgraph_shard_finish_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.vdjgraph_shard_finish.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_release_retired.argtypes = [C.c_void_p]
     lib.vdjgraph_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
@@ -388,10 +389,20 @@ class GraphBuilder:
         a = np.ascontiguousarray(survivors_all, np.uint64)
         self._check(self._lib.vdjgraph_shard_gather_plan(self._ctx, a.ctypes.data))
 
-    def shard_send(self):
-        self._check(self._lib.vdjgraph_shard_send(self._ctx))
+    def shard_finish_bytes(self, survivors_all, rank: int) -> int:
+        """Bytes rank `rank`'s exchange buffer (BUF_GATHER) must hold for the finish of these survivor counts."""
+        a = np.ascontiguousarray(survivors_all, np.uint64)
+        n = C.c_size_t(0)
+        self._check(self._lib.vdjgraph_shard_finish_bytes(a.ctypes.data, len(a), rank, C.byref(n)))
+        return int(n.value)
+
+    def shard_finish_step(self, step: int, device_barrier: bool):
+        """Step 0, 1, 2 of the distributed finish.  device_barrier: the devices meet in peer memory and the call
+        returns at once; otherwise it returns with the stream synchronised and the caller holds the barrier."""
+        self._check(self._lib.vdjgraph_shard_finish_step(self._ctx, step, 1 if device_barrier else 0))
 
     def shard_finish(self):
+        """Every rank, after the three steps; the graph is then on rank 0's device."""
         self._check(self._lib.vdjgraph_shard_finish(self._ctx))
 
     def shard_release_retired(self):

@@ -4,11 +4,13 @@ Records are split into contiguous ranges (rank order = record order), k-mers are
 every hash unit (a group of minimizer buckets) belongs to one rank, chosen by the library from the
 all-gathered window counts.  This module is only the host plumbing between the library's phases:
 six small collectives per build (histograms + HyperLogLog registers + IPC handles in one all-gather,
-a flag gather that doubles as a barrier, one barrier per round, survivor counts, two barriers around
-the send and the finish).  The bulk exchange is inside the kernels: k_scatter writes every run (a
+a flag gather that doubles as a barrier, one barrier per round, survivor counts, a barrier before and
+one after the finish).  The bulk exchange is inside the kernels: k_scatter writes every run (a
 stretch of consecutive windows, 32 bytes) straight into the owner's buffer through peer-mapped memory
 (NVLink / NVSwitch), the exact read comparison and the quality rows of border k-mers are peer
-loads, and the survivors travel to rank 0 as one device-to-device copy per rank.
+loads; the finish is distributed too: every rank ranks and links its own survivors (neighbours
+owned by a peer are peer loads), the finished node rows are stored into rank 0's result buffer,
+and the three steps of it are separated by barriers the devices keep in peer memory.
 
 Two ways to run it:
   * one process per GPU (torchrun): `build_distributed(builder, primary, secondary)` with
@@ -21,6 +23,7 @@ Two ways to run it:
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -93,9 +96,12 @@ def build_local(builders: list[GraphBuilder], parts: list[tuple], devices: list[
     table = [b.shard_buffers()[0] for b in builders]
     for b in builders:
         b.shard_set_peers(table)
+    # the ranks share this thread: a step is queued and waited for on every rank before the next begins
+    for step in range(3):
+        for b in builders:
+            b.shard_finish_step(step, False)
     for b in builders:
-        b.shard_send()
-    builders[0].shard_finish()
+        b.shard_finish()
     return builders[0].fetch(copy=copy)
 
 
@@ -150,11 +156,13 @@ class DistributedBuilder:
     """One rank of the sharded build (one process per GPU).  `dist`: torch.distributed (initialised);
     `group`: process group for the small host exchanges (default group if None); `device`: where
     the exchanged tensors live ("cuda:N" with an NCCL group: a few microseconds per exchange over
-    NVLink; None = CPU tensors, e.g. a gloo group).  This process' records are its `primary` /
+    NVLink; None = CPU tensors, e.g. a gloo group); `device_barriers`: False = the steps of the finish
+    are separated by host barriers instead of the ones the devices keep in peer memory (also:
+    VDJGRAPH_HOST_BARRIERS=1).  This process' records are its `primary` /
     `secondary`; rank order = record order.  close() before the GraphBuilder is closed: it unmaps
     the peers' buffers."""
 
-    def __init__(self, builder: GraphBuilder, dist=None, group=None, device=None):
+    def __init__(self, builder: GraphBuilder, dist=None, group=None, device=None, device_barriers: bool | None = None):
         if dist is None:
             import torch.distributed as dist  # noqa: PLW0642
         self.b, self.dist, self.group, self.device = builder, dist, group, device
@@ -163,6 +171,8 @@ class DistributedBuilder:
         self.counts = None
         self._err = None
         self._gather_mapped = False
+        # the three steps of the finish meet at barriers in peer memory (default) or at host barriers
+        self.device_barriers = os.environ.get("VDJGRAPH_HOST_BARRIERS", "0") != "1" if device_barriers is None else device_barriers
         self.peers = _Peers()
         self.table = [[0] * SHARD_NBUF for _ in range(self.G)]
 
@@ -239,9 +249,9 @@ class DistributedBuilder:
             self._try(self.b.shard_stage, primary, secondary, self.G, self.rank, base, int(sum(self.counts)))
 
     def run(self):
-        """count -> plan -> scatter (= the all-to-all) -> passes -> gather -> finish on the staged
-        records.  Every phase returns with its stream synchronised, so the host barriers order the
-        devices.  The graph then sits on rank 0's device: fetch() copies it to the host.
+        """count -> plan -> scatter (= the all-to-all) -> passes -> distributed finish on the staged
+        records.  Up to the finish every phase returns with its stream synchronised, so the host
+        barriers order the devices.  The graph then sits on rank 0's device: fetch() copies it to the host.
         self.phase_ms holds the wall time of each phase of the last run."""
         import time
         b = self.b
@@ -291,26 +301,28 @@ class DistributedBuilder:
             t_pa += time.perf_counter() - t1
         t.append(t[-1] + t_sc)
         t.append(t[-1] + t_pa)
-        # survivor counts, and how much the finishing rank's gather buffer holds: every rank can tell
-        # whether rank 0 has to grow it (only then is its handle exchanged again)
+        # survivor counts, and how much every rank's exchange buffer holds: every rank can tell whether one of
+        # them has to grow (only then do the handles travel again)
         got = self._gather(np.array([n_surv, sizes[BUF_GATHER] if sizes else 0, 1 if self._gather_mapped else 0], np.int64))
         surv = [int(x) for x in got[:, 0]]
         self._try(b.shard_gather_plan, surv)
-        if max(sum(surv), 1) * 64 > int(got[0, 1]) or not got[:, 2].all():
+        need = [self._try(b.shard_finish_bytes, surv, r, default=0) for r in range(self.G)]
+        if any(need[r] > int(got[r, 1]) for r in range(self.G)) or not got[:, 2].all():
             self._exchange([BUF_GATHER])
             self._gather_mapped = True
         else:
             self._try(self.b.shard_set_peers, self.table)
+        # (a rank's barrier flags are in place before its handle travels, or since the plan of this build)
         mark()
-        self._try(b.shard_send)
-        self._barrier()                     # rank 0 holds every survivor record
-        mark()
-        self._try(b.shard_release_retired)
-        if self.rank == 0:
-            self._try(b.shard_finish)
+        for step in range(3):
+            self._try(b.shard_finish_step, step, self.device_barriers)
+            if not self.device_barriers:
+                self._barrier()
+        self._try(b.shard_finish)
         self._barrier()                     # nobody returns before the finish is known to have worked
+        self._try(b.shard_release_retired)  # ... and every peer has let go of a buffer that was replaced
         mark()
-        names = ["count", "x_hist", "plan", "x_peers", "scatter+barrier", "passes", "x_surv", "send+barrier", "finish"]
+        names = ["count", "x_hist", "plan", "x_peers", "scatter+barrier", "passes", "x_surv", "finish"]
         self.phase_ms = {n: (t[i + 1] - t[i]) * 1e3 for i, n in enumerate(names)}
 
     def fetch(self, copy: bool = True):
