@@ -24,6 +24,8 @@ for line in sys.stdin:
     if "roofline_atomic" in d:
         ra = d["roofline_atomic"]
         print("atomic roof: pass1", round(ra["k_pass1"]["frac"], 3), "pass2", round(ra["k_pass2"]["frac"], 3))
+    if "shard_phase_ms_rank0" in d:
+        print("phases (rank 0)", d["shard_phase_ms_rank0"])
     if "parity_check" in d:
         print("parity_check", d["parity_check"])
     if "digest_check" in d:
