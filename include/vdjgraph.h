@@ -259,9 +259,10 @@ int vdjgraph_shard_set_peers(vdjgraph_ctx *ctx, void *const *ptrs /*[n_ranks][NB
 int vdjgraph_shard_scatter(vdjgraph_ctx *ctx);
 int vdjgraph_shard_passes(vdjgraph_ctx *ctx, uint64_t *n_survivors /* of this rank, all rounds so far */);
 int vdjgraph_shard_gather_plan(vdjgraph_ctx *ctx, const uint64_t *survivors_all /*[n_ranks]*/);
-/* bytes of rank `rank`'s GATHER buffer that vdjgraph_shard_gather_plan will ask for (a pure function of the
- * survivor counts: every rank can tell which buffers have to grow, i.e. which handles travel again) */
-int vdjgraph_shard_finish_bytes(const uint64_t *survivors_all /*[n_ranks]*/, uint32_t n_ranks, uint32_t rank, size_t *bytes);
+/* bytes of rank `rank`'s GATHER buffer that vdjgraph_shard_gather_plan will ask for (a function of the
+ * survivor counts and of the build flags, which are the same on every rank: every rank can tell which
+ * buffers have to grow, i.e. which handles travel again) */
+int vdjgraph_shard_finish_bytes(vdjgraph_ctx *ctx, const uint64_t *survivors_all /*[n_ranks]*/, uint32_t rank, size_t *bytes);
 /* step 0: own survivor table + sorted stamps; 1: creation ranks; 2: edge lists, node rows to rank 0 */
 int vdjgraph_shard_finish_step(vdjgraph_ctx *ctx, int step, int device_barrier);
 /* every rank: waits for its stream, checks its counters; rank 0 also unpacks the rows into the result */

@@ -83,7 +83,7 @@ class FakeBuilder:
         return "graph"
 
 
-def _worker(rank, world, port, out_dir, rounds=1):
+def _worker(rank, world, port, out_dir, rounds=1, exchange="auto"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     # identity "IPC": a handle is the pointer's decimal text
@@ -91,15 +91,18 @@ def _worker(rank, world, port, out_dir, rounds=1):
     shard._Peers.map = lambda self, r, i, h: int(h) + 5 if h else 0      # +5: a mapping is a different address
     shard._Peers.close = lambda self: None
     b = FakeBuilder(rank, 100 + 20 * rank, rounds)
-    g = shard.build_distributed(b, None, None, dist=dist)
+    g = shard.build_distributed(b, None, None, dist=dist, exchange=exchange)
     np.save(os.path.join(out_dir, f"log{rank}.npy"), np.array([b.log, g], dtype=object), allow_pickle=True)
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(120)
-def test_two_rank_plumbing_over_gloo(tmp_path):
-    world, port = 2, 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("exchange", ["shm", "torch"])
+def test_two_rank_plumbing_over_gloo(tmp_path, exchange):
+    """exchange: the small host messages through shared memory (ranks of one host, the default) or through
+    torch.distributed collectives"""
+    world, port = 2, 29500 + os.getpid() % 2000 + (7 if exchange == "shm" else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), 1, exchange), nprocs=world, join=True)
     logs = [np.load(tmp_path / f"log{r}.npy", allow_pickle=True) for r in range(world)]
     (l0, g0), (l1, g1) = logs
     assert g0 == "graph" and g1 is None
@@ -178,6 +181,40 @@ def test_a_failing_rank_aborts_every_rank(tmp_path, where):
     o1 = open(tmp_path / "outcome1.txt").read()
     assert o0.startswith("aborted") and "[1]" in o0, o0
     assert o1.startswith("own error"), o1
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    import time
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = shard._HostExchange(dist, None, rank, world, timeout_s=60)
+    rng = np.random.default_rng(rank)
+    ok = True
+    for it in range(400):
+        n = 1 + (it * 37) % 5000                              # every rank sends n bytes that depend on (rank, it)
+        mine = ((np.arange(n) * (rank + 3) + it) % 251).astype(np.uint8)
+        if rng.random() < 0.05:
+            time.sleep(rng.random() * 0.003)                  # ranks drift apart: one is an exchange ahead at most
+        got = x.all_gather(mine)
+        for r in range(world):
+            ok &= bool(np.array_equal(got[r], ((np.arange(n) * (r + 3) + it) % 251).astype(np.uint8)))
+    big = np.full(shard._HostExchange.SLOT, rank, np.uint8)   # a full slot
+    got = x.all_gather(big)
+    ok &= all(bool((got[r] == r).all()) for r in range(world))
+    x.close()
+    open(os.path.join(out_dir, f"x{rank}.txt"), "w").write("ok" if ok else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_host_exchange_through_shared_memory(tmp_path):
+    """_HostExchange: 400 all-gathers of varying size between three drifting processes return every rank's
+    payload of THAT exchange (double-buffered slots), and the backing file is gone from /dev/shm."""
+    world, port = 3, 35500 + os.getpid() % 2000
+    before = set(os.listdir("/dev/shm"))
+    mp.spawn(_exchange_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"x{r}.txt").read() for r in range(world)] == ["ok"] * world
+    assert not [f for f in set(os.listdir("/dev/shm")) - before if f.startswith("vdjgraph_")]
 
 
 def test_shard_ranges_and_split():

@@ -1962,19 +1962,24 @@ k_export(ExportArgs a, Geom g, Part pt) {
 /*       window numbers: no two nodes share one); written into the table slot for the peers       */
 /*   F3  edge lists: a neighbour is looked up in the table of the device that owns its minimizer  */
 /*       bucket (a peer load over NVLink for about one neighbour in eight: consecutive k-mers     */
-/*       mostly share their minimizer), the finished 64-byte row is stored at its creation rank   */
-/*       in the finishing device's row buffer (peer stores), which unpacks the rows into the      */
-/*       result arrays.                                                                           */
+/*       mostly share their minimizer), the finished 32-byte row is stored at its creation rank   */
+/*       in the finishing device's row buffer (one peer store per node), which unpacks the rows   */
+/*       into the result arrays.                                                                  */
 /* Between the steps the devices meet at k_peer_barrier (flags in peer memory), not on the host.  */
 /* ------------------------------------------------------------------------------------------ */
-struct __align__(32) NodeRow {
-    u64 first_pos;
-    u16 frequency; u8 out_deg, in_deg; u32 pad;
-    u32 out_succ[4];
-    u32 in_pred[4];
-    u64 kmer_lo, kmer_hi;
+/* A finished node as it travels to the finishing device: one 32-byte sector.
+ * w0 = first_pos (STAMP_BITS) | frequency << 40 | out_deg << 56 | in_deg << 59 ; w1..w3 = the first three
+ * successors and the first three predecessors (NIL32 beyond the degree).  A node with four successors or four
+ * predecessors (rare) also appends {rank | 4th successor << 32, 4th predecessor} to an overflow list; the
+ * k-mer, when the caller wants it, goes to a second array of 16-byte entries. */
+constexpr int ROW_WORDS = 4;
+static_assert(STAMP_BITS <= 40, "first_pos shares a word with the frequency and the degrees");
+struct RowSink {
+    u64 *rows;         /* [n][ROW_WORDS], indexed by creation rank */
+    ulonglong2 *over;  /* overflow entries */
+    u32 *n_over;
+    ulonglong2 *kmers; /* [n] or null */
 };
-static_assert(sizeof(NodeRow) == 64, "NodeRow must be two sectors");
 
 struct PeerTables {
     const Slot2 *table[MAX_DEV];   /* every device's flat survivor table (own: local pointer) */
@@ -2016,7 +2021,7 @@ struct ExportDistArgs {
     const u32 *vals;   /* slot (own table) of its i-th node */
     const u32 *gid;    /* creation rank of its i-th node */
     u64 n;
-    NodeRow *rows;     /* the finishing device's row buffer, indexed by creation rank */
+    RowSink sink;      /* the finishing device's row buffer (peer memory) */
     int self;
 };
 
@@ -2061,27 +2066,42 @@ k_export_dist(ExportDistArgs a, const __grid_constant__ PeerTables pt, Geom g, c
     }
     sort_desc4(tt, vv, n);
     for (int e = 0; e < 4; e++) pred[e] = e < n ? vv[e] : NIL32;
-    NodeRow *row = a.rows + a.gid[i];
-    const u64 w1 = (u64)(u16)(cnt > CNT_CAP ? CNT_CAP : cnt) | ((u64)(u8)n_out << 16) | ((u64)(u8)n << 24);
-    st_sector(row, a.keys[i], w1, (u64)succ[0] | ((u64)succ[1] << 32), (u64)succ[2] | ((u64)succ[3] << 32));
-    st_sector(reinterpret_cast<char *>(row) + 32, (u64)pred[0] | ((u64)pred[1] << 32), (u64)pred[2] | ((u64)pred[3] << 32), lo, hi);
+    const u32 id = a.gid[i];
+    const u64 w0 = a.keys[i] | ((u64)(cnt > CNT_CAP ? CNT_CAP : cnt) << 40) | ((u64)n_out << 56) | ((u64)n << 59);
+    st_sector(a.sink.rows + (u64)id * ROW_WORDS, w0, (u64)succ[0] | ((u64)succ[1] << 32), (u64)succ[2] | ((u64)pred[0] << 32),
+              (u64)pred[1] | ((u64)pred[2] << 32));
+    if (n_out == 4 || n == 4) {
+        const u32 at = atomicAdd_system(a.sink.n_over, 1u);
+        a.sink.over[at] = make_ulonglong2((u64)id | ((u64)succ[3] << 32), (u64)pred[3]);
+    }
+    if (a.sink.kmers) a.sink.kmers[id] = make_ulonglong2(lo, hi);
 }
 
 /* the finishing device: rows (creation order) -> the result arrays */
 __global__ void __launch_bounds__(THREADS)
-k_unpack_rows(const NodeRow *rows, u64 n, ExportArgs a) {
+k_unpack_rows(RowSink r, u64 n, ExportArgs a) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    u64 q0, q1, q2, q3, r0, r1, r2, r3;
-    ld_sector(rows + i, q0, q1, q2, q3);
-    ld_sector(reinterpret_cast<const char *>(rows + i) + 32, r0, r1, r2, r3);
-    a.first_pos[i] = q0;
-    a.frequency[i] = (u16)q1;
-    a.out_deg[i] = (u8)(q1 >> 16);
-    a.in_deg[i] = (u8)(q1 >> 24);
-    reinterpret_cast<uint4 *>(a.out_succ)[i] = make_uint4((u32)q2, (u32)(q2 >> 32), (u32)q3, (u32)(q3 >> 32));
-    reinterpret_cast<uint4 *>(a.in_pred)[i] = make_uint4((u32)r0, (u32)(r0 >> 32), (u32)r1, (u32)(r1 >> 32));
-    if (a.kmer_lo) { a.kmer_lo[i] = r2; a.kmer_hi[i] = r3; }
+    u64 w0, w1, w2, w3;
+    ld_sector(r.rows + i * ROW_WORDS, w0, w1, w2, w3);
+    a.first_pos[i] = w0 & ((1ull << 40) - 1);
+    a.frequency[i] = (u16)(w0 >> 40);
+    a.out_deg[i] = (u8)((w0 >> 56) & 7u);
+    a.in_deg[i] = (u8)((w0 >> 59) & 7u);
+    reinterpret_cast<uint4 *>(a.out_succ)[i] = make_uint4((u32)w1, (u32)(w1 >> 32), (u32)w2, NIL32);
+    reinterpret_cast<uint4 *>(a.in_pred)[i] = make_uint4((u32)(w2 >> 32), (u32)w3, (u32)(w3 >> 32), NIL32);
+    if (a.kmer_lo) { const ulonglong2 km = r.kmers[i]; a.kmer_lo[i] = km.x; a.kmer_hi[i] = km.y; }
+}
+/* ... and the fourth edges of the few nodes that have them (after k_unpack_rows) */
+__global__ void __launch_bounds__(THREADS)
+k_unpack_overflow(RowSink r, ExportArgs a) {
+    const u32 n = *r.n_over;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const ulonglong2 e = r.over[j];
+        const u32 id = (u32)e.x;
+        a.out_succ[(u64)id * 4 + 3] = (u32)(e.x >> 32);
+        a.in_pred[(u64)id * 4 + 3] = (u32)e.y;
+    }
 }
 
 /* Barrier between the devices of a sharded finish, on the device: every device owns a block of

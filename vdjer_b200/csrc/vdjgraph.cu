@@ -1276,33 +1276,47 @@ int run_finish(vdjgraph_ctx *c) {
 }
 
 /* The finish of a build over several devices (kernels.cuh, "K5 on several devices").  Every device's exchange
- * buffer (BUF_GATHER, mapped by its peers) holds: 256 bytes of barrier flags | the sorted stamps of ALL devices
- * (its own segment is sorted into place, the peers' are copied in) | its flat survivor table | on the finishing
- * device, the node rows of the whole graph.  Every offset follows from the all-gathered survivor counts. */
-struct FinishLayout { size_t keys_off, table_off, rows_off, bytes; uint64_t n_total, cap; };
-FinishLayout finish_layout(const uint64_t *surv, int G, int rank) {
+ * buffer (BUF_GATHER, mapped by its peers) holds: 256 bytes of barrier flags and counters | the sorted stamps of ALL
+ * devices (its own segment is sorted into place, the peers' are copied in) | its flat survivor table | on the
+ * finishing device, the node rows of the whole graph, their overflow list and (when wanted) their k-mers.  Every
+ * offset follows from the all-gathered survivor counts and the build flags (the same on every rank). */
+constexpr size_t FLAGS_BYTES = 256;      /* [0, 64): barrier flags; [128, 132): overflow entries of the node rows */
+constexpr size_t OVER_COUNT_OFF = 128;
+struct FinishLayout { size_t keys_off, table_off, rows_off, over_off, kmers_off, bytes; uint64_t n_total, cap; };
+FinishLayout finish_layout(const uint64_t *surv, int G, int rank, uint32_t flags) {
     FinishLayout f;
     f.n_total = 0;
     for (int d = 0; d < G; d++) f.n_total += surv[d];
     const uint64_t na = std::max<uint64_t>(f.n_total, 1);
-    f.keys_off = 256;
+    const bool want_keys = flags & (VDJGRAPH_FLAG_EXPORT_KEYS | VDJGRAPH_FLAG_HASHMAP_LAYOUT);
+    f.keys_off = FLAGS_BYTES;
     f.table_off = (f.keys_off + na * 8 + 255) & ~(size_t)255;
     f.cap = std::max<uint64_t>(1024, (uint64_t)((double)surv[rank] * MERGED_SLOTS_PER_NODE) + 64);
     f.rows_off = f.table_off + f.cap * sizeof(Slot2);
-    f.bytes = f.rows_off + (rank == 0 ? na * sizeof(NodeRow) : 0);
+    f.over_off = f.rows_off + (rank == 0 ? na * ROW_WORDS * 8 : 0);
+    f.kmers_off = f.over_off + (rank == 0 ? na * 16 : 0);
+    f.bytes = f.kmers_off + (rank == 0 && want_keys ? na * 16 : 0);
     return f;
+}
+RowSink row_sink(char *arena0, const FinishLayout &f0, uint32_t flags) {
+    RowSink r;
+    r.rows = reinterpret_cast<u64 *>(arena0 + f0.rows_off);
+    r.over = reinterpret_cast<ulonglong2 *>(arena0 + f0.over_off);
+    r.n_over = reinterpret_cast<u32 *>(arena0 + OVER_COUNT_OFF);
+    r.kmers = (flags & (VDJGRAPH_FLAG_EXPORT_KEYS | VDJGRAPH_FLAG_HASHMAP_LAYOUT)) ? reinterpret_cast<ulonglong2 *>(arena0 + f0.kmers_off) : nullptr;
+    return r;
 }
 
 int finish_plan(vdjgraph_ctx *c) {
     Shard &sh = c->sh;
     int rc;
-    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank);
+    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank, c->prm.flags);
     if (f.n_total >= NIL32) return fail(VDJGRAPH_ERR_TOO_MANY_NODES, "%llu nodes", (unsigned long long)f.n_total);
     /* everything the finish needs is allocated here: its steps are queued without a host synchronisation in
      * between (an allocation would be one) */
     void *before = c->d_gather.p;
     if ((rc = c->d_gather.ensure(f.bytes))) return rc;
-    if (c->d_gather.p != before) CK(cudaMemset(c->d_gather.p, 0, 256));   /* fresh barrier flags */
+    if (c->d_gather.p != before) CK(cudaMemset(c->d_gather.p, 0, FLAGS_BYTES));   /* fresh barrier flags */
     const size_t nr = std::max<uint64_t>(sh.surv_all[sh.rank], 1);
     if ((rc = c->d_keys[0].ensure(nr * 8)) || (rc = c->d_vals[0].ensure(nr * 4)) || (rc = c->d_vals[1].ensure(nr * 4)) ||
         (rc = c->d_gid.ensure(nr * 4)) || (rc = c->d_owner.ensure(NBUCKET)))
@@ -1334,7 +1348,7 @@ int finish_step(vdjgraph_ctx *c, int step, bool device_barrier) {
     cudaStream_t s = c->stream;
     vdjgraph_result &res = c->res;
     Counters *d_ctr = c->d_ctr.as<Counters>();
-    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank);
+    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank, c->prm.flags);
     char *arena = c->d_gather.as<char>();
     const uint64_t n_r = sh.surv_all[sh.rank];
     Slot2 *table = reinterpret_cast<Slot2 *>(arena + f.table_off);
@@ -1375,17 +1389,17 @@ int finish_step(vdjgraph_ctx *c, int step, bool device_barrier) {
             PeerTables pt;
             for (int d = 0; d < MAX_DEV; d++) { pt.table[d] = nullptr; pt.len[d] = 1; }
             for (int d = 0; d < sh.G; d++) {
-                const FinishLayout fd = finish_layout(sh.surv_all, sh.G, d);
+                const FinishLayout fd = finish_layout(sh.surv_all, sh.G, d, c->prm.flags);
                 pt.table[d] = reinterpret_cast<const Slot2 *>((const char *)sh.peer[d][BUF_GATHER] + fd.table_off);
                 pt.len[d] = (u32)fd.cap;
             }
             pt.owner = c->d_owner.as<u8>();
             pt.ushift = (u32)sh.ushift;
-            const FinishLayout f0 = finish_layout(sh.surv_all, sh.G, 0);
+            const FinishLayout f0 = finish_layout(sh.surv_all, sh.G, 0, c->prm.flags);
             ExportDistArgs a;
             a.keys = all_keys + sh.surv_off[sh.rank]; a.vals = c->d_vals[1].as<u32>(); a.gid = c->d_gid.as<u32>();
             a.n = n_r; a.self = sh.rank;
-            a.rows = reinterpret_cast<NodeRow *>((char *)sh.peer[0][BUF_GATHER] + f0.rows_off);
+            a.sink = row_sink((char *)sh.peer[0][BUF_GATHER], f0, c->prm.flags);
             k_export_dist<<<gb, THREADS, 0, s>>>(a, pt, g, d_ctr);
             res.kernel_launches++;
         }
@@ -1413,7 +1427,7 @@ int finish_end(vdjgraph_ctx *c) {
     vdjgraph_result &res = c->res;
     Counters *d_ctr = c->d_ctr.as<Counters>();
     Counters *h_ctr = c->h_ctr.as<Counters>();
-    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank);
+    const FinishLayout f = finish_layout(sh.surv_all, sh.G, sh.rank, c->prm.flags);
     int rc;
     res.hm_buckets = 0; res.ms_hashmap = 0;
     if (sh.rank == 0) {
@@ -1426,8 +1440,10 @@ int finish_end(vdjgraph_ctx *c) {
             ae.out_deg = c->d_odeg.as<u8>(); ae.in_deg = c->d_ideg.as<u8>();
             ae.out_succ = c->d_osucc.as<u32>(); ae.in_pred = c->d_ipred.as<u32>();
             ae.kmer_lo = want_keys ? c->d_klo.as<u64>() : nullptr; ae.kmer_hi = want_keys ? c->d_khi.as<u64>() : nullptr;
-            k_unpack_rows<<<(int)((f.n_total + THREADS - 1) / THREADS), THREADS, 0, s>>>(
-                reinterpret_cast<const NodeRow *>(c->d_gather.as<char>() + f.rows_off), f.n_total, ae);
+            const RowSink sink = row_sink(c->d_gather.as<char>(), f, c->prm.flags);
+            k_unpack_rows<<<(int)((f.n_total + THREADS - 1) / THREADS), THREADS, 0, s>>>(sink, f.n_total, ae);
+            k_unpack_overflow<<<c->sm_count, THREADS, 0, s>>>(sink, ae);
+            res.kernel_launches++;
             res.kernel_launches++;
             CK(cudaGetLastError());
         }
@@ -1550,7 +1566,7 @@ extern "C" int vdjgraph_shard_plan(vdjgraph_ctx *c, const uint64_t *hist_all, co
     /* the barrier flags of the finish start every build at zero (the peers' stores of this build come after
      * several host exchanges; those of the last build arrived before its final one) */
     sh.bar_seq = 0;
-    if (sh.G > 1 && c->d_gather.p) CK(cudaMemset(c->d_gather.p, 0, 256));
+    if (sh.G > 1 && c->d_gather.p) CK(cudaMemset(c->d_gather.p, 0, FLAGS_BYTES));
     return 0;
 }
 
@@ -1614,9 +1630,9 @@ extern "C" int vdjgraph_shard_gather_plan(vdjgraph_ctx *c, const uint64_t *survi
     return 0;
 }
 
-extern "C" int vdjgraph_shard_finish_bytes(const uint64_t *survivors_all, uint32_t n_ranks, uint32_t rank, size_t *bytes) {
-    if (!survivors_all || !bytes || n_ranks < 1 || n_ranks > MAX_DEV || rank >= n_ranks) return fail(VDJGRAPH_ERR_PARAM, "bad argument");
-    *bytes = n_ranks > 1 ? finish_layout(survivors_all, (int)n_ranks, (int)rank).bytes : 0;
+extern "C" int vdjgraph_shard_finish_bytes(vdjgraph_ctx *c, const uint64_t *survivors_all, uint32_t rank, size_t *bytes) {
+    if (!c || !survivors_all || !bytes || rank >= (uint32_t)c->sh.G) return fail(VDJGRAPH_ERR_PARAM, "bad argument");
+    *bytes = c->sh.G > 1 ? finish_layout(survivors_all, c->sh.G, (int)rank, c->prm.flags).bytes : 0;
     return 0;
 }
 

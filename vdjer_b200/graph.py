@@ -125,7 +125,7 @@ def load_library():
     lib.vdjgraph_shard_scatter.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_passes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.vdjgraph_shard_gather_plan.argtypes = [C.c_void_p, C.c_void_p]
-    lib.vdjgraph_shard_finish_bytes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]
+    lib.vdjgraph_shard_finish_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_size_t)]
     lib.vdjgraph_shard_finish_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.vdjgraph_shard_finish.argtypes = [C.c_void_p]
     lib.vdjgraph_shard_release_retired.argtypes = [C.c_void_p]
@@ -393,7 +393,7 @@ class GraphBuilder:
         """Bytes rank `rank`'s exchange buffer (BUF_GATHER) must hold for the finish of these survivor counts."""
         a = np.ascontiguousarray(survivors_all, np.uint64)
         n = C.c_size_t(0)
-        self._check(self._lib.vdjgraph_shard_finish_bytes(a.ctypes.data, len(a), rank, C.byref(n)))
+        self._check(self._lib.vdjgraph_shard_finish_bytes(self._ctx, a.ctypes.data, rank, C.byref(n)))
         return int(n.value)
 
     def shard_finish_step(self, step: int, device_barrier: bool):
