@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -406,7 +407,9 @@ double hll_estimate(const uint8_t *reg) {
     const int M = BHLL;
     double sum = 0;
     int zeros = 0;
-    for (int i = 0; i < M; i++) { sum += std::ldexp(1.0, -(int)reg[i]); zeros += reg[i] == 0; }
+    /* 2^-r from a table: the plan adds up 32768 registers per build */
+    static const std::array<double, 256> pow2neg = [] { std::array<double, 256> t{}; for (int r = 0; r < 256; r++) t[r] = std::ldexp(1.0, -r); return t; }();
+    for (int i = 0; i < M; i++) { sum += pow2neg[reg[i]]; zeros += reg[i] == 0; }
     double alpha = 0.7213 / (1.0 + 1.079 / M);
     double e = alpha * M * (double)M / sum;
     if (e <= 2.5 * M && zeros) e = M * std::log((double)M / zeros);
