@@ -2002,16 +2002,28 @@ __device__ __forceinline__ u64 lower_bound_u64(const u64 *a, u64 n, u64 key) {
     return lo;
 }
 
+/* One thread per own node, in stamp order.  The block's first and last stamp bracket every other one of the block:
+ * 2 G threads first find those two positions in each peer's array, the per-node searches then run over the
+ * short stretch between them (about THREADS elements, not the whole array). */
 __global__ void __launch_bounds__(THREADS)
 k_global_rank(const u64 *all_keys, const __grid_constant__ KeySegs ks, int G, int self, Slot2 *table, const u32 *vals, u32 *gid, const Counters *ctr) {
-    if (ctr->internal) return;
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ u64 s_lo[MAX_DEV], s_hi[MAX_DEV];
+    if (ctr->internal) return;   /* block-uniform */
     const u64 n = ks.off[self + 1] - ks.off[self];
+    const u64 b0 = (u64)blockIdx.x * blockDim.x, i = b0 + threadIdx.x;
+    const u64 *mine = all_keys + ks.off[self];
+    if (threadIdx.x < 2 * G && b0 < n) {
+        const int d = threadIdx.x % G;
+        const u64 key = threadIdx.x < G ? mine[b0] : mine[min(b0 + blockDim.x, n) - 1];
+        const u64 at = d == self ? 0 : lower_bound_u64(all_keys + ks.off[d], ks.off[d + 1] - ks.off[d], key);
+        if (threadIdx.x < G) s_lo[d] = at; else s_hi[d] = at;
+    }
+    __syncthreads();
     if (i >= n) return;
-    const u64 key = all_keys[ks.off[self] + i];
+    const u64 key = mine[i];
     u64 r = i;
     for (int d = 0; d < G; d++)
-        if (d != self) r += lower_bound_u64(all_keys + ks.off[d], ks.off[d + 1] - ks.off[d], key);
+        if (d != self) r += s_lo[d] + lower_bound_u64(all_keys + ks.off[d] + s_lo[d], s_hi[d] - s_lo[d], key);
     gid[i] = (u32)r;
     table[vals[i]].rank = (u32)r;
 }

@@ -203,6 +203,7 @@ struct vdjgraph_ctx {
     DevBuf d_hm_hash, d_hm_probe, d_hm_prev, d_hm_owner, d_hm_slots, d_hm_flag;
     PinBuf h_hm_slots, h_hm_flag;
     cudaEvent_t ev_hm[2] = {};
+    cudaEvent_t ev_fin[6] = {};                   /* after each step of a distributed finish and after the barrier behind it */
     PinBuf h_tbase;
     Shard sh;
 
@@ -456,6 +457,7 @@ extern "C" int vdjgraph_create(const vdjgraph_params *params, vdjgraph_ctx **out
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 13 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev_hm[i]);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev_fin[i]);
     if (e != cudaSuccess) { delete c; return fail(VDJGRAPH_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return 0;
@@ -482,6 +484,7 @@ extern "C" void vdjgraph_destroy(vdjgraph_ctx *c) {
     for (PinBuf *b : pb) b->release();
     for (int i = 0; i < 13; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->ev_hm[i]) cudaEventDestroy(c->ev_hm[i]);
+    for (int i = 0; i < 6; i++) if (c->ev_fin[i]) cudaEventDestroy(c->ev_fin[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1408,6 +1411,7 @@ int finish_step(vdjgraph_ctx *c, int step, bool device_barrier) {
         }
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_fin[2 * step], s));
     if (device_barrier) {
         PeerFlags pf;
         for (int d = 0; d < MAX_DEV; d++) pf.flags[d] = reinterpret_cast<u64 *>(sh.peer[d < sh.G ? d : sh.rank][BUF_GATHER]);
@@ -1418,6 +1422,7 @@ int finish_step(vdjgraph_ctx *c, int step, bool device_barrier) {
     } else {
         CK(cudaStreamSynchronize(s));
     }
+    CK(cudaEventRecord(c->ev_fin[2 * step + 1], s));
     sh.phase = 6 + step;
     return 0;
 }
@@ -1472,6 +1477,15 @@ int finish_end(vdjgraph_ctx *c) {
     res.ms_scatter = sh.acc[0]; res.ms_init1 = sh.acc[1]; res.ms_pass1 = sh.acc[2];
     res.ms_prune = sh.acc[3]; res.ms_table2 = sh.acc[4]; res.ms_pass2 = sh.acc[5];
     cudaEventElapsedTime(&res.ms_export, c->ev[12], c->ev[8]);
+    if (env_double("VDJGRAPH_FINISH_TIMES", 0) > 0) {
+        /* where a distributed finish spends its time on this device: the three steps, the wait at the barrier
+         * behind each, and (finishing device) unpacking the rows */
+        float t[7];
+        cudaEvent_t seq[8] = { c->ev[12], c->ev_fin[0], c->ev_fin[1], c->ev_fin[2], c->ev_fin[3], c->ev_fin[4], c->ev_fin[5], c->ev[8] };
+        for (int i = 0; i < 7; i++) cudaEventElapsedTime(&t[i], seq[i], seq[i + 1]);
+        fprintf(stderr, "vdjgraph finish rank %d: table+sort %.3f wait %.3f | rank %.3f wait %.3f | edges+rows %.3f wait %.3f | unpack %.3f ms\n",
+                sh.rank, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+    }
     res.ms_device = res.ms_scatter + res.ms_init1 + res.ms_pass1 + res.ms_prune + res.ms_table2 + res.ms_pass2 + res.ms_export;
     res.n_nodes = sh.rank == 0 ? f.n_total : 0;
     if (sh.rank == 0) res.n_pre = f.n_total;   /* (the other ranks keep their own survivor count) */
