@@ -808,10 +808,14 @@ int run_plan(vdjgraph_ctx *c, const uint64_t *hist_all, const uint8_t *hll) {
             const double tables = cap1_dev * sizeof(Slot1)
                                 + std::min((double)gated_rnd[i], cap1_dev * load1 / 1.15 * 1.3) * NBq * 8.0
                                 + nodes / ((double)G * sh.S) * 4.0 * sizeof(Slot2);
-            /* the finish (on the finishing device): gathered records, merged table, sort buffers, result.  A
-             * merged finish runs when the tables of the last round are no longer needed; with
-             * VDJGRAPH_FREE_TABLES_MB set, run_finish frees them first (see there) */
-            const double finish = merged ? nodes * (sizeof(Slot2) + MERGED_SLOTS_PER_NODE * sizeof(Slot2) + 70.0) : nodes * 70.0;
+            /* the finish.  One device, several rounds: merged table over all survivor records, sort buffers,
+             * result (with VDJGRAPH_FREE_TABLES_MB set, run_finish first frees the last round's tables, see
+             * there).  Several devices (finish_layout): everybody's sorted stamps, a table and sort buffers for
+             * the device's own share, and on the finishing device the node rows, their overflow list and the
+             * result arrays of the whole graph. */
+            const double finish = !merged ? nodes * 70.0
+                                : G == 1 ? nodes * (sizeof(Slot2) + MERGED_SLOTS_PER_NODE * sizeof(Slot2) + 70.0)
+                                         : nodes * (8.0 + ROW_WORDS * 8.0 + 16.0 + 60.0) + nodes / (double)G * (MERGED_SLOTS_PER_NODE * sizeof(Slot2) + 20.0);
             const double records = merged ? nodes * sizeof(Slot2) / (double)G : 0.0;
             const double ws = reads_bytes + (double)load_rnd[i] * RUN_WORDS * 8 + records + (merged && free_tables ? std::max(tables, finish) : tables + finish);
             worst = std::max(worst, ws);
