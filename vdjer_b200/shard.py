@@ -202,6 +202,8 @@ class _HostExchange:
             spins = 0
             while self.head[r, par, 0] != self.seq:
                 spins += 1
+                if spins % 64 == 0:
+                    os.sched_yield()                           # fewer cores than ranks: let the late rank run
                 if spins % 4096 == 0:
                     t0 = t0 or time.perf_counter()
                     if time.perf_counter() - t0 > self.timeout_s:
