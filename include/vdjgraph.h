@@ -276,6 +276,26 @@ int vdjgraph_ipc_open(const unsigned char *handle64, void **device_ptr);
 int vdjgraph_ipc_close(void *device_ptr);
 int vdjgraph_enable_peer_access(int device, int peer_device);
 
+/*
+ * The same sharded build as ONE call, for a caller that is a single process (V'DJer is): one context
+ * per entry of `devices` (1, 2, 4 or 8 CUDA device ordinals; peer access between them is enabled),
+ * and inside vdjgraph_multi_build one host thread per device walks the phases above, meeting the
+ * others at thread barriers (and, between the steps of the finish, at the barriers the devices keep
+ * in peer memory).  Records are split into contiguous, even-sized ranges in rank order; stamps and
+ * node positions are those of the one-device build on the same buffers, and so is the result, which
+ * lands on devices[0] and is fetched from there.  `params->device` is ignored.  The same device may be
+ * named more than once (tests on one GPU).  _forward: the buffers hold forward reads only
+ * (vdjgraph_build_forward).  vdjgraph_multi_stats: counters of one rank's share.
+ */
+typedef struct vdjgraph_multi vdjgraph_multi;
+int vdjgraph_multi_create(const vdjgraph_params *params, const int *devices, uint32_t n_devices, vdjgraph_multi **out);
+void vdjgraph_multi_destroy(vdjgraph_multi *m);
+int vdjgraph_multi_build(vdjgraph_multi *m, const char *primary, size_t n_primary_records,
+                         const char *secondary, size_t n_secondary_records, vdjgraph_result *out);
+int vdjgraph_multi_build_forward(vdjgraph_multi *m, const char *primary_reads, size_t n_primary_reads,
+                                 const char *secondary_reads, size_t n_secondary_reads, vdjgraph_result *out);
+int vdjgraph_multi_stats(vdjgraph_multi *m, uint32_t rank, vdjgraph_result *out);
+
 /* Counters and timings of the last run without copying the graph (array pointers are NULL). */
 int vdjgraph_stats(vdjgraph_ctx *ctx, vdjgraph_result *out);
 

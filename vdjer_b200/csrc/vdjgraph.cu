@@ -16,10 +16,12 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1851,4 +1853,176 @@ extern "C" int vdjgraph_fetch_pre_table(vdjgraph_ctx *c, vdjgraph_pre_table *out
     out->kmer_hi = c->h_pre_khi.as<uint64_t>();
     out->frequency = c->h_pre_freq.as<uint16_t>();
     return 0;
+}
+
+/* ========================================================================================== */
+/* One graph over several devices of THIS process: the sharded phases above, driven by one host  */
+/* thread per device inside the call (what vdjer_b200/shard.py does with one process per GPU).   */
+/* ========================================================================================== */
+struct vdjgraph_multi {
+    int G = 0;
+    bool device_barriers = false;           /* distinct devices: the steps of the finish meet in peer memory */
+    std::vector<vdjgraph_ctx *> ctx;
+    std::vector<int> dev;
+    /* what the ranks exchange during a build */
+    std::vector<uint64_t> hist;             /* [G][HIST_WORDS] */
+    std::vector<uint8_t> hll;               /* [G][HLL_BYTES] */
+    std::vector<uint64_t> counts, surv;     /* [G] */
+    std::vector<void *> ptrs;               /* [G][NBUF] */
+    std::vector<int> rounds;                /* [G]; 0 = this rank's plan failed */
+    std::vector<int> rc;
+    std::vector<std::string> err;
+    std::atomic<int> failed{0};
+    /* barrier of the G worker threads */
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    uint64_t generation = 0;
+    void barrier() {
+        std::unique_lock<std::mutex> l(mu);
+        const uint64_t g = generation;
+        if (++waiting == G) { waiting = 0; generation++; cv.notify_all(); }
+        else cv.wait(l, [&] { return generation != g; });
+    }
+};
+
+namespace {
+
+/* rank r's part of a build.  Every rank walks the same sequence of barriers whatever happens: a rank
+ * whose library call failed records the status, skips its remaining calls and keeps meeting the others. */
+void multi_worker(vdjgraph_multi *m, int r, const char *primary, size_t np, const char *secondary, size_t ns, int fwd) {
+    vdjgraph_ctx *c = m->ctx[r];
+    const int G = m->G;
+    auto step = [&](int rc_) {
+        if (rc_ && !m->rc[r]) { m->rc[r] = rc_; m->err[r] = g_err; m->failed = 1; }
+        return rc_ == 0;
+    };
+    auto ok = [&] { return m->failed.load() == 0; };
+    /* contiguous record ranges in rank order, even-sized: a read and its reverse complement stay together */
+    const size_t rec_bytes = (size_t)2 * (size_t)c->prm.read_length + 1;
+    const uint64_t total = ((uint64_t)np + ns) << fwd;
+    uint64_t per = (total + G - 1) / G;
+    per += per & 1;
+    const uint64_t lo = std::min<uint64_t>(total, (uint64_t)r * per), hi = std::min<uint64_t>(total, (uint64_t)(r + 1) * per);
+    const uint64_t lo_i = lo >> fwd, hi_i = hi >> fwd;      /* in items of the caller's buffers (records, or forward reads) */
+    const uint64_t p_lo = std::min<uint64_t>(lo_i, np), p_hi = std::min<uint64_t>(hi_i, np);
+    const uint64_t s_lo = std::max<uint64_t>(lo_i, np) - np, s_hi = std::max<uint64_t>(hi_i, np) - np;
+    vdjgraph_shard_info info;
+    info.n_ranks = (uint32_t)G; info.rank = (uint32_t)r; info.record_base = lo; info.total_records = total;
+    m->counts[r] = hi - lo;
+    const char *pp = primary ? primary + p_lo * rec_bytes : nullptr, *sp = secondary ? secondary + s_lo * rec_bytes : nullptr;
+    if (ok()) step(fwd ? vdjgraph_shard_stage_forward(c, pp, p_hi - p_lo, sp, s_hi - s_lo, &info)
+                       : vdjgraph_shard_stage(c, pp, p_hi - p_lo, sp, s_hi - s_lo, &info));
+    if (ok()) step(vdjgraph_shard_count(c, m->hist.data() + (size_t)r * HIST_WORDS, m->hll.data() + (size_t)r * HLL_BYTES));
+    m->barrier();
+    m->rounds[r] = 0;
+    if (ok()) {
+        std::vector<uint8_t> merged(m->hll.begin(), m->hll.begin() + HLL_BYTES);   /* registers merge by maximum */
+        for (int d = 1; d < G; d++)
+            for (size_t i = 0; i < HLL_BYTES; i++) merged[i] = std::max(merged[i], m->hll[(size_t)d * HLL_BYTES + i]);
+        if (step(vdjgraph_shard_plan(c, m->hist.data(), merged.data(), m->counts.data()))) m->rounds[r] = vdjgraph_shard_rounds(c);
+    }
+    if (ok()) step(vdjgraph_shard_buffers(c, m->ptrs.data() + (size_t)r * NBUF, nullptr));
+    m->barrier();
+    int n_rounds = m->rounds[0];
+    for (int d = 0; d < G; d++) n_rounds = std::min(n_rounds, m->rounds[d]);    /* 0 when any rank has failed so far */
+    if (n_rounds < 0) n_rounds = 0;
+    if (ok()) step(vdjgraph_shard_set_peers(c, m->ptrs.data()));
+    m->barrier();                                       /* nobody still uses a buffer that was replaced */
+    if (ok()) step(vdjgraph_shard_release_retired(c));
+    uint64_t n_surv = 0;
+    for (int rnd = 0; rnd < n_rounds; rnd++) {
+        if (rnd) m->barrier();                          /* the owners have consumed the previous round's runs */
+        if (ok()) step(vdjgraph_shard_scatter(c));
+        m->barrier();                                   /* every rank's runs of this round have arrived */
+        if (ok()) step(vdjgraph_shard_passes(c, &n_surv));
+    }
+    m->surv[r] = n_surv;
+    m->barrier();
+    if (ok()) step(vdjgraph_shard_gather_plan(c, m->surv.data()));
+    if (ok()) step(vdjgraph_shard_buffers(c, m->ptrs.data() + (size_t)r * NBUF, nullptr));
+    m->barrier();                                       /* every exchange buffer exists, its barrier flags cleared */
+    if (ok()) step(vdjgraph_shard_set_peers(c, m->ptrs.data()));
+    for (int st = 0; st < 3; st++) {
+        if (ok()) step(vdjgraph_shard_finish_step(c, st, m->device_barriers ? 1 : 0));
+        if (!m->device_barriers) m->barrier();
+    }
+    if (ok()) step(vdjgraph_shard_finish(c));
+    m->barrier();
+    if (ok()) step(vdjgraph_shard_release_retired(c));
+}
+
+int multi_build(vdjgraph_multi *m, const char *primary, size_t np, const char *secondary, size_t ns, int fwd, vdjgraph_result *out) {
+    if (!m || !out) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if ((np && !primary) || (ns && !secondary)) return fail(VDJGRAPH_ERR_PARAM, "NULL record buffer");
+    const int G = m->G;
+    m->failed = 0;
+    std::fill(m->rc.begin(), m->rc.end(), 0);
+    for (auto &e : m->err) e.clear();
+    std::vector<std::thread> th;
+    for (int r = 1; r < G; r++) th.emplace_back(multi_worker, m, r, primary, np, secondary, ns, fwd);
+    multi_worker(m, 0, primary, np, secondary, ns, fwd);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < G; r++)
+        if (m->rc[r]) return fail(m->rc[r], "device %d (rank %d of %d): %s", m->dev[r], r, G, m->err[r].c_str());
+    return vdjgraph_fetch(m->ctx[0], out);
+}
+
+} // namespace
+
+extern "C" int vdjgraph_multi_create(const vdjgraph_params *params, const int *devices, uint32_t n_devices, vdjgraph_multi **out) {
+    if (!out) return fail(VDJGRAPH_ERR_PARAM, "out is NULL");
+    *out = nullptr;
+    if (!params || !devices) return fail(VDJGRAPH_ERR_PARAM, "NULL argument");
+    if (n_devices < 1 || n_devices > (uint32_t)MAX_DEV || (n_devices & (n_devices - 1)))
+        return fail(VDJGRAPH_ERR_PARAM, "n_devices %u must be 1, 2, 4 or 8", n_devices);
+    vdjgraph_multi *m = new vdjgraph_multi();
+    const int G = (int)n_devices;
+    m->G = G;
+    m->dev.assign(devices, devices + G);
+    bool distinct = true;
+    for (int a = 0; a < G; a++)
+        for (int b = a + 1; b < G; b++) distinct = distinct && devices[a] != devices[b];
+    /* the same device twice (tests on one GPU): host barriers, a kernel that waits for a peer on its own device
+     * could keep that peer's kernels from starting */
+    m->device_barriers = distinct && G > 1 && env_double("VDJGRAPH_HOST_BARRIERS", 0) == 0;
+    m->hist.assign((size_t)G * HIST_WORDS, 0); m->hll.assign((size_t)G * HLL_BYTES, 0);
+    m->counts.assign(G, 0); m->surv.assign(G, 0); m->ptrs.assign((size_t)G * NBUF, nullptr);
+    m->rounds.assign(G, 0); m->rc.assign(G, 0); m->err.assign(G, std::string());
+    int rc = 0;
+    for (int r = 0; r < G && !rc; r++) {
+        vdjgraph_params prm = *params;
+        prm.device = devices[r];
+        /* the ranks stage at the same time: they share the host's cores */
+        if (!prm.host_threads && G > 1) prm.host_threads = (int32_t)std::max(2u, std::thread::hardware_concurrency() / (unsigned)G);
+        vdjgraph_ctx *c = nullptr;
+        rc = vdjgraph_create(&prm, &c);
+        if (!rc) m->ctx.push_back(c);
+    }
+    for (int a = 0; a < G && !rc; a++)
+        for (int b = 0; b < G && !rc; b++) rc = vdjgraph_enable_peer_access(devices[a], devices[b]);
+    if (rc) { vdjgraph_multi_destroy(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+extern "C" void vdjgraph_multi_destroy(vdjgraph_multi *m) {
+    if (!m) return;
+    for (vdjgraph_ctx *c : m->ctx) vdjgraph_destroy(c);
+    delete m;
+}
+
+extern "C" int vdjgraph_multi_build(vdjgraph_multi *m, const char *primary, size_t np, const char *secondary, size_t ns,
+                                    vdjgraph_result *out) {
+    return multi_build(m, primary, np, secondary, ns, 0, out);
+}
+
+extern "C" int vdjgraph_multi_build_forward(vdjgraph_multi *m, const char *primary_reads, size_t np, const char *secondary_reads,
+                                            size_t ns, vdjgraph_result *out) {
+    return multi_build(m, primary_reads, np, secondary_reads, ns, 1, out);
+}
+
+extern "C" int vdjgraph_multi_stats(vdjgraph_multi *m, uint32_t rank, vdjgraph_result *out) {
+    if (!m || rank >= (uint32_t)m->G) return fail(VDJGRAPH_ERR_PARAM, "bad argument");
+    return vdjgraph_stats(m->ctx[rank], out);
 }

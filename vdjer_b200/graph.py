@@ -75,6 +75,7 @@ EXPORTS = [
     "vdjgraph_shard_set_peers", "vdjgraph_shard_scatter", "vdjgraph_shard_passes", "vdjgraph_shard_gather_plan",
     "vdjgraph_shard_finish_bytes", "vdjgraph_shard_finish_step", "vdjgraph_shard_finish", "vdjgraph_shard_release_retired", "vdjgraph_ipc_export", "vdjgraph_ipc_open",
     "vdjgraph_ipc_close", "vdjgraph_enable_peer_access",
+    "vdjgraph_multi_create", "vdjgraph_multi_destroy", "vdjgraph_multi_build", "vdjgraph_multi_build_forward", "vdjgraph_multi_stats",
 ]
 
 SHARD_NBUF, SHARD_HIST, SHARD_HLL = 6, 768, 32768   # buffers; uint64 counts; uint8 registers
@@ -133,6 +134,12 @@ def load_library():
     lib.vdjgraph_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.vdjgraph_ipc_close.argtypes = [C.c_void_p]
     lib.vdjgraph_enable_peer_access.argtypes = [C.c_int, C.c_int]
+    lib.vdjgraph_multi_create.argtypes = [C.POINTER(_Params), C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.vdjgraph_multi_destroy.argtypes = [C.c_void_p]
+    lib.vdjgraph_multi_destroy.restype = None
+    lib.vdjgraph_multi_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(_Result)]
+    lib.vdjgraph_multi_build_forward.argtypes = lib.vdjgraph_multi_build.argtypes
+    lib.vdjgraph_multi_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_Result)]
     _lib = lib
     return lib
 
@@ -431,3 +438,62 @@ class GraphBuilder:
             _np_from(r.kmer_lo, n, np.uint64, 1, copy) if r.kmer_lo else None,
             _np_from(r.kmer_hi, n, np.uint64, 1, copy) if r.kmer_hi else None, stats,
             _np_from(r.hm_slots, int(r.hm_buckets), np.uint32, 1, copy) if r.hm_slots else None)
+
+
+class MultiBuilder:
+    """One graph over several GPUs of THIS process (vdjgraph_multi_*): one context per entry of `devices`
+    (1, 2, 4 or 8 ordinals; the same one may repeat, for tests on one GPU), one host thread per device inside
+    every build.  The result is the one-device result; it is fetched from devices[0]."""
+
+    def __init__(self, read_length: int, k: int = 35, mf: int = 3, mq: int = 90, devices=(0,), host_threads: int = 0,
+                 export_keys: bool = False, partitions: int = 0, wide_tuples: bool = False, rounds: int = 0,
+                 hashmap_layout: bool = False):
+        self._lib = load_library()
+        self._m = C.c_void_p()
+        self.devices = [int(d) for d in devices]
+        self._p = _Params(read_length, k, mf, mq, -1, host_threads, 0,
+                          (FLAG_EXPORT_KEYS if export_keys else 0) | (FLAG_WIDE_TUPLES if wide_tuples else 0) |
+                          (FLAG_HASHMAP_LAYOUT if hashmap_layout else 0),
+                          partitions, rounds, 0)
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        self._check(self._lib.vdjgraph_multi_create(C.byref(self._p), dev, len(self.devices), C.byref(self._m)))
+
+    _check = GraphBuilder._check
+    _counts = GraphBuilder._counts
+    _graph = GraphBuilder._graph
+    _stats = staticmethod(GraphBuilder._stats)
+
+    def close(self):
+        if self._m:
+            self._lib.vdjgraph_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build(self, primary, secondary=b"", copy: bool = True) -> Graph:
+        p, s, n_p, n_s = self._counts(primary, secondary)
+        r = _Result()
+        self._check(self._lib.vdjgraph_multi_build(self._m, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
+        return self._graph(r, copy)
+
+    def build_forward(self, primary_reads, secondary_reads=b"", copy: bool = True) -> Graph:
+        p, s, n_p, n_s = self._counts(primary_reads, secondary_reads)
+        r = _Result()
+        self._check(self._lib.vdjgraph_multi_build_forward(self._m, p.ctypes.data, n_p, s.ctypes.data, n_s, C.byref(r)))
+        return self._graph(r, copy)
+
+    def rank_stats(self, rank: int) -> dict:
+        """Counters and timings of one rank's share of the last build."""
+        r = _Result()
+        self._check(self._lib.vdjgraph_multi_stats(self._m, rank, C.byref(r)))
+        return self._stats(r)
