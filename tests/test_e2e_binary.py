@@ -61,6 +61,22 @@ def test_vdjer_binary_with_gpu_graph_matches_reference_binary(built, tmp_path, e
 
 
 @needs_bins
+@pytest.mark.gpu
+def test_vdjer_binary_over_several_devices_matches_reference_binary(built, tmp_path):
+    """VDJGRAPH_DEVICES: the glue builds the graph through vdjgraph_multi_* (here: this GPU named twice, one host
+    thread each); vdjer.dot, contigs and SAM stay byte-identical."""
+    work = str(tmp_path)
+    sam, _ = e2e_data.make_case(work, n_clones=4)
+    bam = os.path.join(work, "x.bam")
+    subprocess.run([BIN["sam2bam"], sam, bam], check=True, capture_output=True)
+    ref = _run(BIN["vdjer_ref"], bam, os.path.join(work, "ref"), os.path.join(work, "cpu"), [])
+    gpu = _run(BIN["vdjer_gpu"], bam, os.path.join(work, "ref"), os.path.join(work, "gpu2"), [], env={"VDJGRAPH_DEVICES": "0,0"})
+    assert "vdjgraph: one graph over 2 devices" in gpu["err"]
+    assert gpu["log"] == ref["log"] and gpu["dot"] == ref["dot"] and gpu["contigs"] == ref["contigs"] and gpu["sam"] == ref["sam"]
+    assert len(ref["contigs"]) > 100
+
+
+@needs_bins
 def test_reference_binary_runs_on_the_synthetic_bam(built, tmp_path):
     """CPU: the stand-in for BASELINE configs[0] drives the unmodified pipeline to contigs."""
     work = str(tmp_path)
