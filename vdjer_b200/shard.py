@@ -3,14 +3,15 @@
 Records are split into contiguous ranges (rank order = record order), k-mers are owner-computed:
 every hash unit (a group of minimizer buckets) belongs to one rank, chosen by the library from the
 all-gathered window counts.  This module is only the host plumbing between the library's phases:
-six small collectives per build (histograms + HyperLogLog registers + IPC handles in one all-gather,
-a flag gather that doubles as a barrier, one barrier per round, survivor counts, a barrier before and
-one after the finish).  The bulk exchange is inside the kernels: k_scatter writes every run (a
+a handful of small exchanges per build (histograms + HyperLogLog registers + IPC handles in one all-gather,
+a flag gather that doubles as a barrier, one barrier per round, survivor counts, one barrier after
+the finish).  The bulk exchange is inside the kernels: k_scatter writes every run (a
 stretch of consecutive windows, 32 bytes) straight into the owner's buffer through peer-mapped memory
 (NVLink / NVSwitch), the exact read comparison and the quality rows of border k-mers are peer
 loads; the finish is distributed too: every rank ranks and links its own survivors (neighbours
 owned by a peer are peer loads), the finished node rows are stored into rank 0's result buffer,
-and the three steps of it are separated by barriers the devices keep in peer memory.
+and the three steps of it are separated by barriers the devices keep in peer memory.  The small
+exchanges themselves go through a shared-memory file when all ranks share the host (_HostExchange).
 
 Two ways to run it:
   * one process per GPU (torchrun): `build_distributed(builder, primary, secondary)` with
@@ -18,7 +19,8 @@ Two ways to run it:
     buffers are mapped with CUDA IPC handles;
   * several ranks inside one process (`build_local`): G contexts on one or several devices, peer
     buffers are plain device pointers.  Used by the tests to check on ONE GPU that the sharded
-    result is identical to the single-device result.
+    result is identical to the single-device result.  (The library's own one-process driver, with
+    one host thread per device, is vdjgraph_multi_* / `MultiBuilder`.)
 """
 from __future__ import annotations
 
