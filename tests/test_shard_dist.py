@@ -183,6 +183,32 @@ def test_a_failing_rank_aborts_every_rank(tmp_path, where):
     assert o1.startswith("own error"), o1
 
 
+def _hostbar_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard._Peers.export = lambda self, ptr: str(ptr).encode().ljust(64, b" ") if ptr else b""
+    shard._Peers.map = lambda self, r, i, h: int(h) + 5 if h else 0
+    shard._Peers.close = lambda self: None
+    b = FakeBuilder(rank, 100 + 20 * rank)
+    db = shard.DistributedBuilder(b, dist, device_barriers=False)
+    g = db.build(None, None)
+    db.close()
+    np.save(os.path.join(out_dir, f"log{rank}.npy"), np.array([b.log, g], dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_host_barriers_between_the_steps_of_the_finish(tmp_path):
+    """device_barriers=False (also VDJGRAPH_HOST_BARRIERS=1): every step is asked to synchronise its stream and
+    the ranks meet on the host after each; same phase order, nobody hangs."""
+    world, port = 2, 37500 + os.getpid() % 2000
+    mp.spawn(_hostbar_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        log, _ = np.load(tmp_path / f"log{r}.npy", allow_pickle=True)
+        assert [e[1:] for e in log if e[0] == "step"] == [(0, False), (1, False), (2, False)]
+        assert [e[0] for e in log][-5:] == ["step", "step", "step", "finish", "release"]
+
+
 def _exchange_worker(rank, world, port, out_dir):
     import time
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
